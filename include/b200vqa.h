@@ -1,0 +1,184 @@
+/*
+ * b200vqa.h — C-ABI of libb200vqa.so: the sm_100a kernels behind the AutoViVQA fusion + MOE hot path.
+ *
+ * The reference (richardnguyen0715/vqa-model-builder) has no native/FFI layer: its hot path is Python
+ * nn.Modules whose arithmetic is ATen library calls.  Each entry point below replaces the group of ATen
+ * calls issued by the cited reference lines; the Python drop-in modules in vqa_model_builder_b200/ bind
+ * these symbols with ctypes (see INTEGRATION.md for the reference-side binding).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a B200_ERR_* code; b200_last_error_string() gives the
+ *     thread-local message.  No exception crosses the ABI.
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch caching allocator); the library never
+ *     allocates or frees device memory and never synchronises: launches are asynchronous on `stream`
+ *     (a cudaStream_t passed as void*), so calls are CUDA-graph capturable.
+ *   - `dtype` is B200_F32 or B200_BF16 and names the activation storage type; router outputs, LayerNorm
+ *     statistics, softmax statistics and all parameter gradients are always fp32.
+ *   - activations are dense row-major; row pitches must be multiples of 16 bytes.
+ *   - integer maps are int32.
+ */
+#ifndef B200VQA_H_
+#define B200VQA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VQA_ABI_VERSION 1
+
+enum { B200_OK = 0, B200_ERR_INVALID = 1, B200_ERR_CUDA = 2, B200_ERR_UNSUPPORTED = 3 };
+enum { B200_F32 = 0, B200_BF16 = 1 };
+/* operand storage for GEMMs: K = reduction dimension contiguous ([rows, k]); MN = [k, rows] */
+enum { B200_LAYOUT_K = 0, B200_LAYOUT_MN = 1 };
+enum { B200_ACT_NONE = 0, B200_ACT_GELU = 1, B200_ACT_RELU = 2, B200_ACT_SILU = 3, B200_ACT_TANH = 4 };
+/* GEMM epilogues */
+enum {
+  B200_EPI_NONE = 0,     /* out = acc (+bias)                                              */
+  B200_EPI_ACT = 1,      /* pre = acc+bias; aux_out = pre (if given); out = act(pre)        */
+  B200_EPI_ADD = 2,      /* out = acc (+bias) + aux_in          (residual add)              */
+  B200_EPI_DACT = 3,     /* out = acc * act'(aux_in)            (backward through act)      */
+  B200_EPI_ACCUM = 4     /* out(fp32) += acc                    (atomic, split-K wgrad)     */
+};
+
+#define B200_GROUP_TILE 128 /* expert row segments are padded to this many rows */
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+int b200_init(int device);
+const char* b200_last_error_string(void);
+int b200_abi_version(void);
+/* kernels launched by this library since the last reset (host-side counter; bench.py's gpu_launches) */
+long long b200_launch_count(void);
+void b200_reset_launch_count(void);
+
+/* ---- elementwise ----------------------------------------------------------------------------- */
+/* dtype conversion (autocast's weight/activation casts; torch/amp/autocast_mode, called around every
+ * nn.Linear in the reference under training_pipeline.py:457). */
+int b200_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, void* stream);
+/* out[g, :] = sum over rows r with group(r)==g of x[r, :]   (bias gradients).  tile_group==NULL: G=1.
+ * row_limit (device int, may be NULL) bounds the rows actually used. workspace >= b200_colsum_ws(R,N) */
+size_t b200_colsum_ws(int R, int N);
+int b200_colsum(const void* x, int dtype, int R, int N, const int32_t* tile_group, int G, float* out,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- GEMM ------------------------------------------------------------------------------------ */
+/* out[M,N] = A[M,K] * B[N,K]^T with epilogue.  Replaces nn.Linear fwd/bwd (vqa_model.py:258-271,
+ * expert_types.py:54-55, fusion_approaches.py:210-241) — F.linear -> cuBLAS in the reference.
+ * a_layout/b_layout select [rows,K] (B200_LAYOUT_K) or [K,rows] (B200_LAYOUT_MN) storage, which gives
+ * forward (K,K), dgrad (K,MN) and wgrad (MN,MN) from one kernel.  dtype BF16 -> tcgen05/TMEM/TMA kernel,
+ * F32 -> SIMT fp32 kernel (validation mode).  out_dtype may be F32 for BF16 inputs (wgrad).
+ * lda/ldb/ldo/ld_aux are row pitches in elements. bias is fp32 [N] or NULL.                        */
+int b200_gemm(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, void* out,
+              int ldo, int M, int N, int K, int dtype, int out_dtype, const float* bias, int epi,
+              int act, const void* aux_in, void* aux_out, int ld_aux, void* stream);
+
+/* Grouped GEMM over expert row segments (FeedForwardExpert fc1/fc2 fwd + dgrad, expert_types.py:79-83,
+ * evaluated sparsely instead of moe_layer.py:151-168's dense loop).  A is [R, K] (permuted rows, each
+ * expert's segment padded to B200_GROUP_TILE rows); tile_group[R/128] gives the expert of every 128-row
+ * tile (-1 = unused tile).  B is the stacked expert weight [G, N, K] (b_layout K) or [G, K, N] (MN).
+ * bias is [G, N] fp32 or NULL.                                                                      */
+int b200_ggemm(const void* A, int lda, const void* B, int b_layout, void* out, int ldo, int R, int N,
+               int K, int G, const int32_t* tile_group, int dtype, int out_dtype, const float* bias,
+               int epi, int act, const void* aux_in, void* aux_out, int ld_aux, void* stream);
+
+/* Grouped weight gradient: out[g] (fp32 [Mo, No]) = A[rows of g, :Mo]^T * B[rows of g, :No], rows of g =
+ * [group_off[g], group_off[g+1]) (device int32, multiples of 128; pad rows must be zero in A or B).  */
+int b200_ggemm_wgrad(const void* A, int lda, const void* B, int ldb, float* out, int Mo, int No, int R,
+                     int G, const int32_t* group_off, int dtype, void* stream);
+
+/* ---- LayerNorm (+ residual) ------------------------------------------------------------------- */
+/* y = LN(x + res) * gamma[g] + beta[g]   (res may be NULL).  nn.LayerNorm after the residual adds at
+ * vqa_model.py:301,305,309, expert_types.py:85-90, moe_layer.py:171, fusion_approaches.py:268-279.
+ * tile_group (may be NULL -> group 0) picks per-expert affine parameters gamma/beta [G, D].
+ * Saves mean/rstd [R] for backward.                                                                */
+int b200_add_ln_fwd(const void* x, const void* res, const float* gamma, const float* beta,
+                    const int32_t* tile_group, float eps, void* y, float* mean, float* rstd, int R, int D,
+                    int dtype, void* stream);
+/* dsum = d(x+res); dgamma/dbeta [G, D] fp32 (overwritten).  workspace >= b200_add_ln_bwd_ws(R, D)   */
+size_t b200_add_ln_bwd_ws(int R, int D);
+int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float* mean, const float* rstd,
+                    const float* gamma, const int32_t* tile_group, int G, void* dsum, float* dgamma,
+                    float* dbeta, int R, int D, int dtype, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ---- attention ------------------------------------------------------------------------------- */
+/* o[b,t,h,:] = softmax_s(scale * q[b,t,h,:].k[b,s,h,:] + mask) v[b,s,h,:]; nn.MultiheadAttention core
+ * (vqa_model.py:300,304; fusion_approaches.py:262-277; TransformerEncoderLayer self-attn in
+ * generative_vqa_model.py:203-214).  q/k/v are [B, T|S, H, dh] views with row pitches ldq/ldk/ldv
+ * (elements; lets q,k,v alias one packed in-proj output).  key_pad [B,S] uint8, 1 = ignore, or NULL.
+ * lse [B,H,T] fp32 is saved for backward.  The [B,H,T,S] score tensor never touches HBM.            */
+int b200_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                  const uint8_t* key_pad, void* o, int ldo, float* lse, int B, int H, int T, int S, int dh,
+                  float scale, int dtype, void* stream);
+int b200_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                  const uint8_t* key_pad, const void* o, int ldo, const void* d_o, int lddo,
+                  const float* lse, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int B,
+                  int H, int T, int S, int dh, float scale, int dtype, void* stream);
+
+/* ---- MOE router ------------------------------------------------------------------------------ */
+/* TopKRouter / NoisyTopKRouter forward (router.py:105-178, 287-366): logits = x Wg^T in fp32,
+ * optional noise eps * softplus(x Wn^T) * noise_std, softmax, top-k (descending, lowest index wins
+ * exact ties), renormalise; clean probs and the Switch load-balance loss
+ *   loss = lb_weight * E * sum_e (count_e / N) * (sum_n p_clean[n,e] / N).
+ * Outputs: idx int32 [N,K], w fp32 [N,K], topk_sum fp32 [N], probs fp32 [N,E] (clean),
+ * probs_noisy fp32 [N,E] (only when eps != NULL), counts fp32 [E], loss fp32 [1],
+ * noise_scale_mean fp32 [1] (only when eps != NULL).  workspace >= b200_router_ws(N, E).          */
+size_t b200_router_ws(int N, int E);
+int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* w_noise, const float* eps,
+                    float noise_std, float lb_weight, int N, int D, int E, int K, int32_t* idx, float* w,
+                    float* topk_sum, float* probs, float* probs_noisy, float* counts, float* loss,
+                    float* noise_scale_mean, void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of the above.  d_w [N,K] (may be NULL), d_loss device fp32 scalar (may be NULL).
+ * Produces dx [N,D] (overwrite), d_w_gate [E,D] fp32, d_w_noise [E,D] fp32 (if noisy).
+ * workspace >= b200_router_bwd_ws(N, D, E).                                                         */
+size_t b200_router_bwd_ws(int N, int D, int E);
+int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* w_noise, const float* eps,
+                    float noise_std, float lb_weight, int N, int D, int E, int K, const int32_t* idx,
+                    const float* w, const float* topk_sum, const float* probs, const float* probs_noisy,
+                    const float* counts, const float* d_w, const float* d_loss, void* dx, float* d_w_gate,
+                    float* d_w_noise, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- MOE dispatch / combine ------------------------------------------------------------------- */
+/* Upper bound of padded rows for NK (token,slot) pairs over E experts (host-side, no sync).        */
+int b200_moe_max_rows(int NK, int E);
+/* Routing plan (replaces nonzero/any/len host syncs of moe_layer.py:151-160, 317-337).  idx [NK] int32
+ * (entries <0 or >=E are dropped).  Canonical order = stable sort of the flattened (n,k) list by expert
+ * id (== (expert asc, token asc), the order SparseMOELayer's nonzero() produces, moe_layer.py:326).
+ * counts[E], cmp_off[E+1] (compact offsets), pad_off[E+1] (offsets with every segment padded to 128),
+ * dest_row[NK] (row in the padded layout, -1 dropped), cmp_pos[NK] (position in the compact canonical
+ * order, -1 dropped), row_src[Rmax] (flattened (n,k) of each padded row, -1 = padding),
+ * tile_group[Rmax/128] (expert per 128-row tile, -1 unused).  workspace >= b200_moe_plan_ws(NK,E).  */
+size_t b200_moe_plan_ws(int NK, int E);
+int b200_moe_plan(const int32_t* idx, int NK, int E, int Rmax, int32_t* counts, int32_t* cmp_off,
+                  int32_t* pad_off, int32_t* dest_row, int32_t* cmp_pos, int32_t* row_src,
+                  int32_t* tile_group, void* workspace, size_t workspace_bytes, void* stream);
+/* SparseMOELayer capacity (moe_layer.py:329-337): for experts with count > capacity keep the `capacity`
+ * largest combine weights (ties: lower token first); others get w_eff = 0 and keep[...] = 0.        */
+int b200_moe_capacity(const int32_t* idx, const float* w, const int32_t* counts, const int32_t* pad_off,
+                      const int32_t* row_src, int NK, int E, int capacity, float* w_eff, uint8_t* keep,
+                      void* stream);
+/* xp[r,:] = x[row_src[r] / K, :] (zeros for padding rows).  128-bit vectorised row gather.           */
+int b200_moe_permute(const void* x, const int32_t* row_src, const int32_t* pad_off, int E, int K, int Rmax,
+                     int D, int dtype, void* xp, void* stream);
+/* dx[n,:] = sum_k dxp[dest_row[n,k], :] (+ add[n,:] if add != NULL)   — backward of permute.        */
+int b200_moe_unpermute(const void* dxp, const int32_t* dest_row, const void* add, int N, int K, int D,
+                       int dtype, void* dx, void* stream);
+/* out[n,:] = LN_out( sum_k w[n,k] * z[dest_row[n,k], :] )   (moe_layer.py:163-171).                  */
+int b200_moe_combine_fwd(const void* z, const int32_t* dest_row, const float* w, const float* gamma,
+                         const float* beta, float eps, int N, int K, int D, int dtype, void* out,
+                         float* mean, float* rstd, void* stream);
+/* dz[dest_row[n,k],:] = w[n,k] * ds[n,:], d_w[n,k] = <ds[n,:], z[dest_row[n,k],:]>, padding rows of dz
+ * zeroed; dgamma/dbeta [D] fp32.  workspace >= b200_moe_combine_bwd_ws(N, D).                       */
+size_t b200_moe_combine_bwd_ws(int N, int D);
+int b200_moe_combine_bwd(const void* dout, const void* z, const int32_t* dest_row, const float* w,
+                         const float* mean, const float* rstd, const float* gamma,
+                         const int32_t* row_src, int N, int K, int D, int Rmax, int dtype, void* dz,
+                         float* d_w, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VQA_H_ */

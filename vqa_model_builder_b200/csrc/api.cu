@@ -1,0 +1,236 @@
+// C-ABI surface: lifecycle, error reporting, casts, column sums and the GEMM entry points.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "gemm_common.cuh"
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static int g_num_sms = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return B200_ERR_CUDA;
+}
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- cast ---------------------------------------------------------------------------------------
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      float v[4];
+      if constexpr (sizeof(S) == 4) {
+        float4 t = *reinterpret_cast<const float4*>(src + i);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+        uint2 t = *reinterpret_cast<const uint2*>(src + i);
+        float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+      }
+      if constexpr (sizeof(D) == 4) {
+        *reinterpret_cast<float4*>(dst + i) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        uint2 t;
+        t.x = pack_bf16x2(v[0], v[1]);
+        t.y = pack_bf16x2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(dst + i) = t;
+      }
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = from_f32<D>(to_f32<S>(src[j]));
+    }
+  }
+}
+
+// ---- column sums (bias gradients), deterministic two-stage ---------------------------------------
+// stage 1: block b sums rows [b*128, b*128+128) for a 128-column slab -> part[b][N]
+template <typename T>
+__global__ void colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part) {
+  const int col = blockIdx.x * 128 + threadIdx.x;
+  const int r0 = blockIdx.y * B200_GROUP_TILE, r1 = min(R, r0 + B200_GROUP_TILE);
+  if (col >= N) return;
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += to_f32<T>(x[(long long)r * N + col]);
+  part[(long long)blockIdx.y * N + col] = s;
+}
+// stage 2: out[g][col] = sum over tiles t with group(t)==g of part[t][col]
+__global__ void colsum_stage2(const float* __restrict__ part, int tiles, int N, const int* __restrict__ tile_group,
+                              int G, float* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
+  if (col >= N) return;
+  float s = 0.f;
+  for (int t = 0; t < tiles; ++t) {
+    const int tg = tile_group ? tile_group[t] : 0;
+    if (tg == g) s += part[(long long)t * N + col];
+  }
+  out[(long long)g * N + col] = s;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_init(int device) {
+  B200_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B200_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("b200vqa requires an sm_100 (Blackwell B200) device; device %d is sm_%d%d", device, prop.major,
+              prop.minor);
+    return B200_ERR_UNSUPPORTED;
+  }
+  return 0;
+}
+const char* b200_last_error_string(void) { return g_err; }
+int b200_abi_version(void) { return B200VQA_ABI_VERSION; }
+long long b200_launch_count(void) { return g_launches.load(); }
+void b200_reset_launch_count(void) { g_launches.store(0); }
+
+int b200_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n <= 0) return 0;
+  B200_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "cast: pointers must be 16-byte aligned");
+  const int threads = 256;
+  long long blocks = (n / 4 + threads - 1) / threads;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (src_dtype == B200_F32 && dst_dtype == B200_BF16)
+    cast_kernel<float, bf16><<<(int)blocks, threads, 0, stream>>>((const float*)src, (bf16*)dst, n);
+  else if (src_dtype == B200_BF16 && dst_dtype == B200_F32)
+    cast_kernel<bf16, float><<<(int)blocks, threads, 0, stream>>>((const bf16*)src, (float*)dst, n);
+  else if (src_dtype == B200_F32 && dst_dtype == B200_F32)
+    cast_kernel<float, float><<<(int)blocks, threads, 0, stream>>>((const float*)src, (float*)dst, n);
+  else if (src_dtype == B200_BF16 && dst_dtype == B200_BF16)
+    cast_kernel<bf16, bf16><<<(int)blocks, threads, 0, stream>>>((const bf16*)src, (bf16*)dst, n);
+  else {
+    set_error("cast: bad dtypes %d -> %d", src_dtype, dst_dtype);
+    return B200_ERR_INVALID;
+  }
+  B200_LAUNCH_CHECK("cast_kernel");
+  count_launch();
+  return 0;
+}
+
+size_t b200_colsum_ws(int R, int N) {
+  const size_t tiles = (size_t)(R + B200_GROUP_TILE - 1) / B200_GROUP_TILE;
+  return tiles * (size_t)N * sizeof(float);
+}
+int b200_colsum(const void* x, int dtype, int R, int N, const int32_t* tile_group, int G, float* out,
+                void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(R > 0 && N > 0 && G > 0, "colsum: bad shape R=%d N=%d G=%d", R, N, G);
+  B200_CHECK_ARG(workspace_bytes >= b200_colsum_ws(R, N), "colsum: workspace too small");
+  const int tiles = (R + B200_GROUP_TILE - 1) / B200_GROUP_TILE;
+  float* part = (float*)workspace;
+  dim3 g1((N + 127) / 128, tiles);
+  if (dtype == B200_F32) colsum_stage1<float><<<g1, 128, 0, stream>>>((const float*)x, R, N, part);
+  else colsum_stage1<bf16><<<g1, 128, 0, stream>>>((const bf16*)x, R, N, part);
+  B200_LAUNCH_CHECK("colsum_stage1");
+  dim3 g2((N + 127) / 128, G);
+  colsum_stage2<<<g2, 128, 0, stream>>>(part, tiles, N, tile_group, G, out);
+  B200_LAUNCH_CHECK("colsum_stage2");
+  count_launch(2);
+  return 0;
+}
+
+static int check_epi(int epi, int act, const void* aux_in, int out_dtype) {
+  B200_CHECK_ARG(epi >= B200_EPI_NONE && epi <= B200_EPI_ACCUM, "gemm: bad epilogue %d", epi);
+  B200_CHECK_ARG(act >= B200_ACT_NONE && act <= B200_ACT_TANH, "gemm: bad activation %d", act);
+  B200_CHECK_ARG(!(epi == B200_EPI_ADD || epi == B200_EPI_DACT) || aux_in != nullptr, "gemm: epilogue needs aux_in");
+  B200_CHECK_ARG(epi != B200_EPI_ACCUM || out_dtype == B200_F32, "gemm: ACCUM epilogue needs fp32 output");
+  return 0;
+}
+
+int b200_gemm(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, void* out, int ldo,
+              int M, int N, int K, int dtype, int out_dtype, const float* bias, int epi, int act,
+              const void* aux_in, void* aux_out, int ld_aux, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  B200_CHECK_ARG(dtype == B200_F32 || dtype == B200_BF16, "gemm: bad dtype %d", dtype);
+  B200_CHECK_ARG(dtype == B200_BF16 || out_dtype == B200_F32, "gemm: fp32 inputs need fp32 output");
+  if (int rc = check_epi(epi, act, aux_in, out_dtype)) return rc;
+  GemmArgs a{};
+  a.M = M; a.N = N; a.K = K; a.mode = GEMM_DENSE; a.epi = epi; a.act = act;
+  a.out_f32 = (out_dtype == B200_F32); a.ldo = ldo; a.ld_aux = ld_aux; a.out = out; a.aux_in = aux_in;
+  a.aux_out = aux_out; a.bias = bias; a.k_splits = 1;
+  const int m_tiles = (M + B200_GROUP_TILE - 1) / B200_GROUP_TILE;
+  if (epi == B200_EPI_ACCUM)  // accumulate into a zeroed buffer (split-K partial sums are added atomically)
+    B200_CUDA(cudaMemsetAsync(out, 0, (size_t)M * ldo * sizeof(float), stream));
+  if (dtype == B200_BF16) {
+    return launch_gemm_tc(A, lda, a_layout, M, K, B, ldb, b_layout, N, K, a, m_tiles, 1, stream);
+  }
+  a.A = A; a.B = B;
+  a.sa_m = a_layout == B200_LAYOUT_K ? lda : 1; a.sa_k = a_layout == B200_LAYOUT_K ? 1 : lda;
+  a.sb_n = b_layout == B200_LAYOUT_K ? ldb : 1; a.sb_k = b_layout == B200_LAYOUT_K ? 1 : ldb;
+  return launch_gemm_simt(a, m_tiles, 1, stream);
+}
+
+int b200_ggemm(const void* A, int lda, const void* B, int b_layout, void* out, int ldo, int R, int N, int K, int G,
+               const int32_t* tile_group, int dtype, int out_dtype, const float* bias, int epi, int act,
+               const void* aux_in, void* aux_out, int ld_aux, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(R > 0 && R % B200_GROUP_TILE == 0, "ggemm: R=%d must be a positive multiple of %d", R,
+                 B200_GROUP_TILE);
+  B200_CHECK_ARG(N > 0 && K > 0 && G > 0 && tile_group != nullptr, "ggemm: bad arguments");
+  B200_CHECK_ARG(epi != B200_EPI_ACCUM, "ggemm: ACCUM epilogue not supported");
+  B200_CHECK_ARG(dtype == B200_BF16 || out_dtype == B200_F32, "ggemm: fp32 inputs need fp32 output");
+  if (int rc = check_epi(epi, act, aux_in, out_dtype)) return rc;
+  GemmArgs a{};
+  a.M = R; a.N = N; a.K = K; a.mode = GEMM_GROUP_ROWS; a.epi = epi; a.act = act;
+  a.out_f32 = (out_dtype == B200_F32); a.ldo = ldo; a.ld_aux = ld_aux; a.out = out; a.aux_in = aux_in;
+  a.aux_out = aux_out; a.bias = bias; a.tile_group = tile_group; a.k_splits = 1;
+  a.b_group_rows = (b_layout == B200_LAYOUT_K) ? N : K;
+  a.b_group_elems = (long long)N * K;
+  const int m_tiles = R / B200_GROUP_TILE;
+  if (dtype == B200_BF16) {
+    if (b_layout == B200_LAYOUT_K)  // B stacked [G*N, K]
+      return launch_gemm_tc(A, lda, B200_LAYOUT_K, R, K, B, K, b_layout, (long long)G * N, K, a, m_tiles, G, stream);
+    // B stacked [G*K, N]
+    return launch_gemm_tc(A, lda, B200_LAYOUT_K, R, K, B, N, b_layout, N, (long long)G * K, a, m_tiles, G, stream);
+  }
+  a.A = A; a.B = B; a.sa_m = lda; a.sa_k = 1;
+  a.sb_n = b_layout == B200_LAYOUT_K ? K : 1; a.sb_k = b_layout == B200_LAYOUT_K ? 1 : N;
+  return launch_gemm_simt(a, m_tiles, G, stream);
+}
+
+int b200_ggemm_wgrad(const void* A, int lda, const void* B, int ldb, float* out, int Mo, int No, int R, int G,
+                     const int32_t* group_off, int dtype, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(R > 0 && R % B200_GROUP_TILE == 0 && Mo > 0 && No > 0 && G > 0 && group_off != nullptr,
+                 "ggemm_wgrad: bad arguments");
+  GemmArgs a{};
+  a.M = Mo; a.N = No; a.K = 0; a.mode = GEMM_GROUP_WGRAD; a.epi = B200_EPI_NONE; a.act = B200_ACT_NONE;
+  a.out_f32 = 1; a.ldo = No; a.out = out; a.group_off = group_off; a.out_group_elems = (long long)Mo * No;
+  a.k_splits = 1;
+  const int m_tiles = (Mo + B200_GROUP_TILE - 1) / B200_GROUP_TILE;
+  if (dtype == B200_BF16)
+    return launch_gemm_tc(A, lda, B200_LAYOUT_MN, Mo, R, B, ldb, B200_LAYOUT_MN, No, R, a, m_tiles, G, stream);
+  a.A = A; a.B = B; a.sa_m = 1; a.sa_k = lda; a.sb_n = 1; a.sb_k = ldb;
+  return launch_gemm_simt(a, m_tiles, G, stream);
+}
+
+}  // extern "C"

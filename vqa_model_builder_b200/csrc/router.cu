@@ -1,0 +1,412 @@
+// MOE router: gate dot-products, (noisy) softmax, top-k, renormalisation and the Switch load-balance
+// statistics in one pass over x; backward produces dx and the gate-weight gradients.
+// One warp per token, fp32 throughout (routing decisions must not depend on the activation dtype),
+// gate weights staged in shared memory, lane e owns expert e (and e+32).
+#include "rowops.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int RT_MAX_E = 64;
+constexpr int RT_WARPS = 8;
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(__expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// dot products of one token row (held as 16-byte vectors across the warp) with E weight rows in smem.
+// On return lane e (and slot 1: e+32) holds logit e.
+template <typename T>
+__device__ __forceinline__ void gate_dots(const T* __restrict__ xrow, const float* __restrict__ ws, int D, int E,
+                                          int lane, float& l0, float& l1) {
+  constexpr int VT = Vec16<T>::N;
+  const int nv = D / VT;
+  l0 = 0.f;
+  l1 = 0.f;
+  for (int e = 0; e < E; ++e) {
+    const float* wr = ws + (long long)e * D;
+    float s = 0.f;
+    for (int v = lane; v < nv; v += 32) {
+      Vec16<T> xv;
+      xv.load(xrow + v * VT);
+#pragma unroll
+      for (int u = 0; u < VT; ++u) s = fmaf(xv.v[u], wr[v * VT + u], s);
+    }
+    s = warp_sum(s);
+    if ((e & 31) == lane) {
+      if (e < 32) l0 = s; else l1 = s;
+    }
+  }
+}
+
+// softmax over the E logits spread as (lane, slot); invalid slots must hold -inf
+__device__ __forceinline__ void warp_softmax(float& a, float& b) {
+  const float m = warp_max(fmaxf(a, b));
+  const float ea = __expf(a - m), eb = __expf(b - m);
+  const float s = warp_sum(ea + eb);
+  a = ea / s;
+  b = eb / s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RT_WARPS * 32)
+router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, const float* __restrict__ w_noise,
+                  const float* __restrict__ eps, float noise_std, int N, int D, int E, int K, int* __restrict__ idx,
+                  float* __restrict__ w, float* __restrict__ topk_sum, float* __restrict__ probs,
+                  float* __restrict__ probs_noisy, float* __restrict__ part /* [grid][3][RT_MAX_E] */) {
+  extern __shared__ float smem[];
+  float* wg = smem;                                  // [E][D]
+  float* wn = smem + (size_t)E * D;                  // [E][D] (noisy only)
+  __shared__ float red[RT_WARPS][3][RT_MAX_E];
+  const bool noisy = (eps != nullptr);
+  for (int i = threadIdx.x; i < E * D; i += blockDim.x) {
+    wg[i] = w_gate[i];
+    if (noisy) wn[i] = w_noise[i];
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool v0 = lane < E, v1 = lane + 32 < E;
+  float cnt0 = 0.f, cnt1 = 0.f, ps0 = 0.f, ps1 = 0.f, ns0 = 0.f, ns1 = 0.f;
+
+  for (int n = blockIdx.x * RT_WARPS + warp; n < N; n += gridDim.x * RT_WARPS) {
+    const T* xrow = x + (long long)n * D;
+    float c0, c1;  // clean logits -> clean probs
+    gate_dots<T>(xrow, wg, D, E, lane, c0, c1);
+    float q0 = c0, q1 = c1;  // logits used for selection
+    if (noisy) {
+      float u0, u1;
+      gate_dots<T>(xrow, wn, D, E, lane, u0, u1);
+      const float sp0 = softplus_f(u0), sp1 = softplus_f(u1);
+      if (v0) { q0 = c0 + eps[(long long)n * E + lane] * sp0 * noise_std; ns0 += sp0; }
+      if (v1) { q1 = c1 + eps[(long long)n * E + lane + 32] * sp1 * noise_std; ns1 += sp1; }
+    }
+    if (!v0) { c0 = -INFINITY; q0 = -INFINITY; }
+    if (!v1) { c1 = -INFINITY; q1 = -INFINITY; }
+    warp_softmax(c0, c1);
+    if (noisy) warp_softmax(q0, q1);
+    else { q0 = c0; q1 = c1; }
+    if (v0) { probs[(long long)n * E + lane] = c0; ps0 += c0; }
+    if (v1) { probs[(long long)n * E + lane + 32] = c1; ps1 += c1; }
+    if (noisy) {
+      if (v0) probs_noisy[(long long)n * E + lane] = q0;
+      if (v1) probs_noisy[(long long)n * E + lane + 32] = q1;
+    }
+    // top-k by repeated warp arg-max (descending; exact ties -> lowest expert index)
+    float a0 = v0 ? q0 : -1.f, a1 = v1 ? q1 : -1.f;
+    float sel_sum = 0.f;
+    float my_w = 0.f;
+    int my_i = 0;
+    for (int k = 0; k < K; ++k) {
+      float bv = a0;
+      int bi = lane;
+      if (a1 > bv) { bv = a1; bi = lane + 32; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      sel_sum += bv;
+      if (lane == k) { my_w = bv; my_i = bi; }
+      if (bi == lane) { a0 = -2.f; cnt0 += 1.f; }
+      if (bi == lane + 32) { a1 = -2.f; cnt1 += 1.f; }
+    }
+    if (lane < K) {
+      idx[(long long)n * K + lane] = my_i;
+      w[(long long)n * K + lane] = my_w / sel_sum;
+    }
+    if (lane == 0) topk_sum[n] = sel_sum;
+  }
+
+  // block partials: [0] counts, [1] sum of clean probs, [2] sum of softplus noise scales
+  red[warp][0][lane] = cnt0; red[warp][0][lane + 32] = cnt1;
+  red[warp][1][lane] = ps0;  red[warp][1][lane + 32] = ps1;
+  red[warp][2][lane] = ns0;  red[warp][2][lane + 32] = ns1;
+  __syncthreads();
+  for (int c = threadIdx.x; c < 3 * RT_MAX_E; c += blockDim.x) {
+    const int which = c / RT_MAX_E, e = c % RT_MAX_E;
+    float s = 0.f;
+#pragma unroll
+    for (int wp = 0; wp < RT_WARPS; ++wp) s += red[wp][which][e];
+    part[((long long)blockIdx.x * 3 + which) * RT_MAX_E + e] = s;
+  }
+}
+
+// counts[e], loss = lb_weight * E * sum_e (counts[e]/N) * (psum[e]/N), mean softplus noise scale
+__global__ void router_finalize_kernel(const float* __restrict__ part, int blocks, int N, int E, float lb_weight,
+                                       float* __restrict__ counts, float* __restrict__ loss,
+                                       float* __restrict__ noise_scale_mean) {
+  __shared__ float s_cnt[RT_MAX_E], s_ps[RT_MAX_E], s_ns[RT_MAX_E];
+  const int e = threadIdx.x;
+  if (e < RT_MAX_E) {
+    float c = 0.f, p = 0.f, q = 0.f;
+    for (int b = 0; b < blocks; ++b) {
+      c += part[((long long)b * 3 + 0) * RT_MAX_E + e];
+      p += part[((long long)b * 3 + 1) * RT_MAX_E + e];
+      q += part[((long long)b * 3 + 2) * RT_MAX_E + e];
+    }
+    s_cnt[e] = c; s_ps[e] = p; s_ns[e] = q;
+    if (e < E) counts[e] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float acc = 0.f, ns = 0.f;
+    for (int i = 0; i < E; ++i) {
+      acc += (s_cnt[i] / (float)N) * (s_ps[i] / (float)N);
+      ns += s_ns[i];
+    }
+    loss[0] = lb_weight * (float)E * acc;
+    if (noise_scale_mean != nullptr) noise_scale_mean[0] = ns / ((float)N * (float)E);
+  }
+}
+
+// ---- backward --------------------------------------------------------------------------------------------
+// per token: d logits (clean) and d noise-logits, then dx = dl Wg + du Wn.  dl/du are also written to the
+// workspace for the weight-gradient reduction.
+template <typename T>
+__global__ void __launch_bounds__(RT_WARPS * 32)
+router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, const float* __restrict__ w_noise,
+                  const float* __restrict__ eps, float noise_std, float lb_weight, int N, int D, int E, int K,
+                  const int* __restrict__ idx, const float* __restrict__ w, const float* __restrict__ topk_sum,
+                  const float* __restrict__ probs, const float* __restrict__ probs_noisy,
+                  const float* __restrict__ counts, const float* __restrict__ d_w, const float* __restrict__ d_loss,
+                  T* __restrict__ dx, float* __restrict__ dl_out, float* __restrict__ du_out) {
+  constexpr int VT = Vec16<T>::N;
+  extern __shared__ float smem[];
+  float* wg = smem;
+  float* wn = smem + (size_t)E * D;
+  __shared__ float s_dl[RT_WARPS][RT_MAX_E], s_du[RT_WARPS][RT_MAX_E];
+  const bool noisy = (eps != nullptr);
+  for (int i = threadIdx.x; i < E * D; i += blockDim.x) {
+    wg[i] = w_gate[i];
+    if (noisy) wn[i] = w_noise[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool v0 = lane < E, v1 = lane + 32 < E;
+  const float gl = (d_loss != nullptr) ? d_loss[0] : 0.f;
+  const int nv = D / VT;
+
+  for (int n = blockIdx.x * RT_WARPS + warp; n < N; n += gridDim.x * RT_WARPS) {
+    const float* qrow = (noisy ? probs_noisy : probs) + (long long)n * E;
+    const float q0 = v0 ? qrow[lane] : 0.f, q1 = v1 ? qrow[lane + 32] : 0.f;
+    // gradient wrt the selection probabilities q through w_k = q_{i_k} / sum_j q_{i_j}
+    float dq0 = 0.f, dq1 = 0.f;
+    if (d_w != nullptr) {
+      const float ssum = topk_sum[n];
+      float dot = 0.f;
+      for (int k = 0; k < K; ++k) dot = fmaf(d_w[(long long)n * K + k], w[(long long)n * K + k], dot);
+      for (int k = 0; k < K; ++k) {
+        const int ik = idx[(long long)n * K + k];
+        const float g = (d_w[(long long)n * K + k] - dot) / ssum;
+        if (ik == lane) dq0 += g;
+        if (ik == lane + 32) dq1 += g;
+      }
+    }
+    float qdq = warp_sum(q0 * dq0 + q1 * dq1);
+    float dsel0 = q0 * (dq0 - qdq), dsel1 = q1 * (dq1 - qdq);  // d (selection logits)
+    // aux loss: d loss / d p_clean[n,e] = lb_weight * E * (counts[e]/N) / N
+    float dc0 = 0.f, dc1 = 0.f;
+    if (gl != 0.f) {
+      const float* prow = probs + (long long)n * E;
+      const float p0 = v0 ? prow[lane] : 0.f, p1 = v1 ? prow[lane + 32] : 0.f;
+      const float sc = gl * lb_weight * (float)E / ((float)N * (float)N);
+      const float dp0 = v0 ? sc * counts[lane] : 0.f, dp1 = v1 ? sc * counts[lane + 32] : 0.f;
+      const float pdp = warp_sum(p0 * dp0 + p1 * dp1);
+      dc0 = p0 * (dp0 - pdp);
+      dc1 = p1 * (dp1 - pdp);
+    }
+    const T* xrow = x + (long long)n * D;
+    float du0 = 0.f, du1 = 0.f;
+    if (noisy) {
+      float u0, u1;
+      gate_dots<T>(xrow, wn, D, E, lane, u0, u1);
+      if (v0) du0 = dsel0 * eps[(long long)n * E + lane] * noise_std * sigmoid_f(u0);
+      if (v1) du1 = dsel1 * eps[(long long)n * E + lane + 32] * noise_std * sigmoid_f(u1);
+    }
+    const float dl0 = dsel0 + dc0, dl1 = dsel1 + dc1;
+    s_dl[warp][lane] = dl0; s_dl[warp][lane + 32] = dl1;
+    s_du[warp][lane] = du0; s_du[warp][lane + 32] = du1;
+    if (v0) dl_out[(long long)n * E + lane] = dl0;
+    if (v1) dl_out[(long long)n * E + lane + 32] = dl1;
+    if (noisy) {
+      if (v0) du_out[(long long)n * E + lane] = du0;
+      if (v1) du_out[(long long)n * E + lane + 32] = du1;
+    }
+    __syncwarp();
+    T* dxrow = dx + (long long)n * D;
+    for (int v = lane; v < nv; v += 32) {
+      Vec16<T> o;
+#pragma unroll
+      for (int u = 0; u < VT; ++u) o.v[u] = 0.f;
+      for (int e = 0; e < E; ++e) {
+        const float a = s_dl[warp][e];
+        const float* wr = wg + (long long)e * D + v * VT;
+#pragma unroll
+        for (int u = 0; u < VT; ++u) o.v[u] = fmaf(a, wr[u], o.v[u]);
+        if (noisy) {
+          const float b = s_du[warp][e];
+          const float* nr = wn + (long long)e * D + v * VT;
+#pragma unroll
+          for (int u = 0; u < VT; ++u) o.v[u] = fmaf(b, nr[u], o.v[u]);
+        }
+      }
+      o.store(dxrow + v * VT);
+    }
+    __syncwarp();
+  }
+}
+
+// dW[e][d] partial over a chunk of tokens: part[chunk][E][D]; thread per column.
+constexpr int RW_CHUNK = 256;
+template <typename T>
+__global__ void __launch_bounds__(128)
+router_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ dl, int N, int D, int E,
+                    float* __restrict__ part) {
+  __shared__ float s_dl[32][RT_MAX_E];
+  const int d = blockIdx.x * 128 + threadIdx.x;
+  const int n0 = blockIdx.y * RW_CHUNK, n1 = min(N, n0 + RW_CHUNK);
+  float acc[RT_MAX_E];
+#pragma unroll
+  for (int e = 0; e < RT_MAX_E; ++e) acc[e] = 0.f;
+  for (int nb = n0; nb < n1; nb += 32) {
+    const int cnt = min(32, n1 - nb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * E; i += blockDim.x) s_dl[i / E][i % E] = dl[(long long)(nb + i / E) * E + i % E];
+    __syncthreads();
+    if (d < D) {
+      for (int t = 0; t < cnt; ++t) {
+        const float xv = to_f32<T>(x[(long long)(nb + t) * D + d]);
+#pragma unroll
+        for (int e = 0; e < RT_MAX_E; ++e)
+          if (e < E) acc[e] = fmaf(s_dl[t][e], xv, acc[e]);
+      }
+    }
+  }
+  if (d < D) {
+#pragma unroll
+    for (int e = 0; e < RT_MAX_E; ++e)
+      if (e < E) part[((long long)blockIdx.y * E + e) * D + d] = acc[e];
+  }
+}
+__global__ void router_wgrad_reduce_kernel(const float* __restrict__ part, int chunks, int ED, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ED) return;
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += part[(long long)c * ED + i];
+  out[i] = s;
+}
+
+inline int router_grid(int N) {
+  int blocks = (N + RT_WARPS - 1) / RT_WARPS;
+  const int cap = num_sms() * 2;
+  if (blocks > cap) blocks = cap;
+  return blocks < 1 ? 1 : blocks;
+}
+
+template <typename K>
+int set_smem(K kern, size_t bytes) {
+  if (bytes > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+size_t b200_router_ws(int N, int E) {
+  (void)E;
+  return (size_t)router_grid(N) * 3 * RT_MAX_E * sizeof(float);
+}
+
+int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* w_noise, const float* eps,
+                    float noise_std, float lb_weight, int N, int D, int E, int K, int32_t* idx, float* w,
+                    float* topk_sum, float* probs, float* probs_noisy, float* counts, float* loss,
+                    float* noise_scale_mean, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(N > 0 && D > 0 && E > 0 && E <= RT_MAX_E && K > 0 && K <= E && K <= 32,
+                 "router_fwd: bad shape N=%d D=%d E=%d K=%d (E<=64, K<=min(E,32))", N, D, E, K);
+  B200_CHECK_ARG((eps == nullptr) || (w_noise != nullptr && probs_noisy != nullptr),
+                 "router_fwd: noisy routing needs w_noise and probs_noisy");
+  B200_CHECK_ARG(workspace_bytes >= b200_router_ws(N, E), "router_fwd: workspace too small");
+  B200_CHECK_ARG(dtype == B200_BF16 ? D % 8 == 0 : D % 4 == 0, "router_fwd: D=%d not vectorisable", D);
+  const size_t smem = (size_t)E * D * sizeof(float) * (eps != nullptr ? 2 : 1);
+  B200_CHECK_ARG(smem <= 200 * 1024, "router_fwd: gate weights (%zu B) do not fit in shared memory", smem);
+  const int blocks = router_grid(N);
+  float* part = (float*)workspace;
+  if (dtype == B200_BF16) {
+    if (int rc = set_smem(router_fwd_kernel<bf16>, smem)) return rc;
+    router_fwd_kernel<bf16><<<blocks, RT_WARPS * 32, smem, stream>>>((const bf16*)x, w_gate, w_noise, eps, noise_std, N,
+                                                                     D, E, K, idx, w, topk_sum, probs, probs_noisy, part);
+  } else {
+    if (int rc = set_smem(router_fwd_kernel<float>, smem)) return rc;
+    router_fwd_kernel<float><<<blocks, RT_WARPS * 32, smem, stream>>>((const float*)x, w_gate, w_noise, eps, noise_std,
+                                                                      N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
+                                                                      part);
+  }
+  B200_LAUNCH_CHECK("router_fwd_kernel");
+  router_finalize_kernel<<<1, RT_MAX_E, 0, stream>>>(part, blocks, N, E, lb_weight, counts, loss,
+                                                     eps != nullptr ? noise_scale_mean : nullptr);
+  B200_LAUNCH_CHECK("router_finalize_kernel");
+  count_launch(2);
+  return 0;
+}
+
+size_t b200_router_bwd_ws(int N, int D, int E) {
+  const size_t chunks = (size_t)(N + RW_CHUNK - 1) / RW_CHUNK;
+  // dl [N,E] + du [N,E] + partial weight grads [chunks][E][D]
+  return ((size_t)2 * N * E + chunks * (size_t)E * D) * sizeof(float);
+}
+
+int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* w_noise, const float* eps,
+                    float noise_std, float lb_weight, int N, int D, int E, int K, const int32_t* idx, const float* w,
+                    const float* topk_sum, const float* probs, const float* probs_noisy, const float* counts,
+                    const float* d_w, const float* d_loss, void* dx, float* d_w_gate, float* d_w_noise, void* workspace,
+                    size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(N > 0 && D > 0 && E > 0 && E <= RT_MAX_E && K > 0 && K <= E, "router_bwd: bad shape");
+  B200_CHECK_ARG(workspace_bytes >= b200_router_bwd_ws(N, D, E), "router_bwd: workspace too small");
+  B200_CHECK_ARG(dtype == B200_BF16 ? D % 8 == 0 : D % 4 == 0, "router_bwd: D=%d not vectorisable", D);
+  const bool noisy = eps != nullptr;
+  B200_CHECK_ARG(!noisy || (w_noise != nullptr && probs_noisy != nullptr && d_w_noise != nullptr),
+                 "router_bwd: noisy routing needs w_noise, probs_noisy, d_w_noise");
+  const size_t smem = (size_t)E * D * sizeof(float) * (noisy ? 2 : 1);
+  B200_CHECK_ARG(smem <= 200 * 1024, "router_bwd: gate weights do not fit in shared memory");
+  float* dl = (float*)workspace;
+  float* du = dl + (size_t)N * E;
+  float* part = du + (size_t)N * E;
+  const int blocks = router_grid(N);
+  const int chunks = (N + RW_CHUNK - 1) / RW_CHUNK;
+  dim3 wg_grid((D + 127) / 128, chunks);
+  const int ED = E * D;
+  if (dtype == B200_BF16) {
+    if (int rc = set_smem(router_bwd_kernel<bf16>, smem)) return rc;
+    router_bwd_kernel<bf16><<<blocks, RT_WARPS * 32, smem, stream>>>(
+        (const bf16*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
+        counts, d_w, d_loss, (bf16*)dx, dl, du);
+  } else {
+    if (int rc = set_smem(router_bwd_kernel<float>, smem)) return rc;
+    router_bwd_kernel<float><<<blocks, RT_WARPS * 32, smem, stream>>>(
+        (const float*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
+        counts, d_w, d_loss, (float*)dx, dl, du);
+  }
+  B200_LAUNCH_CHECK("router_bwd_kernel");
+  count_launch();
+  for (int pass = 0; pass < (noisy ? 2 : 1); ++pass) {
+    const float* g = pass == 0 ? dl : du;
+    float* out = pass == 0 ? d_w_gate : d_w_noise;
+    if (dtype == B200_BF16) router_wgrad_kernel<bf16><<<wg_grid, 128, 0, stream>>>((const bf16*)x, g, N, D, E, part);
+    else router_wgrad_kernel<float><<<wg_grid, 128, 0, stream>>>((const float*)x, g, N, D, E, part);
+    B200_LAUNCH_CHECK("router_wgrad_kernel");
+    router_wgrad_reduce_kernel<<<(ED + 255) / 256, 256, 0, stream>>>(part, chunks, ED, out);
+    B200_LAUNCH_CHECK("router_wgrad_reduce_kernel");
+    count_launch(2);
+  }
+  return 0;
+}
+
+}  // extern "C"
