@@ -1,0 +1,60 @@
+"""Shared building blocks of the fusion modules: multi-head attention (self / cross) and the FFN, expressed
+over the library's autograd Functions.  torch's nn.MultiheadAttention / nn.Linear / nn.LayerNorm objects are
+used as PARAMETER CONTAINERS only (identical state_dict keys and initialisation to the reference); their
+forward() is never called."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from .. import ops
+from .._lib import ACT_GELU
+from ..slab import ParamSlab
+
+
+def pad_mask_u8(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """bool/int key-padding mask (True = ignore) -> contiguous uint8 for the attention kernels."""
+    if mask is None:
+        return None
+    return mask.to(torch.uint8).contiguous()
+
+
+def self_attention(x2, B, T, mha: nn.MultiheadAttention, slab: ParamSlab, key_pad_u8, residual=None):
+    """out_proj(softmax(q k^T / sqrt(dh) + mask) v) over x2 [B*T, D]; optional residual fused into out_proj."""
+    cdt = x2.dtype
+    qkv = ops.LinearFn.apply(x2, mha.in_proj_weight, mha.in_proj_bias, slab.compute_view(mha.in_proj_weight, cdt),
+                             None)
+    ctx = ops.AttentionFn.apply(qkv, None, key_pad_u8, B, T, T, mha.num_heads, True)
+    return ops.LinearFn.apply(ctx, mha.out_proj.weight, mha.out_proj.bias,
+                              slab.compute_view(mha.out_proj.weight, cdt), residual)
+
+
+def cross_attention(x2, kv2, B, T, S, mha: nn.MultiheadAttention, slab: ParamSlab, key_pad_u8, residual=None):
+    """Queries from x2 [B*T, D], keys/values from kv2 [B*S, D] (question -> image patches)."""
+    cdt = x2.dtype
+    q, kvp = ops.CrossProjFn.apply(x2, kv2, mha.in_proj_weight, mha.in_proj_bias,
+                                   slab.compute_view(mha.in_proj_weight, cdt))
+    ctx = ops.AttentionFn.apply(q, kvp, key_pad_u8, B, T, S, mha.num_heads, False)
+    return ops.LinearFn.apply(ctx, mha.out_proj.weight, mha.out_proj.bias,
+                              slab.compute_view(mha.out_proj.weight, cdt), residual)
+
+
+def ffn(x2, lin1: nn.Linear, lin2: nn.Linear, slab: ParamSlab, act: int = ACT_GELU, residual=None):
+    cdt = x2.dtype
+    return ops.FFNFn.apply(x2, lin1.weight, lin1.bias, lin2.weight, lin2.bias, slab.compute_view(lin1.weight, cdt),
+                           slab.compute_view(lin2.weight, cdt), act, residual)
+
+
+def add_ln(x2, branch, ln: nn.LayerNorm):
+    return ops.AddLNFn.apply(x2, branch, ln.weight, ln.bias, ln.eps)
+
+
+def linear(x2, lin: nn.Linear, slab: ParamSlab, residual=None):
+    return ops.LinearFn.apply(x2, lin.weight, lin.bias, slab.compute_view(lin.weight, x2.dtype), residual)
+
+
+def param_groups(module: nn.Module, prefix: str = ""):
+    """One slab group per parameter (no stacking needed for the fusion blocks)."""
+    return [[(prefix + n, p)] for n, p in module.named_parameters()]

@@ -1,0 +1,123 @@
+"""The fusion the classification pipeline actually runs (reference: src/modeling/meta_arch/vqa_model.py,
+CrossModalAttention :237-311 and MultimodalFusion :314-433)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .. import ops
+from .._lib import ACT_RELU
+from ..runtime import SlabOwner, resolve_compute_dtype
+from . import blocks
+
+
+@dataclass
+class FusionConfig:
+    """vqa_config.py:86-105."""
+    fusion_type: str = "cross_attention"
+    hidden_dim: int = 512
+    output_dim: int = 512
+    num_heads: int = 8
+    num_layers: int = 2
+    dropout: float = 0.1
+    use_layer_norm: bool = True
+
+
+class CrossModalAttention(SlabOwner, nn.Module):
+    """Post-LN block: x = LN1(q + SelfAttn(q)); x = LN2(x + CrossAttn(x, kv)); x = LN3(x + FFN(x))."""
+
+    def __init__(self, embed_dim: int, num_heads: int = 8, dropout: float = 0.1):
+        nn.Module.__init__(self)
+        self.self_attn = nn.MultiheadAttention(embed_dim, num_heads, dropout=dropout, batch_first=True)
+        self.cross_attn = nn.MultiheadAttention(embed_dim, num_heads, dropout=dropout, batch_first=True)
+        self.ffn = nn.Sequential(nn.Linear(embed_dim, embed_dim * 4), nn.GELU(), nn.Dropout(dropout),
+                                 nn.Linear(embed_dim * 4, embed_dim), nn.Dropout(dropout))
+        self.norm1 = nn.LayerNorm(embed_dim)
+        self.norm2 = nn.LayerNorm(embed_dim)
+        self.norm3 = nn.LayerNorm(embed_dim)
+        self.dropout = nn.Dropout(dropout)
+
+    def _slab_groups(self):
+        return blocks.param_groups(self)
+
+    def _block(self, x2, kv2, B, T, S, qmask_u8, kvmask_u8, slab):
+        a = blocks.self_attention(x2, B, T, self.self_attn, slab, qmask_u8)
+        x2 = blocks.add_ln(x2, a, self.norm1)
+        c = blocks.cross_attention(x2, kv2, B, T, S, self.cross_attn, slab, kvmask_u8)
+        x2 = blocks.add_ln(x2, c, self.norm2)
+        f = blocks.ffn(x2, self.ffn[0], self.ffn[3], slab)
+        return blocks.add_ln(x2, f, self.norm3)
+
+    def forward(self, query: torch.Tensor, key_value: torch.Tensor, query_mask: Optional[torch.Tensor] = None,
+                kv_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, T, D = query.shape
+        S = key_value.shape[1]
+        cdt = resolve_compute_dtype(query)
+        slab = self._get_slab(query.device, cdt)
+        x2 = ops.to_compute(query.reshape(B * T, D), cdt)
+        kv2 = ops.to_compute(key_value.reshape(B * S, D), cdt)
+        out = self._block(x2, kv2, B, T, S, blocks.pad_mask_u8(query_mask), blocks.pad_mask_u8(kv_mask), slab)
+        return ops.to_compute(out, query.dtype).view(B, T, D)
+
+
+class MultimodalFusion(SlabOwner, nn.Module):
+    """cross_attention: L CrossModalAttention layers on the text stream, CLS pooling, output_proj, LayerNorm.
+    Other fusion_type values keep the reference's (small) branches: concat, bilinear, default add."""
+
+    def __init__(self, config):
+        nn.Module.__init__(self)
+        self.config = config
+        if config.fusion_type == "cross_attention":
+            self.fusion_layers = nn.ModuleList([
+                CrossModalAttention(config.hidden_dim, config.num_heads, config.dropout)
+                for _ in range(config.num_layers)])
+            self.output_proj = nn.Linear(config.hidden_dim, config.output_dim)
+        elif config.fusion_type == "concat":
+            self.fusion_layer = nn.Sequential(nn.Linear(config.hidden_dim * 2, config.hidden_dim), nn.ReLU(),
+                                              nn.Dropout(config.dropout),
+                                              nn.Linear(config.hidden_dim, config.output_dim))
+        elif config.fusion_type == "bilinear":
+            self.bilinear = nn.Bilinear(config.hidden_dim, config.hidden_dim, config.output_dim)
+        else:
+            self.fusion_layer = nn.Linear(config.hidden_dim, config.output_dim)
+        self.layer_norm = nn.LayerNorm(config.output_dim) if config.use_layer_norm else None
+
+    def _slab_groups(self):
+        return blocks.param_groups(self)
+
+    @staticmethod
+    def _pool(t: torch.Tensor) -> torch.Tensor:
+        return t[:, 0, :] if t.dim() == 3 else t
+
+    def forward(self, visual_features: torch.Tensor, text_features: torch.Tensor,
+                visual_mask: Optional[torch.Tensor] = None, text_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        ft = self.config.fusion_type
+        cdt = resolve_compute_dtype(text_features)
+        slab = self._get_slab(text_features.device, cdt)
+        if ft == "cross_attention":
+            B, T, D = text_features.shape
+            S = visual_features.shape[1]
+            x2 = ops.to_compute(text_features.reshape(B * T, D), cdt)
+            kv2 = ops.to_compute(visual_features.reshape(B * S, D), cdt)
+            qm, km = blocks.pad_mask_u8(text_mask), blocks.pad_mask_u8(visual_mask)
+            for layer in self.fusion_layers:
+                x2 = layer._block(x2, kv2, B, T, S, qm, km, slab)
+            cls = x2.view(B, T, D)[:, 0, :]                      # CLS position, strided rows (no copy)
+            fused = blocks.linear(cls, self.output_proj, slab)
+        elif ft == "concat":
+            both = torch.cat([self._pool(visual_features), self._pool(text_features)], dim=-1)
+            fused = blocks.ffn(ops.to_compute(both.contiguous(), cdt), self.fusion_layer[0], self.fusion_layer[3],
+                               slab, act=ACT_RELU)
+        elif ft == "bilinear":
+            # 768^3-parameter tensor contraction; not on the cross-attention path (left to torch)
+            fused = self.bilinear(self._pool(visual_features), self._pool(text_features))
+            fused = ops.to_compute(fused.contiguous(), cdt)
+        else:
+            pooled = self._pool(visual_features) + self._pool(text_features)
+            fused = blocks.linear(ops.to_compute(pooled.contiguous(), cdt), self.fusion_layer, slab)
+        if self.layer_norm is not None:
+            fused = blocks.add_ln(fused, None, self.layer_norm)
+        return ops.to_compute(fused, text_features.dtype)

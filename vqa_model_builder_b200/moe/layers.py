@@ -1,0 +1,223 @@
+"""MOE layers behind the reference's module API (src/modeling/moe/moe_layer.py).
+
+MOELayer.forward keeps the reference's contract — call `self.router(x)` (whatever module or monkey-patched
+callable that is), then combine expert outputs with the routing weights and apply `output_norm` — but for
+homogeneous FeedForwardExperts the dense "every expert on every token" loop (moe_layer.py:151-168) becomes
+plan -> permute -> grouped tcgen05 FFN -> weighted combine + LayerNorm, with no host synchronisation.
+Heterogeneous experts stay PyTorch modules; only routing and the combine run in the library."""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .. import ops
+from ..runtime import SlabOwner, resolve_compute_dtype
+from .config import MOEConfig
+from .experts import FeedForwardExpert, create_expert
+from .router import NoisyTopKRouter, create_router
+
+
+class MOELayer(SlabOwner, nn.Module):
+    """moe_layer.py:29-196."""
+
+    def __init__(self, config: Optional[MOEConfig] = None, input_dim: int = 768, hidden_dim: int = 3072,
+                 output_dim: int = 768, num_experts: int = 8, top_k: int = 2, router_type: str = "topk",
+                 expert_type: str = "feedforward", dropout: float = 0.1, use_aux_loss: bool = True,
+                 load_balance_weight: float = 0.01):
+        nn.Module.__init__(self)
+        if config is not None:  # config overrides dims/top_k/dropout/router settings but not expert_type
+            input_dim, hidden_dim, output_dim = config.input_dim, config.hidden_dim, config.output_dim
+            num_experts, top_k, dropout = config.num_experts, config.num_experts_per_token, config.expert_dropout
+            if config.router_config:
+                router_type = config.router_config.router_type
+                use_aux_loss = config.router_config.use_aux_loss
+                load_balance_weight = config.router_config.load_balance_weight
+        self.input_dim, self.hidden_dim, self.output_dim = input_dim, hidden_dim, output_dim
+        self.num_experts, self.top_k = num_experts, top_k
+        self.router = create_router(router_type=router_type, input_dim=input_dim, num_experts=num_experts,
+                                    top_k=top_k, use_aux_loss=use_aux_loss, load_balance_weight=load_balance_weight)
+        self.experts = nn.ModuleList([
+            create_expert(expert_type=expert_type, input_dim=input_dim, hidden_dim=hidden_dim, output_dim=output_dim,
+                          expert_id=i, dropout=dropout) for i in range(num_experts)])
+        self.output_norm = nn.LayerNorm(output_dim)
+        self.aux_outputs: Dict[str, Any] = {}
+        self.capacity_factor: Optional[float] = None   # set by SparseMOELayer
+
+    # -- parameter slab -------------------------------------------------------------------------------------
+    def _homogeneous(self) -> bool:
+        ex = list(self.experts)
+        if not ex or not all(type(e) is FeedForwardExpert for e in ex):
+            return False
+        e0 = ex[0]
+        return all((e.input_dim, e.hidden_dim, e.output_dim, e.activation_name) ==
+                   (e0.input_dim, e0.hidden_dim, e0.output_dim, e0.activation_name) for e in ex)
+
+    def _slab_groups(self) -> List[List[Tuple[str, nn.Parameter]]]:
+        ex = list(self.experts)
+        groups = []
+        for attr in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "layer_norm.weight", "layer_norm.bias"):
+            mod, leaf = attr.split(".")
+            groups.append([(f"experts.{i}.{attr}", getattr(getattr(e, mod), leaf)) for i, e in enumerate(ex)])
+        return groups
+
+    # -- forward ----------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
+        B, S, D = x.shape
+        weights, indices, aux = self.router(x)
+        self.aux_outputs = aux
+        if self._homogeneous():
+            return self._forward_grouped(x, weights, indices, aux)
+        return self._forward_dense(x, weights, indices, mask, kwargs)
+
+    def _plan(self, indices: torch.Tensor, aux: Dict[str, Any]) -> "ops.RoutingPlan":
+        stash = aux.get("_b200_idx32") if isinstance(aux, dict) else None
+        if stash is not None and stash[0] is indices:
+            idx32 = stash[1]
+        else:
+            idx32 = indices.reshape(-1, indices.shape[-1]).to(torch.int32)
+        return ops.RoutingPlan(idx32, self.num_experts)
+
+    def _forward_grouped(self, x, weights, indices, aux) -> torch.Tensor:
+        B, S, D = x.shape
+        N = B * S
+        K = indices.shape[-1]
+        cdt = resolve_compute_dtype(x)
+        ex = list(self.experts)
+        E = len(ex)
+        F, Do = ex[0].hidden_dim, ex[0].output_dim
+        slab = self._get_slab(x.device, cdt)
+        w1s = slab.span(ex[0].fc1.weight, E * F * D, cdt).view(E, F, D)
+        w2s = slab.span(ex[0].fc2.weight, E * Do * F, cdt).view(E, Do, F)
+        b1s = slab.span(ex[0].fc1.bias, E * F, torch.float32).view(E, F)
+        b2s = slab.span(ex[0].fc2.bias, E * Do, torch.float32).view(E, Do)
+        lng = slab.span(ex[0].layer_norm.weight, E * Do, torch.float32).view(E, Do)
+        lnb = slab.span(ex[0].layer_norm.bias, E * Do, torch.float32).view(E, Do)
+        x2 = ops.to_compute(x.reshape(N, D), cdt)
+        plan = self._plan(indices, aux)
+        w2d = weights.reshape(N, K).to(torch.float32)
+        if self.capacity_factor is not None:
+            capacity = int(self.capacity_factor * N * self.top_k / self.num_experts)
+            w_eff, keep = plan.apply_capacity(w2d.detach(), capacity)
+            # dropped (token, expert) pairs leave the graph: zero weight, zero gradient
+            w2d = w2d * keep.view(N, K).to(w2d.dtype)
+        params: List[nn.Parameter] = []
+        for attr in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "layer_norm.weight", "layer_norm.bias"):
+            mod, leaf = attr.split(".")
+            params.extend(getattr(getattr(e, mod), leaf) for e in ex)
+        out = ops.MoeExpertsFn.apply(x2, w2d, plan, (w1s, b1s, w2s, b2s, lng, lnb), self.output_norm.weight,
+                                     self.output_norm.bias, ex[0].act_code, D == Do, self.output_norm.eps, *params)
+        self.last_plan = plan
+        return ops.to_compute(out, x.dtype).view(B, S, Do)
+
+    def _forward_dense(self, x, weights, indices, mask, kwargs) -> torch.Tensor:
+        """Heterogeneous experts see the whole sequence (they contain attention), exactly as in the reference;
+        experts no token selected are skipped with ONE host read for all experts (reference: one per expert)."""
+        B, S, D = x.shape
+        N = B * S
+        E = len(self.experts)
+        used = torch.zeros(E + 1, dtype=torch.bool, device=x.device)
+        used[indices.reshape(-1).clamp(min=-1, max=E - 1) + 1] = True
+        used = used[1:].tolist()
+        outs = []
+        zero = None
+        for e, expert in enumerate(self.experts):
+            if used[e]:
+                outs.append(expert(x, mask=mask, **kwargs).reshape(N, -1))
+            else:
+                if zero is None:
+                    zero = torch.zeros(N, self.output_dim, dtype=x.dtype, device=x.device)
+                outs.append(zero)
+        cdt = resolve_compute_dtype(x)
+        ys = torch.stack([ops.to_compute(o.contiguous(), cdt) for o in outs], dim=0)
+        out = ops.DenseCombineFn.apply(ys, weights.reshape(N, -1), indices.reshape(N, -1), self.output_norm.weight,
+                                       self.output_norm.bias, self.output_norm.eps)
+        return ops.to_compute(out, x.dtype).view(B, S, self.output_dim)
+
+    # -- reference accessors ------------------------------------------------------------------------------------
+    def get_aux_loss(self) -> torch.Tensor:
+        if "load_balance_loss" in self.aux_outputs:
+            return self.aux_outputs["load_balance_loss"]
+        return torch.tensor(0.0)
+
+    def get_expert_usage(self) -> Dict[int, float]:
+        return {i: e.get_usage_ratio() for i, e in enumerate(self.experts)}
+
+
+class SparseMOELayer(MOELayer):
+    """moe_layer.py:199-358: NoisyTopKRouter + capacity factor.  Same dispatch kernels; pairs beyond an
+    expert's capacity (lowest combine weights) are masked instead of synchronising on counts."""
+
+    def __init__(self, input_dim: int = 768, hidden_dim: int = 3072, output_dim: int = 768, num_experts: int = 8,
+                 top_k: int = 2, capacity_factor: float = 1.25, dropout: float = 0.1, use_aux_loss: bool = True,
+                 expert_type: str = "feedforward"):
+        nn.Module.__init__(self)
+        self.input_dim, self.hidden_dim, self.output_dim = input_dim, hidden_dim, output_dim
+        self.num_experts, self.top_k = num_experts, top_k
+        self.capacity_factor = capacity_factor
+        self.router = NoisyTopKRouter(input_dim=input_dim, num_experts=num_experts, top_k=top_k,
+                                      use_aux_loss=use_aux_loss)
+        self.experts = nn.ModuleList([
+            create_expert(expert_type=expert_type, input_dim=input_dim, hidden_dim=hidden_dim, output_dim=output_dim,
+                          expert_id=i, dropout=dropout) for i in range(num_experts)])
+        self.output_norm = nn.LayerNorm(output_dim)
+        self.aux_outputs: Dict[str, Any] = {}
+
+    def _compute_capacity(self, num_tokens: int) -> int:
+        return int(self.capacity_factor * num_tokens * self.top_k / self.num_experts)
+
+
+class VQAMOELayer(MOELayer):
+    """moe_layer.py:551-692: NoisyTopKRouter over a heterogeneous expert list (vision / text / multimodal /
+    specialised).  The expert bodies are outside the kernel scope (they are attention-bearing sequence modules);
+    pass them in with `experts=[...]`, or let `install()` bind the reference's expert classes so the reference
+    constructor signature builds them."""
+
+    expert_factories: Dict[str, Any] = {}
+
+    def __init__(self, input_dim: int = 768, hidden_dim: int = 3072, output_dim: int = 768,
+                 num_vision_experts: int = 2, num_text_experts: int = 2, num_multimodal_experts: int = 2,
+                 num_specialized_experts: int = 2, top_k: int = 2, dropout: float = 0.1,
+                 vietnamese_optimized: bool = True, experts: Optional[List[nn.Module]] = None):
+        nn.Module.__init__(self)
+        total = num_vision_experts + num_text_experts + num_multimodal_experts + num_specialized_experts
+        if experts is not None:
+            total = len(experts)
+        self.input_dim, self.hidden_dim, self.output_dim = input_dim, hidden_dim, output_dim
+        self.num_experts, self.top_k = total, top_k
+        self.capacity_factor = None
+        self.router = NoisyTopKRouter(input_dim=input_dim, num_experts=total, top_k=top_k, use_aux_loss=True)
+        if experts is None:
+            experts = self._build_reference_experts(input_dim, hidden_dim, output_dim, num_vision_experts,
+                                                    num_text_experts, num_multimodal_experts,
+                                                    num_specialized_experts, dropout, vietnamese_optimized)
+        self.experts = nn.ModuleList(experts)
+        self.output_norm = nn.LayerNorm(output_dim)
+        self.aux_outputs: Dict[str, Any] = {}
+
+    @classmethod
+    def _build_reference_experts(cls, input_dim, hidden_dim, output_dim, n_vis, n_txt, n_mm, n_spec, dropout,
+                                 vietnamese_optimized) -> List[nn.Module]:
+        f = cls.expert_factories
+        need = ["vision", "text", "multimodal", "specialized"]
+        if any(k not in f for k in need):
+            raise RuntimeError(
+                "VQAMOELayer needs the heterogeneous expert classes: call vqa_model_builder_b200.install() with the "
+                "reference on PYTHONPATH, or pass experts=[...] explicitly")
+        out: List[nn.Module] = []
+        eid = 0
+        common = dict(input_dim=input_dim, hidden_dim=hidden_dim, output_dim=output_dim, dropout=dropout)
+        for kind, count in (("vision", n_vis), ("text", n_txt), ("multimodal", n_mm)):
+            for _ in range(count):
+                out.append(f[kind](expert_id=eid, **common))
+                eid += 1
+        spec = f["specialized"]  # ordered list cycled as in moe_layer.py:659-683
+        for i in range(n_spec):
+            klass = spec[i % len(spec)]
+            kw = dict(common, expert_id=eid)
+            if klass.__name__ == "OCRExpert":
+                kw["vietnamese_optimized"] = vietnamese_optimized
+            out.append(klass(**kw))
+            eid += 1
+        return out

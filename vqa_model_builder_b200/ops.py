@@ -1,0 +1,532 @@
+"""torch.autograd Functions over the C-ABI kernels.
+
+Each Function is the fwd/bwd pair of one fused stage of the hot path.  Activations are 2-D row-major
+[rows, features] tensors in the compute dtype (bf16 or fp32); parameters arrive twice: the fp32
+nn.Parameter (so autograd routes the gradient) and its compute-dtype view from the ParamSlab (what the
+kernel reads).  Parameter gradients are always fp32.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_CODES, ACT_NONE, EPI_ACCUM, EPI_ACT, EPI_ADD, EPI_DACT, EPI_NONE, GROUP_TILE, LAYOUT_K,
+                   LAYOUT_MN, call, dtype_code, query, stream_ptr)
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _rows(x: torch.Tensor) -> Tuple[int, int]:
+    """(row pitch, dtype code) of a 2-D activation whose last dim is contiguous."""
+    assert x.dim() == 2 and x.stride(1) == 1, "activations must be 2-D with a contiguous last dim"
+    return x.stride(0), dtype_code(x.dtype)
+
+
+def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """dtype conversion with the library's kernel (no autograd)."""
+    if x.dtype == dtype:
+        return x
+    _lib.ensure_device(x)
+    x = x.contiguous()
+    out = torch.empty_like(x, dtype=dtype)
+    call("b200_cast", x, dtype_code(x.dtype), out, dtype_code(dtype), x.numel(), stream_ptr())
+    return out
+
+
+class CastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src_dtype = x.dtype
+        return cast(x, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return cast(g, ctx.src_dtype), None
+
+
+def to_compute(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    return x if x.dtype == dtype else CastFn.apply(x, dtype)
+
+
+# ---- raw GEMM helpers (no autograd) ------------------------------------------------------------------
+def gemm(a: torch.Tensor, a_layout: int, b: torch.Tensor, b_layout: int, M: int, N: int, K: int, *,
+         out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None, bias=None, epi=EPI_NONE,
+         act=ACT_NONE, aux_in=None, aux_out=None) -> torch.Tensor:
+    lda, dt = _rows(a)
+    ldb, _ = _rows(b)
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype or a.dtype, device=a.device)
+    ld_aux = 0
+    for t in (aux_in, aux_out):
+        if t is not None:
+            ld_aux = t.stride(0)
+    call("b200_gemm", a, lda, a_layout, b, ldb, b_layout, out, out.stride(0), M, N, K, dt, dtype_code(out.dtype),
+         bias, epi, act, aux_in, aux_out, ld_aux, stream_ptr())
+    return out
+
+
+def colsum(x: torch.Tensor, tile_group=None, G: int = 1) -> torch.Tensor:
+    R, N = x.shape
+    assert x.is_contiguous()
+    out = torch.empty((G, N), dtype=torch.float32, device=x.device)
+    nb = query("b200_colsum_ws", R, N)
+    ws = _ws(nb, x.device)
+    call("b200_colsum", x, dtype_code(x.dtype), R, N, tile_group, G, out, ws, nb, stream_ptr())
+    return out if tile_group is not None else out[0]
+
+
+# ---- Linear (+bias, + optional residual) ---------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b (+ residual).  nn.Linear / MHA in-proj / out-proj (vqa_model.py:258-263)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w_c, residual):
+        _lib.ensure_device(x)
+        M, K = x.shape
+        N = w_c.shape[0]
+        epi = EPI_ADD if residual is not None else EPI_NONE
+        y = gemm(x, LAYOUT_K, w_c, LAYOUT_K, M, N, K, bias=bias, epi=epi, aux_in=residual)
+        ctx.save_for_backward(x, w_c)
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_c = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, K = x.shape
+        N = w_c.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy, LAYOUT_K, w_c, LAYOUT_MN, M, K, N)
+        if ctx.needs_input_grad[1]:
+            flat = torch.empty(N * K + (N if ctx.has_bias else 0), dtype=torch.float32, device=x.device)
+            dw = flat[:N * K].view(N, K)
+            # split-K accumulates atomically when the [N,K] tile grid cannot fill the machine
+            epi = EPI_ACCUM if x.dtype == torch.bfloat16 else EPI_NONE
+            gemm(dy, LAYOUT_MN, x, LAYOUT_MN, N, K, M, out=dw, epi=epi)
+            if ctx.has_bias:
+                db = flat[N * K:]
+                _colsum_into(dy, db)
+        elif ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy)
+        return dx, dw, db, None, (dy if ctx.has_res else None)
+
+
+def _colsum_into(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    R, N = x.shape
+    nb = query("b200_colsum_ws", R, N)
+    ws = _ws(nb, x.device)
+    call("b200_colsum", x, dtype_code(x.dtype), R, N, None, 1, out, ws, nb, stream_ptr())
+    return out
+
+
+# ---- two-layer FFN with fused activation ----------------------------------------------------------------
+class FFNFn(torch.autograd.Function):
+    """y = act(x W1^T + b1) W2^T + b2   (ffn of vqa_model.py:265-271; TransformerEncoderLayer FF).
+    The activation runs in GEMM-1's epilogue; its derivative in the epilogue of GEMM-2's dgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w1_c, w2_c, act, residual):
+        _lib.ensure_device(x)
+        M, D = x.shape
+        F = w1_c.shape[0]
+        Do = w2_c.shape[0]
+        pre = torch.empty((M, F), dtype=x.dtype, device=x.device)
+        h = gemm(x, LAYOUT_K, w1_c, LAYOUT_K, M, F, D, bias=b1, epi=EPI_ACT, act=act, aux_out=pre)
+        epi = EPI_ADD if residual is not None else EPI_NONE
+        y = gemm(h, LAYOUT_K, w2_c, LAYOUT_K, M, Do, F, bias=b2, epi=epi, aux_in=residual)
+        ctx.save_for_backward(x, pre, h, w1_c, w2_c)
+        ctx.act = act
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, pre, h, w1_c, w2_c = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, D = x.shape
+        F = w1_c.shape[0]
+        Do = w2_c.shape[0]
+        bf = x.dtype == torch.bfloat16
+        wepi = EPI_ACCUM if bf else EPI_NONE
+        flat = torch.empty(F * D + F + Do * F + Do, dtype=torch.float32, device=x.device)
+        dw1 = flat[:F * D].view(F, D)
+        db1 = flat[F * D:F * D + F]
+        dw2 = flat[F * D + F:F * D + F + Do * F].view(Do, F)
+        db2 = flat[F * D + F + Do * F:]
+        gemm(dy, LAYOUT_MN, h, LAYOUT_MN, Do, F, M, out=dw2, epi=wepi)
+        _colsum_into(dy, db2)
+        dpre = gemm(dy, LAYOUT_K, w2_c, LAYOUT_MN, M, F, Do, epi=EPI_DACT, act=ctx.act, aux_in=pre)
+        gemm(dpre, LAYOUT_MN, x, LAYOUT_MN, F, D, M, out=dw1, epi=wepi)
+        _colsum_into(dpre, db1)
+        dx = gemm(dpre, LAYOUT_K, w1_c, LAYOUT_MN, M, D, F) if ctx.needs_input_grad[0] else None
+        return dx, dw1, db1, dw2, db2, None, None, None, (dy if ctx.has_res else None)
+
+
+# ---- residual add + LayerNorm ------------------------------------------------------------------------------
+class AddLNFn(torch.autograd.Function):
+    """y = LayerNorm(x + branch)   (post-LN residual blocks, vqa_model.py:301,305,309); branch may be None."""
+
+    @staticmethod
+    def forward(ctx, x, branch, gamma, beta, eps):
+        _lib.ensure_device(x)
+        x = x.contiguous()
+        if branch is not None:
+            branch = branch.contiguous()
+        R, D = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(R, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(R, dtype=torch.float32, device=x.device)
+        call("b200_add_ln_fwd", x, branch, gamma, beta, None, float(eps), y, mean, rstd, R, D, dtype_code(x.dtype),
+             stream_ptr())
+        ctx.save_for_backward(x, branch, mean, rstd, gamma)
+        ctx.has_branch = branch is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, branch, mean, rstd, gamma = ctx.saved_tensors
+        dy = dy.contiguous()
+        R, D = x.shape
+        dsum = torch.empty_like(x)
+        flat = torch.empty(2 * D, dtype=torch.float32, device=x.device)
+        nb = query("b200_add_ln_bwd_ws", R, D)
+        ws = _ws(nb, x.device)
+        call("b200_add_ln_bwd", dy, x, branch, mean, rstd, gamma, None, 1, dsum, flat[:D], flat[D:], R, D,
+             dtype_code(x.dtype), ws, nb, stream_ptr())
+        return dsum, (dsum if ctx.has_branch else None), flat[:D], flat[D:], None
+
+
+# ---- attention -----------------------------------------------------------------------------------------------
+class AttentionFn(torch.autograd.Function):
+    """Multi-head attention core on packed projections.
+    self-attention : q_src = kv_src = qkv [B*T, 3D]  (q | k | v column blocks)
+    cross-attention: q_src = q [B*T, D], kv_src = kv [B*S, 2D] (k | v column blocks)."""
+
+    @staticmethod
+    def forward(ctx, q_src, kv_src, key_pad, B, T, S, H, self_attn):
+        _lib.ensure_device(q_src)
+        es = q_src.element_size()
+        if self_attn:
+            D = q_src.shape[1] // 3
+            qp, kp, vp = q_src.data_ptr(), q_src.data_ptr() + D * es, q_src.data_ptr() + 2 * D * es
+            ldq = ldk = ldv = q_src.stride(0)
+        else:
+            D = q_src.shape[1]
+            qp, kp, vp = q_src.data_ptr(), kv_src.data_ptr(), kv_src.data_ptr() + D * es
+            ldq, ldk = q_src.stride(0), kv_src.stride(0)
+            ldv = ldk
+        dh = D // H
+        scale = 1.0 / float(dh) ** 0.5
+        o = torch.empty((B * T, D), dtype=q_src.dtype, device=q_src.device)
+        lse = torch.empty((B, H, T), dtype=torch.float32, device=q_src.device)
+        call("b200_attn_fwd", qp, ldq, kp, ldk, vp, ldv, key_pad, o, D, lse, B, H, T, S, dh, scale,
+             dtype_code(q_src.dtype), stream_ptr())
+        ctx.save_for_backward(q_src, kv_src if not self_attn else None, key_pad, o, lse)
+        ctx.dims = (B, T, S, H, D, dh, scale, self_attn)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q_src, kv_src, key_pad, o, lse = ctx.saved_tensors
+        B, T, S, H, D, dh, scale, self_attn = ctx.dims
+        do = do.contiguous()
+        es = q_src.element_size()
+        if self_attn:
+            dqkv = torch.empty((B * T, 3 * D), dtype=q_src.dtype, device=q_src.device)
+            qp, kp, vp = q_src.data_ptr(), q_src.data_ptr() + D * es, q_src.data_ptr() + 2 * D * es
+            ldq = ldk = ldv = q_src.stride(0)
+            dqp, dkp, dvp = dqkv.data_ptr(), dqkv.data_ptr() + D * es, dqkv.data_ptr() + 2 * D * es
+            ldd = 3 * D
+            call("b200_attn_bwd", qp, ldq, kp, ldk, vp, ldv, key_pad, o, D, do, D, lse, dqp, ldd, dkp, ldd, dvp, ldd,
+                 B, H, T, S, dh, scale, dtype_code(q_src.dtype), stream_ptr())
+            return dqkv, None, None, None, None, None, None, None
+        dq = torch.empty((B * T, D), dtype=q_src.dtype, device=q_src.device)
+        dkv = torch.empty((B * S, 2 * D), dtype=q_src.dtype, device=q_src.device)
+        qp, kp, vp = q_src.data_ptr(), kv_src.data_ptr(), kv_src.data_ptr() + D * es
+        call("b200_attn_bwd", qp, q_src.stride(0), kp, kv_src.stride(0), vp, kv_src.stride(0), key_pad, o, D, do, D,
+             lse, dq, D, dkv.data_ptr(), 2 * D, dkv.data_ptr() + D * es, 2 * D, B, H, T, S, dh, scale,
+             dtype_code(q_src.dtype), stream_ptr())
+        return dq, dkv, None, None, None, None, None, None
+
+
+# ---- MOE router ----------------------------------------------------------------------------------------------
+class RouterFn(torch.autograd.Function):
+    """TopK / NoisyTopK routing (router.py:105-178, 287-366).  Returns (weights [N,K] f32, indices [N,K] i32,
+    load-balance loss [1] f32, clean probs [N,E] f32, mean noise scale [1] f32, topk_sum, counts)."""
+
+    @staticmethod
+    def forward(ctx, x, w_gate, w_noise, eps, noise_std, lb_weight, K):
+        _lib.ensure_device(x)
+        x = x.contiguous()
+        N, D = x.shape
+        E = w_gate.shape[0]
+        dev = x.device
+        noisy = eps is not None
+        idx = torch.empty((N, K), dtype=torch.int32, device=dev)
+        w = torch.empty((N, K), dtype=torch.float32, device=dev)
+        topk_sum = torch.empty(N, dtype=torch.float32, device=dev)
+        probs = torch.empty((N, E), dtype=torch.float32, device=dev)
+        probs_noisy = torch.empty((N, E), dtype=torch.float32, device=dev) if noisy else None
+        counts = torch.empty(E, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        nsm = torch.zeros(1, dtype=torch.float32, device=dev)
+        nb = query("b200_router_ws", N, E)
+        ws = _ws(nb, dev)
+        wg = w_gate.detach().contiguous()
+        wn = w_noise.detach().contiguous() if noisy else None
+        if noisy:
+            eps = eps.contiguous()
+        call("b200_router_fwd", x, dtype_code(x.dtype), wg, wn, eps, float(noise_std), float(lb_weight), N, D, E, K,
+             idx, w, topk_sum, probs, probs_noisy, counts, loss, nsm, ws, nb, stream_ptr())
+        ctx.save_for_backward(x, wg, wn, eps, idx, w, topk_sum, probs, probs_noisy, counts)
+        ctx.cfg = (float(noise_std), float(lb_weight), N, D, E, K, noisy)
+        ctx.mark_non_differentiable(idx, probs, nsm, topk_sum, counts)
+        return w, idx, loss, probs, nsm, topk_sum, counts
+
+    @staticmethod
+    def backward(ctx, d_w, _d_idx, d_loss, _d_probs, _d_nsm, _d_ts, _d_counts):
+        x, wg, wn, eps, idx, w, topk_sum, probs, probs_noisy, counts = ctx.saved_tensors
+        noise_std, lb_weight, N, D, E, K, noisy = ctx.cfg
+        dev = x.device
+        dx = torch.empty_like(x)
+        flat = torch.empty((2 if noisy else 1) * E * D, dtype=torch.float32, device=dev)
+        dwg = flat[:E * D].view(E, D)
+        dwn = flat[E * D:].view(E, D) if noisy else None
+        nb = query("b200_router_bwd_ws", N, D, E)
+        ws = _ws(nb, dev)
+        if d_w is not None:
+            d_w = d_w.contiguous().float()
+        if d_loss is not None:
+            d_loss = d_loss.contiguous().float()
+        call("b200_router_bwd", x, dtype_code(x.dtype), wg, wn, eps, noise_std, lb_weight, N, D, E, K, idx, w,
+             topk_sum, probs, probs_noisy, counts, d_w, d_loss, dx, dwg, dwn, ws, nb, stream_ptr())
+        return dx, dwg, dwn, None, None, None, None
+
+
+# ---- MOE dispatch -> grouped expert FFN -> combine ---------------------------------------------------------------
+class RoutingPlan:
+    """Device-resident maps produced by b200_moe_plan (no host reads)."""
+
+    def __init__(self, idx: torch.Tensor, E: int):
+        _lib.ensure_device(idx)
+        idx = idx.contiguous()
+        if idx.dtype != torch.int32:
+            idx = idx.to(torch.int32)
+        self.idx = idx
+        self.NK = idx.numel()
+        self.E = E
+        dev = idx.device
+        self.Rmax = query("b200_moe_max_rows", self.NK, E)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.counts = torch.empty(E, **i32)
+        self.cmp_off = torch.empty(E + 1, **i32)
+        self.pad_off = torch.empty(E + 1, **i32)
+        self.dest_row = torch.empty(self.NK, **i32)
+        self.cmp_pos = torch.empty(self.NK, **i32)
+        self.row_src = torch.empty(self.Rmax, **i32)
+        self.tile_group = torch.empty(self.Rmax // GROUP_TILE, **i32)
+        nb = query("b200_moe_plan_ws", self.NK, E)
+        ws = _ws(nb, dev)
+        call("b200_moe_plan", idx, self.NK, E, self.Rmax, self.counts, self.cmp_off, self.pad_off, self.dest_row,
+             self.cmp_pos, self.row_src, self.tile_group, ws, nb, stream_ptr())
+
+    def apply_capacity(self, w: torch.Tensor, capacity: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        w = w.contiguous()
+        w_eff = torch.empty_like(w)
+        keep = torch.empty(self.NK, dtype=torch.uint8, device=w.device)
+        call("b200_moe_capacity", self.idx, w, self.counts, self.pad_off, self.row_src, self.NK, self.E, int(capacity),
+             w_eff, keep, stream_ptr())
+        return w_eff, keep
+
+
+class MoeExpertsFn(torch.autograd.Function):
+    """Sparse evaluation of MOELayer's expert loop + combine + output_norm (moe_layer.py:146-171) for
+    homogeneous FeedForwardExperts (expert_types.py:75-92):
+        out[n] = LN_out( sum_k w[n,k] * LN_e( fc2_e(act(fc1_e x_n)) + x_n ) ),  e = idx[n,k]
+    Inputs after `act`: flattened per-expert fp32 Parameters in the order
+        fc1.weight x E, fc1.bias x E, fc2.weight x E, fc2.bias x E, ln.weight x E, ln.bias x E."""
+
+    @staticmethod
+    def forward(ctx, x, w, plan, stacks, out_gamma, out_beta, act, residual, eps, *expert_params):
+        _lib.ensure_device(x)
+        x = x.contiguous()
+        N, D = x.shape
+        K = plan.NK // N
+        E = plan.E
+        w1s, b1s, w2s, b2s, lng, lnb = stacks  # [E,F,D] c, [E,F] f32, [E,Do,F] c, [E,Do] f32, [E,Do] f32 x2
+        F = w1s.shape[1]
+        Do = w2s.shape[1]
+        R = plan.Rmax
+        dt = dtype_code(x.dtype)
+        st = stream_ptr()
+        dev = x.device
+        xp = torch.empty((R, D), dtype=x.dtype, device=dev)
+        call("b200_moe_permute", x, plan.row_src, plan.pad_off, E, K, R, D, dt, xp, st)
+        pre = torch.empty((R, F), dtype=x.dtype, device=dev)
+        h = torch.empty((R, F), dtype=x.dtype, device=dev)
+        call("b200_ggemm", xp, D, w1s, LAYOUT_K, h, F, R, F, D, E, plan.tile_group, dt, dt, b1s, EPI_ACT, act, None,
+             pre, F, st)
+        y2 = torch.empty((R, Do), dtype=x.dtype, device=dev)
+        call("b200_ggemm", h, F, w2s, LAYOUT_K, y2, Do, R, Do, F, E, plan.tile_group, dt, dt, b2s, EPI_NONE, ACT_NONE,
+             None, None, 0, st)
+        z = torch.empty((R, Do), dtype=x.dtype, device=dev)
+        mean_e = torch.empty(R, dtype=torch.float32, device=dev)
+        rstd_e = torch.empty(R, dtype=torch.float32, device=dev)
+        call("b200_add_ln_fwd", y2, xp if residual else None, lng, lnb, plan.tile_group, float(eps), z, mean_e, rstd_e,
+             R, Do, dt, st)
+        w = w.contiguous()
+        out = torch.empty((N, Do), dtype=x.dtype, device=dev)
+        mean_o = torch.empty(N, dtype=torch.float32, device=dev)
+        rstd_o = torch.empty(N, dtype=torch.float32, device=dev)
+        call("b200_moe_combine_fwd", z, plan.dest_row, w, out_gamma, out_beta, float(eps), N, K, Do, dt, out, mean_o,
+             rstd_o, st)
+        ctx.save_for_backward(xp, pre, h, y2, z, mean_e, rstd_e, w, mean_o, rstd_o, w1s, w2s, lng, out_gamma)
+        ctx.plan = plan
+        ctx.cfg = (N, D, K, E, F, Do, R, act, residual)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xp, pre, h, y2, z, mean_e, rstd_e, w, mean_o, rstd_o, w1s, w2s, lng, out_gamma = ctx.saved_tensors
+        plan = ctx.plan
+        N, D, K, E, F, Do, R, act, residual = ctx.cfg
+        dout = dout.contiguous()
+        dev = dout.device
+        dt = dtype_code(dout.dtype)
+        st = stream_ptr()
+        # one flat fp32 buffer for every parameter gradient of this layer (one DP all-reduce bucket)
+        sizes = [E * F * D, E * F, E * Do * F, E * Do, E * Do, E * Do, Do, Do]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + s)
+        dw1, db1, dw2, db2, dlng, dlnb, dog, dob = [flat[offs[i]:offs[i + 1]] for i in range(8)]
+
+        dz = torch.empty((R, Do), dtype=dout.dtype, device=dev)
+        d_w = torch.empty((N, K), dtype=torch.float32, device=dev)
+        nb = query("b200_moe_combine_bwd_ws", N, Do)
+        ws = _ws(nb, dev)
+        call("b200_moe_combine_bwd", dout, z, plan.dest_row, w, mean_o, rstd_o, out_gamma, plan.row_src, N, K, Do, R,
+             dt, dz, d_w, dog, dob, ws, nb, st)
+        dr = torch.empty((R, Do), dtype=dout.dtype, device=dev)
+        nb = query("b200_add_ln_bwd_ws", R, Do)
+        ws = _ws(nb, dev)
+        call("b200_add_ln_bwd", dz, y2, xp if residual else None, mean_e, rstd_e, lng, plan.tile_group, E, dr, dlng,
+             dlnb, R, Do, dt, ws, nb, st)
+        nb = query("b200_colsum_ws", R, max(F, Do))
+        ws = _ws(nb, dev)
+        call("b200_colsum", dr, dt, R, Do, plan.tile_group, E, db2, ws, nb, st)
+        call("b200_ggemm_wgrad", dr, Do, h, F, dw2, Do, F, R, E, plan.pad_off, dt, st)
+        dpre = torch.empty((R, F), dtype=dout.dtype, device=dev)
+        call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, plan.tile_group, dt, dt, None, EPI_DACT, act,
+             pre, None, F, st)
+        call("b200_colsum", dpre, dt, R, F, plan.tile_group, E, db1, ws, nb, st)
+        call("b200_ggemm_wgrad", dpre, F, xp, D, dw1, F, D, R, E, plan.pad_off, dt, st)
+        dxp = torch.empty((R, D), dtype=dout.dtype, device=dev)
+        if residual:
+            call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, plan.tile_group, dt, dt, None, EPI_ADD,
+                 ACT_NONE, dr, None, Do, st)
+        else:
+            call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, plan.tile_group, dt, dt, None, EPI_NONE,
+                 ACT_NONE, None, None, 0, st)
+        dx = torch.empty((N, D), dtype=dout.dtype, device=dev)
+        call("b200_moe_unpermute", dxp, plan.dest_row, None, N, K, D, dt, dx, st)
+
+        # hand every per-expert Parameter its slice of the flat buffer
+        grads: List[torch.Tensor] = []
+        for buf, shape in ((dw1, (F, D)), (db1, (F,)), (dw2, (Do, F)), (db2, (Do,)), (dlng, (Do,)), (dlnb, (Do,))):
+            per = buf.view(E, *shape)
+            grads.extend(per[e] for e in range(E))
+        return (dx, d_w, None, None, dog, dob, None, None, None, *grads)
+
+
+class DenseCombineFn(torch.autograd.Function):
+    """Combine for heterogeneous (PyTorch) experts, VQAMOELayer (moe_layer.py:551-692 via :146-171):
+    ys [E, N, D] holds every expert's output; out[n] = LN_out(sum_k w[n,k] * ys[idx[n,k], n])."""
+
+    @staticmethod
+    def forward(ctx, ys, w, idx, out_gamma, out_beta, eps):
+        _lib.ensure_device(ys)
+        E, N, D = ys.shape
+        K = idx.shape[1]
+        ys = ys.contiguous()
+        w = w.contiguous().float()
+        idx = idx.to(torch.int64)
+        n_ar = torch.arange(N, device=ys.device).unsqueeze(1)
+        valid = (idx >= 0) & (idx < E)
+        dest = torch.where(valid, idx * N + n_ar, torch.full_like(idx, -1)).to(torch.int32).contiguous()
+        out = torch.empty((N, D), dtype=ys.dtype, device=ys.device)
+        mean = torch.empty(N, dtype=torch.float32, device=ys.device)
+        rstd = torch.empty(N, dtype=torch.float32, device=ys.device)
+        call("b200_moe_combine_fwd", ys, dest, w, out_gamma, out_beta, float(eps), N, K, D, dtype_code(ys.dtype), out,
+             mean, rstd, stream_ptr())
+        ctx.save_for_backward(ys, dest, w, mean, rstd, out_gamma)
+        ctx.cfg = (E, N, K, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ys, dest, w, mean, rstd, out_gamma = ctx.saved_tensors
+        E, N, K, D = ctx.cfg
+        dev = dout.device
+        dout = dout.contiguous()
+        # rows of ys that no token selected get a zero gradient: mark them as "padding" for the kernel
+        row_src = torch.full((E * N,), -1, dtype=torch.int32, device=dev)
+        flat_dest = dest.view(-1).to(torch.int64)
+        ok = flat_dest >= 0
+        row_src[flat_dest[ok]] = torch.arange(N * K, device=dev, dtype=torch.int32)[ok]
+        dys = torch.empty_like(ys)
+        d_w = torch.empty((N, K), dtype=torch.float32, device=dev)
+        flat = torch.empty(2 * D, dtype=torch.float32, device=dev)
+        nb = query("b200_moe_combine_bwd_ws", N, D)
+        ws = _ws(nb, dev)
+        call("b200_moe_combine_bwd", dout, ys, dest, w, mean, rstd, out_gamma, row_src, N, K, D, E * N,
+             dtype_code(ys.dtype), dys, d_w, flat[:D], flat[D:], ws, nb, stream_ptr())
+        return dys, d_w, None, flat[:D], flat[D:], None
+
+
+# ---- cross-attention projections from one packed in_proj ------------------------------------------------------
+class CrossProjFn(torch.autograd.Function):
+    """nn.MultiheadAttention with key != query (vqa_model.py:304; fusion_approaches.py:262-277) slices its
+    packed in_proj_weight [3D, D]: q = x Wq^T + bq (rows 0:D), [k|v] = kv W_kv^T + b_kv (rows D:3D).
+    One Function so the packed parameter receives one gradient written in place (no slice/cat kernels)."""
+
+    @staticmethod
+    def forward(ctx, x, kv, in_w, in_b, in_w_c):
+        _lib.ensure_device(x)
+        M, D = x.shape
+        Mk = kv.shape[0]
+        bq = in_b[:D] if in_b is not None else None
+        bkv = in_b[D:] if in_b is not None else None
+        q = gemm(x, LAYOUT_K, in_w_c[:D], LAYOUT_K, M, D, D, bias=bq)
+        kvp = gemm(kv, LAYOUT_K, in_w_c[D:], LAYOUT_K, Mk, 2 * D, D, bias=bkv)
+        ctx.save_for_backward(x, kv, in_w_c)
+        ctx.has_bias = in_b is not None
+        return q, kvp
+
+    @staticmethod
+    def backward(ctx, dq, dkvp):
+        x, kv, in_w_c = ctx.saved_tensors
+        M, D = x.shape
+        Mk = kv.shape[0]
+        dq = dq.contiguous()
+        dkvp = dkvp.contiguous()
+        bf = x.dtype == torch.bfloat16
+        wepi = EPI_ACCUM if bf else EPI_NONE
+        flat = torch.empty(3 * D * D + 3 * D, dtype=torch.float32, device=x.device)
+        dw = flat[:3 * D * D].view(3 * D, D)
+        db = flat[3 * D * D:]
+        gemm(dq, LAYOUT_MN, x, LAYOUT_MN, D, D, M, out=dw[:D], epi=wepi)
+        gemm(dkvp, LAYOUT_MN, kv, LAYOUT_MN, 2 * D, D, Mk, out=dw[D:], epi=wepi)
+        _colsum_into(dq, db[:D])
+        _colsum_into(dkvp, db[D:])
+        dx = gemm(dq, LAYOUT_K, in_w_c[:D], LAYOUT_MN, M, D, D) if ctx.needs_input_grad[0] else None
+        dkv = gemm(dkvp, LAYOUT_K, in_w_c[D:], LAYOUT_MN, Mk, D, 2 * D) if ctx.needs_input_grad[1] else None
+        return dx, dkv, dw, (db if ctx.has_bias else None), None

@@ -1,0 +1,65 @@
+"""Compute-dtype policy and small shared helpers for the drop-in modules."""
+from __future__ import annotations
+
+import copy
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .slab import ParamSlab
+
+_COMPUTE = "auto"
+
+
+def set_compute_dtype(mode: str) -> None:
+    """'auto' (bf16 under autocast or for bf16 inputs, else fp32), 'bf16' or 'fp32'."""
+    global _COMPUTE
+    if mode not in ("auto", "bf16", "fp32"):
+        raise ValueError(f"compute dtype must be auto|bf16|fp32, got {mode}")
+    _COMPUTE = mode
+
+
+def get_compute_dtype_mode() -> str:
+    return _COMPUTE
+
+
+def resolve_compute_dtype(x: torch.Tensor) -> torch.dtype:
+    """The reference trains under fp16 autocast (training_pipeline.py:457); the B200 path computes in bf16
+    with fp32 accumulation, statistics, routing and parameter gradients."""
+    if _COMPUTE == "bf16":
+        return torch.bfloat16
+    if _COMPUTE == "fp32":
+        return torch.float32
+    if torch.is_autocast_enabled() or x.dtype in (torch.bfloat16, torch.float16):
+        return torch.bfloat16
+    return torch.float32
+
+
+class SlabOwner:
+    """Mixin: lazily packs the module's parameters into a ParamSlab (rebuilt if parameters were replaced,
+    moved by .to(), or the module was deep-copied)."""
+
+    def _slab_groups(self) -> List[List[Tuple[str, nn.Parameter]]]:
+        raise NotImplementedError
+
+    def _get_slab(self, device: torch.device, dtype: torch.dtype) -> ParamSlab:
+        groups = self._slab_groups()
+        flat = [p for g in groups for _, p in g]
+        slab: Optional[ParamSlab] = self.__dict__.get("_slab")
+        if slab is None or len(slab.params) != len(flat) or any(a is not b for a, b in zip(slab.params, flat)):
+            slab = ParamSlab(groups)
+            self.__dict__["_slab"] = slab
+        slab.refresh(device, dtype)
+        return slab
+
+    def __deepcopy__(self, memo):
+        # drop the slab (it is rebuilt on first use) so deepcopy does not duplicate the flat buffers
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k == "_slab":
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
