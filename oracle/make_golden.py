@@ -1,0 +1,198 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own modules (imported from /root/reference) on seeded
+synthetic inputs, forward + backward, CPU fp32.  Run here (the GPU box has no /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+Weights and inputs come from numpy's PCG64 streams (stable across torch versions) and are loaded into the reference
+modules via load_state_dict; dropout is 0 so train-mode code paths are deterministic."""
+from __future__ import annotations
+
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REF = os.environ.get("B200VQA_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def rnd_state_dict(module: torch.nn.Module, seed: int) -> dict:
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for k, v in module.state_dict().items():
+        if not v.dtype.is_floating_point or v.dim() == 0:
+            sd[k] = v.clone()
+            continue
+        if k.endswith("norm.weight") or ".norm" in k and k.endswith("weight") or k.endswith("layer_norm.weight") \
+                or k.split(".")[-2].startswith("norm") and k.endswith("weight"):
+            a = 1.0 + 0.1 * rng.standard_normal(v.shape)
+        elif v.dim() >= 2:
+            a = rng.standard_normal(v.shape) / np.sqrt(v.shape[-1])
+        else:
+            a = 0.1 * rng.standard_normal(v.shape)
+        sd[k] = torch.tensor(a, dtype=torch.float32)
+    return sd
+
+
+def save(name: str, **arrays):
+    OUT.mkdir(parents=True, exist_ok=True)
+    flat = {}
+    for k, v in arrays.items():
+        if isinstance(v, dict):
+            for kk, vv in v.items():
+                flat[f"{k}/{kk}"] = vv.detach().numpy() if isinstance(vv, torch.Tensor) else np.asarray(vv)
+        else:
+            flat[k] = v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    np.savez_compressed(OUT / f"{name}.npz", **flat)
+    print(name, sum(a.nbytes for a in flat.values()) // 1024, "KiB")
+
+
+def grads_of(module):
+    return {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in module.named_parameters()}
+
+
+def lengths_mask(rng, B, T):
+    lens = rng.integers(low=max(2, T // 3), high=T + 1, size=B)
+    m = torch.zeros(B, T, dtype=torch.bool)
+    for b, n in enumerate(lens):
+        m[b, :n] = True
+    return m  # True = valid
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(4)
+    from src.modeling.meta_arch.vqa_model import MultimodalFusion
+    from src.modeling.meta_arch.vqa_config import FusionConfig
+    from src.modeling.fusion.fusion_approaches import CrossAttentionFusion
+    from src.modeling.moe.moe_layer import MOELayer, SparseMOELayer
+    from src.modeling.moe.router import TopKRouter, NoisyTopKRouter
+    from src.modeling.meta_arch.generative_vqa_model import CrossModalFusion, GenerativeVQAConfig
+
+    rng = np.random.default_rng(20261018)
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+
+    # ---- MultimodalFusion, cross_attention (A1+A2) -------------------------------------------------------
+    B, T, V, D, H, L = 3, 12, 7, 64, 4, 2
+    m = MultimodalFusion(FusionConfig(fusion_type="cross_attention", hidden_dim=D, output_dim=D, num_heads=H,
+                                      num_layers=L, dropout=0.0, use_layer_norm=True))
+    sd = rnd_state_dict(m, 1)
+    m.load_state_dict(sd)
+    m.train()
+    vis = f32(rng.standard_normal((B, V, D))).requires_grad_()
+    txt = f32(rng.standard_normal((B, T, D))).requires_grad_()
+    valid = lengths_mask(rng, B, T)
+    gout = f32(rng.standard_normal((B, D)))
+    out = m(vis, txt, text_mask=~valid)           # call-site polarity: True = PAD (vqa_model.py:662-666)
+    (out * gout).sum().backward()
+    save("multimodal_fusion_xattn", cfg=np.array([B, T, V, D, H, L]), sd=sd, visual=vis, text=txt,
+         text_valid=valid, gout=gout, out=out, d_visual=vis.grad, d_text=txt.grad, grads=grads_of(m))
+
+    # ---- MultimodalFusion other branches (forward only) ------------------------------------------------------
+    for ft in ("concat", "add"):
+        m = MultimodalFusion(FusionConfig(fusion_type=ft, hidden_dim=D, output_dim=D, num_heads=H, num_layers=L,
+                                          dropout=0.0, use_layer_norm=True))
+        sd = rnd_state_dict(m, 2)
+        m.load_state_dict(sd)
+        out = m(vis.detach(), txt.detach())
+        save(f"multimodal_fusion_{ft}", sd=sd, visual=vis, text=txt, out=out)
+
+    # ---- CrossAttentionFusion (A3) ---------------------------------------------------------------------------
+    Bc, Tc, Vc, Dc, Hc, Lc, Ic = 2, 20, 36, 64, 4, 2, 128   # token counts of examples/fusion_examples.py:24-29
+    m = CrossAttentionFusion(vision_dim=Dc, text_dim=Dc, output_dim=Dc, num_attention_heads=Hc, num_layers=Lc,
+                             intermediate_dim=Ic, dropout=0.0, fusion_method="concat")
+    sd = rnd_state_dict(m, 3)
+    m.load_state_dict(sd)
+    m.train()
+    vis2 = f32(rng.standard_normal((Bc, Vc, Dc))).requires_grad_()
+    txt2 = f32(rng.standard_normal((Bc, Tc, Dc))).requires_grad_()
+    tvalid = torch.ones(Bc, Tc, dtype=torch.bool)
+    tvalid[:, -5:] = False                                   # last 5 text tokens padded (fusion_examples.py:113-127)
+    gout2 = f32(rng.standard_normal((Bc, Dc)))
+    out = m(vis2, txt2, text_mask=tvalid)
+    (out * gout2).sum().backward()
+    save("cross_attention_fusion", cfg=np.array([Bc, Tc, Vc, Dc, Hc, Lc, Ic]), sd=sd, vision=vis2, text=txt2,
+         text_valid=tvalid, gout=gout2, out=out, d_vision=vis2.grad, d_text=txt2.grad, grads=grads_of(m))
+
+    # ---- routers (A5) ------------------------------------------------------------------------------------------
+    Br, Sr, Dr, Er, Kr = 4, 32, 64, 8, 2
+    xr = f32(rng.standard_normal((Br, Sr, Dr))).requires_grad_()
+    r = TopKRouter(Dr, Er, top_k=Kr)
+    sd = rnd_state_dict(r, 4)
+    r.load_state_dict(sd)
+    w, idx, aux = r(xr)
+    gw = f32(rng.standard_normal(w.shape))
+    ((w * gw).sum() + 3.0 * aux["load_balance_loss"]).backward()
+    save("topk_router", cfg=np.array([Br, Sr, Dr, Er, Kr]), sd=sd, x=xr, w=w, idx=idx, loss=aux["load_balance_loss"],
+         probs=aux["router_probs"], gw=gw, d_x=xr.grad, grads=grads_of(r))
+
+    xr2 = f32(rng.standard_normal((Br, Sr, Dr))).requires_grad_()
+    nr = NoisyTopKRouter(Dr, Er, top_k=Kr, noise_std=1.0)
+    sd = rnd_state_dict(nr, 5)
+    nr.load_state_dict(sd)
+    nr.train()
+    eps = f32(rng.standard_normal((Br, Sr, Er)))
+    orig = torch.randn_like
+    torch.randn_like = lambda t, **kw: eps.to(t.dtype)       # feed the recorded N(0,1) draw (router.py:308)
+    try:
+        w, idx, aux = nr(xr2)
+    finally:
+        torch.randn_like = orig
+    gw2 = f32(rng.standard_normal(w.shape))
+    ((w * gw2).sum() + 3.0 * aux["load_balance_loss"]).backward()
+    save("noisy_router", cfg=np.array([Br, Sr, Dr, Er, Kr]), sd=sd, x=xr2, eps=eps, w=w, idx=idx,
+         loss=aux["load_balance_loss"], probs=aux["router_probs"], noise_scale=aux["noise_scale"], gw=gw2,
+         d_x=xr2.grad, grads=grads_of(nr))
+
+    # ---- MOELayer, homogeneous FFN experts (A6+A7) -------------------------------------------------------------------
+    Bm, Sm, Dm, Fm, Em, Km = 4, 16, 64, 128, 4, 2
+    m = MOELayer(input_dim=Dm, hidden_dim=Fm, output_dim=Dm, num_experts=Em, top_k=Km, dropout=0.0)
+    sd = rnd_state_dict(m, 6)
+    m.load_state_dict(sd)
+    m.train()
+    xm = f32(rng.standard_normal((Bm, Sm, Dm))).requires_grad_()
+    gm = f32(rng.standard_normal((Bm, Sm, Dm)))
+    out = m(xm)
+    ((out * gm).sum() + 2.0 * m.get_aux_loss()).backward()
+    save("moe_layer", cfg=np.array([Bm, Sm, Dm, Fm, Em, Km]), sd=sd, x=xm, gout=gm, out=out,
+         loss=m.get_aux_loss(), probs=m.aux_outputs["router_probs"], d_x=xm.grad, grads=grads_of(m))
+
+    # ---- SparseMOELayer with an active capacity limit (A8) ------------------------------------------------------------
+    m = SparseMOELayer(input_dim=Dm, hidden_dim=Fm, output_dim=Dm, num_experts=Em, top_k=Km, capacity_factor=0.6,
+                       dropout=0.0)
+    sd = rnd_state_dict(m, 7)
+    m.load_state_dict(sd)
+    m.eval()                                                # eval: NoisyTopKRouter is noise-free
+    xs = f32(rng.standard_normal((Bm, Sm, Dm)))
+    with torch.no_grad():
+        out = m(xs)
+    save("sparse_moe_layer", cfg=np.array([Bm, Sm, Dm, Fm, Em, Km]), capacity_factor=np.array(0.6), sd=sd, x=xs,
+         out=out)
+
+    # ---- CrossModalFusion with the standard MOE layer (A4) -------------------------------------------------------------
+    Bg, Vg, Tg, Dg, Hg, Fg, Eg = 2, 10, 14, 64, 4, 128, 4
+    cfg = GenerativeVQAConfig()
+    cfg.fusion_dim, cfg.fusion_num_heads, cfg.fusion_num_layers, cfg.fusion_dropout = Dg, Hg, 2, 0.0
+    cfg.decoder_ff_dim, cfg.use_moe, cfg.moe_type, cfg.moe_position = Fg, True, "standard", "fusion"
+    cfg.num_experts, cfg.num_experts_per_token = Eg, 2
+    m = CrossModalFusion(cfg)
+    sd = rnd_state_dict(m, 8)
+    m.load_state_dict(sd)
+    m.train()
+    visg = f32(rng.standard_normal((Bg, Vg, Dg))).requires_grad_()
+    qg = f32(rng.standard_normal((Bg, Tg, Dg))).requires_grad_()
+    qvalid = lengths_mask(rng, Bg, Tg)
+    gg = f32(rng.standard_normal((Bg, Vg + Tg, Dg)))
+    out, aux = m(visg, qg, qvalid.long())
+    (out * gg).sum().backward()
+    save("cross_modal_fusion_moe", cfg=np.array([Bg, Vg, Tg, Dg, Hg, Fg, Eg]), sd=sd, visual=visg, question=qg,
+         question_valid=qvalid, gout=gg, out=out, aux=np.array(aux), d_visual=visg.grad, d_question=qg.grad,
+         grads=grads_of(m))
+
+
+if __name__ == "__main__":
+    main()

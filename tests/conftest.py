@@ -1,0 +1,47 @@
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name: str) -> dict:
+    """npz -> nested dict of torch tensors ('sd/..', 'grads/..' prefixes become sub-dicts)."""
+    raw = np.load(GOLDEN / f"{name}.npz")
+    out: dict = {}
+    for k in raw.files:
+        v = torch.from_numpy(np.array(raw[k]))
+        if "/" in k:
+            head, tail = k.split("/", 1)
+            out.setdefault(head, {})[tail] = v
+        else:
+            out[k] = v
+    return out
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """||a - b||_F / ||b||_F in fp64 (the relative-error measure of the parity targets)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    den = float(b.norm())
+    return float((a - b).norm()) / (den if den > 0 else 1.0)
