@@ -1,0 +1,208 @@
+"""GPU: router, routing plan, permute/combine kernels and the MOE drop-in layers through the C-ABI, against the
+golden vectors of the reference and the CPU oracle.  Integer outputs (expert indices, permutation maps, offsets)
+are compared bit-exactly (rows whose top-k probabilities tie within 1e-6 are exempt)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import reference_port as rp
+from oracle import routing_np
+
+pytestmark = pytest.mark.gpu
+
+from vqa_model_builder_b200 import moe, ops  # noqa: E402
+import vqa_model_builder_b200 as pkg  # noqa: E402
+
+DEV = "cuda"
+
+
+def cuda_sd(sd):
+    return {k: v.to(DEV) for k, v in sd.items()}
+
+
+def check_indices(idx_got, probs_ref, K):
+    top, amb = routing_np.topk_with_ties(probs_ref.reshape(-1, probs_ref.shape[-1]).cpu().numpy(), K)
+    got = idx_got.reshape(-1, K).cpu().numpy()
+    bad = (got != top).any(axis=-1) & ~amb
+    assert not bad.any(), f"{int(bad.sum())} non-tied rows differ"
+    return float(amb.mean())
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_topk_router_matches_reference(mode):
+    g = load_golden("topk_router")
+    B, S, D, E, K = [int(v) for v in g["cfg"]]
+    r = moe.TopKRouter(D, E, top_k=K).to(DEV)
+    r.load_state_dict(g["sd"])
+    x = g["x"].to(DEV)
+    if mode == "bf16":
+        x = x.to(torch.bfloat16)
+        sd = {k: v.clone().requires_grad_() for k, v in g["sd"].items()}
+        xr = x.float().cpu().requires_grad_()
+        w_ref, idx_ref, loss_ref, probs_ref, _ = rp.topk_router(sd, "", xr, K)
+        ((w_ref * g["gw"]).sum() + 3.0 * loss_ref).backward()
+        ref = dict(w=w_ref, idx=idx_ref, loss=loss_ref, probs=probs_ref, d_x=xr.grad,
+                   grads={k: v.grad for k, v in sd.items()})
+    else:
+        ref = g
+    x.requires_grad_()
+    w, idx, aux = r(x)
+    assert w.dtype == torch.float32 and idx.dtype == torch.int64 and w.shape == (B, S, K)
+    check_indices(idx, ref["probs"], K)
+    assert torch.equal(idx.cpu(), ref["idx"])
+    assert rel_err(w, ref["w"]) < 1e-5 and rel_err(aux["router_probs"], ref["probs"]) < 1e-5
+    assert abs(float(aux["load_balance_loss"]) - float(ref["loss"])) < 1e-7
+    ((w * g["gw"].to(DEV)).sum() + 3.0 * aux["load_balance_loss"]).backward()
+    t = 1e-4 if mode == "fp32" else 1e-2
+    assert rel_err(x.grad, ref["d_x"]) < t, rel_err(x.grad, ref["d_x"])
+    assert rel_err(r.gate.weight.grad, ref["grads"]["gate.weight"]) < 1e-4
+
+
+def test_noisy_router_matches_reference():
+    g = load_golden("noisy_router")
+    B, S, D, E, K = [int(v) for v in g["cfg"]]
+    r = moe.NoisyTopKRouter(D, E, top_k=K, noise_std=1.0).to(DEV)
+    r.load_state_dict(g["sd"])
+    r.train()
+    x = g["x"].to(DEV).requires_grad_()
+    w, idx, aux = r(x, noise=g["eps"].to(DEV))
+    assert torch.equal(idx.cpu(), g["idx"])
+    assert rel_err(w, g["w"]) < 1e-5 and rel_err(aux["router_probs"], g["probs"]) < 1e-5
+    assert abs(float(aux["noise_scale"]) - float(g["noise_scale"])) < 1e-6
+    ((w * g["gw"].to(DEV)).sum() + 3.0 * aux["load_balance_loss"]).backward()
+    assert rel_err(x.grad, g["d_x"]) < 1e-4
+    assert rel_err(r.gate.weight.grad, g["grads"]["gate.weight"]) < 1e-4
+    assert rel_err(r.w_noise.weight.grad, g["grads"]["w_noise.weight"]) < 1e-4
+    r.eval()
+    w2, idx2, aux2 = r(x.detach())
+    assert aux2["noise_scale"] == 0.0
+
+
+@pytest.mark.parametrize("N,K,E", [(32, 2, 8), (3648, 2, 8), (14592, 2, 8), (5000, 2, 32), (4097, 1, 16), (100000, 2, 64)])
+def test_routing_plan_bit_exact(N, K, E):
+    rng = np.random.default_rng(N + E)
+    idx = np.stack([rng.permutation(E)[:K] for _ in range(N)]).astype(np.int32)
+    drop = rng.random(idx.shape) < 0.01
+    idx[drop] = -1
+    plan = ops.RoutingPlan(torch.from_numpy(idx).to(DEV), E)
+    want = routing_np.routing_plan(idx, E, plan.Rmax)
+    assert plan.Rmax == routing_np.max_rows(N * K, E)
+    for name in ("counts", "cmp_off", "pad_off", "cmp_pos", "dest_row", "row_src", "tile_group"):
+        got = getattr(plan, name).cpu().numpy()
+        assert np.array_equal(got, want[name]), name
+
+
+def test_capacity_mask_bit_exact():
+    rng = np.random.default_rng(0)
+    N, K, E = 2000, 2, 8
+    logits = rng.standard_normal((N, E)) + np.array([2.0, 0, 0, 0, 0, 0, 0, -1.0])   # expert 0 over-subscribed
+    idx = np.argsort(-logits, axis=-1)[:, :K].astype(np.int32)
+    w = rng.random((N, K)).astype(np.float32)
+    cap = int(1.25 * N * K / E)
+    plan = ops.RoutingPlan(torch.from_numpy(idx).to(DEV), E)
+    w_eff, keep = plan.apply_capacity(torch.from_numpy(w).to(DEV), cap)
+    want = routing_np.capacity_keep(idx, w, E, cap)
+    assert want.sum() < N * K
+    assert np.array_equal(keep.cpu().numpy(), want)
+    assert np.array_equal(w_eff.cpu().numpy().reshape(-1), w.reshape(-1) * want)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_moe_layer_matches_reference(mode, tol):
+    g = load_golden("moe_layer")
+    B, S, D, F, E, K = [int(v) for v in g["cfg"]]
+    pkg.set_compute_dtype(mode)
+    try:
+        m = moe.MOELayer(input_dim=D, hidden_dim=F, output_dim=D, num_experts=E, top_k=K, dropout=0.0).to(DEV)
+        m.load_state_dict(g["sd"])
+        m.train()
+        x = g["x"].to(DEV).requires_grad_()
+        out = m(x)
+        assert out.shape == (B, S, D) and out.dtype == torch.float32
+        ((out * g["gout"].to(DEV)).sum() + 2.0 * m.get_aux_loss()).backward()
+    finally:
+        pkg.set_compute_dtype("auto")
+    if mode == "fp32":
+        assert abs(float(m.get_aux_loss()) - float(g["loss"])) < 1e-7
+        assert rel_err(m.aux_outputs["router_probs"], g["probs"]) < 1e-5
+    assert rel_err(out, g["out"]) < tol, rel_err(out, g["out"])
+    assert rel_err(x.grad, g["d_x"]) < tol, rel_err(x.grad, g["d_x"])
+    worst = max((rel_err(p.grad, g["grads"][k]), k) for k, p in m.named_parameters())
+    assert worst[0] < tol * (1 if mode == "fp32" else 2), worst
+    # the permutation the kernels used is the canonical (expert asc, token asc) order
+    idx = m.last_plan.idx.cpu().numpy().reshape(-1, K)
+    want = routing_np.routing_plan(idx, E, m.last_plan.Rmax)
+    assert np.array_equal(m.last_plan.cmp_pos.cpu().numpy(), want["cmp_pos"])
+    assert np.array_equal(m.last_plan.cmp_off.cpu().numpy(), want["cmp_off"])
+
+
+def test_sparse_moe_layer_capacity_matches_reference():
+    g = load_golden("sparse_moe_layer")
+    B, S, D, F, E, K = [int(v) for v in g["cfg"]]
+    m = moe.SparseMOELayer(input_dim=D, hidden_dim=F, output_dim=D, num_experts=E, top_k=K,
+                           capacity_factor=float(g["capacity_factor"]), dropout=0.0).to(DEV)
+    m.load_state_dict(g["sd"])
+    m.eval()
+    with torch.no_grad():
+        out = m(g["x"].to(DEV))
+    assert rel_err(out, g["out"]) < 1e-4, rel_err(out, g["out"])
+
+
+def test_moe_layer_tolerates_swapped_router_and_masked_experts():
+    """Ablation consumers replace moe.router / patch router.forward and emit expert index -1
+    (ablation_trainer.py:171-224)."""
+    g = load_golden("moe_layer")
+    B, S, D, F, E, K = [int(v) for v in g["cfg"]]
+    m = moe.MOELayer(input_dim=D, hidden_dim=F, output_dim=D, num_experts=E, top_k=K, dropout=0.0).to(DEV)
+    m.load_state_dict(g["sd"])
+    x = g["x"].to(DEV)
+    orig = m.router.forward
+
+    def patched(inp, **kw):
+        w, idx, aux = orig(inp, **kw)
+        w = w.clone()
+        idx = idx.clone()
+        dead = idx == 1
+        w[dead] = 0.0
+        idx[dead] = -1
+        w = w / (w.sum(-1, keepdim=True) + 1e-9)
+        return w, idx, aux
+
+    m.router.forward = patched
+    out = m(x)
+    sd = {k: v for k, v in g["sd"].items()}
+    w_ref, idx_ref, _, _, _ = rp.topk_router({"gate.weight": sd["router.gate.weight"]}, "", g["x"], K)
+    dead = idx_ref == 1
+    w_ref = w_ref.clone()
+    w_ref[dead] = 0.0
+    idx_ref = idx_ref.clone()
+    idx_ref[dead] = -1
+    w_ref = w_ref / (w_ref.sum(-1, keepdim=True) + 1e-9)
+    ref, *_ = rp.moe_layer(sd, g["x"], E, K, weights_indices=(w_ref, idx_ref))
+    assert rel_err(out, ref) < 1e-4, rel_err(out, ref)
+    m.forward = lambda t, **kw: t          # disable_moe-style identity patch keeps working
+    assert m(x) is x
+
+
+def test_heterogeneous_experts_dense_combine():
+    """VQAMOELayer path: PyTorch expert bodies, library router + combine + output_norm."""
+    torch.manual_seed(0)
+    D, E, K, B, S = 64, 4, 2, 3, 5
+    experts = [torch.nn.Sequential(torch.nn.Linear(D, D), torch.nn.Tanh()) for _ in range(E)]
+    m = moe.VQAMOELayer(input_dim=D, hidden_dim=2 * D, output_dim=D, top_k=K, experts=experts).to(DEV)
+    m.eval()
+    x = torch.randn(B, S, D, device=DEV, requires_grad=True)
+    out = m(x)
+    w, idx, aux = m.router(x)
+    acc = torch.zeros_like(x)
+    for e in range(E):
+        we = (w * (idx == e).float()).sum(-1, keepdim=True)
+        acc = acc + experts[e](x) * we
+    ref = torch.nn.functional.layer_norm(acc, (D,), m.output_norm.weight, m.output_norm.bias)
+    assert rel_err(out, ref) < 1e-4
+    gout = torch.randn_like(out)
+    gx, = torch.autograd.grad((out * gout).sum(), x, retain_graph=True)
+    gxr, = torch.autograd.grad((ref * gout).sum(), x)
+    # reference-side router weights are constants in `ref` only through idx; both paths differentiate w
+    assert rel_err(gx, gxr) < 1e-3, rel_err(gx, gxr)
