@@ -1,0 +1,41 @@
+"""ORACLE — test infrastructure only.  Random-init state_dicts with the reference's key layout, built from plain
+torch.nn containers (same constructors, hence the same initialisers, as the reference modules:
+vqa_model.py:258-277,331-359 and moe_layer.py:95-117) — used by the CPU baseline so it never touches the product."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+
+def multimodal_fusion_sd(D: int, H: int, L: int, out_dim: int | None = None) -> dict:
+    out_dim = out_dim or D
+    sd = {}
+    for l in range(L):
+        p = f"fusion_layers.{l}."
+        for name in ("self_attn", "cross_attn"):
+            m = nn.MultiheadAttention(D, H, batch_first=True)
+            for k, v in m.state_dict().items():
+                sd[p + name + "." + k] = v
+        f0, f3 = nn.Linear(D, 4 * D), nn.Linear(4 * D, D)
+        for i, m in (("0", f0), ("3", f3)):
+            sd[p + f"ffn.{i}.weight"], sd[p + f"ffn.{i}.bias"] = m.weight.detach(), m.bias.detach()
+        for n in ("norm1", "norm2", "norm3"):
+            sd[p + n + ".weight"], sd[p + n + ".bias"] = torch.ones(D), torch.zeros(D)
+    proj = nn.Linear(D, out_dim)
+    sd["output_proj.weight"], sd["output_proj.bias"] = proj.weight.detach(), proj.bias.detach()
+    sd["layer_norm.weight"], sd["layer_norm.bias"] = torch.ones(out_dim), torch.zeros(out_dim)
+    return {k: v.detach().clone() for k, v in sd.items()}
+
+
+def moe_layer_sd(D: int, F: int, E: int, noisy: bool = False) -> dict:
+    sd = {"router.gate.weight": nn.Linear(D, E, bias=False).weight.detach()}
+    if noisy:
+        sd["router.w_noise.weight"] = nn.Linear(D, E, bias=False).weight.detach()
+    for e in range(E):
+        fc1, fc2 = nn.Linear(D, F), nn.Linear(F, D)
+        p = f"experts.{e}."
+        sd[p + "fc1.weight"], sd[p + "fc1.bias"] = fc1.weight.detach(), fc1.bias.detach()
+        sd[p + "fc2.weight"], sd[p + "fc2.bias"] = fc2.weight.detach(), fc2.bias.detach()
+        sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"] = torch.ones(D), torch.zeros(D)
+    sd["output_norm.weight"], sd["output_norm.bias"] = torch.ones(D), torch.zeros(D)
+    return {k: v.detach().clone() for k, v in sd.items()}

@@ -45,3 +45,18 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     b = b.detach().double().cpu()
     den = float(b.norm())
     return float((a - b).norm()) / (den if den > 0 else 1.0)
+
+
+def bf16_representable(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def round_sd_for_bf16(sd: dict) -> dict:
+    """What the bf16 compute path sees: matrices are rounded to bf16, vectors (biases, LayerNorm affine) and
+    buffers stay fp32.  Both implementations then start from identical values."""
+    return {k: (bf16_representable(v) if v.dtype.is_floating_point and v.dim() >= 2 else v.clone())
+            for k, v in sd.items()}
+
+
+def leafs(sd: dict) -> dict:
+    return {k: v.clone().requires_grad_(v.dtype.is_floating_point and v.dim() > 0) for k, v in sd.items()}

@@ -12,7 +12,7 @@ from vqa_model_builder_b200._lib import (ACT_GELU, ACT_NONE, ACT_RELU, EPI_ACCUM
                                          EPI_NONE, LAYOUT_K, LAYOUT_MN)
 
 DEV = "cuda"
-SHAPES = [(128, 64, 64), (256, 128, 192), (300, 200, 136), (2048, 768, 768), (2048, 2304, 768), (96, 3072, 768),
+SHAPES = [(128, 64, 64), (256, 128, 192), (304, 200, 136), (2048, 768, 768), (2048, 2304, 768), (96, 3072, 768),
           (128, 64, 32), (32, 768, 768)]
 
 

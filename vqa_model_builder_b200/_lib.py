@@ -122,10 +122,23 @@ def ensure_device(t: torch.Tensor) -> None:
         _initialized_devices.add(dev)
 
 
+#: set to a list to time every entry-point call with CUDA events on the launching stream:
+#: entries are (name, start_event, end_event, scalar_args)
+PROFILE = None
+
+
 def call(name: str, *args):
     """Invoke an int-returning entry point; tensors -> device pointers; non-zero return raises."""
     lib = load()
-    rc = getattr(lib, name)(*[_ptr(a) for a in args])
+    fn = getattr(lib, name)
+    if PROFILE is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*[_ptr(a) for a in args])
+        e.record()
+        PROFILE.append((name, s, e, tuple(a for a in args if isinstance(a, (int, float)) and not isinstance(a, bool))))
+    else:
+        rc = fn(*[_ptr(a) for a in args])
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
 

@@ -18,6 +18,11 @@ from . import _lib
 
 _ALIGN = 64  # elements; keeps every parameter 256-byte aligned (TMA needs 16)
 
+#: re-cast the bf16 compute copy on EVERY forward even when no parameter changed (what autocast does in the
+#: reference, one cast per nn.Linear call); benchmarks set this so a step without an optimizer update still
+#: pays for the cast.
+ALWAYS_REFRESH = False
+
 
 class ParamSlab:
     def __init__(self, groups: Iterable[List[Tuple[str, torch.nn.Parameter]]]):
@@ -113,6 +118,6 @@ class ParamSlab:
         if self.shadow is None:
             self.shadow = torch.empty(self.total, dtype=torch.bfloat16, device=device)
             self._versions = []
-        if capturing or versions != self._versions:
+        if capturing or ALWAYS_REFRESH or versions != self._versions:
             _lib.call("b200_cast", self.master, _lib.F32, self.shadow, _lib.BF16, self.total, _lib.stream_ptr())
             self._versions = versions
