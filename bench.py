@@ -120,6 +120,7 @@ def cpu_reference_step_factory(c, threads: int):
     from oracle import init_weights
     from oracle import reference_port as rp
     torch.set_num_threads(threads)
+    torch.set_flush_denormal(True)   # give the CPU arm its best case: softmax tails underflow into denormals
     torch.manual_seed(0)
     sd_f = {k: v.requires_grad_() for k, v in init_weights.multimodal_fusion_sd(c["D"], c["H"], c["L"]).items()}
     sd_m = {k: v.requires_grad_() for k, v in init_weights.moe_layer_sd(c["D"], c["F"], c["E"]).items()}
