@@ -64,29 +64,53 @@ __global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, long
 }
 
 // ---- column sums (bias gradients), deterministic two-stage ---------------------------------------
-// stage 1: block b sums rows [b*128, b*128+128) for a 128-column slab -> part[b][N]
+constexpr int CS_ROWS = 64;  // rows per partial block; divides B200_GROUP_TILE
+// stage 1: 8 warps x 16-byte vectors: block (slab, rb) sums rows [rb*64, rb*64+64) of a 32*VT-column slab
 template <typename T>
-__global__ void colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part) {
+__global__ void __launch_bounds__(256)
+colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part) {
+  constexpr int VT = Vec16<T>::N;
+  __shared__ float red[8][32 * VT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = (blockIdx.x * 32 + lane) * VT;
+  const int r0 = blockIdx.y * CS_ROWS, r1 = min(R, r0 + CS_ROWS);
+  float acc[VT];
+#pragma unroll
+  for (int u = 0; u < VT; ++u) acc[u] = 0.f;
+  if (col < N) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      Vec16<T> v;
+      v.load(x + (long long)r * N + col);
+#pragma unroll
+      for (int u = 0; u < VT; ++u) acc[u] += v.v[u];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < VT; ++u) red[warp][lane * VT + u] = acc[u];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VT; c += 256) {
+    const int gc = blockIdx.x * 32 * VT + c;
+    if (gc < N) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][c];
+      part[(long long)blockIdx.y * N + gc] = s;
+    }
+  }
+}
+// scalar fallback for widths that are not a multiple of the vector length
+template <typename T>
+__global__ void colsum_stage1_scalar(const T* __restrict__ x, int R, int N, float* __restrict__ part) {
   const int col = blockIdx.x * 128 + threadIdx.x;
-  const int r0 = blockIdx.y * B200_GROUP_TILE, r1 = min(R, r0 + B200_GROUP_TILE);
+  const int r0 = blockIdx.y * CS_ROWS, r1 = min(R, r0 + CS_ROWS);
   if (col >= N) return;
   float s = 0.f;
   for (int r = r0; r < r1; ++r) s += to_f32<T>(x[(long long)r * N + col]);
   part[(long long)blockIdx.y * N + col] = s;
 }
-// stage 2: out[g][col] = sum over tiles t with group(t)==g of part[t][col]
-__global__ void colsum_stage2(const float* __restrict__ part, int tiles, int N, const int* __restrict__ tile_group,
-                              int G, float* __restrict__ out) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  const int g = blockIdx.y;
-  if (col >= N) return;
-  float s = 0.f;
-  for (int t = 0; t < tiles; ++t) {
-    const int tg = tile_group ? tile_group[t] : 0;
-    if (tg == g) s += part[(long long)t * N + col];
-  }
-  out[(long long)g * N + col] = s;
-}
+
+int launch_partial_reduce(const float* part, int blocks, int rows_per_block, int width, const int* tile_group, int G,
+                          float* out, cudaStream_t stream);
 
 }  // namespace b200
 
@@ -136,25 +160,29 @@ int b200_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long lon
 }
 
 size_t b200_colsum_ws(int R, int N) {
-  const size_t tiles = (size_t)(R + B200_GROUP_TILE - 1) / B200_GROUP_TILE;
-  return tiles * (size_t)N * sizeof(float);
+  const size_t blocks = (size_t)(R + CS_ROWS - 1) / CS_ROWS;
+  return blocks * (size_t)N * sizeof(float);
 }
 int b200_colsum(const void* x, int dtype, int R, int N, const int32_t* tile_group, int G, float* out,
                 void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(R > 0 && N > 0 && G > 0, "colsum: bad shape R=%d N=%d G=%d", R, N, G);
   B200_CHECK_ARG(workspace_bytes >= b200_colsum_ws(R, N), "colsum: workspace too small");
-  const int tiles = (R + B200_GROUP_TILE - 1) / B200_GROUP_TILE;
+  const int blocks = (R + CS_ROWS - 1) / CS_ROWS;
   float* part = (float*)workspace;
-  dim3 g1((N + 127) / 128, tiles);
-  if (dtype == B200_F32) colsum_stage1<float><<<g1, 128, 0, stream>>>((const float*)x, R, N, part);
-  else colsum_stage1<bf16><<<g1, 128, 0, stream>>>((const bf16*)x, R, N, part);
+  const int vt = dtype == B200_F32 ? 4 : 8;
+  if (N % vt == 0 && ((uintptr_t)x & 15) == 0) {
+    dim3 g1((N + 32 * vt - 1) / (32 * vt), blocks);
+    if (dtype == B200_F32) colsum_stage1<float><<<g1, 256, 0, stream>>>((const float*)x, R, N, part);
+    else colsum_stage1<bf16><<<g1, 256, 0, stream>>>((const bf16*)x, R, N, part);
+  } else {
+    dim3 g1((N + 127) / 128, blocks);
+    if (dtype == B200_F32) colsum_stage1_scalar<float><<<g1, 128, 0, stream>>>((const float*)x, R, N, part);
+    else colsum_stage1_scalar<bf16><<<g1, 128, 0, stream>>>((const bf16*)x, R, N, part);
+  }
   B200_LAUNCH_CHECK("colsum_stage1");
-  dim3 g2((N + 127) / 128, G);
-  colsum_stage2<<<g2, 128, 0, stream>>>(part, tiles, N, tile_group, G, out);
-  B200_LAUNCH_CHECK("colsum_stage2");
-  count_launch(2);
-  return 0;
+  count_launch();
+  return launch_partial_reduce(part, blocks, CS_ROWS, N, tile_group, G, out, stream);
 }
 
 static int check_epi(int epi, int act, const void* aux_in, int out_dtype) {

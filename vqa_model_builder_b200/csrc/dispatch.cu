@@ -217,16 +217,17 @@ combine_fwd_kernel(const T* __restrict__ z, const int* __restrict__ dest_row, co
   }
 }
 
-constexpr int CMB_TOKENS_PER_BLOCK = 16;  // 4 warps x 4 tokens
+constexpr int CMB_WARPS = 8;
+constexpr int CMB_TOKENS_PER_BLOCK = 8;  // one token per warp
 
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(CMB_WARPS * 32)
 combine_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ z, const int* __restrict__ dest_row,
                    const float* __restrict__ w, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                    const float* __restrict__ gamma, int N, int K, int D, T* __restrict__ dz, float* __restrict__ d_w,
                    float* __restrict__ part) {
   constexpr int VT = Vec16<T>::N;
-  extern __shared__ float red[];  // [4][2][D]
+  extern __shared__ float red[];  // [CMB_WARPS][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / VT;
   float dg[ROW_MAXV][VT], db[ROW_MAXV][VT];
@@ -235,8 +236,8 @@ combine_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ z, const in
 #pragma unroll
     for (int u = 0; u < VT; ++u) dg[j][u] = db[j][u] = 0.f;
 
-  for (int i = 0; i < CMB_TOKENS_PER_BLOCK / 4; ++i) {
-    const int n = blockIdx.x * CMB_TOKENS_PER_BLOCK + warp * (CMB_TOKENS_PER_BLOCK / 4) + i;
+  for (int i = 0; i < CMB_TOKENS_PER_BLOCK / CMB_WARPS; ++i) {
+    const int n = blockIdx.x * CMB_TOKENS_PER_BLOCK + warp * (CMB_TOKENS_PER_BLOCK / CMB_WARPS) + i;
     if (n >= N) break;
     RowRegs<T> s, g;
     s.zero();
@@ -317,7 +318,7 @@ combine_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ z, const in
     const int which = c / D, d = c % D;
     float sum = 0.f;
 #pragma unroll
-    for (int wp = 0; wp < 4; ++wp) sum += red[(wp * 2 + which) * D + d];
+    for (int wp = 0; wp < CMB_WARPS; ++wp) sum += red[(wp * 2 + which) * D + d];
     part[((long long)blockIdx.x * 2 + which) * D + d] = sum;
   }
 }
@@ -465,17 +466,21 @@ int b200_moe_combine_bwd(const void* dout, const void* z, const int32_t* dest_ro
   B200_ROW_DISPATCH(dtype, D, "moe_combine_bwd");
   B200_CHECK_ARG(workspace_bytes >= b200_moe_combine_bwd_ws(N, D), "moe_combine_bwd: workspace too small");
   const int blocks = (N + CMB_TOKENS_PER_BLOCK - 1) / CMB_TOKENS_PER_BLOCK;
-  const size_t smem = (size_t)4 * 2 * D * sizeof(float);
-  B200_CHECK_ARG(smem <= 48 * 1024, "moe_combine_bwd: D=%d too large", D);
+  const size_t smem = (size_t)CMB_WARPS * 2 * D * sizeof(float);
+  B200_CHECK_ARG(smem <= 160 * 1024, "moe_combine_bwd: D=%d too large", D);
+  if (smem > 48 * 1024) {
+    B200_CUDA(cudaFuncSetAttribute(combine_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(combine_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   float* part = (float*)workspace;
   const int zb = row_grid(Rmax);
   if (dtype == B200_BF16) {
     zero_unwritten_rows_kernel<bf16><<<zb, 256, 0, stream>>>(row_src, w, Rmax, D, (bf16*)dz);
-    combine_bwd_kernel<bf16><<<blocks, 128, smem, stream>>>((const bf16*)dout, (const bf16*)z, dest_row, w, mean, rstd,
+    combine_bwd_kernel<bf16><<<blocks, CMB_WARPS * 32, smem, stream>>>((const bf16*)dout, (const bf16*)z, dest_row, w, mean, rstd,
                                                             gamma, N, K, D, (bf16*)dz, d_w, part);
   } else {
     zero_unwritten_rows_kernel<float><<<zb, 256, 0, stream>>>(row_src, w, Rmax, D, (float*)dz);
-    combine_bwd_kernel<float><<<blocks, 128, smem, stream>>>((const float*)dout, (const float*)z, dest_row, w, mean,
+    combine_bwd_kernel<float><<<blocks, CMB_WARPS * 32, smem, stream>>>((const float*)dout, (const float*)z, dest_row, w, mean,
                                                              rstd, gamma, N, K, D, (float*)dz, d_w, part);
   }
   B200_LAUNCH_CHECK("combine_bwd_kernel");

@@ -6,18 +6,19 @@ namespace b200 {
 
 namespace {
 
-constexpr int LN_ROWS_PER_BLOCK = 16;  // 4 warps x 4 rows; divides B200_GROUP_TILE so a block sees one expert
+constexpr int LN_WARPS = 8;
+constexpr int LN_ROWS_PER_BLOCK = 8;  // one row per warp; divides B200_GROUP_TILE so a block sees one expert
 
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(LN_WARPS * 32)
 add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
                   const float* __restrict__ beta, const int* __restrict__ tile_group, float eps,
                   T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int R, int D) {
   constexpr int VT = Vec16<T>::N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / VT;
-  for (int i = 0; i < LN_ROWS_PER_BLOCK / 4; ++i) {
-    const int r = blockIdx.x * LN_ROWS_PER_BLOCK + warp * (LN_ROWS_PER_BLOCK / 4) + i;
+  for (int i = 0; i < LN_ROWS_PER_BLOCK / LN_WARPS; ++i) {
+    const int r = blockIdx.x * LN_ROWS_PER_BLOCK + warp * (LN_ROWS_PER_BLOCK / LN_WARPS) + i;
     if (r >= R) return;
     int g = 0;
     if (tile_group != nullptr) {
@@ -54,13 +55,13 @@ add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const floa
 // dsum = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma.
 // Per-block partial dgamma/dbeta are written to part[block][2][D]; a second kernel reduces them per group.
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(LN_WARPS * 32)
 add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                   const float* __restrict__ gamma, const int* __restrict__ tile_group, T* __restrict__ dsum,
                   float* __restrict__ part, int R, int D) {
   constexpr int VT = Vec16<T>::N;
-  extern __shared__ float red[];  // [4 warps][2][D]
+  extern __shared__ float red[];  // [LN_WARPS][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / VT;
   float dg[ROW_MAXV][VT], db[ROW_MAXV][VT];
@@ -69,8 +70,8 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
 #pragma unroll
     for (int u = 0; u < VT; ++u) dg[j][u] = db[j][u] = 0.f;
 
-  for (int i = 0; i < LN_ROWS_PER_BLOCK / 4; ++i) {
-    const int r = blockIdx.x * LN_ROWS_PER_BLOCK + warp * (LN_ROWS_PER_BLOCK / 4) + i;
+  for (int i = 0; i < LN_ROWS_PER_BLOCK / LN_WARPS; ++i) {
+    const int r = blockIdx.x * LN_ROWS_PER_BLOCK + warp * (LN_ROWS_PER_BLOCK / LN_WARPS) + i;
     if (r >= R) break;
     int g = 0;
     if (tile_group != nullptr) {
@@ -130,27 +131,35 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
     const int which = c / D, d = c % D;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) s += red[(w * 2 + which) * D + d];
+    for (int w = 0; w < LN_WARPS; ++w) s += red[(w * 2 + which) * D + d];
     part[((long long)blockIdx.x * 2 + which) * D + d] = s;
   }
 }
 
-__global__ void ln_param_reduce_kernel(const float* __restrict__ part, int blocks, int rows_per_block, int D,
-                                       const int* __restrict__ tile_group, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  const int g = blockIdx.y;
-  if (d >= D) return;
-  float sg = 0.f, sb = 0.f;
-  for (int b = 0; b < blocks; ++b) {
-    const int bg = tile_group ? tile_group[(b * rows_per_block) / B200_GROUP_TILE] : 0;
-    if (bg == g) {
-      sg += part[((long long)b * 2 + 0) * D + d];
-      sb += part[((long long)b * 2 + 1) * D + d];
+// out_z[g][c] = sum over partial blocks b of group g of part[b][z][c]   (z = blockIdx.z selects dgamma / dbeta).
+// 32 columns x 8 partial-lanes per block: loads are independent across threads instead of one serial chain.
+__global__ void __launch_bounds__(256)
+partial_reduce_kernel(const float* __restrict__ part, int blocks, int rows_per_block, int width, int nz,
+                      const int* __restrict__ tile_group, float* __restrict__ out0, float* __restrict__ out1) {
+  __shared__ float red[8][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + x;
+  const int g = blockIdx.y, z = blockIdx.z;
+  float s = 0.f;
+  if (c < width) {
+    for (int b = y; b < blocks; b += 8) {
+      const int bg = tile_group ? tile_group[(b * rows_per_block) / B200_GROUP_TILE] : 0;
+      if (bg == g) s += part[((long long)b * nz + z) * width + c];
     }
   }
-  dgamma[(long long)g * D + d] = sg;
-  dbeta[(long long)g * D + d] = sb;
+  red[y][x] = s;
+  __syncthreads();
+  if (y == 0 && c < width) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][x];
+    (z == 0 ? out0 : out1)[(long long)g * width + c] = t;
+  }
 }
 
 }  // namespace
@@ -158,9 +167,19 @@ __global__ void ln_param_reduce_kernel(const float* __restrict__ part, int block
 // shared with dispatch.cu (combine backward uses the same partial layout)
 int launch_ln_param_reduce(const float* part, int blocks, int rows_per_block, int D, const int* tile_group, int G,
                            float* dgamma, float* dbeta, cudaStream_t stream) {
-  dim3 grid((D + 127) / 128, G);
-  ln_param_reduce_kernel<<<grid, 128, 0, stream>>>(part, blocks, rows_per_block, D, tile_group, dgamma, dbeta);
-  B200_LAUNCH_CHECK("ln_param_reduce_kernel");
+  dim3 grid((D + 31) / 32, G, 2);
+  partial_reduce_kernel<<<grid, 256, 0, stream>>>(part, blocks, rows_per_block, D, 2, tile_group, dgamma, dbeta);
+  B200_LAUNCH_CHECK("partial_reduce_kernel");
+  count_launch();
+  return 0;
+}
+
+// single-array variant (column sums)
+int launch_partial_reduce(const float* part, int blocks, int rows_per_block, int width, const int* tile_group, int G,
+                          float* out, cudaStream_t stream) {
+  dim3 grid((width + 31) / 32, G, 1);
+  partial_reduce_kernel<<<grid, 256, 0, stream>>>(part, blocks, rows_per_block, width, 1, tile_group, out, out);
+  B200_LAUNCH_CHECK("partial_reduce_kernel");
   count_launch();
   return 0;
 }
@@ -179,11 +198,11 @@ int b200_add_ln_fwd(const void* x, const void* res, const float* gamma, const fl
   const int blocks = (R + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK;
   if (dtype == B200_BF16) {
     B200_CHECK_ARG(RowRegs<bf16>::supported(D), "add_ln_fwd: D=%d unsupported for bf16 (need D%%8==0, D<=2048)", D);
-    add_ln_fwd_kernel<bf16><<<blocks, 128, 0, stream>>>((const bf16*)x, (const bf16*)res, gamma, beta, tile_group,
+    add_ln_fwd_kernel<bf16><<<blocks, LN_WARPS * 32, 0, stream>>>((const bf16*)x, (const bf16*)res, gamma, beta, tile_group,
                                                         eps, (bf16*)y, mean, rstd, R, D);
   } else {
     B200_CHECK_ARG(RowRegs<float>::supported(D), "add_ln_fwd: D=%d unsupported for fp32 (need D%%4==0, D<=1024)", D);
-    add_ln_fwd_kernel<float><<<blocks, 128, 0, stream>>>((const float*)x, (const float*)res, gamma, beta,
+    add_ln_fwd_kernel<float><<<blocks, LN_WARPS * 32, 0, stream>>>((const float*)x, (const float*)res, gamma, beta,
                                                          tile_group, eps, (float*)y, mean, rstd, R, D);
   }
   B200_LAUNCH_CHECK("add_ln_fwd_kernel");
@@ -204,16 +223,20 @@ int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float*
   B200_CHECK_ARG(workspace_bytes >= b200_add_ln_bwd_ws(R, D), "add_ln_bwd: workspace too small");
   const int blocks = (R + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK;
   float* part = (float*)workspace;
-  const size_t smem = (size_t)4 * 2 * D * sizeof(float);
+  const size_t smem = (size_t)LN_WARPS * 2 * D * sizeof(float);
   if (tile_group != nullptr)  // unused tiles leave their partial slots untouched
     B200_CUDA(cudaMemsetAsync(part, 0, b200_add_ln_bwd_ws(R, D), stream));
   if (dtype == B200_BF16) {
     B200_CHECK_ARG(RowRegs<bf16>::supported(D), "add_ln_bwd: D=%d unsupported for bf16", D);
-    add_ln_bwd_kernel<bf16><<<blocks, 128, smem, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)res, mean,
+    if (smem > 48 * 1024)
+      B200_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    add_ln_bwd_kernel<bf16><<<blocks, LN_WARPS * 32, smem, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)res, mean,
                                                            rstd, gamma, tile_group, (bf16*)dsum, part, R, D);
   } else {
     B200_CHECK_ARG(RowRegs<float>::supported(D), "add_ln_bwd: D=%d unsupported for fp32", D);
-    add_ln_bwd_kernel<float><<<blocks, 128, smem, stream>>>((const float*)dy, (const float*)x, (const float*)res,
+    if (smem > 48 * 1024)
+      B200_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    add_ln_bwd_kernel<float><<<blocks, LN_WARPS * 32, smem, stream>>>((const float*)dy, (const float*)x, (const float*)res,
                                                             mean, rstd, gamma, tile_group, (float*)dsum, part, R, D);
   }
   B200_LAUNCH_CHECK("add_ln_bwd_kernel");
