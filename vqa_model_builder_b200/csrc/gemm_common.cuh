@@ -134,5 +134,8 @@ int launch_gemm_tc(const void* A, int lda, int a_layout, long long a_mn_extent, 
                    const void* B, int ldb, int b_layout, long long b_mn_extent, long long b_k_extent,
                    GemmArgs args, int grid_m_tiles, int groups, cudaStream_t stream);
 int launch_gemm_simt(GemmArgs args, int grid_m_tiles, int groups, cudaStream_t stream);
+// 128B-swizzled 2-D bf16 tensor map (box = 64 inner elements x box_outer rows); map_out is a CUtensorMap*
+int make_tma_map_bf16(void* map_out, const void* ptr, long long inner, long long outer, long long pitch,
+                      int box_outer);
 
 }  // namespace b200

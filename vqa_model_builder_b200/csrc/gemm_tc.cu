@@ -2,10 +2,14 @@
 // tcgen05.ld epilogue.  One kernel serves the dense Linear layers of the fusion blocks and the grouped
 // expert FFN (forward, dgrad, wgrad) through operand major-ness flags and a tile->expert map.
 //
-// CTA = 128 threads: warp 0 lane 0 is the TMA producer, warp 1 lane 0 issues the UMMAs (and warp 1 owns
-// the TMEM allocation); afterwards all four warps drain the 128 x BN fp32 accumulator (warp w owns TMEM
-// lanes 32w..32w+31 = output rows) through the fused epilogue.  Tiles are not persistent: small problems
-// keep >= 2 CTAs per SM resident (BN=64) so one CTA's epilogue overlaps another's main loop.
+// Persistent, warp-specialised CTA (one per SM, 320 threads):
+//   warp 0      TMA producer (one elected lane) — ring of STAGES {A,B} k-blocks, full/empty mbarriers
+//   warp 1      UMMA issuer (one elected lane); owns the TMEM allocation
+//   warps 2..9  epilogue: two 128 x BN fp32 accumulators live in TMEM, so the epilogue of tile i overlaps the
+//               main loop of tile i+1 (tmem_full / tmem_empty mbarriers).  Warp w reads TMEM lanes
+//               32*(w%4)..+31 (its hardware quadrant) and one half of the BN columns, 32 columns at a time:
+//               tcgen05.ld -> bias / activation / residual in registers -> transpose through a padded
+//               shared-memory staging tile -> row-contiguous 16-byte global stores (full 32-byte sectors).
 #include <cuda.h>
 
 #include "gemm_common.cuh"
@@ -18,54 +22,215 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int CHUNK_BYTES = 64 * BK * 2;  // one 64(MN) x 64(K) MN-major TMA box
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
+constexpr int STG_PITCH = 144;                     // bytes per staged row: 128 B payload + 16 B pad (bank spread)
+constexpr int STG_BYTES = 32 * STG_PITCH;          // per epilogue warp
+constexpr int BIAS_FLOATS = 128;                   // per epilogue warp: its BN/2 columns
 
+template <int BN> constexpr int num_stages() { return BN == 256 ? 3 : (BN == 128 ? 5 : 6); }
 template <int BN> constexpr int stage_bytes() { return A_BYTES + BN * BK * 2; }
-template <int BN> constexpr int smem_bytes() { return STAGES * stage_bytes<BN>() + 1024 + 256; }
+template <int BN> constexpr int smem_bytes() {
+  return num_stages<BN>() * stage_bytes<BN>() + NUM_EPI_WARPS * (STG_BYTES + BIAS_FLOATS * 4) + 1024 + 256;
+}
+
+struct TileInfo {
+  int valid, group, m_tile, n_tile;
+  int a_mn0, a_k0, b_mn0, b_k0, k_begin, k_blocks;
+};
+
+template <int BN, bool B_MN>
+__device__ __forceinline__ TileInfo get_tile(const GemmArgs& p, int tile, int m_tiles, int n_tiles) {
+  TileInfo t;
+  const int per_z = m_tiles * n_tiles;
+  const int z = tile / per_z, rem = tile - z * per_z;
+  t.m_tile = rem / n_tiles;
+  t.n_tile = rem - t.m_tile * n_tiles;
+  t.valid = 1;
+  t.group = 0;
+  t.a_mn0 = t.m_tile * BM; t.a_k0 = 0; t.b_mn0 = t.n_tile * BN; t.b_k0 = 0;
+  t.k_begin = 0;
+  t.k_blocks = (p.K + BK - 1) / BK;
+  if (p.mode == GEMM_GROUP_ROWS) {
+    t.group = p.tile_group[t.m_tile];
+    if (t.group < 0) { t.valid = 0; return t; }
+    if (B_MN) t.b_k0 = t.group * p.b_group_rows; else t.b_mn0 += t.group * p.b_group_rows;
+  } else if (p.mode == GEMM_GROUP_WGRAD) {
+    t.group = z;
+    const int r0 = p.group_off[z], r1 = p.group_off[z + 1];
+    t.a_k0 = t.b_k0 = r0;
+    t.k_blocks = (r1 - r0 + BK - 1) / BK;
+  } else if (p.k_splits > 1) {
+    const int per = (t.k_blocks + p.k_splits - 1) / p.k_splits;
+    t.k_begin = z * per;
+    t.k_blocks = min(per, t.k_blocks - t.k_begin);
+    if (t.k_blocks <= 0) t.valid = 0;
+  }
+  return t;
+}
+
+// erf with |error| < 1.5e-7 (Abramowitz & Stegun 7.1.26): far below bf16 resolution, ~half the cost of erff
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float r = 1.0f - poly * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+// Activation applied to a 32-value register tile with the activation kind resolved ONCE per tile (a per-element
+// runtime switch made every element pay for all branches: 100+ instructions per GELU).
+template <int ACT>
+__device__ __forceinline__ float act1_fwd(float x) {
+  if (ACT == B200_ACT_GELU) return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752440f));
+  if (ACT == B200_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == B200_ACT_SILU) return x * __frcp_rn(1.0f + __expf(-x));
+  if (ACT == B200_ACT_TANH) return tanhf(x);
+  return x;
+}
+template <int ACT>
+__device__ __forceinline__ float act1_bwd(float x) {
+  if (ACT == B200_ACT_GELU) {
+    const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752440f));
+    return fmaf(x * 0.39894228040143267794f, __expf(-0.5f * x * x), cdf);
+  }
+  if (ACT == B200_ACT_RELU) return x > 0.f ? 1.f : 0.f;
+  if (ACT == B200_ACT_SILU) {
+    const float sg = __frcp_rn(1.0f + __expf(-x));
+    return sg * (1.0f + x * (1.0f - sg));
+  }
+  if (ACT == B200_ACT_TANH) {
+    const float th = tanhf(x);
+    return 1.0f - th * th;
+  }
+  return 1.f;
+}
+template <int ACT>
+__device__ __forceinline__ void tile_act_fwd(float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = act1_fwd<ACT>(v[j]);
+}
+template <int ACT>
+__device__ __forceinline__ void tile_act_bwd(float (&v)[32], const float (&aux)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] *= act1_bwd<ACT>(aux[j]);
+}
+__device__ __forceinline__ void tile_act_fwd(float (&v)[32], int act) {
+  switch (act) {
+    case B200_ACT_GELU: tile_act_fwd<B200_ACT_GELU>(v); break;
+    case B200_ACT_RELU: tile_act_fwd<B200_ACT_RELU>(v); break;
+    case B200_ACT_SILU: tile_act_fwd<B200_ACT_SILU>(v); break;
+    case B200_ACT_TANH: tile_act_fwd<B200_ACT_TANH>(v); break;
+    default: break;
+  }
+}
+__device__ __forceinline__ void tile_act_bwd(float (&v)[32], const float (&aux)[32], int act) {
+  switch (act) {
+    case B200_ACT_GELU: tile_act_bwd<B200_ACT_GELU>(v, aux); break;
+    case B200_ACT_RELU: tile_act_bwd<B200_ACT_RELU>(v, aux); break;
+    case B200_ACT_SILU: tile_act_bwd<B200_ACT_SILU>(v, aux); break;
+    case B200_ACT_TANH: tile_act_bwd<B200_ACT_TANH>(v, aux); break;
+    default: break;
+  }
+}
+
+// ---- epilogue helpers: a warp moves a 32-row x 32-column tile between registers (thread = row) and global
+// memory (row-contiguous 16-byte accesses) through its padded staging buffer -----------------------------------
+template <int ELEM_BYTES>  // 2 (bf16) or 4 (fp32)
+__device__ __forceinline__ void stage_store_tile(uint8_t* stg, int lane, const float (&v)[32], void* gbase, long long ld,
+                                                 long long row0, int rows_ok, int col0) {
+  constexpr int ROW_BYTES = 32 * ELEM_BYTES;       // 64 or 128
+  constexpr int LPR = ROW_BYTES / 16;              // lanes per row: 4 or 8
+  constexpr int RPI = 32 / LPR;                    // rows per instruction: 8 or 4
+  uint8_t* mine = stg + lane * STG_PITCH;
+  if (ELEM_BYTES == 2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 t;
+      t.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); t.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+      t.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); t.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      *reinterpret_cast<uint4*>(mine + 16 * j) = t;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(mine + 16 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  __syncwarp();
+  const int sub = lane % LPR, rsel = lane / LPR;
+#pragma unroll
+  for (int i = 0; i < 32 / RPI; ++i) {
+    const int r = i * RPI + rsel;
+    if (r < rows_ok) {
+      const uint4 t = *reinterpret_cast<const uint4*>(stg + r * STG_PITCH + 16 * sub);
+      uint8_t* dst = reinterpret_cast<uint8_t*>(gbase) + ((row0 + r) * ld + col0) * ELEM_BYTES + 16 * sub;
+      *reinterpret_cast<uint4*>(dst) = t;
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void stage_accum_tile(uint8_t* stg, int lane, const float (&v)[32], float* gbase, long long ld,
+                                                 long long row0, int rows_ok, int col0) {
+  uint8_t* mine = stg + lane * STG_PITCH;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(mine + 16 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  for (int r = 0; r < rows_ok; ++r)   // one row (32 consecutive floats) per warp instruction
+    atomicAdd(gbase + (row0 + r) * ld + col0 + lane, *reinterpret_cast<const float*>(stg + r * STG_PITCH + 4 * lane));
+  __syncwarp();
+}
+
+__device__ __forceinline__ void stage_load_tile_bf16(uint8_t* stg, int lane, float (&v)[32], const void* gbase,
+                                                     long long ld, long long row0, int rows_ok, int col0) {
+  const int sub = lane % 4, rsel = lane / 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + rsel;
+    uint4 t = make_uint4(0, 0, 0, 0);
+    if (r < rows_ok)
+      t = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(gbase) +
+                                               ((row0 + r) * ld + col0) * 2 + 16 * sub));
+    *reinterpret_cast<uint4*>(stg + r * STG_PITCH + 16 * sub) = t;
+  }
+  __syncwarp();
+  const uint8_t* mine = stg + lane * STG_PITCH;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 t = *reinterpret_cast<const uint4*>(mine + 16 * j);
+    const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+    v[8 * j + 0] = a.x; v[8 * j + 1] = a.y; v[8 * j + 2] = b.x; v[8 * j + 3] = b.y;
+    v[8 * j + 4] = c.x; v[8 * j + 5] = c.y; v[8 * j + 6] = d.x; v[8 * j + 7] = d.y;
+  }
+  __syncwarp();
+}
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const GemmArgs p) {
+               const GemmArgs p, const int m_tiles, const int n_tiles, const int total_tiles) {
+  constexpr int STAGES = num_stages<BN>();
+  constexpr int STAGE = stage_bytes<BN>();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  constexpr int STAGE = stage_bytes<BN>();
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
-  const uint32_t bar0 = base + STAGES * STAGE;
+  uint8_t* stg_all = smem + STAGES * STAGE;
+  float* bias_all = reinterpret_cast<float*>(stg_all + NUM_EPI_WARPS * STG_BYTES);
+  const uint32_t bar0 = base + STAGES * STAGE + NUM_EPI_WARPS * (STG_BYTES + BIAS_FLOATS * 4);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar0 + 8u * (2 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  auto tmem_full_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar0 - base) + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x, m_tile = blockIdx.y;
 
-  // ---- which problem does this CTA work on ------------------------------------------------------
-  int group = 0;
-  int a_mn0 = m_tile * BM, a_k0 = 0, b_mn0 = n_tile * BN, b_k0 = 0;
-  int k_begin = 0, k_blocks = (p.K + BK - 1) / BK;
-  if (p.mode == GEMM_GROUP_ROWS) {
-    group = p.tile_group[m_tile];
-    if (group < 0) return;
-    if (B_MN) b_k0 = group * p.b_group_rows; else b_mn0 += group * p.b_group_rows;
-  } else if (p.mode == GEMM_GROUP_WGRAD) {
-    group = blockIdx.z;
-    const int r0 = p.group_off[group], r1 = p.group_off[group + 1];
-    a_k0 = b_k0 = r0;
-    k_blocks = (r1 - r0 + BK - 1) / BK;
-  } else if (p.k_splits > 1) {
-    const int per = (k_blocks + p.k_splits - 1) / p.k_splits;
-    k_begin = blockIdx.z * per;
-    k_blocks = min(per, k_blocks - k_begin);
-    if (k_blocks <= 0) return;
-  }
-  const bool have_acc = k_blocks > 0;
-
-  // ---- one-time setup ---------------------------------------------------------------------------
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tma_a);
     ptx::prefetch_tensormap(&tma_b);
@@ -73,89 +238,178 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tmem_full_bar(a), 1);
+      ptx::mbar_init(tmem_empty_bar(a), NUM_EPI_WARPS);
+    }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), BN);
+  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 2 * BN);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // ---- main loop: producer / MMA issuer ---------------------------------------------------------
-  if (warp == 0 && lane == 0) {
-    for (int kb = 0; kb < k_blocks; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-      ptx::mbar_arrive_expect_tx(full_bar(s), STAGE);
-      const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
-      const int kc = (k_begin + kb) * BK;
-      if (!A_MN) {
-        ptx::tma_load_2d(sa, &tma_a, full_bar(s), a_k0 + kc, a_mn0);
-      } else {
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileInfo t = get_tile<BN, B_MN>(p, tile, m_tiles, n_tiles);
+        if (!t.valid) continue;
+        for (int kb = 0; kb < t.k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+          ptx::mbar_arrive_expect_tx(full_bar(s), STAGE);
+          const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+          const int kc = (t.k_begin + kb) * BK;
+          if (!A_MN) {
+            ptx::tma_load_2d(sa, &tma_a, full_bar(s), t.a_k0 + kc, t.a_mn0);
+          } else {
 #pragma unroll
-        for (int c = 0; c < BM / 64; ++c)
-          ptx::tma_load_2d(sa + c * CHUNK_BYTES, &tma_a, full_bar(s), a_mn0 + 64 * c, a_k0 + kc);
-      }
-      if (!B_MN) {
-        ptx::tma_load_2d(sb, &tma_b, full_bar(s), b_k0 + kc, b_mn0);
-      } else {
+            for (int c = 0; c < BM / 64; ++c)
+              ptx::tma_load_2d(sa + c * CHUNK_BYTES, &tma_a, full_bar(s), t.a_mn0 + 64 * c, t.a_k0 + kc);
+          }
+          if (!B_MN) {
+            ptx::tma_load_2d(sb, &tma_b, full_bar(s), t.b_k0 + kc, t.b_mn0);
+          } else {
 #pragma unroll
-        for (int c = 0; c < BN / 64; ++c)
-          ptx::tma_load_2d(sb + c * CHUNK_BYTES, &tma_b, full_bar(s), b_mn0 + 64 * c, b_k0 + kc);
+            for (int c = 0; c < BN / 64; ++c)
+              ptx::tma_load_2d(sb + c * CHUNK_BYTES, &tma_b, full_bar(s), t.b_mn0 + 64 * c, t.b_k0 + kc);
+          }
+        }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN, B_MN);
-    for (int kb = 0; kb < k_blocks; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      ptx::mbar_wait(full_bar(s), ph);
-      ptx::tc_fence_after();
-      const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+  } else if (warp == 1) {
+    // ================= UMMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int it = 0, acc_it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileInfo t = get_tile<BN, B_MN>(p, tile, m_tiles, n_tiles);
+        if (!t.valid || t.k_blocks == 0) continue;
+        const int acc = acc_it & 1;
+        const uint32_t acc_ph = (acc_it >> 1) & 1;
+        ptx::mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);   // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < t.k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(full_bar(s), ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
 #pragma unroll
-      for (int k = 0; k < BK / UMMA_K; ++k) {
-        // K-major: step 16 elements (32 B) inside the 128-byte swizzle row.
-        // MN-major: step 16 k-rows (2048 B); LBO = distance between 64-wide MN chunks.
-        const uint64_t ad = A_MN ? ptx::umma_smem_desc(sa + k * (UMMA_K * 128), CHUNK_BYTES, 1024)
-                                 : ptx::umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-        const uint64_t bd = B_MN ? ptx::umma_smem_desc(sb + k * (UMMA_K * 128), CHUNK_BYTES, 1024)
-                                 : ptx::umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-        ptx::umma_bf16(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: step 16 elements (32 B) inside the 128-byte swizzle row.
+            // MN-major: step 16 k-rows (2048 B); LBO = distance between 64-wide MN chunks.
+            const uint64_t ad = A_MN ? ptx::umma_smem_desc(sa + k * (UMMA_K * 128), CHUNK_BYTES, 1024)
+                                     : ptx::umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bd = B_MN ? ptx::umma_smem_desc(sb + k * (UMMA_K * 128), CHUNK_BYTES, 1024)
+                                     : ptx::umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            ptx::umma_bf16(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(s));       // frees the smem slot once these MMAs retire
+        }
+        ptx::umma_commit(tmem_full_bar(acc));   // accumulator complete -> epilogue
+        ++acc_it;
       }
-      ptx::umma_commit(empty_bar(s));  // frees the smem slot once these MMAs retire
     }
-    if (have_acc) ptx::umma_commit(tmem_full_bar);
-  }
-  __syncwarp();
-
-  // ---- epilogue: TMEM -> registers -> fused op -> global ----------------------------------------
-  if (have_acc) {
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
-  }
-  const long long row = (long long)m_tile * BM + warp * 32 + lane;
-  const bool row_ok = row < p.M;
+  } else {
+    // ================= epilogue warps =================
+    const int ew = warp - 2;                 // 0..7
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;                // which half of the BN columns
+    constexpr int HALF_N = BN / 2;
+    uint8_t* stg = stg_all + ew * STG_BYTES;
+    float* bias_s = bias_all + ew * BIAS_FLOATS;
+    const bool out_bf16 = !p.out_f32;
+    // fast path: every 16-byte group of a row is either fully inside or fully outside the matrix
+    const bool vec_ok = (p.N % 8 == 0) && (p.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                        (p.ld_aux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0) &&
+                        (p.mode != GEMM_GROUP_WGRAD || p.out_group_elems % 4 == 0);
+    int acc_it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileInfo t = get_tile<BN, B_MN>(p, tile, m_tiles, n_tiles);
+      if (!t.valid) continue;
+      const bool have_acc = t.k_blocks > 0;
+      const int acc = acc_it & 1;
+      const uint32_t acc_ph = (acc_it >> 1) & 1;
+      const int ncol0 = t.n_tile * BN + half * HALF_N;         // first column of this warp
+      // bias slice of this warp -> shared memory (broadcast reads later)
+      const float* bias = p.bias;
+      if (bias != nullptr) {
+        if (p.mode == GEMM_GROUP_ROWS) bias += (long long)t.group * p.N;
+        for (int c = lane; c < HALF_N; c += 32) bias_s[c] = (ncol0 + c < p.N) ? __ldg(bias + ncol0 + c) : 0.f;
+        __syncwarp();
+      }
+      if (have_acc) {
+        ptx::mbar_wait(tmem_full_bar(acc), acc_ph);
+        ptx::tc_fence_after();
+      }
+      const long long row0 = (long long)t.m_tile * BM + quad * 32;
+      const long long my_row = row0 + lane;
+      long long rows_left = (long long)p.M - row0;
+      const int rows_ok = rows_left >= 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);
+      const long long obase = (p.mode == GEMM_GROUP_WGRAD) ? (long long)t.group * p.out_group_elems : 0ll;
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    float acc[32];
-    if (have_acc) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), r);
-      ptx::tmem_ld_wait();
+      for (int c = 0; c < HALF_N / 32; ++c) {
+        const int col0 = ncol0 + c * 32;
+        float v[32];
+        if (have_acc) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF_N + c * 32), r);
+          ptx::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-    } else {
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (col0 >= p.N) continue;               // warp-uniform
+        if (vec_ok && col0 + 32 <= p.N) {
+          if (bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += bias_s[c * 32 + j];
+          }
+          if (p.epi == B200_EPI_ACT) {
+            if (p.aux_out != nullptr) stage_store_tile<2>(stg, lane, v, p.aux_out, p.ld_aux, row0, rows_ok, col0);
+            tile_act_fwd(v, p.act);
+          } else if (p.epi == B200_EPI_ADD || p.epi == B200_EPI_DACT) {
+            float aux[32];
+            stage_load_tile_bf16(stg, lane, aux, p.aux_in, p.ld_aux, row0, rows_ok, col0);
+            if (p.epi == B200_EPI_ADD) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += aux[j];
+            } else {
+              tile_act_bwd(v, aux, p.act);
+            }
+          }
+          if (p.epi == B200_EPI_ACCUM)
+            stage_accum_tile(stg, lane, v, reinterpret_cast<float*>(p.out) + obase, p.ldo, row0, rows_ok, col0);
+          else if (out_bf16)
+            stage_store_tile<2>(stg, lane, v, reinterpret_cast<bf16*>(p.out) + obase, p.ldo, row0, rows_ok, col0);
+          else
+            stage_store_tile<4>(stg, lane, v, reinterpret_cast<float*>(p.out) + obase, p.ldo, row0, rows_ok, col0);
+        } else {
+          // ragged / unaligned tile: per-thread row path (bias handled inside)
+          epilogue_store<bf16, 32>(p, t.group, my_row, col0, v, my_row < p.M);
+        }
+      }
+      if (have_acc) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(acc));   // accumulator may be overwritten
+        ++acc_it;
+      }
     }
-    epilogue_store<bf16, 32>(p, group, row, n_tile * BN + c * 32, acc, row_ok);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, BN);
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -176,9 +430,13 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+}  // namespace
+
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch `pitch` elements; the box is
-// 64 (inner, = 128 B swizzle span) x box_outer.
-int make_map(CUtensorMap* m, const void* ptr, long long inner, long long outer, long long pitch, int box_outer) {
+// 64 (inner, = 128 B swizzle span) x box_outer.  Shared with the attention kernels.
+int make_tma_map_bf16(void* map_out, const void* ptr, long long inner, long long outer, long long pitch,
+                      int box_outer) {
+  CUtensorMap* m = reinterpret_cast<CUtensorMap*>(map_out);
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -199,28 +457,31 @@ int make_map(CUtensorMap* m, const void* ptr, long long inner, long long outer, 
   return 0;
 }
 
+namespace {
+
 template <int BN, bool A_MN, bool B_MN>
-int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, dim3 grid,
-                   cudaStream_t stream) {
+int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int m_tiles, int n_tiles,
+                   int total_tiles, cudaStream_t stream) {
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN>()));
     configured = true;
   }
-  kern<<<grid, 128, smem_bytes<BN>(), stream>>>(ta, tb, args);
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  kern<<<grid, NUM_THREADS, smem_bytes<BN>(), stream>>>(ta, tb, args, m_tiles, n_tiles, total_tiles);
   B200_LAUNCH_CHECK("gemm_tc_kernel");
   count_launch();
   return 0;
 }
 
 template <int BN>
-int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
-              dim3 grid, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_variant<BN, false, false>(ta, tb, args, grid, stream);
-  if (!a_mn && b_mn) return launch_variant<BN, false, true>(ta, tb, args, grid, stream);
-  if (a_mn && b_mn) return launch_variant<BN, true, true>(ta, tb, args, grid, stream);
-  return launch_variant<BN, true, false>(ta, tb, args, grid, stream);
+int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int m_tiles,
+              int n_tiles, int total_tiles, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_variant<BN, false, false>(ta, tb, args, m_tiles, n_tiles, total_tiles, stream);
+  if (!a_mn && b_mn) return launch_variant<BN, false, true>(ta, tb, args, m_tiles, n_tiles, total_tiles, stream);
+  if (a_mn && b_mn) return launch_variant<BN, true, true>(ta, tb, args, m_tiles, n_tiles, total_tiles, stream);
+  return launch_variant<BN, true, false>(ta, tb, args, m_tiles, n_tiles, total_tiles, stream);
 }
 
 }  // namespace
@@ -234,34 +495,35 @@ int launch_gemm_tc(const void* A, int lda, int a_layout, long long a_mn_extent, 
   B200_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: bf16 operand pitches must be multiples of 8 (lda=%d ldb=%d)",
                  lda, ldb);
 
-  // tile-N selection: largest tile that still gives every SM a CTA
+  // tile-N selection: the largest tile that still gives (nearly) every SM a tile
   const int sms = num_sms();
   const long long m_tiles = grid_m_tiles;
-  int splits = 1;
-  auto ctas = [&](int bn) { return m_tiles * ((args.N + bn - 1) / bn) * (args.mode == GEMM_GROUP_WGRAD ? groups : 1); };
+  const int zdim = args.mode == GEMM_GROUP_WGRAD ? groups : 1;
+  auto tiles = [&](int bn) { return m_tiles * ((args.N + bn - 1) / bn) * zdim; };
   int bn = 64;
-  if (ctas(256) >= sms) bn = 256;
-  else if (ctas(128) >= sms) bn = 128;
+  if (tiles(256) >= sms) bn = 256;
+  else if (tiles(128) >= (sms * 3) / 4) bn = 128;
+  int splits = 1;
   if (args.mode == GEMM_DENSE && args.epi == B200_EPI_ACCUM) {
     const int kblocks = (args.K + BK - 1) / BK;
-    while (ctas(bn) * splits < sms && kblocks / (splits * 2) >= 4 && splits < 16) splits *= 2;
+    while (tiles(bn) * splits * 2 <= sms && kblocks / (splits * 2) >= 4 && splits < 16) splits *= 2;
   }
   args.k_splits = splits;
 
   CUtensorMap ta, tb;
   int rc;
-  if (!a_mn) rc = make_map(&ta, A, a_k_extent, a_mn_extent, lda, BM);
-  else rc = make_map(&ta, A, a_mn_extent, a_k_extent, lda, BK);
+  if (!a_mn) rc = make_tma_map_bf16(&ta, A, a_k_extent, a_mn_extent, lda, BM);
+  else rc = make_tma_map_bf16(&ta, A, a_mn_extent, a_k_extent, lda, BK);
   if (rc) return rc;
-  if (!b_mn) rc = make_map(&tb, B, b_k_extent, b_mn_extent, ldb, bn);
-  else rc = make_map(&tb, B, b_mn_extent, b_k_extent, ldb, BK);
+  if (!b_mn) rc = make_tma_map_bf16(&tb, B, b_k_extent, b_mn_extent, ldb, bn);
+  else rc = make_tma_map_bf16(&tb, B, b_mn_extent, b_k_extent, ldb, BK);
   if (rc) return rc;
 
-  dim3 grid((args.N + bn - 1) / bn, (unsigned)m_tiles,
-            args.mode == GEMM_GROUP_WGRAD ? groups : splits);
-  if (bn == 256) return launch_bn<256>(a_mn, b_mn, ta, tb, args, grid, stream);
-  if (bn == 128) return launch_bn<128>(a_mn, b_mn, ta, tb, args, grid, stream);
-  return launch_bn<64>(a_mn, b_mn, ta, tb, args, grid, stream);
+  const int n_tiles = (args.N + bn - 1) / bn;
+  const int total = (int)(m_tiles * n_tiles * (args.mode == GEMM_GROUP_WGRAD ? groups : splits));
+  if (bn == 256) return launch_bn<256>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, stream);
+  if (bn == 128) return launch_bn<128>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, stream);
+  return launch_bn<64>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, stream);
 }
 
 }  // namespace b200
