@@ -5,6 +5,8 @@
 //   backward: two passes over (query tile, key chunk) pairs with 4x4 register-tiled shared-memory GEMMs:
 //             pass 0 owns a key chunk and accumulates dK,dV over query tiles; pass 1 owns a query tile and
 //             accumulates dQ over key chunks (S/P recomputed from the saved log-sum-exp; no atomics).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -280,6 +282,25 @@ int set_smem(K kern, size_t bytes) {
 }
 
 }  // namespace
+
+// tensor-core path (attn_tc.cu)
+bool attn_tc_supported(int T, int S, int dh, int ldq, int ldk, int ldv, const void* q, const void* k, const void* v);
+int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
+                       void* o, int ldo, float* lse, int B, int H, int T, int S, int dh, float scale,
+                       cudaStream_t stream);
+int launch_attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
+                       const void* o, int ldo, const void* d_o, int lddo, const float* lse, void* dq, int lddq, void* dk,
+                       int lddk, void* dv, int lddv, int B, int H, int T, int S, int dh, float scale,
+                       cudaStream_t stream);
+
+static bool use_tc_attention() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200VQA_ATTN");   // "simt" forces the CUDA-core kernels (A/B testing)
+    v = (e != nullptr && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
 }  // namespace b200
 
 using namespace b200;
@@ -292,6 +313,9 @@ int b200_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v,
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(B > 0 && H > 0 && T > 0 && S > 0 && dh > 0 && dh <= 128 && dh % 4 == 0,
                  "attn_fwd: bad shape B=%d H=%d T=%d S=%d dh=%d (dh<=128, dh%%4==0)", B, H, T, S, dh);
+  if (dtype == B200_BF16 && use_tc_attention() && attn_tc_supported(T, S, dh, ldq, ldk, ldv, q, k, v) &&
+      ldo % 8 == 0 && ((uintptr_t)o & 15) == 0)
+    return launch_attn_fwd_tc(q, ldq, k, ldk, v, ldv, key_pad, o, ldo, lse, B, H, T, S, dh, scale, stream);
   dim3 grid(B * H, (T + FA_TQ - 1) / FA_TQ);
   const size_t smem = fwd_smem(dh);
   if (dtype == B200_BF16) {
@@ -317,6 +341,11 @@ int b200_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v,
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(B > 0 && H > 0 && T > 0 && S > 0 && dh > 0 && dh <= 128 && dh % 4 == 0,
                  "attn_bwd: bad shape B=%d H=%d T=%d S=%d dh=%d (dh<=128, dh%%4==0)", B, H, T, S, dh);
+  if (dtype == B200_BF16 && use_tc_attention() && attn_tc_supported(T, S, dh, ldq, ldk, ldv, q, k, v) &&
+      ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 &&
+      (((uintptr_t)o | (uintptr_t)d_o | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0)
+    return launch_attn_bwd_tc(q, ldq, k, ldk, v, ldv, key_pad, o, ldo, d_o, lddo, lse, dq, lddq, dk, lddk, dv, lddv, B,
+                              H, T, S, dh, scale, stream);
   const int bt = bwd_smem(dh, 64) <= 200 * 1024 ? 64 : 32;
   const size_t smem = bwd_smem(dh, bt);
   dim3 g0(B * H, (S + bt - 1) / bt), g1(B * H, (T + bt - 1) / bt);

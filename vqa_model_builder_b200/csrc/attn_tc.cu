@@ -1,0 +1,492 @@
+// Fused attention core on the 5th-gen tensor cores (bf16 in, fp32 softmax/accumulate), forward and backward.
+// One CTA per (batch, head): all T <= 128 query rows form the M=128 dimension of every UMMA; keys/values are
+// walked in tiles of 128.  Q/K/V/dO tiles arrive by TMA into 128B-swizzled shared memory; S = Q K^T, dP = dO V^T,
+// O/dQ/dK/dV accumulate in TMEM; the 128 threads (thread = TMEM lane = matrix row) do the softmax math in
+// registers and hand P / dS back to the tensor core through shared memory written in the same swizzled layout.
+// The [B,H,T,S] score tensor never exists in HBM.
+//
+// Layout trick used throughout: a [rows x 64-column chunk] tile with 128-byte rows and the 128B XOR swizzle is at
+// the same time a K-major operand (M/N = rows, K = columns) and an MN-major operand (K = rows, M/N = columns), so
+// one copy of P (or dS, Q, K, dO) serves both A*B and A^T*B products.
+#include <cuda.h>
+
+#include "gemm_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int ROWS = 128;              // query rows per CTA == kv rows per tile == TMA box rows
+constexpr int CHB = ROWS * 128;        // bytes of one [128 rows x 64 bf16] chunk
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnTcArgs {
+  int B, H, T, S, dh;
+  float scale;
+  const uint8_t* key_pad;   // [B,S] 1 = ignore, or null
+  bf16* o; int ldo;         // fwd out
+  float* lse;               // [B,H,T]
+  // backward
+  const bf16* o_in; int ldo_in;
+  const bf16* d_o; int lddo;
+  bf16* dq; int lddq;
+  bf16* dk; int lddk;
+  bf16* dv; int lddv;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 16-byte unit `u` (0..7) of row `r` inside a swizzled [128 x 64] chunk
+__device__ __forceinline__ uint32_t swz(int r, int u) { return (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4)); }
+
+// store 32 consecutive columns (32-col block `c32` of a 128-col tile) of row r as bf16 into a swizzled tile buffer
+__device__ __forceinline__ void store_row32(uint8_t* tile, int r, int c32, const float (&v)[32]) {
+  uint8_t* chunk = tile + (c32 >> 1) * CHB;
+  const int u0 = (c32 & 1) * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 t;
+    t.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); t.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+    t.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); t.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(chunk + swz(r, u0 + j)) = t;
+  }
+}
+
+__device__ __forceinline__ void ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  ptx::tmem_ld_32x32(taddr, r);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__device__ __forceinline__ uint32_t idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// K-major operand: k-step kk covers columns 16kk..16kk+15 -> chunk kk/4, 32-byte step inside the 128-byte row
+__device__ __forceinline__ uint64_t desc_k(uint32_t tile, int kk) {
+  return ptx::umma_smem_desc(tile + (kk >> 2) * CHB + (kk & 3) * 32, 16, 1024);
+}
+// MN-major operand: k-step kk covers rows 16kk..16kk+15 (2048 bytes); 64-wide MN chunks are CHB apart
+__device__ __forceinline__ uint64_t desc_mn(uint32_t tile, int kk) {
+  return ptx::umma_smem_desc(tile + kk * 2048, CHB, 1024);
+}
+
+struct Smem {
+  uint32_t base;     // 1024-aligned shared address
+  uint8_t* ptr;
+};
+__device__ __forceinline__ Smem align_smem(uint8_t* raw) {
+  const uint32_t r = ptx::smem_u32(raw);
+  const uint32_t b = (r + 1023u) & ~1023u;
+  return Smem{b, raw + (b - r)};
+}
+
+// ============================================ forward ==============================================
+// smem: Q[nch] | K[nch] | V[nch] | P[2] chunks, then barriers.  TMEM: S tiles at columns 128*j, O at 128*NT.
+template <int NT>
+__global__ void __launch_bounds__(128)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                   const __grid_constant__ CUtensorMap vmap, const AttnTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const Smem sm = align_smem(smem_raw);
+  const int nch = (a.dh + 63) / 64;
+  const uint32_t sQ = sm.base, sK = sQ + nch * CHB, sV = sK + nch * CHB, sP = sV + nch * CHB;
+  uint8_t* pP = sm.ptr + 3 * nch * CHB;
+  const uint32_t bars = sP + 2 * CHB;
+  const uint32_t bar_q = bars, bar_k = bars + 8, bar_v = bars + 16, bar_mma = bars + 24;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.ptr + 3 * nch * CHB + 2 * CHB + 32);
+  constexpr uint32_t TCOLS = NT == 1 ? 256 : 512;
+  constexpr uint32_t O_COL = NT * 128;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int ksteps_d = a.dh / 16;
+
+  if (tid == 0) {
+    ptx::prefetch_tensormap(&qmap);
+    ptx::prefetch_tensormap(&kmap);
+    ptx::prefetch_tensormap(&vmap);
+    ptx::mbar_init(bar_q, 1);
+    ptx::mbar_init(bar_k, 1);
+    ptx::mbar_init(bar_v, 1);
+    ptx::mbar_init(bar_mma, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), TCOLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  uint32_t ph_k = 0, ph_v = 0, ph_mma = 0;
+
+  // ---- S_j = Q K_j^T for every kv tile (K buffer reused serially; the tensor-core work here is tiny) ----
+  if (tid == 0) {
+    ptx::mbar_arrive_expect_tx(bar_q, nch * CHB);
+    for (int c = 0; c < nch; ++c) ptx::tma_load_2d(sQ + c * CHB, &qmap, bar_q, h * a.dh + 64 * c, b * a.T);
+  }
+  for (int j = 0; j < NT; ++j) {
+    const int n_valid = min(ROWS, a.S - j * ROWS);
+    if (n_valid <= 0) break;
+    const int n16 = (n_valid + 15) & ~15;
+    if (tid == 0) {
+      ptx::mbar_arrive_expect_tx(bar_k, nch * CHB);
+      for (int c = 0; c < nch; ++c)
+        ptx::tma_load_2d(sK + c * CHB, &kmap, bar_k, h * a.dh + 64 * c, b * a.S + j * ROWS);
+      if (j == 0) ptx::mbar_wait(bar_q, 0);
+      ptx::mbar_wait(bar_k, ph_k);
+      ptx::tc_fence_after();
+      const uint32_t id = idesc(128, n16, false, false);
+      for (int kk = 0; kk < ksteps_d; ++kk)
+        ptx::umma_bf16(tmem + j * 128, desc_k(sQ, kk), desc_k(sK, kk), id, kk > 0 ? 1u : 0u);
+      ptx::umma_commit(bar_mma);
+    }
+    ph_k ^= 1;
+    ptx::mbar_wait(bar_mma, ph_mma);   // every thread: S_j complete and the K buffer is free again
+    ph_mma ^= 1;
+  }
+  ptx::tc_fence_after();
+  if (tid == 0) {   // prefetch V_0 while the softmax statistics are computed
+    ptx::mbar_arrive_expect_tx(bar_v, nch * CHB);
+    for (int c = 0; c < nch; ++c) ptx::tma_load_2d(sV + c * CHB, &vmap, bar_v, h * a.dh + 64 * c, b * a.S);
+  }
+
+  // ---- softmax: thread = query row -------------------------------------------------------------------
+  const int r = tid;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint8_t* kp = a.key_pad ? a.key_pad + (long long)b * a.S : nullptr;
+  float m = -INFINITY;
+  for (int j = 0; j < NT; ++j) {
+    const int n_valid = min(ROWS, a.S - j * ROWS);
+    if (n_valid <= 0) break;
+    for (int c = 0; c * 32 < n_valid; ++c) {
+      float v[32];
+      ld32(lane_base + j * 128 + c * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int col = c * 32 + i;
+        const bool ok = col < n_valid && !(kp && kp[j * ROWS + col]);
+        if (ok) m = fmaxf(m, v[i]);
+      }
+    }
+  }
+  const float sl2 = a.scale * LOG2E;
+  const float m_s = (m == -INFINITY) ? 0.f : m * sl2;
+  float l = 0.f;
+  for (int j = 0; j < NT; ++j) {
+    const int n_valid = min(ROWS, a.S - j * ROWS);
+    if (n_valid <= 0) break;
+    const int n16 = (n_valid + 15) & ~15;
+    for (int c = 0; c * 32 < n16; ++c) {
+      float v[32];
+      ld32(lane_base + j * 128 + c * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int col = c * 32 + i;
+        const bool ok = col < n_valid && !(kp && kp[j * ROWS + col]);
+        const float p = ok ? ex2(fmaf(v[i], sl2, -m_s)) : 0.f;
+        // round to bf16 first so the normaliser matches the probabilities the tensor core actually sees
+        const float pr = __bfloat162float(__float2bfloat16_rn(p));
+        l += pr;
+        v[i] = pr;
+      }
+      store_row32(pP, r, c, v);
+    }
+    fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      ptx::mbar_wait(bar_v, ph_v);
+      const uint32_t id = idesc(128, a.dh, false, true);
+      for (int kk = 0; kk < n16 / 16; ++kk)
+        ptx::umma_bf16(tmem + O_COL, desc_k(sP, kk), desc_mn(sV, kk), id, (j > 0 || kk > 0) ? 1u : 0u);
+      ptx::umma_commit(bar_mma);
+    }
+    ph_v ^= 1;
+    ptx::mbar_wait(bar_mma, ph_mma);   // P and V buffers are free again
+    ph_mma ^= 1;
+    if (tid == 0 && j + 1 < NT && a.S - (j + 1) * ROWS > 0) {
+      ptx::mbar_arrive_expect_tx(bar_v, nch * CHB);
+      for (int c = 0; c < nch; ++c)
+        ptx::tma_load_2d(sV + c * CHB, &vmap, bar_v, h * a.dh + 64 * c, b * a.S + (j + 1) * ROWS);
+    }
+  }
+  ptx::tc_fence_after();
+
+  // ---- epilogue: O / l -> bf16 -> global; log-sum-exp for backward -----------------------------------------
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  {
+    bf16* orow = a.o + ((long long)b * a.T + r) * a.ldo + h * a.dh;
+    for (int c = 0; c < a.dh / 32; ++c) {
+      float v[32];
+      ld32(lane_base + O_COL + c * 32, v);   // .aligned: executed by the whole warp, stores are predicated
+      if (r < a.T) {
+#pragma unroll
+        for (int jv = 0; jv < 4; ++jv) {
+          uint4 t;
+          t.x = pack_bf16x2(v[8 * jv + 0] * inv, v[8 * jv + 1] * inv); t.y = pack_bf16x2(v[8 * jv + 2] * inv, v[8 * jv + 3] * inv);
+          t.z = pack_bf16x2(v[8 * jv + 4] * inv, v[8 * jv + 5] * inv); t.w = pack_bf16x2(v[8 * jv + 6] * inv, v[8 * jv + 7] * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + jv * 8) = t;
+        }
+      }
+    }
+    if (r < a.T) a.lse[((long long)b * a.H + h) * a.T + r] = (l > 0.f) ? m * a.scale + __logf(l) : -INFINITY;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, TCOLS);
+}
+
+// ============================================ backward =============================================
+// smem: Q[nch] | dO[nch] | K[nch] | V[nch] | P[2] | dS[2].  TMEM: S/dV at 0, dP/dK at 128, dQ at 256.
+__global__ void __launch_bounds__(128)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                   const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap domap,
+                   const AttnTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const Smem sm = align_smem(smem_raw);
+  const int nch = (a.dh + 63) / 64;
+  const uint32_t sQ = sm.base, sdO = sQ + nch * CHB, sK = sdO + nch * CHB, sV = sK + nch * CHB;
+  const uint32_t sP = sV + nch * CHB, sdS = sP + 2 * CHB;
+  uint8_t* pP = sm.ptr + 4 * nch * CHB;
+  uint8_t* pdS = pP + 2 * CHB;
+  const uint32_t bars = sdS + 2 * CHB;
+  const uint32_t bar_q = bars, bar_kv = bars + 8, bar_mma = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.ptr + 4 * nch * CHB + 4 * CHB + 32);
+  constexpr uint32_t TCOLS = 512, C_S = 0, C_DP = 128, C_DQ = 256;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int ksteps_d = a.dh / 16;
+  const int ksteps_t = (min(a.T, ROWS) + 15) / 16;
+  const int ntiles = (a.S + ROWS - 1) / ROWS;
+
+  if (tid == 0) {
+    ptx::prefetch_tensormap(&qmap);
+    ptx::prefetch_tensormap(&kmap);
+    ptx::prefetch_tensormap(&vmap);
+    ptx::prefetch_tensormap(&domap);
+    ptx::mbar_init(bar_q, 1);
+    ptx::mbar_init(bar_kv, 1);
+    ptx::mbar_init(bar_mma, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), TCOLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t ph_kv = 0, ph_mma = 0;
+
+  if (tid == 0) {
+    ptx::mbar_arrive_expect_tx(bar_q, 2 * nch * CHB);
+    for (int c = 0; c < nch; ++c) {
+      ptx::tma_load_2d(sQ + c * CHB, &qmap, bar_q, h * a.dh + 64 * c, b * a.T);
+      ptx::tma_load_2d(sdO + c * CHB, &domap, bar_q, h * a.dh + 64 * c, b * a.T);
+    }
+  }
+  // per-row statistics: delta = sum_d dO*O, lse
+  const int r = tid;
+  float delta = 0.f, lse_l2 = 0.f;
+  const bool row_ok = r < a.T;
+  if (row_ok) {
+    const bf16* orow = a.o_in + ((long long)b * a.T + r) * a.ldo_in + h * a.dh;
+    const bf16* grow = a.d_o + ((long long)b * a.T + r) * a.lddo + h * a.dh;
+    for (int d = 0; d < a.dh; d += 8) {
+      Vec16<bf16> ov, gv;
+      ov.load(orow + d);
+      gv.load(grow + d);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) delta = fmaf(ov.v[u], gv.v[u], delta);
+    }
+    lse_l2 = a.lse[((long long)b * a.H + h) * a.T + r] * LOG2E;
+  }
+  const float sl2 = a.scale * LOG2E;
+  const uint8_t* kp = a.key_pad ? a.key_pad + (long long)b * a.S : nullptr;
+
+  for (int j = 0; j < ntiles; ++j) {
+    const int n_valid = min(ROWS, a.S - j * ROWS);
+    const int n16 = (n_valid + 15) & ~15;
+    if (tid == 0) {
+      ptx::mbar_arrive_expect_tx(bar_kv, 2 * nch * CHB);
+      for (int c = 0; c < nch; ++c) {
+        ptx::tma_load_2d(sK + c * CHB, &kmap, bar_kv, h * a.dh + 64 * c, b * a.S + j * ROWS);
+        ptx::tma_load_2d(sV + c * CHB, &vmap, bar_kv, h * a.dh + 64 * c, b * a.S + j * ROWS);
+      }
+      if (j == 0) ptx::mbar_wait(bar_q, 0);
+      ptx::mbar_wait(bar_kv, ph_kv);
+      ptx::tc_fence_after();
+      const uint32_t id = idesc(128, n16, false, false);
+      for (int kk = 0; kk < ksteps_d; ++kk)   // S = Q K^T
+        ptx::umma_bf16(tmem + C_S, desc_k(sQ, kk), desc_k(sK, kk), id, kk > 0 ? 1u : 0u);
+      for (int kk = 0; kk < ksteps_d; ++kk)   // dP = dO V^T
+        ptx::umma_bf16(tmem + C_DP, desc_k(sdO, kk), desc_k(sV, kk), id, kk > 0 ? 1u : 0u);
+      ptx::umma_commit(bar_mma);
+    }
+    ph_kv ^= 1;
+    ptx::mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    ptx::tc_fence_after();
+
+    // P = exp(S*scale - lse), dS = P * (dP - delta) * scale  -> swizzled smem tiles (bf16)
+    for (int c = 0; c < 4; ++c) {
+      float s[32], dp[32];
+      if (c * 32 < n16) {
+        ld32(lane_base + C_S + c * 32, s);
+        ld32(lane_base + C_DP + c * 32, dp);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int col = c * 32 + i;
+        const bool ok = row_ok && col < n_valid && !(kp && kp[j * ROWS + col]);
+        const float p = ok ? ex2(fmaf(s[i], sl2, -lse_l2)) : 0.f;
+        s[i] = p;
+        dp[i] = ok ? p * (dp[i] - delta) * a.scale : 0.f;
+      }
+      // columns >= n16 are written as zeros too: the dV/dK products read all 128 columns of these tiles (M dim)
+      store_row32(pP, r, c, s);
+      store_row32(pdS, r, c, dp);
+    }
+    fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      const uint32_t id_t = idesc(128, a.dh, true, true);    // A^T B with A = P / dS (MN-major), B = dO / Q (MN-major)
+      for (int kk = 0; kk < ksteps_t; ++kk)   // dV = P^T dO
+        ptx::umma_bf16(tmem + C_S, desc_mn(sP, kk), desc_mn(sdO, kk), id_t, kk > 0 ? 1u : 0u);
+      for (int kk = 0; kk < ksteps_t; ++kk)   // dK = dS^T Q
+        ptx::umma_bf16(tmem + C_DP, desc_mn(sdS, kk), desc_mn(sQ, kk), id_t, kk > 0 ? 1u : 0u);
+      const uint32_t id_q = idesc(128, a.dh, false, true);   // dQ += dS K  (A = dS K-major, B = K MN-major)
+      for (int kk = 0; kk < n16 / 16; ++kk)
+        ptx::umma_bf16(tmem + C_DQ, desc_k(sdS, kk), desc_mn(sK, kk), id_q, (j > 0 || kk > 0) ? 1u : 0u);
+      ptx::umma_commit(bar_mma);
+    }
+    ptx::mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    ptx::tc_fence_after();
+    // dV, dK rows of this tile: thread = kv row
+    {
+      const int srow = j * ROWS + r;
+      const bool ok = r < n_valid;
+      bf16* dvrow = a.dv + ((long long)b * a.S + srow) * a.lddv + h * a.dh;
+      bf16* dkrow = a.dk + ((long long)b * a.S + srow) * a.lddk + h * a.dh;
+      for (int c = 0; c < a.dh / 32; ++c) {
+        float v[32], k[32];
+        ld32(lane_base + C_S + c * 32, v);
+        ld32(lane_base + C_DP + c * 32, k);
+        if (ok) {
+#pragma unroll
+          for (int jv = 0; jv < 4; ++jv) {
+            uint4 t;
+            t.x = pack_bf16x2(v[8 * jv + 0], v[8 * jv + 1]); t.y = pack_bf16x2(v[8 * jv + 2], v[8 * jv + 3]);
+            t.z = pack_bf16x2(v[8 * jv + 4], v[8 * jv + 5]); t.w = pack_bf16x2(v[8 * jv + 6], v[8 * jv + 7]);
+            *reinterpret_cast<uint4*>(dvrow + c * 32 + jv * 8) = t;
+            t.x = pack_bf16x2(k[8 * jv + 0], k[8 * jv + 1]); t.y = pack_bf16x2(k[8 * jv + 2], k[8 * jv + 3]);
+            t.z = pack_bf16x2(k[8 * jv + 4], k[8 * jv + 5]); t.w = pack_bf16x2(k[8 * jv + 6], k[8 * jv + 7]);
+            *reinterpret_cast<uint4*>(dkrow + c * 32 + jv * 8) = t;
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();   // TMEM S/dP regions and the K/V/P/dS buffers may be overwritten by the next tile
+  }
+
+  // dQ rows
+  ptx::tc_fence_after();
+  {
+    bf16* dqrow = a.dq + ((long long)b * a.T + r) * a.lddq + h * a.dh;
+    for (int c = 0; c < a.dh / 32; ++c) {
+      float v[32];
+      ld32(lane_base + C_DQ + c * 32, v);
+      if (row_ok) {
+#pragma unroll
+        for (int jv = 0; jv < 4; ++jv) {
+          uint4 t;
+          t.x = pack_bf16x2(v[8 * jv + 0], v[8 * jv + 1]); t.y = pack_bf16x2(v[8 * jv + 2], v[8 * jv + 3]);
+          t.z = pack_bf16x2(v[8 * jv + 4], v[8 * jv + 5]); t.w = pack_bf16x2(v[8 * jv + 6], v[8 * jv + 7]);
+          *reinterpret_cast<uint4*>(dqrow + c * 32 + jv * 8) = t;
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, TCOLS);
+}
+
+size_t fwd_smem(int dh) { return (size_t)(3 * ((dh + 63) / 64) + 2) * CHB + 1024 + 128; }
+size_t bwd_smem(int dh) { return (size_t)(4 * ((dh + 63) / 64) + 4) * CHB + 1024 + 128; }
+
+}  // namespace
+
+bool attn_tc_supported(int T, int S, int dh, int ldq, int ldk, int ldv, const void* q, const void* k, const void* v) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return T <= ROWS && S <= 3 * ROWS && dh % 32 == 0 && dh <= 128 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 &&
+         al(q) && al(k) && al(v);
+}
+
+int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
+                       void* o, int ldo, float* lse, int B, int H, int T, int S, int dh, float scale,
+                       cudaStream_t stream) {
+  CUtensorMap qm, km, vm;
+  const long long cols = (long long)H * dh;
+  if (int rc = make_tma_map_bf16(&qm, q, cols, (long long)B * T, ldq, ROWS)) return rc;
+  if (int rc = make_tma_map_bf16(&km, k, cols, (long long)B * S, ldk, ROWS)) return rc;
+  if (int rc = make_tma_map_bf16(&vm, v, cols, (long long)B * S, ldv, ROWS)) return rc;
+  AttnTcArgs a{};
+  a.B = B; a.H = H; a.T = T; a.S = S; a.dh = dh; a.scale = scale; a.key_pad = key_pad;
+  a.o = (bf16*)o; a.ldo = ldo; a.lse = lse;
+  const size_t smem = fwd_smem(dh);
+  const int nt = (S + ROWS - 1) / ROWS;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(128)));
+    B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(128)));
+    configured = true;
+  }
+  if (nt == 1) attn_fwd_tc_kernel<1><<<B * H, 128, smem, stream>>>(qm, km, vm, a);
+  else attn_fwd_tc_kernel<3><<<B * H, 128, smem, stream>>>(qm, km, vm, a);
+  B200_LAUNCH_CHECK("attn_fwd_tc_kernel");
+  count_launch();
+  return 0;
+}
+
+int launch_attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
+                       const void* o, int ldo, const void* d_o, int lddo, const float* lse, void* dq, int lddq, void* dk,
+                       int lddk, void* dv, int lddv, int B, int H, int T, int S, int dh, float scale,
+                       cudaStream_t stream) {
+  CUtensorMap qm, km, vm, dom;
+  const long long cols = (long long)H * dh;
+  if (int rc = make_tma_map_bf16(&qm, q, cols, (long long)B * T, ldq, ROWS)) return rc;
+  if (int rc = make_tma_map_bf16(&km, k, cols, (long long)B * S, ldk, ROWS)) return rc;
+  if (int rc = make_tma_map_bf16(&vm, v, cols, (long long)B * S, ldv, ROWS)) return rc;
+  if (int rc = make_tma_map_bf16(&dom, d_o, cols, (long long)B * T, lddo, ROWS)) return rc;
+  AttnTcArgs a{};
+  a.B = B; a.H = H; a.T = T; a.S = S; a.dh = dh; a.scale = scale; a.key_pad = key_pad;
+  a.lse = const_cast<float*>(lse);
+  a.o_in = (const bf16*)o; a.ldo_in = ldo; a.d_o = (const bf16*)d_o; a.lddo = lddo;
+  a.dq = (bf16*)dq; a.lddq = lddq; a.dk = (bf16*)dk; a.lddk = lddk; a.dv = (bf16*)dv; a.lddv = lddv;
+  const size_t smem = bwd_smem(dh);
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem(128)));
+    configured = true;
+  }
+  attn_bwd_tc_kernel<<<B * H, 128, smem, stream>>>(qm, km, vm, dom, a);
+  B200_LAUNCH_CHECK("attn_bwd_tc_kernel");
+  count_launch();
+  return 0;
+}
+
+}  // namespace b200
