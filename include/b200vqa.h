@@ -123,12 +123,13 @@ int b200_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v,
  * exact ties), renormalise; clean probs and the Switch load-balance loss
  *   loss = lb_weight * E * sum_e (count_e / N) * (sum_n p_clean[n,e] / N).
  * Outputs: idx int32 [N,K], w fp32 [N,K], topk_sum fp32 [N], probs fp32 [N,E] (clean),
- * probs_noisy fp32 [N,E] (only when eps != NULL), counts fp32 [E], loss fp32 [1],
- * noise_scale_mean fp32 [1] (only when eps != NULL).  workspace >= b200_router_ws(N, E).          */
+ * probs_noisy fp32 [N,E] (only when eps != NULL), counts fp32 [E], psum fp32 [E] = sum_n p_clean[n,e] (may be
+ * NULL; with counts it is what ranks all-reduce for a global aux loss), loss fp32 [1], noise_scale_mean fp32 [1]
+ * (only when eps != NULL).  workspace >= b200_router_ws(N, E).                                          */
 size_t b200_router_ws(int N, int E);
 int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* w_noise, const float* eps,
                     float noise_std, float lb_weight, int N, int D, int E, int K, int32_t* idx, float* w,
-                    float* topk_sum, float* probs, float* probs_noisy, float* counts, float* loss,
+                    float* topk_sum, float* probs, float* probs_noisy, float* counts, float* psum, float* loss,
                     float* noise_scale_mean, void* workspace, size_t workspace_bytes, void* stream);
 /* Backward of the above.  d_w [N,K] (may be NULL), d_loss device fp32 scalar (may be NULL).
  * Produces dx [N,D] (overwrite), d_w_gate [E,D] fp32, d_w_noise [E,D] fp32 (if noisy).

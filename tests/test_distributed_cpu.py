@@ -1,0 +1,99 @@
+"""CPU, world_size 2 over gloo: host-side logic of the multi-GPU path — gradient bucketing + all-reduce,
+the autograd all-to-all used by expert parallelism, count exchange and expert placement."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vqa_model_builder_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    try:
+        parallel.init_distributed("gloo")
+        fn(rank, world)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def run2(fn):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, fn, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, status in res:
+        assert status == "ok", f"rank {rank}: {status}"
+
+
+def _dp_buckets(rank, world):
+    torch.manual_seed(0)
+    a = torch.nn.Parameter(torch.zeros(4, 3))
+    b = torch.nn.Parameter(torch.zeros(5))
+    c = torch.nn.Parameter(torch.zeros(2))
+    flat = torch.arange(17, dtype=torch.float32) * (rank + 1)        # one stage returned views of one flat buffer
+    a.grad, b.grad = flat[:12].view(4, 3), flat[12:]
+    c.grad = torch.full((2,), float(rank + 1))
+    buckets = parallel.grad_buckets([a, b, c])
+    assert len(buckets) == 2 and buckets[0].data_ptr() == flat.data_ptr()
+    n = parallel.allreduce_gradients([a, b, c], average=True)
+    assert n == 2
+    assert torch.allclose(a.grad, (torch.arange(12, dtype=torch.float32) * 1.5).view(4, 3))
+    assert torch.allclose(b.grad, torch.arange(12, 17, dtype=torch.float32) * 1.5)
+    assert torch.allclose(c.grad, torch.full((2,), 1.5))
+
+
+def _a2a_autograd(rank, world):
+    # rank r sends (r+1) rows to rank 0 and 2 rows to rank 1
+    in_splits = [rank + 1, 2]
+    counts = torch.tensor([rank + 1, 2])
+    send, recv = parallel.exchange_counts(counts, world)
+    assert send == [[rank + 1], [2]]
+    assert recv == ([[1], [2]] if rank == 0 else [[2], [2]])
+    out_splits = [r[0] for r in recv]
+    x = (torch.arange(sum(in_splits) * 3, dtype=torch.float32).view(-1, 3) + 100 * rank).requires_grad_()
+    y = parallel.AllToAllRows.apply(x, in_splits, out_splits, None)
+    assert y.shape[0] == sum(out_splits)
+    if rank == 0:   # got my own first row and rank 1's first two rows
+        assert torch.equal(y[0], x[0].detach()) and float(y[1, 0]) == 100.0
+    (y * (rank + 1)).sum().backward()
+    # rows sent to rank d come back scaled by (d+1)
+    want = torch.cat([torch.full((in_splits[0], 3), 1.0), torch.full((in_splits[1], 3), 2.0)])
+    assert torch.equal(x.grad, want)
+
+
+def test_dp_gradient_buckets_allreduce_world2():
+    run2(_dp_buckets)
+
+
+def test_all_to_all_rows_autograd_world2():
+    run2(_a2a_autograd)
+
+
+def test_expert_owner_placement():
+    assert [parallel.expert_owner(e, 32, 8) for e in (0, 3, 4, 31)] == [0, 0, 1, 7]
+    assert parallel.expert_owner(7, 8, 8) == 7
+    with pytest.raises(ValueError):
+        parallel.expert_owner(0, 6, 4)

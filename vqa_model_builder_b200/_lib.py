@@ -43,7 +43,7 @@ SIGNATURES = {
     "b200_attn_fwd": ("i", "pipipippipiiiiifip"),
     "b200_attn_bwd": ("i", "pipipippipippipipiiiiiifip"),
     "b200_router_ws": ("z", "ii"),
-    "b200_router_fwd": ("i", "pipppffiiiipppppppppzp"),
+    "b200_router_fwd": ("i", "pipppffiiiippppppppppzp"),
     "b200_router_bwd_ws": ("z", "iii"),
     "b200_router_bwd": ("i", "pipppffiiiippppppppppppzp"),
     "b200_moe_max_rows": ("i", "ii"),

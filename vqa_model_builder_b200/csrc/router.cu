@@ -135,7 +135,7 @@ router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
 
 // counts[e], loss = lb_weight * E * sum_e (counts[e]/N) * (psum[e]/N), mean softplus noise scale
 __global__ void router_finalize_kernel(const float* __restrict__ part, int blocks, int N, int E, float lb_weight,
-                                       float* __restrict__ counts, float* __restrict__ loss,
+                                       float* __restrict__ counts, float* __restrict__ psum, float* __restrict__ loss,
                                        float* __restrict__ noise_scale_mean) {
   __shared__ float s_cnt[RT_MAX_E], s_ps[RT_MAX_E], s_ns[RT_MAX_E];
   const int e = threadIdx.x;
@@ -147,7 +147,10 @@ __global__ void router_finalize_kernel(const float* __restrict__ part, int block
       q += part[((long long)b * 3 + 2) * RT_MAX_E + e];
     }
     s_cnt[e] = c; s_ps[e] = p; s_ns[e] = q;
-    if (e < E) counts[e] = c;
+    if (e < E) {
+      counts[e] = c;
+      if (psum != nullptr) psum[e] = p;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -325,7 +328,7 @@ size_t b200_router_ws(int N, int E) {
 
 int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* w_noise, const float* eps,
                     float noise_std, float lb_weight, int N, int D, int E, int K, int32_t* idx, float* w,
-                    float* topk_sum, float* probs, float* probs_noisy, float* counts, float* loss,
+                    float* topk_sum, float* probs, float* probs_noisy, float* counts, float* psum, float* loss,
                     float* noise_scale_mean, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(N > 0 && D > 0 && E > 0 && E <= RT_MAX_E && K > 0 && K <= E && K <= 32,
@@ -349,7 +352,7 @@ int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* 
                                                                       part);
   }
   B200_LAUNCH_CHECK("router_fwd_kernel");
-  router_finalize_kernel<<<1, RT_MAX_E, 0, stream>>>(part, blocks, N, E, lb_weight, counts, loss,
+  router_finalize_kernel<<<1, RT_MAX_E, 0, stream>>>(part, blocks, N, E, lb_weight, counts, psum, loss,
                                                      eps != nullptr ? noise_scale_mean : nullptr);
   B200_LAUNCH_CHECK("router_finalize_kernel");
   count_launch(2);

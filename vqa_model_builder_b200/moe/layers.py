@@ -62,6 +62,26 @@ class MOELayer(SlabOwner, nn.Module):
             groups.append([(f"experts.{i}.{attr}", getattr(getattr(e, mod), leaf)) for i, e in enumerate(ex)])
         return groups
 
+    def _expert_params(self) -> List[nn.Parameter]:
+        ex = list(self.experts)
+        params: List[nn.Parameter] = []
+        for attr in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "layer_norm.weight", "layer_norm.bias"):
+            mod, leaf = attr.split(".")
+            params.extend(getattr(getattr(e, mod), leaf) for e in ex)
+        return params
+
+    def _expert_stacks(self, device, cdt):
+        """Stacked views of the expert parameters inside the slab (no copy)."""
+        ex = list(self.experts)
+        E, D, F, Do = len(ex), ex[0].input_dim, ex[0].hidden_dim, ex[0].output_dim
+        slab = self._get_slab(device, cdt)
+        return (slab.span(ex[0].fc1.weight, E * F * D, cdt).view(E, F, D),
+                slab.span(ex[0].fc1.bias, E * F, torch.float32).view(E, F),
+                slab.span(ex[0].fc2.weight, E * Do * F, cdt).view(E, Do, F),
+                slab.span(ex[0].fc2.bias, E * Do, torch.float32).view(E, Do),
+                slab.span(ex[0].layer_norm.weight, E * Do, torch.float32).view(E, Do),
+                slab.span(ex[0].layer_norm.bias, E * Do, torch.float32).view(E, Do))
+
     # -- forward ----------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
         B, S, D = x.shape
@@ -87,13 +107,7 @@ class MOELayer(SlabOwner, nn.Module):
         ex = list(self.experts)
         E = len(ex)
         F, Do = ex[0].hidden_dim, ex[0].output_dim
-        slab = self._get_slab(x.device, cdt)
-        w1s = slab.span(ex[0].fc1.weight, E * F * D, cdt).view(E, F, D)
-        w2s = slab.span(ex[0].fc2.weight, E * Do * F, cdt).view(E, Do, F)
-        b1s = slab.span(ex[0].fc1.bias, E * F, torch.float32).view(E, F)
-        b2s = slab.span(ex[0].fc2.bias, E * Do, torch.float32).view(E, Do)
-        lng = slab.span(ex[0].layer_norm.weight, E * Do, torch.float32).view(E, Do)
-        lnb = slab.span(ex[0].layer_norm.bias, E * Do, torch.float32).view(E, Do)
+        w1s, b1s, w2s, b2s, lng, lnb = self._expert_stacks(x.device, cdt)
         x2 = ops.to_compute(x.reshape(N, D), cdt)
         plan = self._plan(indices, aux)
         w2d = weights.reshape(N, K).to(torch.float32)
@@ -102,12 +116,12 @@ class MOELayer(SlabOwner, nn.Module):
             w_eff, keep = plan.apply_capacity(w2d.detach(), capacity)
             # dropped (token, expert) pairs leave the graph: zero weight, zero gradient
             w2d = w2d * keep.view(N, K).to(w2d.dtype)
-        params: List[nn.Parameter] = []
-        for attr in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "layer_norm.weight", "layer_norm.bias"):
-            mod, leaf = attr.split(".")
-            params.extend(getattr(getattr(e, mod), leaf) for e in ex)
-        out = ops.MoeExpertsFn.apply(x2, w2d, plan, (w1s, b1s, w2s, b2s, lng, lnb), self.output_norm.weight,
-                                     self.output_norm.bias, ex[0].act_code, D == Do, self.output_norm.eps, *params)
+        params = self._expert_params()
+        xp = ops.PermuteFn.apply(x2, plan.row_src, plan.pad_off, plan.dest_row, E, K, plan.Rmax)
+        z = ops.ExpertFFNFn.apply(xp, plan.tile_group, plan.pad_off, (w1s, b1s, w2s, b2s, lng, lnb), ex[0].act_code,
+                                  D == Do, ex[0].layer_norm.eps, *params)
+        out = ops.CombineFn.apply(z, w2d, plan.dest_row, plan.row_src, self.output_norm.weight, self.output_norm.bias,
+                                  self.output_norm.eps)
         self.last_plan = plan
         return ops.to_compute(out, x.dtype).view(B, S, Do)
 

@@ -57,7 +57,8 @@ class _FusedTopK(BaseRouter):
             eps = eps.reshape(B * S, self.num_experts).to(torch.float32)
         lb = float(self.load_balance_weight) if self.use_aux_loss else 0.0
         w, idx32, loss, probs, nsm, _ts, _cnt = ops.RouterFn.apply(
-            x2, self.gate.weight, w_noise, eps, float(self.noise_std), lb, int(self.top_k))
+            x2, self.gate.weight, w_noise, eps, float(self.noise_std), lb, int(self.top_k),
+            getattr(self, "stats_group", None))
         idx = idx32.to(torch.int64).view(B, S, self.top_k)
         aux: Dict[str, Any] = {}
         if self.use_aux_loss:

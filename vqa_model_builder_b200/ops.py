@@ -259,10 +259,12 @@ class AttentionFn(torch.autograd.Function):
 # ---- MOE router ----------------------------------------------------------------------------------------------
 class RouterFn(torch.autograd.Function):
     """TopK / NoisyTopK routing (router.py:105-178, 287-366).  Returns (weights [N,K] f32, indices [N,K] i32,
-    load-balance loss [1] f32, clean probs [N,E] f32, mean noise scale [1] f32, topk_sum, counts)."""
+    load-balance loss [1] f32, clean probs [N,E] f32, mean noise scale [1] f32, topk_sum, counts).
+    With `stats_group` (a torch.distributed group) the load-balance statistics (pairs per expert, summed
+    probabilities: 2E floats) are all-reduced so the loss equals the single-process loss on the concatenated batch."""
 
     @staticmethod
-    def forward(ctx, x, w_gate, w_noise, eps, noise_std, lb_weight, K):
+    def forward(ctx, x, w_gate, w_noise, eps, noise_std, lb_weight, K, stats_group=None):
         _lib.ensure_device(x)
         x = x.contiguous()
         N, D = x.shape
@@ -274,7 +276,8 @@ class RouterFn(torch.autograd.Function):
         topk_sum = torch.empty(N, dtype=torch.float32, device=dev)
         probs = torch.empty((N, E), dtype=torch.float32, device=dev)
         probs_noisy = torch.empty((N, E), dtype=torch.float32, device=dev) if noisy else None
-        counts = torch.empty(E, dtype=torch.float32, device=dev)
+        stats = torch.empty(2 * E, dtype=torch.float32, device=dev)
+        counts, psum = stats[:E], stats[E:]
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         nsm = torch.zeros(1, dtype=torch.float32, device=dev)
         nb = query("b200_router_ws", N, E)
@@ -284,8 +287,20 @@ class RouterFn(torch.autograd.Function):
         if noisy:
             eps = eps.contiguous()
         call("b200_router_fwd", x, dtype_code(x.dtype), wg, wn, eps, float(noise_std), float(lb_weight), N, D, E, K,
-             idx, w, topk_sum, probs, probs_noisy, counts, loss, nsm, ws, nb, stream_ptr())
-        ctx.save_for_backward(x, wg, wn, eps, idx, w, topk_sum, probs, probs_noisy, counts)
+             idx, w, topk_sum, probs, probs_noisy, counts, psum, loss, nsm, ws, nb, stream_ptr())
+        counts_bwd = counts
+        if stats_group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(stats_group)
+            if world > 1:
+                local_counts = counts.clone()
+                dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=stats_group)
+                n_tot = float(N * world)
+                loss = (float(lb_weight) * E / (n_tot * n_tot)) * (stats[:E] * stats[E:]).sum().reshape(1)
+                # d loss / d p_local[n,e] = lb*E*C_e/N_tot^2 ; the kernel computes lb*E*counts[e]/N^2
+                counts_bwd = stats[:E] * (float(N) / n_tot) ** 2
+                counts = local_counts
+        ctx.save_for_backward(x, wg, wn, eps, idx, w, topk_sum, probs, probs_noisy, counts_bwd.contiguous())
         ctx.cfg = (float(noise_std), float(lb_weight), N, D, E, K, noisy)
         ctx.mark_non_differentiable(idx, probs, nsm, topk_sum, counts)
         return w, idx, loss, probs, nsm, topk_sum, counts
@@ -307,7 +322,7 @@ class RouterFn(torch.autograd.Function):
             d_loss = d_loss.contiguous().float()
         call("b200_router_bwd", x, dtype_code(x.dtype), wg, wn, eps, noise_std, lb_weight, N, D, E, K, idx, w,
              topk_sum, probs, probs_noisy, counts, d_w, d_loss, dx, dwg, dwn, ws, nb, stream_ptr())
-        return dx, dwg, dwn, None, None, None, None
+        return dx, dwg, dwn, None, None, None, None, None
 
 
 # ---- MOE dispatch -> grouped expert FFN -> combine ---------------------------------------------------------------
@@ -346,105 +361,170 @@ class RoutingPlan:
         return w_eff, keep
 
 
-class MoeExpertsFn(torch.autograd.Function):
-    """Sparse evaluation of MOELayer's expert loop + combine + output_norm (moe_layer.py:146-171) for
-    homogeneous FeedForwardExperts (expert_types.py:75-92):
-        out[n] = LN_out( sum_k w[n,k] * LN_e( fc2_e(act(fc1_e x_n)) + x_n ) ),  e = idx[n,k]
-    Inputs after `act`: flattened per-expert fp32 Parameters in the order
-        fc1.weight x E, fc1.bias x E, fc2.weight x E, fc2.bias x E, ln.weight x E, ln.bias x E."""
+class PermuteFn(torch.autograd.Function):
+    """xp[r] = x[row_src[r] // K] (zeros on padding rows); backward sums the K copies back per token.
+    `row_src`/`offsets`/`dest` describe either the padded layout (pad_off, dest_row) or the compact one
+    (cmp_off, cmp_pos) of a RoutingPlan."""
 
     @staticmethod
-    def forward(ctx, x, w, plan, stacks, out_gamma, out_beta, act, residual, eps, *expert_params):
+    def forward(ctx, x, row_src, offsets, dest, E, K, rows):
         _lib.ensure_device(x)
         x = x.contiguous()
         N, D = x.shape
-        K = plan.NK // N
-        E = plan.E
-        w1s, b1s, w2s, b2s, lng, lnb = stacks  # [E,F,D] c, [E,F] f32, [E,Do,F] c, [E,Do] f32, [E,Do] f32 x2
-        F = w1s.shape[1]
-        Do = w2s.shape[1]
-        R = plan.Rmax
-        dt = dtype_code(x.dtype)
-        st = stream_ptr()
-        dev = x.device
-        xp = torch.empty((R, D), dtype=x.dtype, device=dev)
-        call("b200_moe_permute", x, plan.row_src, plan.pad_off, E, K, R, D, dt, xp, st)
-        pre = torch.empty((R, F), dtype=x.dtype, device=dev)
-        h = torch.empty((R, F), dtype=x.dtype, device=dev)
-        call("b200_ggemm", xp, D, w1s, LAYOUT_K, h, F, R, F, D, E, plan.tile_group, dt, dt, b1s, EPI_ACT, act, None,
-             pre, F, st)
-        y2 = torch.empty((R, Do), dtype=x.dtype, device=dev)
-        call("b200_ggemm", h, F, w2s, LAYOUT_K, y2, Do, R, Do, F, E, plan.tile_group, dt, dt, b2s, EPI_NONE, ACT_NONE,
-             None, None, 0, st)
-        z = torch.empty((R, Do), dtype=x.dtype, device=dev)
-        mean_e = torch.empty(R, dtype=torch.float32, device=dev)
-        rstd_e = torch.empty(R, dtype=torch.float32, device=dev)
-        call("b200_add_ln_fwd", y2, xp if residual else None, lng, lnb, plan.tile_group, float(eps), z, mean_e, rstd_e,
-             R, Do, dt, st)
-        w = w.contiguous()
-        out = torch.empty((N, Do), dtype=x.dtype, device=dev)
-        mean_o = torch.empty(N, dtype=torch.float32, device=dev)
-        rstd_o = torch.empty(N, dtype=torch.float32, device=dev)
-        call("b200_moe_combine_fwd", z, plan.dest_row, w, out_gamma, out_beta, float(eps), N, K, Do, dt, out, mean_o,
-             rstd_o, st)
-        ctx.save_for_backward(xp, pre, h, y2, z, mean_e, rstd_e, w, mean_o, rstd_o, w1s, w2s, lng, out_gamma)
-        ctx.plan = plan
-        ctx.cfg = (N, D, K, E, F, Do, R, act, residual)
-        return out
+        xp = torch.empty((rows, D), dtype=x.dtype, device=x.device)
+        call("b200_moe_permute", x, row_src, offsets, E, K, rows, D, dtype_code(x.dtype), xp, stream_ptr())
+        ctx.save_for_backward(dest)
+        ctx.cfg = (N, K, D)
+        return xp
 
     @staticmethod
-    def backward(ctx, dout):
-        xp, pre, h, y2, z, mean_e, rstd_e, w, mean_o, rstd_o, w1s, w2s, lng, out_gamma = ctx.saved_tensors
-        plan = ctx.plan
-        N, D, K, E, F, Do, R, act, residual = ctx.cfg
-        dout = dout.contiguous()
-        dev = dout.device
-        dt = dtype_code(dout.dtype)
+    def backward(ctx, dxp):
+        (dest,) = ctx.saved_tensors
+        N, K, D = ctx.cfg
+        dxp = dxp.contiguous()
+        dx = torch.empty((N, D), dtype=dxp.dtype, device=dxp.device)
+        call("b200_moe_unpermute", dxp, dest, None, N, K, D, dtype_code(dxp.dtype), dx, stream_ptr())
+        return dx, None, None, None, None, None, None
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """y[i] = z[dest[i]]  (inverse of a K=1 permute; used to return expert outputs to arrival order under
+    expert parallelism).  Backward scatters with the matching row_src map (padding rows zero)."""
+
+    @staticmethod
+    def forward(ctx, z, dest, row_src, offsets, E):
+        _lib.ensure_device(z)
+        z = z.contiguous()
+        n = dest.numel()
+        D = z.shape[1]
+        y = torch.empty((n, D), dtype=z.dtype, device=z.device)
+        call("b200_moe_unpermute", z, dest, None, n, 1, D, dtype_code(z.dtype), y, stream_ptr())
+        ctx.save_for_backward(row_src, offsets)
+        ctx.cfg = (E, z.shape[0], D)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        row_src, offsets = ctx.saved_tensors
+        E, rows, D = ctx.cfg
+        dy = dy.contiguous()
+        dz = torch.empty((rows, D), dtype=dy.dtype, device=dy.device)
+        call("b200_moe_permute", dy, row_src, offsets, E, 1, rows, D, dtype_code(dy.dtype), dz, stream_ptr())
+        return dz, None, None, None, None
+
+
+class ExpertFFNFn(torch.autograd.Function):
+    """Grouped FeedForwardExpert over permuted rows (expert_types.py:75-92, all experts in two grouped GEMMs):
+        z[r] = LN_e( fc2_e(act(fc1_e xp[r])) (+ xp[r]) ),  e = tile_group[r / 128]
+    Inputs after `eps`: flattened per-expert fp32 Parameters in the order
+        fc1.weight x E, fc1.bias x E, fc2.weight x E, fc2.bias x E, ln.weight x E, ln.bias x E."""
+
+    @staticmethod
+    def forward(ctx, xp, tile_group, pad_off, stacks, act, residual, eps, *expert_params):
+        _lib.ensure_device(xp)
+        R, D = xp.shape
+        w1s, b1s, w2s, b2s, lng, lnb = stacks  # [E,F,D] c, [E,F] f32, [E,Do,F] c, [E,Do] f32, [E,Do] f32 x2
+        E, F = w1s.shape[0], w1s.shape[1]
+        Do = w2s.shape[1]
+        dt = dtype_code(xp.dtype)
         st = stream_ptr()
-        # one flat fp32 buffer for every parameter gradient of this layer (one DP all-reduce bucket)
-        sizes = [E * F * D, E * F, E * Do * F, E * Do, E * Do, E * Do, Do, Do]
+        dev = xp.device
+        pre = torch.empty((R, F), dtype=xp.dtype, device=dev)
+        h = torch.empty((R, F), dtype=xp.dtype, device=dev)
+        call("b200_ggemm", xp, D, w1s, LAYOUT_K, h, F, R, F, D, E, tile_group, dt, dt, b1s, EPI_ACT, act, None, pre, F,
+             st)
+        y2 = torch.empty((R, Do), dtype=xp.dtype, device=dev)
+        call("b200_ggemm", h, F, w2s, LAYOUT_K, y2, Do, R, Do, F, E, tile_group, dt, dt, b2s, EPI_NONE, ACT_NONE, None,
+             None, 0, st)
+        z = torch.empty((R, Do), dtype=xp.dtype, device=dev)
+        mean_e = torch.empty(R, dtype=torch.float32, device=dev)
+        rstd_e = torch.empty(R, dtype=torch.float32, device=dev)
+        call("b200_add_ln_fwd", y2, xp if residual else None, lng, lnb, tile_group, float(eps), z, mean_e, rstd_e, R,
+             Do, dt, st)
+        ctx.save_for_backward(xp, pre, h, y2, mean_e, rstd_e, w1s, w2s, lng, tile_group, pad_off)
+        ctx.cfg = (R, D, E, F, Do, act, residual)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        xp, pre, h, y2, mean_e, rstd_e, w1s, w2s, lng, tile_group, pad_off = ctx.saved_tensors
+        R, D, E, F, Do, act, residual = ctx.cfg
+        dz = dz.contiguous()
+        dev = dz.device
+        dt = dtype_code(dz.dtype)
+        st = stream_ptr()
+        # one flat fp32 buffer for every parameter gradient of the expert bank (one DP all-reduce bucket)
+        sizes = [E * F * D, E * F, E * Do * F, E * Do, E * Do, E * Do]
         flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
         offs = [0]
-        for s in sizes:
-            offs.append(offs[-1] + s)
-        dw1, db1, dw2, db2, dlng, dlnb, dog, dob = [flat[offs[i]:offs[i + 1]] for i in range(8)]
-
-        dz = torch.empty((R, Do), dtype=dout.dtype, device=dev)
-        d_w = torch.empty((N, K), dtype=torch.float32, device=dev)
-        nb = query("b200_moe_combine_bwd_ws", N, Do)
-        ws = _ws(nb, dev)
-        call("b200_moe_combine_bwd", dout, z, plan.dest_row, w, mean_o, rstd_o, out_gamma, plan.row_src, N, K, Do, R,
-             dt, dz, d_w, dog, dob, ws, nb, st)
-        dr = torch.empty((R, Do), dtype=dout.dtype, device=dev)
+        for sz in sizes:
+            offs.append(offs[-1] + sz)
+        dw1, db1, dw2, db2, dlng, dlnb = [flat[offs[i]:offs[i + 1]] for i in range(6)]
+        dr = torch.empty((R, Do), dtype=dz.dtype, device=dev)
         nb = query("b200_add_ln_bwd_ws", R, Do)
         ws = _ws(nb, dev)
-        call("b200_add_ln_bwd", dz, y2, xp if residual else None, mean_e, rstd_e, lng, plan.tile_group, E, dr, dlng,
-             dlnb, R, Do, dt, ws, nb, st)
+        call("b200_add_ln_bwd", dz, y2, xp if residual else None, mean_e, rstd_e, lng, tile_group, E, dr, dlng, dlnb, R,
+             Do, dt, ws, nb, st)
         nb = query("b200_colsum_ws", R, max(F, Do))
         ws = _ws(nb, dev)
-        call("b200_colsum", dr, dt, R, Do, plan.tile_group, E, db2, ws, nb, st)
-        call("b200_ggemm_wgrad", dr, Do, h, F, dw2, Do, F, R, E, plan.pad_off, dt, st)
-        dpre = torch.empty((R, F), dtype=dout.dtype, device=dev)
-        call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, plan.tile_group, dt, dt, None, EPI_DACT, act,
-             pre, None, F, st)
-        call("b200_colsum", dpre, dt, R, F, plan.tile_group, E, db1, ws, nb, st)
-        call("b200_ggemm_wgrad", dpre, F, xp, D, dw1, F, D, R, E, plan.pad_off, dt, st)
-        dxp = torch.empty((R, D), dtype=dout.dtype, device=dev)
-        if residual:
-            call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, plan.tile_group, dt, dt, None, EPI_ADD,
-                 ACT_NONE, dr, None, Do, st)
-        else:
-            call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, plan.tile_group, dt, dt, None, EPI_NONE,
-                 ACT_NONE, None, None, 0, st)
-        dx = torch.empty((N, D), dtype=dout.dtype, device=dev)
-        call("b200_moe_unpermute", dxp, plan.dest_row, None, N, K, D, dt, dx, st)
-
+        call("b200_colsum", dr, dt, R, Do, tile_group, E, db2, ws, nb, st)
+        call("b200_ggemm_wgrad", dr, Do, h, F, dw2, Do, F, R, E, pad_off, dt, st)
+        dpre = torch.empty((R, F), dtype=dz.dtype, device=dev)
+        call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, tile_group, dt, dt, None, EPI_DACT, act, pre,
+             None, F, st)
+        call("b200_colsum", dpre, dt, R, F, tile_group, E, db1, ws, nb, st)
+        call("b200_ggemm_wgrad", dpre, F, xp, D, dw1, F, D, R, E, pad_off, dt, st)
+        dxp = None
+        if ctx.needs_input_grad[0]:
+            dxp = torch.empty((R, D), dtype=dz.dtype, device=dev)
+            if residual:
+                call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, tile_group, dt, dt, None, EPI_ADD,
+                     ACT_NONE, dr, None, Do, st)
+            else:
+                call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, tile_group, dt, dt, None, EPI_NONE,
+                     ACT_NONE, None, None, 0, st)
         # hand every per-expert Parameter its slice of the flat buffer
         grads: List[torch.Tensor] = []
         for buf, shape in ((dw1, (F, D)), (db1, (F,)), (dw2, (Do, F)), (db2, (Do,)), (dlng, (Do,)), (dlnb, (Do,))):
             per = buf.view(E, *shape)
             grads.extend(per[e] for e in range(E))
-        return (dx, d_w, None, None, dog, dob, None, None, None, *grads)
+        return (dxp, None, None, None, None, None, None, *grads)
+
+
+class CombineFn(torch.autograd.Function):
+    """out[n] = LN_out( sum_k w[n,k] * z[dest[n,k]] )   (moe_layer.py:163-171), dest < 0 entries skipped."""
+
+    @staticmethod
+    def forward(ctx, z, w, dest, row_src, out_gamma, out_beta, eps):
+        _lib.ensure_device(z)
+        z = z.contiguous()
+        w = w.contiguous()
+        N, K = w.shape
+        Do = z.shape[1]
+        dev = z.device
+        out = torch.empty((N, Do), dtype=z.dtype, device=dev)
+        mean_o = torch.empty(N, dtype=torch.float32, device=dev)
+        rstd_o = torch.empty(N, dtype=torch.float32, device=dev)
+        call("b200_moe_combine_fwd", z, dest, w, out_gamma, out_beta, float(eps), N, K, Do, dtype_code(z.dtype), out,
+             mean_o, rstd_o, stream_ptr())
+        ctx.save_for_backward(z, w, dest, row_src, mean_o, rstd_o, out_gamma)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, w, dest, row_src, mean_o, rstd_o, out_gamma = ctx.saved_tensors
+        N, K = w.shape
+        R, Do = z.shape
+        dout = dout.contiguous()
+        dev = dout.device
+        dz = torch.empty((R, Do), dtype=dout.dtype, device=dev)
+        d_w = torch.empty((N, K), dtype=torch.float32, device=dev)
+        flat = torch.empty(2 * Do, dtype=torch.float32, device=dev)
+        nb = query("b200_moe_combine_bwd_ws", N, Do)
+        ws = _ws(nb, dev)
+        call("b200_moe_combine_bwd", dout, z, dest, w, mean_o, rstd_o, out_gamma, row_src, N, K, Do, R,
+             dtype_code(dout.dtype), dz, d_w, flat[:Do], flat[Do:], ws, nb, stream_ptr())
+        return dz, d_w, None, None, flat[:Do], flat[Do:], None
 
 
 class DenseCombineFn(torch.autograd.Function):

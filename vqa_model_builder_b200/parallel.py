@@ -66,3 +66,135 @@ def expert_owner(expert: int, num_experts: int, world: int) -> int:
     if num_experts % world != 0:
         raise ValueError(f"expert parallelism needs num_experts ({num_experts}) divisible by world size ({world})")
     return expert // (num_experts // world)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Expert parallelism: experts sharded across ranks, tokens exchanged with all-to-all over NVLink (NCCL)
+# ---------------------------------------------------------------------------------------------------------
+class AllToAllRows(torch.autograd.Function):
+    """Variable-split all-to-all of row blocks; backward is the all-to-all with the splits swapped."""
+
+    @staticmethod
+    def forward(ctx, x, in_splits, out_splits, group):
+        x = x.contiguous()
+        out = torch.empty((sum(out_splits),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_to_all_single(out, x, list(out_splits), list(in_splits), group=group)
+        ctx.splits = (list(in_splits), list(out_splits), group, x.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        in_splits, out_splits, group, n_in = ctx.splits
+        g = g.contiguous()
+        gx = torch.empty((n_in,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+        dist.all_to_all_single(gx, g, in_splits, out_splits, group=group)
+        return gx, None, None, None
+
+
+def exchange_counts(counts: torch.Tensor, world: int, group=None):
+    """counts [E] (pairs routed to every GLOBAL expert on this rank) -> (send [W, E_local], recv [W, E_local]) as
+    Python lists: recv[s][e] = rows rank s sends to my local expert e.  One small all-to-all + one host read."""
+    E = counts.numel()
+    send = counts.to(torch.int64).view(world, E // world).contiguous()
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    both = torch.stack([send, recv]).tolist()
+    return both[0], both[1]
+
+
+class ExpertParallelMOELayer(torch.nn.Module):
+    """MOELayer with its FeedForwardExperts sharded over the ranks of `group` (expert e on rank e // (E/W)).
+
+    forward: router (replicated, global load-balance statistics) -> routing plan -> rows in canonical
+    (expert, token) order, which is also destination-rank order -> all-to-all -> grouped expert FFN on the owner ->
+    all-to-all back -> weighted combine + output_norm on the token's home rank.  Gradients of the sharded experts are
+    complete locally (every token routed to an expert reached its owner); replicated parameters (router gate,
+    output_norm) are all-reduced like any data-parallel parameter."""
+
+    def __init__(self, full_layer, group=None):
+        super().__init__()
+        from .moe.layers import MOELayer
+        assert isinstance(full_layer, MOELayer) and full_layer._homogeneous(), "needs homogeneous FeedForwardExperts"
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        E = full_layer.num_experts
+        if E % self.world != 0:
+            raise ValueError(f"num_experts={E} not divisible by world size {self.world}")
+        self.num_experts = E
+        self.experts_per_rank = E // self.world
+        lo = self.rank * self.experts_per_rank
+        self.local = full_layer
+        # keep only the local shard of the expert bank
+        full_layer.experts = torch.nn.ModuleList(list(full_layer.experts)[lo:lo + self.experts_per_rank])
+        full_layer.router.stats_group = group
+        self.input_dim, self.hidden_dim, self.output_dim = full_layer.input_dim, full_layer.hidden_dim, full_layer.output_dim
+        self.top_k = full_layer.top_k
+        self.aux_outputs = {}
+
+    def replicated_parameters(self):
+        return list(self.local.router.parameters()) + list(self.local.output_norm.parameters())
+
+    def expert_parameters(self):
+        return list(self.local.experts.parameters())
+
+    def get_aux_loss(self):
+        return self.local.get_aux_loss()
+
+    def forward(self, x: torch.Tensor, mask=None, **kwargs) -> torch.Tensor:
+        from . import ops
+        from .runtime import resolve_compute_dtype
+        L = self.local
+        B, S, D = x.shape
+        N, K, E, W, El = B * S, self.top_k, self.num_experts, self.world, self.experts_per_rank
+        weights, indices, aux = L.router(x)
+        L.aux_outputs = self.aux_outputs = aux
+        cdt = resolve_compute_dtype(x)
+        x2 = ops.to_compute(x.reshape(N, D), cdt)
+        stash = aux.get("_b200_idx32")
+        idx32 = stash[1] if stash is not None and stash[0] is indices else indices.reshape(N, K).to(torch.int32)
+        plan = ops.RoutingPlan(idx32, E)
+        NK = plan.NK
+        # compact canonical layout (no padding on the wire)
+        ar = torch.arange(NK, device=x.device, dtype=torch.int32)
+        valid = plan.cmp_pos >= 0
+        row_src_c = torch.full((NK,), -1, dtype=torch.int32, device=x.device)
+        row_src_c[plan.cmp_pos[valid].long()] = ar[valid]
+        xc = ops.PermuteFn.apply(x2, row_src_c, plan.cmp_off, plan.cmp_pos, E, K, NK)
+        send, recv = exchange_counts(plan.counts, W, self.group)
+        in_splits = [sum(r) for r in send]
+        out_splits = [sum(r) for r in recv]
+        n_send, n_recv = sum(in_splits), sum(out_splits)
+        got = AllToAllRows.apply(xc[:n_send], in_splits, out_splits, self.group)
+        if n_recv > 0:
+            flat_counts = torch.tensor([c for r in recv for c in r], device=x.device)
+            ids = torch.arange(El, device=x.device, dtype=torch.int32).repeat(W)
+            idx_recv = torch.repeat_interleave(ids, flat_counts, output_size=n_recv).view(n_recv, 1)
+            plan2 = ops.RoutingPlan(idx_recv, El)
+            stacks = L._expert_stacks(x.device, cdt)
+            ex0 = L.experts[0]
+            xp2 = ops.PermuteFn.apply(got, plan2.row_src, plan2.pad_off, plan2.dest_row, El, 1, plan2.Rmax)
+            z2 = ops.ExpertFFNFn.apply(xp2, plan2.tile_group, plan2.pad_off, stacks, ex0.act_code,
+                                       D == ex0.output_dim, ex0.layer_norm.eps, *L._expert_params())
+            zc = ops.GatherRowsFn.apply(z2, plan2.dest_row, plan2.row_src, plan2.pad_off, El)
+        else:
+            zc = got.new_zeros((0, self.output_dim))
+        back = AllToAllRows.apply(zc, out_splits, in_splits, self.group)
+        w2d = weights.reshape(N, K).to(torch.float32)
+        out = ops.CombineFn.apply(back, w2d, plan.cmp_pos, row_src_c[:max(n_send, 1)], L.output_norm.weight,
+                                  L.output_norm.bias, L.output_norm.eps)
+        self.last_plan = plan
+        return ops.to_compute(out, x.dtype).view(B, S, self.output_dim)
+
+
+def finish_gradients(replicated, expert_sharded, group=None) -> None:
+    """After backward under DP(+EP): average replicated-parameter gradients across ranks; scale the sharded
+    experts' gradients by 1/W so both follow the same mean-over-ranks loss convention."""
+    if not dist.is_initialized():
+        return
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    allreduce_gradients(replicated, average=True, group=group)
+    for b in grad_buckets(expert_sharded):
+        b.div_(world)
