@@ -297,8 +297,10 @@ class RouterFn(torch.autograd.Function):
                 dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=stats_group)
                 n_tot = float(N * world)
                 loss = (float(lb_weight) * E / (n_tot * n_tot)) * (stats[:E] * stats[E:]).sum().reshape(1)
-                # d loss / d p_local[n,e] = lb*E*C_e/N_tot^2 ; the kernel computes lb*E*counts[e]/N^2
-                counts_bwd = stats[:E] * (float(N) / n_tot) ** 2
+                # true partial: d loss / d p_local[n,e] = lb*E*C_e/N_tot^2.  Gradients are AVERAGED over ranks
+                # afterwards (DDP convention), so each rank scales its share by W: lb*E*C_e/(N_tot*N); the kernel
+                # computes lb*E*counts[e]/N^2, hence counts[e] := C_e * N / N_tot.
+                counts_bwd = stats[:E] * (float(N) / n_tot)
                 counts = local_counts
         ctx.save_for_backward(x, wg, wn, eps, idx, w, topk_sum, probs, probs_noisy, counts_bwd.contiguous())
         ctx.cfg = (float(noise_std), float(lb_weight), N, D, E, K, noisy)

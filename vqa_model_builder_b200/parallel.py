@@ -26,7 +26,10 @@ def init_distributed(backend: Optional[str] = None) -> tuple:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        import datetime
+        # short collective timeout: a mismatched collective must fail fast, not hold the GPUs for ten minutes
+        dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("B200VQA_PG_TIMEOUT", "120"))))
     return rank, world, local
 
 
@@ -49,16 +52,33 @@ def grad_buckets(params: Iterable[torch.nn.Parameter]) -> List[torch.Tensor]:
 
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], average: bool = True,
                         group: Optional[dist.ProcessGroup] = None) -> int:
-    """Sum (or average) gradients across ranks, bucket by bucket.  Returns the number of collectives issued."""
+    """Sum (or average) gradients across ranks.  One all-reduce per parameter, issued inside a single NCCL group
+    (one fused launch) — the collective sequence depends only on the parameter list, never on how autograd happened
+    to alias gradient storage on a given rank.  Returns the number of tensors reduced."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
     world = dist.get_world_size(group)
-    buckets = grad_buckets(params)
-    for b in buckets:
-        dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
-        if average:
-            b.div_(world)
-    return len(buckets)
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    op = dist.ReduceOp.AVG if (average and grads[0].is_cuda) else dist.ReduceOp.SUM
+    done = False
+    if grads[0].is_cuda:   # NCCL: fuse into one group launch
+        try:
+            from torch.distributed.distributed_c10d import _coalescing_manager
+            with _coalescing_manager(group=group, device=grads[0].device, async_ops=False):
+                for g in grads:
+                    dist.all_reduce(g, op=op, group=group)
+            done = True
+        except (ImportError, TypeError):
+            done = False
+    if not done:
+        for g in grads:
+            dist.all_reduce(g, op=op, group=group)
+    if average and op == dist.ReduceOp.SUM:
+        for g in grads:
+            g.div_(world)
+    return len(grads)
 
 
 def expert_owner(expert: int, num_experts: int, world: int) -> int:
@@ -127,7 +147,7 @@ class ExpertParallelMOELayer(torch.nn.Module):
         self.local = full_layer
         # keep only the local shard of the expert bank
         full_layer.experts = torch.nn.ModuleList(list(full_layer.experts)[lo:lo + self.experts_per_rank])
-        full_layer.router.stats_group = group
+        full_layer.router.stats_group = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
         self.input_dim, self.hidden_dim, self.output_dim = full_layer.input_dim, full_layer.hidden_dim, full_layer.output_dim
         self.top_k = full_layer.top_k
         self.aux_outputs = {}
@@ -196,5 +216,6 @@ def finish_gradients(replicated, expert_sharded, group=None) -> None:
     if world == 1:
         return
     allreduce_gradients(replicated, average=True, group=group)
-    for b in grad_buckets(expert_sharded):
-        b.div_(world)
+    for p in expert_sharded:
+        if p.grad is not None:
+            p.grad.div_(world)
