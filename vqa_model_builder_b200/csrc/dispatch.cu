@@ -159,14 +159,14 @@ permute_kernel(const T* __restrict__ x, const int* __restrict__ row_src, const i
   }
 }
 
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(256)
 unpermute_kernel(const T* __restrict__ dxp, const int* __restrict__ dest_row, const T* __restrict__ add, int N, int K,
                  int D, T* __restrict__ dx) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int n = warp; n < N; n += nwarps) {
-    RowRegs<T> acc;
+    RowRegs<T, NV> acc;
     if (add != nullptr) acc.load(add + (long long)n * D, D, lane);
     else acc.zero();
     for (int k = 0; k < K; ++k) {
@@ -178,7 +178,7 @@ unpermute_kernel(const T* __restrict__ dxp, const int* __restrict__ dest_row, co
 }
 
 // ---- combine + output LayerNorm ------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(256)
 combine_fwd_kernel(const T* __restrict__ z, const int* __restrict__ dest_row, const float* __restrict__ w,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int N, int K, int D,
@@ -188,7 +188,7 @@ combine_fwd_kernel(const T* __restrict__ z, const int* __restrict__ dest_row, co
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nv = D / VT;
   for (int n = warp; n < N; n += nwarps) {
-    RowRegs<T> acc;
+    RowRegs<T, NV> acc;
     acc.zero();
     for (int k = 0; k < K; ++k) {
       const int d = dest_row[n * K + k];
@@ -199,7 +199,7 @@ combine_fwd_kernel(const T* __restrict__ z, const int* __restrict__ dest_row, co
     const float var = acc.sumsq_centered(mean, D, lane) / D;
     const float rstd = rsqrtf(var + eps);
 #pragma unroll
-    for (int j = 0; j < ROW_MAXV; ++j) {
+    for (int j = 0; j < NV; ++j) {
       const int vi = lane + 32 * j;
       if (vi < nv) {
         float gv[VT], bv[VT];
@@ -218,28 +218,28 @@ combine_fwd_kernel(const T* __restrict__ z, const int* __restrict__ dest_row, co
 }
 
 constexpr int CMB_WARPS = 8;
-constexpr int CMB_TOKENS_PER_BLOCK = 8;  // one token per warp
+constexpr int CMB_TOKENS_PER_BLOCK = 8;  // workspace bound (tokens per block is 8 * tpw, tpw >= 1)
 
-template <typename T>
+// Each warp walks `tpw` tokens keeping the output_norm dgamma/dbeta partials in registers.
+template <typename T, int NV>
 __global__ void __launch_bounds__(CMB_WARPS * 32)
 combine_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ z, const int* __restrict__ dest_row,
                    const float* __restrict__ w, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                    const float* __restrict__ gamma, int N, int K, int D, T* __restrict__ dz, float* __restrict__ d_w,
-                   float* __restrict__ part) {
+                   float* __restrict__ part, int tpw) {
   constexpr int VT = Vec16<T>::N;
   extern __shared__ float red[];  // [CMB_WARPS][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / VT;
-  float dg[ROW_MAXV][VT], db[ROW_MAXV][VT];
-#pragma unroll
-  for (int j = 0; j < ROW_MAXV; ++j)
-#pragma unroll
-    for (int u = 0; u < VT; ++u) dg[j][u] = db[j][u] = 0.f;
-
-  for (int i = 0; i < CMB_TOKENS_PER_BLOCK / CMB_WARPS; ++i) {
-    const int n = blockIdx.x * CMB_TOKENS_PER_BLOCK + warp * (CMB_TOKENS_PER_BLOCK / CMB_WARPS) + i;
+  float* acc_g = red + (warp * 2 + 0) * D;   // per-warp dgamma / dbeta accumulators in shared memory
+  float* acc_b = red + (warp * 2 + 1) * D;
+  for (int d = lane; d < D; d += 32) { acc_g[d] = 0.f; acc_b[d] = 0.f; }
+  __syncwarp();
+  const int n0 = blockIdx.x * (CMB_WARPS * tpw);
+  for (int i = 0; i < tpw; ++i) {
+    const int n = n0 + i * CMB_WARPS + warp;
     if (n >= N) break;
-    RowRegs<T> s, g;
+    RowRegs<T, NV> s, g;
     s.zero();
     for (int k = 0; k < K; ++k) {
       const int d = dest_row[n * K + k];
@@ -250,17 +250,19 @@ combine_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ z, const in
     const float mean = mean_in[n], rstd = rstd_in[n];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < ROW_MAXV; ++j) {
+    for (int j = 0; j < NV; ++j) {
       const int vi = lane + 32 * j;
       if (vi < nv) {
         float gv[VT];
         load_param<VT>(gamma, vi, gv);
+        float* ag = acc_g + vi * VT;
+        float* ab = acc_b + vi * VT;
 #pragma unroll
         for (int u = 0; u < VT; ++u) {
           const float xhat = (s.v[j][u] - mean) * rstd;
           const float d = g.v[j][u];
-          dg[j][u] = fmaf(d, xhat, dg[j][u]);
-          db[j][u] += d;
+          ag[u] = fmaf(d, xhat, ag[u]);
+          ab[u] += d;
           const float gg = d * gv[u];
           s.v[j][u] = xhat;
           g.v[j][u] = gg;
@@ -272,7 +274,7 @@ combine_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ z, const in
     s1 = warp_sum(s1) / D;
     s2 = warp_sum(s2) / D;
 #pragma unroll
-    for (int j = 0; j < ROW_MAXV; ++j)
+    for (int j = 0; j < NV; ++j)
 #pragma unroll
       for (int u = 0; u < VT; ++u) g.v[j][u] = rstd * (g.v[j][u] - s1 - s.v[j][u] * s2);  // ds
     for (int k = 0; k < K; ++k) {
@@ -283,7 +285,7 @@ combine_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ z, const in
         const T* zr = z + (long long)d * D;
         T* dzr = dz + (long long)d * D;
 #pragma unroll
-        for (int j = 0; j < ROW_MAXV; ++j) {
+        for (int j = 0; j < NV; ++j) {
           const int vi = lane + 32 * j;
           if (vi < nv) {
             Vec16<T> zv, o;
@@ -302,17 +304,6 @@ combine_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ z, const in
     }
   }
 
-#pragma unroll
-  for (int j = 0; j < ROW_MAXV; ++j) {
-    const int vi = lane + 32 * j;
-    if (vi < nv) {
-#pragma unroll
-      for (int u = 0; u < VT; ++u) {
-        red[(warp * 2 + 0) * D + vi * VT + u] = dg[j][u];
-        red[(warp * 2 + 1) * D + vi * VT + u] = db[j][u];
-      }
-    }
-  }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
     const int which = c / D, d = c % D;
@@ -426,11 +417,13 @@ int b200_moe_unpermute(const void* dxp, const int32_t* dest_row, const void* add
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_ROW_DISPATCH(dtype, D, "moe_unpermute");
   const int blocks = row_grid(N);
-  if (dtype == B200_BF16)
-    unpermute_kernel<bf16><<<blocks, 256, 0, stream>>>((const bf16*)dxp, dest_row, (const bf16*)add, N, K, D, (bf16*)dx);
-  else
-    unpermute_kernel<float><<<blocks, 256, 0, stream>>>((const float*)dxp, dest_row, (const float*)add, N, K, D,
-                                                        (float*)dx);
+  if (dtype == B200_BF16) {
+    B200_NV_SWITCH(row_nv<bf16>(D), unpermute_kernel<bf16, NV><<<blocks, 256, 0, stream>>>(
+        (const bf16*)dxp, dest_row, (const bf16*)add, N, K, D, (bf16*)dx));
+  } else {
+    B200_NV_SWITCH(row_nv<float>(D), unpermute_kernel<float, NV><<<blocks, 256, 0, stream>>>(
+        (const float*)dxp, dest_row, (const float*)add, N, K, D, (float*)dx));
+  }
   B200_LAUNCH_CHECK("unpermute_kernel");
   count_launch();
   return 0;
@@ -442,12 +435,13 @@ int b200_moe_combine_fwd(const void* z, const int32_t* dest_row, const float* w,
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_ROW_DISPATCH(dtype, D, "moe_combine_fwd");
   const int blocks = row_grid(N);
-  if (dtype == B200_BF16)
-    combine_fwd_kernel<bf16><<<blocks, 256, 0, stream>>>((const bf16*)z, dest_row, w, gamma, beta, eps, N, K, D,
-                                                         (bf16*)out, mean, rstd);
-  else
-    combine_fwd_kernel<float><<<blocks, 256, 0, stream>>>((const float*)z, dest_row, w, gamma, beta, eps, N, K, D,
-                                                          (float*)out, mean, rstd);
+  if (dtype == B200_BF16) {
+    B200_NV_SWITCH(row_nv<bf16>(D), combine_fwd_kernel<bf16, NV><<<blocks, 256, 0, stream>>>(
+        (const bf16*)z, dest_row, w, gamma, beta, eps, N, K, D, (bf16*)out, mean, rstd));
+  } else {
+    B200_NV_SWITCH(row_nv<float>(D), combine_fwd_kernel<float, NV><<<blocks, 256, 0, stream>>>(
+        (const float*)z, dest_row, w, gamma, beta, eps, N, K, D, (float*)out, mean, rstd));
+  }
   B200_LAUNCH_CHECK("combine_fwd_kernel");
   count_launch();
   return 0;
@@ -465,27 +459,34 @@ int b200_moe_combine_bwd(const void* dout, const void* z, const int32_t* dest_ro
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_ROW_DISPATCH(dtype, D, "moe_combine_bwd");
   B200_CHECK_ARG(workspace_bytes >= b200_moe_combine_bwd_ws(N, D), "moe_combine_bwd: workspace too small");
-  const int blocks = (N + CMB_TOKENS_PER_BLOCK - 1) / CMB_TOKENS_PER_BLOCK;
+  int tpw = 1;
+  while (tpw < 16 && (N + CMB_WARPS * tpw * 2 - 1) / (CMB_WARPS * tpw * 2) >= 2 * num_sms()) tpw *= 2;
+  const int tokens_per_block = CMB_WARPS * tpw;
+  const int blocks = (N + tokens_per_block - 1) / tokens_per_block;
   const size_t smem = (size_t)CMB_WARPS * 2 * D * sizeof(float);
   B200_CHECK_ARG(smem <= 160 * 1024, "moe_combine_bwd: D=%d too large", D);
-  if (smem > 48 * 1024) {
-    B200_CUDA(cudaFuncSetAttribute(combine_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_CUDA(cudaFuncSetAttribute(combine_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
   float* part = (float*)workspace;
   const int zb = row_grid(Rmax);
   if (dtype == B200_BF16) {
     zero_unwritten_rows_kernel<bf16><<<zb, 256, 0, stream>>>(row_src, w, Rmax, D, (bf16*)dz);
-    combine_bwd_kernel<bf16><<<blocks, CMB_WARPS * 32, smem, stream>>>((const bf16*)dout, (const bf16*)z, dest_row, w, mean, rstd,
-                                                            gamma, N, K, D, (bf16*)dz, d_w, part);
+    B200_NV_SWITCH(row_nv<bf16>(D), {
+      if (smem > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(combine_bwd_kernel<bf16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      combine_bwd_kernel<bf16, NV><<<blocks, CMB_WARPS * 32, smem, stream>>>(
+          (const bf16*)dout, (const bf16*)z, dest_row, w, mean, rstd, gamma, N, K, D, (bf16*)dz, d_w, part, tpw);
+    });
   } else {
     zero_unwritten_rows_kernel<float><<<zb, 256, 0, stream>>>(row_src, w, Rmax, D, (float*)dz);
-    combine_bwd_kernel<float><<<blocks, CMB_WARPS * 32, smem, stream>>>((const float*)dout, (const float*)z, dest_row, w, mean,
-                                                             rstd, gamma, N, K, D, (float*)dz, d_w, part);
+    B200_NV_SWITCH(row_nv<float>(D), {
+      if (smem > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(combine_bwd_kernel<float, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      combine_bwd_kernel<float, NV><<<blocks, CMB_WARPS * 32, smem, stream>>>(
+          (const float*)dout, (const float*)z, dest_row, w, mean, rstd, gamma, N, K, D, (float*)dz, d_w, part, tpw);
+    });
   }
   B200_LAUNCH_CHECK("combine_bwd_kernel");
   count_launch(2);
-  return launch_ln_param_reduce(part, blocks, CMB_TOKENS_PER_BLOCK, D, nullptr, 1, dgamma, dbeta, stream);
+  return launch_ln_param_reduce(part, blocks, tokens_per_block, D, nullptr, 1, dgamma, dbeta, stream);
 }
 
 }  // extern "C"

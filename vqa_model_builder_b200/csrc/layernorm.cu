@@ -7,9 +7,9 @@ namespace b200 {
 namespace {
 
 constexpr int LN_WARPS = 8;
-constexpr int LN_ROWS_PER_BLOCK = 8;  // one row per warp; divides B200_GROUP_TILE so a block sees one expert
+constexpr int LN_ROWS_PER_BLOCK = 8;  // workspace bound: the backward never uses fewer than 8 rows per block
 
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
                   const float* __restrict__ beta, const int* __restrict__ tile_group, float eps,
@@ -17,114 +17,115 @@ add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const floa
   constexpr int VT = Vec16<T>::N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / VT;
-  for (int i = 0; i < LN_ROWS_PER_BLOCK / LN_WARPS; ++i) {
-    const int r = blockIdx.x * LN_ROWS_PER_BLOCK + warp * (LN_ROWS_PER_BLOCK / LN_WARPS) + i;
-    if (r >= R) return;
-    int g = 0;
-    if (tile_group != nullptr) {
-      g = tile_group[r / B200_GROUP_TILE];
-      if (g < 0) continue;
-    }
-    RowRegs<T> row;
-    row.load(x + (long long)r * D, D, lane);
-    if (res != nullptr) row.axpy(res + (long long)r * D, 1.f, D, lane);
-    const float mean = row.sum(D, lane) / D;
-    const float var = row.sumsq_centered(mean, D, lane) / D;
-    const float rstd = rsqrtf(var + eps);
-    const float* gm = gamma + (long long)g * D;
-    const float* bt = beta + (long long)g * D;
+  const int r = blockIdx.x * LN_WARPS + warp;
+  if (r >= R) return;
+  int g = 0;
+  if (tile_group != nullptr) {
+    g = tile_group[r / B200_GROUP_TILE];
+    if (g < 0) return;
+  }
+  RowRegs<T, NV> row;
+  row.load(x + (long long)r * D, D, lane);
+  if (res != nullptr) row.axpy(res + (long long)r * D, 1.f, D, lane);
+  const float mean = row.sum(D, lane) / D;
+  const float var = row.sumsq_centered(mean, D, lane) / D;
+  const float rstd = rsqrtf(var + eps);
+  const float* gm = gamma + (long long)g * D;
+  const float* bt = beta + (long long)g * D;
 #pragma unroll
-    for (int j = 0; j < ROW_MAXV; ++j) {
-      const int vi = lane + 32 * j;
-      if (vi < nv) {
-        float gv[VT], bv[VT];
-        load_param<VT>(gm, vi, gv);
-        load_param<VT>(bt, vi, bv);
+  for (int j = 0; j < NV; ++j) {
+    const int vi = lane + 32 * j;
+    if (vi < nv) {
+      float gv[VT], bv[VT];
+      load_param<VT>(gm, vi, gv);
+      load_param<VT>(bt, vi, bv);
 #pragma unroll
-        for (int u = 0; u < VT; ++u) row.v[j][u] = (row.v[j][u] - mean) * rstd * gv[u] + bv[u];
-      }
+      for (int u = 0; u < VT; ++u) row.v[j][u] = (row.v[j][u] - mean) * rstd * gv[u] + bv[u];
     }
-    row.store(y + (long long)r * D, D, lane);
-    if (lane == 0) {
-      mean_out[r] = mean;
-      rstd_out[r] = rstd;
-    }
+  }
+  row.store(y + (long long)r * D, D, lane);
+  if (lane == 0) {
+    mean_out[r] = mean;
+    rstd_out[r] = rstd;
   }
 }
 
 // dsum = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma.
-// Per-block partial dgamma/dbeta are written to part[block][2][D]; a second kernel reduces them per group.
-template <typename T>
+// Each warp walks `rpw` consecutive rows keeping its dgamma/dbeta partials in registers; the block (8 warps,
+// 8*rpw rows, always inside one 128-row expert tile) reduces them through shared memory into part[block][2][D];
+// a second kernel reduces the partials per group.
+template <typename T, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                   const float* __restrict__ gamma, const int* __restrict__ tile_group, T* __restrict__ dsum,
-                  float* __restrict__ part, int R, int D) {
+                  float* __restrict__ part, int R, int D, int rpw) {
   constexpr int VT = Vec16<T>::N;
   extern __shared__ float red[];  // [LN_WARPS][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / VT;
-  float dg[ROW_MAXV][VT], db[ROW_MAXV][VT];
-#pragma unroll
-  for (int j = 0; j < ROW_MAXV; ++j)
-#pragma unroll
-    for (int u = 0; u < VT; ++u) dg[j][u] = db[j][u] = 0.f;
+  // per-warp dgamma / dbeta accumulators live in shared memory (each lane owns its own 16-byte slots, so no
+  // synchronisation is needed): keeping them in registers cost ~50 registers and left one block per SM
+  float* acc_g = red + (warp * 2 + 0) * D;
+  float* acc_b = red + (warp * 2 + 1) * D;
+  for (int d = lane; d < D; d += 32) { acc_g[d] = 0.f; acc_b[d] = 0.f; }
+  __syncwarp();
 
-  for (int i = 0; i < LN_ROWS_PER_BLOCK / LN_WARPS; ++i) {
-    const int r = blockIdx.x * LN_ROWS_PER_BLOCK + warp * (LN_ROWS_PER_BLOCK / LN_WARPS) + i;
+  const int row0 = blockIdx.x * (LN_WARPS * rpw);
+  int g = 0;
+  bool live = true;
+  if (tile_group != nullptr) {
+    g = tile_group[row0 / B200_GROUP_TILE];
+    live = g >= 0;
+    if (!live) g = 0;
+  }
+  const float* gm = gamma + (long long)g * D;
+  for (int i = 0; i < rpw && live; ++i) {
+    const int r = row0 + i * LN_WARPS + warp;   // interleaved so the 8 warps stream adjacent rows
     if (r >= R) break;
-    int g = 0;
-    if (tile_group != nullptr) {
-      g = tile_group[r / B200_GROUP_TILE];
-      if (g < 0) continue;
-    }
-    RowRegs<T> xr, gr;
+    RowRegs<T, NV> xr, gr;
     xr.load(x + (long long)r * D, D, lane);
     if (res != nullptr) xr.axpy(res + (long long)r * D, 1.f, D, lane);
     gr.load(dy + (long long)r * D, D, lane);
     const float mean = mean_in[r], rstd = rstd_in[r];
-    const float* gm = gamma + (long long)g * D;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < ROW_MAXV; ++j) {
+    for (int j = 0; j < NV; ++j) {
       const int vi = lane + 32 * j;
       if (vi < nv) {
         float gv[VT];
         load_param<VT>(gm, vi, gv);
+        float* ag = acc_g + vi * VT;
+        float* ab = acc_b + vi * VT;
 #pragma unroll
-        for (int u = 0; u < VT; ++u) {
-          const float xhat = (xr.v[j][u] - mean) * rstd;
-          const float d = gr.v[j][u];
-          dg[j][u] = fmaf(d, xhat, dg[j][u]);
-          db[j][u] += d;
-          const float gg = d * gv[u];
-          xr.v[j][u] = xhat;
-          gr.v[j][u] = gg;
-          s1 += gg;
-          s2 = fmaf(gg, xhat, s2);
+        for (int u = 0; u < VT; u += 4) {
+          float4 tg = *reinterpret_cast<float4*>(ag + u), tb = *reinterpret_cast<float4*>(ab + u);
+          float* pg = reinterpret_cast<float*>(&tg);
+          float* pb = reinterpret_cast<float*>(&tb);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float xhat = (xr.v[j][u + q] - mean) * rstd;
+            const float d = gr.v[j][u + q];
+            pg[q] = fmaf(d, xhat, pg[q]);
+            pb[q] += d;
+            const float gg = d * gv[u + q];
+            xr.v[j][u + q] = xhat;
+            gr.v[j][u + q] = gg;
+            s1 += gg;
+            s2 = fmaf(gg, xhat, s2);
+          }
+          *reinterpret_cast<float4*>(ag + u) = tg;
+          *reinterpret_cast<float4*>(ab + u) = tb;
         }
       }
     }
     s1 = warp_sum(s1) / D;
     s2 = warp_sum(s2) / D;
 #pragma unroll
-    for (int j = 0; j < ROW_MAXV; ++j)
+    for (int j = 0; j < NV; ++j)
 #pragma unroll
       for (int u = 0; u < VT; ++u) gr.v[j][u] = rstd * (gr.v[j][u] - s1 - xr.v[j][u] * s2);
     gr.store(dsum + (long long)r * D, D, lane);
-  }
-
-  // cross-warp reduction of the parameter-gradient partials
-#pragma unroll
-  for (int j = 0; j < ROW_MAXV; ++j) {
-    const int vi = lane + 32 * j;
-    if (vi < nv) {
-#pragma unroll
-      for (int u = 0; u < VT; ++u) {
-        red[(warp * 2 + 0) * D + vi * VT + u] = dg[j][u];
-        red[(warp * 2 + 1) * D + vi * VT + u] = db[j][u];
-      }
-    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
@@ -136,21 +137,41 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
   }
 }
 
+// rows per warp for the backward kernels: enough blocks to fill the machine, few enough partials to keep the
+// second-stage reduction small.  Power of two <= 16 so a block (8*rpw rows) never straddles a 128-row tile.
+inline int ln_bwd_rpw(int R) {
+  int rpw = 1;
+  while (rpw < 16 && (R + LN_WARPS * rpw * 2 - 1) / (LN_WARPS * rpw * 2) >= 2 * num_sms()) rpw *= 2;
+  return rpw;
+}
+
 // out_z[g][c] = sum over partial blocks b of group g of part[b][z][c]   (z = blockIdx.z selects dgamma / dbeta).
 // 32 columns x 8 partial-lanes per block: loads are independent across threads instead of one serial chain.
+// Expert segments are contiguous tile ranges, so the block first finds [first,last] tile of its group (parallel scan
+// of the tile map) and then walks only that block range — no per-iteration indirection through tile_group.
 __global__ void __launch_bounds__(256)
 partial_reduce_kernel(const float* __restrict__ part, int blocks, int rows_per_block, int width, int nz,
-                      const int* __restrict__ tile_group, float* __restrict__ out0, float* __restrict__ out1) {
+                      const int* __restrict__ tile_group, int tiles, float* __restrict__ out0,
+                      float* __restrict__ out1) {
   __shared__ float red[8][33];
+  __shared__ int s_lo, s_hi;
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + x;
   const int g = blockIdx.y, z = blockIdx.z;
+  int b_lo = 0, b_hi = blocks;
+  if (tile_group != nullptr) {
+    if (threadIdx.x == 0) { s_lo = tiles; s_hi = -1; }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x)
+      if (tile_group[t] == g) { atomicMin(&s_lo, t); atomicMax(&s_hi, t); }
+    __syncthreads();
+    const int bpt = B200_GROUP_TILE / rows_per_block;   // partial blocks per 128-row tile
+    b_lo = s_lo * bpt;
+    b_hi = min(blocks, (s_hi + 1) * bpt);
+  }
   float s = 0.f;
   if (c < width) {
-    for (int b = y; b < blocks; b += 8) {
-      const int bg = tile_group ? tile_group[(b * rows_per_block) / B200_GROUP_TILE] : 0;
-      if (bg == g) s += part[((long long)b * nz + z) * width + c];
-    }
+    for (int b = b_lo + y; b < b_hi; b += 8) s += part[((long long)b * nz + z) * width + c];
   }
   red[y][x] = s;
   __syncthreads();
@@ -168,7 +189,8 @@ partial_reduce_kernel(const float* __restrict__ part, int blocks, int rows_per_b
 int launch_ln_param_reduce(const float* part, int blocks, int rows_per_block, int D, const int* tile_group, int G,
                            float* dgamma, float* dbeta, cudaStream_t stream) {
   dim3 grid((D + 31) / 32, G, 2);
-  partial_reduce_kernel<<<grid, 256, 0, stream>>>(part, blocks, rows_per_block, D, 2, tile_group, dgamma, dbeta);
+  const int tiles = (int)(((long long)blocks * rows_per_block + B200_GROUP_TILE - 1) / B200_GROUP_TILE);
+  partial_reduce_kernel<<<grid, 256, 0, stream>>>(part, blocks, rows_per_block, D, 2, tile_group, tiles, dgamma, dbeta);
   B200_LAUNCH_CHECK("partial_reduce_kernel");
   count_launch();
   return 0;
@@ -178,7 +200,8 @@ int launch_ln_param_reduce(const float* part, int blocks, int rows_per_block, in
 int launch_partial_reduce(const float* part, int blocks, int rows_per_block, int width, const int* tile_group, int G,
                           float* out, cudaStream_t stream) {
   dim3 grid((width + 31) / 32, G, 1);
-  partial_reduce_kernel<<<grid, 256, 0, stream>>>(part, blocks, rows_per_block, width, 1, tile_group, out, out);
+  const int tiles = (int)(((long long)blocks * rows_per_block + B200_GROUP_TILE - 1) / B200_GROUP_TILE);
+  partial_reduce_kernel<<<grid, 256, 0, stream>>>(part, blocks, rows_per_block, width, 1, tile_group, tiles, out, out);
   B200_LAUNCH_CHECK("partial_reduce_kernel");
   count_launch();
   return 0;
@@ -195,15 +218,15 @@ int b200_add_ln_fwd(const void* x, const void* res, const float* gamma, const fl
                     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(R > 0 && D > 0, "add_ln_fwd: bad shape R=%d D=%d", R, D);
-  const int blocks = (R + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK;
+  const int blocks = (R + LN_WARPS - 1) / LN_WARPS;
   if (dtype == B200_BF16) {
     B200_CHECK_ARG(RowRegs<bf16>::supported(D), "add_ln_fwd: D=%d unsupported for bf16 (need D%%8==0, D<=2048)", D);
-    add_ln_fwd_kernel<bf16><<<blocks, LN_WARPS * 32, 0, stream>>>((const bf16*)x, (const bf16*)res, gamma, beta, tile_group,
-                                                        eps, (bf16*)y, mean, rstd, R, D);
+    B200_NV_SWITCH(row_nv<bf16>(D), add_ln_fwd_kernel<bf16, NV><<<blocks, LN_WARPS * 32, 0, stream>>>(
+        (const bf16*)x, (const bf16*)res, gamma, beta, tile_group, eps, (bf16*)y, mean, rstd, R, D));
   } else {
     B200_CHECK_ARG(RowRegs<float>::supported(D), "add_ln_fwd: D=%d unsupported for fp32 (need D%%4==0, D<=1024)", D);
-    add_ln_fwd_kernel<float><<<blocks, LN_WARPS * 32, 0, stream>>>((const float*)x, (const float*)res, gamma, beta,
-                                                         tile_group, eps, (float*)y, mean, rstd, R, D);
+    B200_NV_SWITCH(row_nv<float>(D), add_ln_fwd_kernel<float, NV><<<blocks, LN_WARPS * 32, 0, stream>>>(
+        (const float*)x, (const float*)res, gamma, beta, tile_group, eps, (float*)y, mean, rstd, R, D));
   }
   B200_LAUNCH_CHECK("add_ln_fwd_kernel");
   count_launch();
@@ -221,27 +244,32 @@ int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float*
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(R > 0 && D > 0 && G > 0, "add_ln_bwd: bad shape R=%d D=%d G=%d", R, D, G);
   B200_CHECK_ARG(workspace_bytes >= b200_add_ln_bwd_ws(R, D), "add_ln_bwd: workspace too small");
-  const int blocks = (R + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK;
+  const int rpw = ln_bwd_rpw(R);
+  const int rows_per_block = LN_WARPS * rpw;
+  const int blocks = (R + rows_per_block - 1) / rows_per_block;
   float* part = (float*)workspace;
   const size_t smem = (size_t)LN_WARPS * 2 * D * sizeof(float);
-  if (tile_group != nullptr)  // unused tiles leave their partial slots untouched
-    B200_CUDA(cudaMemsetAsync(part, 0, b200_add_ln_bwd_ws(R, D), stream));
+  B200_CHECK_ARG(smem <= 160 * 1024, "add_ln_bwd: D=%d too large", D);
   if (dtype == B200_BF16) {
     B200_CHECK_ARG(RowRegs<bf16>::supported(D), "add_ln_bwd: D=%d unsupported for bf16", D);
-    if (smem > 48 * 1024)
-      B200_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    add_ln_bwd_kernel<bf16><<<blocks, LN_WARPS * 32, smem, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)res, mean,
-                                                           rstd, gamma, tile_group, (bf16*)dsum, part, R, D);
+    B200_NV_SWITCH(row_nv<bf16>(D), {
+      if (smem > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<bf16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      add_ln_bwd_kernel<bf16, NV><<<blocks, LN_WARPS * 32, smem, stream>>>(
+          (const bf16*)dy, (const bf16*)x, (const bf16*)res, mean, rstd, gamma, tile_group, (bf16*)dsum, part, R, D, rpw);
+    });
   } else {
     B200_CHECK_ARG(RowRegs<float>::supported(D), "add_ln_bwd: D=%d unsupported for fp32", D);
-    if (smem > 48 * 1024)
-      B200_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    add_ln_bwd_kernel<float><<<blocks, LN_WARPS * 32, smem, stream>>>((const float*)dy, (const float*)x, (const float*)res,
-                                                            mean, rstd, gamma, tile_group, (float*)dsum, part, R, D);
+    B200_NV_SWITCH(row_nv<float>(D), {
+      if (smem > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<float, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      add_ln_bwd_kernel<float, NV><<<blocks, LN_WARPS * 32, smem, stream>>>(
+          (const float*)dy, (const float*)x, (const float*)res, mean, rstd, gamma, tile_group, (float*)dsum, part, R, D, rpw);
+    });
   }
   B200_LAUNCH_CHECK("add_ln_bwd_kernel");
   count_launch();
-  return launch_ln_param_reduce(part, blocks, LN_ROWS_PER_BLOCK, D, tile_group, G, dgamma, dbeta, stream);
+  return launch_ln_param_reduce(part, blocks, rows_per_block, D, tile_group, G, dgamma, dbeta, stream);
 }
 
 }  // extern "C"

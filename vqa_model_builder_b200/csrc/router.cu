@@ -6,6 +6,9 @@
 
 namespace b200 {
 
+int launch_partial_reduce(const float* part, int blocks, int rows_per_block, int width, const int* tile_group, int G,
+                          float* out, cudaStream_t stream);
+
 namespace {
 
 constexpr int RT_MAX_E = 64;
@@ -14,24 +17,43 @@ constexpr int RT_WARPS = 8;
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(__expf(x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
 
-// dot products of one token row (held as 16-byte vectors across the warp) with E weight rows in smem.
+// Gate weights live in shared memory in a lane-interleaved float4 layout so that a warp's reads are conflict-free:
+//   unit(e, j, q, lane) = ((e*NV + j)*(VT/4) + q)*32 + lane   holds elements d = (lane + 32j)*VT + 4q .. +3 of row e
+// (the row-major staging used before produced 8-way bank conflicts: 19.6 M conflicts per call in ncu).
+template <int VT, int NV>
+__device__ __forceinline__ void stage_gate_weights(const float* __restrict__ w, float* __restrict__ ws, int E, int D) {
+  constexpr int DP = NV * 32 * VT;
+  for (int i = threadIdx.x; i < E * DP; i += blockDim.x) {
+    const int e = i / DP, p = i % DP;
+    const int f4 = p >> 2, uu = p & 3;
+    const int lane = f4 & 31, t = f4 >> 5;
+    const int q = t % (VT / 4), j = t / (VT / 4);
+    const int d = (lane + 32 * j) * VT + 4 * q + uu;
+    ws[i] = d < D ? w[(long long)e * D + d] : 0.f;
+  }
+}
+
+// dot products of one token row (held in registers, loaded once) with the E staged weight rows.
 // On return lane e (and slot 1: e+32) holds logit e.
-template <typename T>
-__device__ __forceinline__ void gate_dots(const T* __restrict__ xrow, const float* __restrict__ ws, int D, int E,
-                                          int lane, float& l0, float& l1) {
+template <typename T, int NV>
+__device__ __forceinline__ void gate_dots(const RowRegs<T, NV>& x, const float* __restrict__ ws, int E, int lane,
+                                          float& l0, float& l1) {
   constexpr int VT = Vec16<T>::N;
-  const int nv = D / VT;
+  const float4* ws4 = reinterpret_cast<const float4*>(ws);
   l0 = 0.f;
   l1 = 0.f;
   for (int e = 0; e < E; ++e) {
-    const float* wr = ws + (long long)e * D;
     float s = 0.f;
-    for (int v = lane; v < nv; v += 32) {
-      Vec16<T> xv;
-      xv.load(xrow + v * VT);
 #pragma unroll
-      for (int u = 0; u < VT; ++u) s = fmaf(xv.v[u], wr[v * VT + u], s);
-    }
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int q = 0; q < VT / 4; ++q) {
+        const float4 wv = ws4[((e * NV + j) * (VT / 4) + q) * 32 + lane];
+        s = fmaf(x.v[j][4 * q + 0], wv.x, s);
+        s = fmaf(x.v[j][4 * q + 1], wv.y, s);
+        s = fmaf(x.v[j][4 * q + 2], wv.z, s);
+        s = fmaf(x.v[j][4 * q + 3], wv.w, s);
+      }
     s = warp_sum(s);
     if ((e & 31) == lane) {
       if (e < 32) l0 = s; else l1 = s;
@@ -48,21 +70,21 @@ __device__ __forceinline__ void warp_softmax(float& a, float& b) {
   b = eb / s;
 }
 
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(RT_WARPS * 32)
 router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, const float* __restrict__ w_noise,
                   const float* __restrict__ eps, float noise_std, int N, int D, int E, int K, int* __restrict__ idx,
                   float* __restrict__ w, float* __restrict__ topk_sum, float* __restrict__ probs,
                   float* __restrict__ probs_noisy, float* __restrict__ part /* [grid][3][RT_MAX_E] */) {
+  constexpr int VT = Vec16<T>::N;
+  constexpr int DP = NV * 32 * VT;
   extern __shared__ float smem[];
-  float* wg = smem;                                  // [E][D]
-  float* wn = smem + (size_t)E * D;                  // [E][D] (noisy only)
+  float* wg = smem;                                  // [E][DP] lane-interleaved
+  float* wn = smem + (size_t)E * DP;                 // noisy only
   __shared__ float red[RT_WARPS][3][RT_MAX_E];
   const bool noisy = (eps != nullptr);
-  for (int i = threadIdx.x; i < E * D; i += blockDim.x) {
-    wg[i] = w_gate[i];
-    if (noisy) wn[i] = w_noise[i];
-  }
+  stage_gate_weights<VT, NV>(w_gate, wg, E, D);
+  if (noisy) stage_gate_weights<VT, NV>(w_noise, wn, E, D);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -70,13 +92,14 @@ router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
   float cnt0 = 0.f, cnt1 = 0.f, ps0 = 0.f, ps1 = 0.f, ns0 = 0.f, ns1 = 0.f;
 
   for (int n = blockIdx.x * RT_WARPS + warp; n < N; n += gridDim.x * RT_WARPS) {
-    const T* xrow = x + (long long)n * D;
+    RowRegs<T, NV> xr;
+    xr.load(x + (long long)n * D, D, lane);
     float c0, c1;  // clean logits -> clean probs
-    gate_dots<T>(xrow, wg, D, E, lane, c0, c1);
+    gate_dots<T, NV>(xr, wg, E, lane, c0, c1);
     float q0 = c0, q1 = c1;  // logits used for selection
     if (noisy) {
       float u0, u1;
-      gate_dots<T>(xrow, wn, D, E, lane, u0, u1);
+      gate_dots<T, NV>(xr, wn, E, lane, u0, u1);
       const float sp0 = softplus_f(u0), sp1 = softplus_f(u1);
       if (v0) { q0 = c0 + eps[(long long)n * E + lane] * sp0 * noise_std; ns0 += sp0; }
       if (v1) { q1 = c1 + eps[(long long)n * E + lane + 32] * sp1 * noise_std; ns1 += sp1; }
@@ -134,18 +157,25 @@ router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
 }
 
 // counts[e], loss = lb_weight * E * sum_e (counts[e]/N) * (psum[e]/N), mean softplus noise scale
-__global__ void router_finalize_kernel(const float* __restrict__ part, int blocks, int N, int E, float lb_weight,
-                                       float* __restrict__ counts, float* __restrict__ psum, float* __restrict__ loss,
-                                       float* __restrict__ noise_scale_mean) {
+__global__ void __launch_bounds__(1024)
+router_finalize_kernel(const float* __restrict__ part, int blocks, int N, int E, float lb_weight,
+                       float* __restrict__ counts, float* __restrict__ psum, float* __restrict__ loss,
+                       float* __restrict__ noise_scale_mean) {
+  __shared__ float s_red[16][3][RT_MAX_E];
   __shared__ float s_cnt[RT_MAX_E], s_ps[RT_MAX_E], s_ns[RT_MAX_E];
-  const int e = threadIdx.x;
-  if (e < RT_MAX_E) {
-    float c = 0.f, p = 0.f, q = 0.f;
-    for (int b = 0; b < blocks; ++b) {
-      c += part[((long long)b * 3 + 0) * RT_MAX_E + e];
-      p += part[((long long)b * 3 + 1) * RT_MAX_E + e];
-      q += part[((long long)b * 3 + 2) * RT_MAX_E + e];
-    }
+  const int e = threadIdx.x & (RT_MAX_E - 1), y = threadIdx.x / RT_MAX_E;   // 64 experts x 16 partial lanes
+  float c = 0.f, p = 0.f, q = 0.f;
+  for (int b = y; b < blocks; b += 16) {
+    c += part[((long long)b * 3 + 0) * RT_MAX_E + e];
+    p += part[((long long)b * 3 + 1) * RT_MAX_E + e];
+    q += part[((long long)b * 3 + 2) * RT_MAX_E + e];
+  }
+  s_red[y][0][e] = c; s_red[y][1][e] = p; s_red[y][2][e] = q;
+  __syncthreads();
+  if (y == 0) {
+    c = p = q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { c += s_red[j][0][e]; p += s_red[j][1][e]; q += s_red[j][2][e]; }
     s_cnt[e] = c; s_ps[e] = p; s_ns[e] = q;
     if (e < E) {
       counts[e] = c;
@@ -167,7 +197,7 @@ __global__ void router_finalize_kernel(const float* __restrict__ part, int block
 // ---- backward --------------------------------------------------------------------------------------------
 // per token: d logits (clean) and d noise-logits, then dx = dl Wg + du Wn.  dl/du are also written to the
 // workspace for the weight-gradient reduction.
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(RT_WARPS * 32)
 router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, const float* __restrict__ w_noise,
                   const float* __restrict__ eps, float noise_std, float lb_weight, int N, int D, int E, int K,
@@ -176,20 +206,18 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
                   const float* __restrict__ counts, const float* __restrict__ d_w, const float* __restrict__ d_loss,
                   T* __restrict__ dx, float* __restrict__ dl_out, float* __restrict__ du_out) {
   constexpr int VT = Vec16<T>::N;
+  constexpr int DP = NV * 32 * VT;
   extern __shared__ float smem[];
   float* wg = smem;
-  float* wn = smem + (size_t)E * D;
+  float* wn = smem + (size_t)E * DP;
   __shared__ float s_dl[RT_WARPS][RT_MAX_E], s_du[RT_WARPS][RT_MAX_E];
   const bool noisy = (eps != nullptr);
-  for (int i = threadIdx.x; i < E * D; i += blockDim.x) {
-    wg[i] = w_gate[i];
-    if (noisy) wn[i] = w_noise[i];
-  }
+  stage_gate_weights<VT, NV>(w_gate, wg, E, D);
+  if (noisy) stage_gate_weights<VT, NV>(w_noise, wn, E, D);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool v0 = lane < E, v1 = lane + 32 < E;
   const float gl = (d_loss != nullptr) ? d_loss[0] : 0.f;
-  const int nv = D / VT;
 
   for (int n = blockIdx.x * RT_WARPS + warp; n < N; n += gridDim.x * RT_WARPS) {
     const float* qrow = (noisy ? probs_noisy : probs) + (long long)n * E;
@@ -220,11 +248,12 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
       dc0 = p0 * (dp0 - pdp);
       dc1 = p1 * (dp1 - pdp);
     }
-    const T* xrow = x + (long long)n * D;
     float du0 = 0.f, du1 = 0.f;
     if (noisy) {
+      RowRegs<T, NV> xr;
+      xr.load(x + (long long)n * D, D, lane);
       float u0, u1;
-      gate_dots<T>(xrow, wn, D, E, lane, u0, u1);
+      gate_dots<T, NV>(xr, wn, E, lane, u0, u1);
       if (v0) du0 = dsel0 * eps[(long long)n * E + lane] * noise_std * sigmoid_f(u0);
       if (v1) du1 = dsel1 * eps[(long long)n * E + lane + 32] * noise_std * sigmoid_f(u1);
     }
@@ -238,58 +267,79 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
       if (v1) du_out[(long long)n * E + lane + 32] = du1;
     }
     __syncwarp();
-    T* dxrow = dx + (long long)n * D;
-    for (int v = lane; v < nv; v += 32) {
-      Vec16<T> o;
+    // dx = sum_e dl[e] Wg[e,:] + du[e] Wn[e,:]   (same conflict-free weight layout)
+    RowRegs<T, NV> o;
+    o.zero();
+    const float4* wg4 = reinterpret_cast<const float4*>(wg);
+    const float4* wn4 = reinterpret_cast<const float4*>(wn);
+    for (int e = 0; e < E; ++e) {
+      const float a = s_dl[warp][e];
+      const float bb = noisy ? s_du[warp][e] : 0.f;
 #pragma unroll
-      for (int u = 0; u < VT; ++u) o.v[u] = 0.f;
-      for (int e = 0; e < E; ++e) {
-        const float a = s_dl[warp][e];
-        const float* wr = wg + (long long)e * D + v * VT;
+      for (int j = 0; j < NV; ++j)
 #pragma unroll
-        for (int u = 0; u < VT; ++u) o.v[u] = fmaf(a, wr[u], o.v[u]);
-        if (noisy) {
-          const float b = s_du[warp][e];
-          const float* nr = wn + (long long)e * D + v * VT;
-#pragma unroll
-          for (int u = 0; u < VT; ++u) o.v[u] = fmaf(b, nr[u], o.v[u]);
+        for (int q = 0; q < VT / 4; ++q) {
+          const int unit = ((e * NV + j) * (VT / 4) + q) * 32 + lane;
+          const float4 wv = wg4[unit];
+          o.v[j][4 * q + 0] = fmaf(a, wv.x, o.v[j][4 * q + 0]);
+          o.v[j][4 * q + 1] = fmaf(a, wv.y, o.v[j][4 * q + 1]);
+          o.v[j][4 * q + 2] = fmaf(a, wv.z, o.v[j][4 * q + 2]);
+          o.v[j][4 * q + 3] = fmaf(a, wv.w, o.v[j][4 * q + 3]);
+          if (noisy) {
+            const float4 nvv = wn4[unit];
+            o.v[j][4 * q + 0] = fmaf(bb, nvv.x, o.v[j][4 * q + 0]);
+            o.v[j][4 * q + 1] = fmaf(bb, nvv.y, o.v[j][4 * q + 1]);
+            o.v[j][4 * q + 2] = fmaf(bb, nvv.z, o.v[j][4 * q + 2]);
+            o.v[j][4 * q + 3] = fmaf(bb, nvv.w, o.v[j][4 * q + 3]);
+          }
         }
-      }
-      o.store(dxrow + v * VT);
     }
+    o.store(dx + (long long)n * D, D, lane);
     __syncwarp();
   }
 }
 
 // dW[e][d] partial over a chunk of tokens: part[chunk][E][D]; thread per column.
-constexpr int RW_CHUNK = 256;
-template <typename T>
-__global__ void __launch_bounds__(128)
+constexpr int RW_CHUNK = 64;
+template <typename T, int EB>   // EB = expert-count bucket (8/16/32/64): a runtime bound made every thread issue 64
+__global__ void __launch_bounds__(128)   // predicated FMAs per token even for E = 8
 router_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ dl, int N, int D, int E,
                     float* __restrict__ part) {
-  __shared__ float s_dl[32][RT_MAX_E];
+  __shared__ float s_dl[32][EB];
   const int d = blockIdx.x * 128 + threadIdx.x;
   const int n0 = blockIdx.y * RW_CHUNK, n1 = min(N, n0 + RW_CHUNK);
-  float acc[RT_MAX_E];
+  float acc[EB];
 #pragma unroll
-  for (int e = 0; e < RT_MAX_E; ++e) acc[e] = 0.f;
+  for (int e = 0; e < EB; ++e) acc[e] = 0.f;
   for (int nb = n0; nb < n1; nb += 32) {
     const int cnt = min(32, n1 - nb);
     __syncthreads();
-    for (int i = threadIdx.x; i < cnt * E; i += blockDim.x) s_dl[i / E][i % E] = dl[(long long)(nb + i / E) * E + i % E];
+    for (int i = threadIdx.x; i < cnt * EB; i += blockDim.x) {
+      const int tt = i / EB, ee = i % EB;
+      s_dl[tt][ee] = ee < E ? dl[(long long)(nb + tt) * E + ee] : 0.f;
+    }
     __syncthreads();
     if (d < D) {
-      for (int t = 0; t < cnt; ++t) {
+      int t = 0;
+      for (; t + 4 <= cnt; t += 4) {   // four independent row loads in flight
+        float xv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xv[q] = to_f32<T>(x[(long long)(nb + t + q) * D + d]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int e = 0; e < EB; ++e) acc[e] = fmaf(s_dl[t + q][e], xv[q], acc[e]);
+      }
+      for (; t < cnt; ++t) {
         const float xv = to_f32<T>(x[(long long)(nb + t) * D + d]);
 #pragma unroll
-        for (int e = 0; e < RT_MAX_E; ++e)
-          if (e < E) acc[e] = fmaf(s_dl[t][e], xv, acc[e]);
+        for (int e = 0; e < EB; ++e) acc[e] = fmaf(s_dl[t][e], xv, acc[e]);
       }
     }
   }
   if (d < D) {
 #pragma unroll
-    for (int e = 0; e < RT_MAX_E; ++e)
+    for (int e = 0; e < EB; ++e)
       if (e < E) part[((long long)blockIdx.y * E + e) * D + d] = acc[e];
   }
 }
@@ -303,7 +353,7 @@ __global__ void router_wgrad_reduce_kernel(const float* __restrict__ part, int c
 
 inline int router_grid(int N) {
   int blocks = (N + RT_WARPS - 1) / RT_WARPS;
-  const int cap = num_sms() * 2;
+  const int cap = num_sms() * 6;   // ~2 tokens per warp at config-5 scale: more independent row loads in flight
   if (blocks > cap) blocks = cap;
   return blocks < 1 ? 1 : blocks;
 }
@@ -337,22 +387,28 @@ int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* 
                  "router_fwd: noisy routing needs w_noise and probs_noisy");
   B200_CHECK_ARG(workspace_bytes >= b200_router_ws(N, E), "router_fwd: workspace too small");
   B200_CHECK_ARG(dtype == B200_BF16 ? D % 8 == 0 : D % 4 == 0, "router_fwd: D=%d not vectorisable", D);
-  const size_t smem = (size_t)E * D * sizeof(float) * (eps != nullptr ? 2 : 1);
+  B200_CHECK_ARG(dtype == B200_BF16 ? RowRegs<bf16>::supported(D) : RowRegs<float>::supported(D),
+                 "router_fwd: D=%d unsupported", D);
+  const int nvb = dtype == B200_BF16 ? row_nv<bf16>(D) : row_nv<float>(D);
+  const size_t smem = (size_t)E * nvb * 32 * (dtype == B200_BF16 ? 8 : 4) * sizeof(float) * (eps != nullptr ? 2 : 1);
   B200_CHECK_ARG(smem <= 200 * 1024, "router_fwd: gate weights (%zu B) do not fit in shared memory", smem);
   const int blocks = router_grid(N);
   float* part = (float*)workspace;
   if (dtype == B200_BF16) {
-    if (int rc = set_smem(router_fwd_kernel<bf16>, smem)) return rc;
-    router_fwd_kernel<bf16><<<blocks, RT_WARPS * 32, smem, stream>>>((const bf16*)x, w_gate, w_noise, eps, noise_std, N,
-                                                                     D, E, K, idx, w, topk_sum, probs, probs_noisy, part);
+    B200_NV_SWITCH(nvb, {
+      if (int rc = set_smem(router_fwd_kernel<bf16, NV>, smem)) return rc;
+      router_fwd_kernel<bf16, NV><<<blocks, RT_WARPS * 32, smem, stream>>>(
+          (const bf16*)x, w_gate, w_noise, eps, noise_std, N, D, E, K, idx, w, topk_sum, probs, probs_noisy, part);
+    });
   } else {
-    if (int rc = set_smem(router_fwd_kernel<float>, smem)) return rc;
-    router_fwd_kernel<float><<<blocks, RT_WARPS * 32, smem, stream>>>((const float*)x, w_gate, w_noise, eps, noise_std,
-                                                                      N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
-                                                                      part);
+    B200_NV_SWITCH(nvb, {
+      if (int rc = set_smem(router_fwd_kernel<float, NV>, smem)) return rc;
+      router_fwd_kernel<float, NV><<<blocks, RT_WARPS * 32, smem, stream>>>(
+          (const float*)x, w_gate, w_noise, eps, noise_std, N, D, E, K, idx, w, topk_sum, probs, probs_noisy, part);
+    });
   }
   B200_LAUNCH_CHECK("router_fwd_kernel");
-  router_finalize_kernel<<<1, RT_MAX_E, 0, stream>>>(part, blocks, N, E, lb_weight, counts, psum, loss,
+  router_finalize_kernel<<<1, 1024, 0, stream>>>(part, blocks, N, E, lb_weight, counts, psum, loss,
                                                      eps != nullptr ? noise_scale_mean : nullptr);
   B200_LAUNCH_CHECK("router_finalize_kernel");
   count_launch(2);
@@ -377,7 +433,10 @@ int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* 
   const bool noisy = eps != nullptr;
   B200_CHECK_ARG(!noisy || (w_noise != nullptr && probs_noisy != nullptr && d_w_noise != nullptr),
                  "router_bwd: noisy routing needs w_noise, probs_noisy, d_w_noise");
-  const size_t smem = (size_t)E * D * sizeof(float) * (noisy ? 2 : 1);
+  B200_CHECK_ARG(dtype == B200_BF16 ? RowRegs<bf16>::supported(D) : RowRegs<float>::supported(D),
+                 "router_bwd: D=%d unsupported", D);
+  const int nvb = dtype == B200_BF16 ? row_nv<bf16>(D) : row_nv<float>(D);
+  const size_t smem = (size_t)E * nvb * 32 * (dtype == B200_BF16 ? 8 : 4) * sizeof(float) * (noisy ? 2 : 1);
   B200_CHECK_ARG(smem <= 200 * 1024, "router_bwd: gate weights do not fit in shared memory");
   float* dl = (float*)workspace;
   float* du = dl + (size_t)N * E;
@@ -387,27 +446,35 @@ int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* 
   dim3 wg_grid((D + 127) / 128, chunks);
   const int ED = E * D;
   if (dtype == B200_BF16) {
-    if (int rc = set_smem(router_bwd_kernel<bf16>, smem)) return rc;
-    router_bwd_kernel<bf16><<<blocks, RT_WARPS * 32, smem, stream>>>(
-        (const bf16*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
-        counts, d_w, d_loss, (bf16*)dx, dl, du);
+    B200_NV_SWITCH(nvb, {
+      if (int rc = set_smem(router_bwd_kernel<bf16, NV>, smem)) return rc;
+      router_bwd_kernel<bf16, NV><<<blocks, RT_WARPS * 32, smem, stream>>>(
+          (const bf16*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
+          counts, d_w, d_loss, (bf16*)dx, dl, du);
+    });
   } else {
-    if (int rc = set_smem(router_bwd_kernel<float>, smem)) return rc;
-    router_bwd_kernel<float><<<blocks, RT_WARPS * 32, smem, stream>>>(
-        (const float*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
-        counts, d_w, d_loss, (float*)dx, dl, du);
+    B200_NV_SWITCH(nvb, {
+      if (int rc = set_smem(router_bwd_kernel<float, NV>, smem)) return rc;
+      router_bwd_kernel<float, NV><<<blocks, RT_WARPS * 32, smem, stream>>>(
+          (const float*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
+          counts, d_w, d_loss, (float*)dx, dl, du);
+    });
   }
   B200_LAUNCH_CHECK("router_bwd_kernel");
   count_launch();
   for (int pass = 0; pass < (noisy ? 2 : 1); ++pass) {
     const float* g = pass == 0 ? dl : du;
     float* out = pass == 0 ? d_w_gate : d_w_noise;
-    if (dtype == B200_BF16) router_wgrad_kernel<bf16><<<wg_grid, 128, 0, stream>>>((const bf16*)x, g, N, D, E, part);
-    else router_wgrad_kernel<float><<<wg_grid, 128, 0, stream>>>((const float*)x, g, N, D, E, part);
+#define B200_RW(TT, EBV) router_wgrad_kernel<TT, EBV><<<wg_grid, 128, 0, stream>>>((const TT*)x, g, N, D, E, part)
+    if (dtype == B200_BF16) {
+      if (E <= 8) B200_RW(bf16, 8); else if (E <= 16) B200_RW(bf16, 16); else if (E <= 32) B200_RW(bf16, 32); else B200_RW(bf16, 64);
+    } else {
+      if (E <= 8) B200_RW(float, 8); else if (E <= 16) B200_RW(float, 16); else if (E <= 32) B200_RW(float, 32); else B200_RW(float, 64);
+    }
+#undef B200_RW
     B200_LAUNCH_CHECK("router_wgrad_kernel");
-    router_wgrad_reduce_kernel<<<(ED + 255) / 256, 256, 0, stream>>>(part, chunks, ED, out);
-    B200_LAUNCH_CHECK("router_wgrad_reduce_kernel");
-    count_launch(2);
+    count_launch();
+    if (int rc = launch_partial_reduce(part, chunks, 1, ED, nullptr, 1, out, stream)) return rc;
   }
   return 0;
 }
