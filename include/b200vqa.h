@@ -45,6 +45,17 @@ enum {
 
 #define B200_GROUP_TILE 128 /* expert row segments are padded to this many rows */
 
+/* Dropout (nn.Dropout / MHA attention dropout in train mode: vqa_model.py:258-277, expert_types.py:56,81-83).
+ * Masks are never stored: every kernel regenerates keep/drop decisions from a counter-based Philox4x32-10 stream
+ * keyed by (rng_state[0] = seed, rng_state[1] = step offset, site, element index), so forward and backward of the same
+ * site see the same mask.  rng_state is a DEVICE pointer to two uint64 (read at execution time: CUDA-graph replays
+ * get fresh masks when the offset is advanced on the device).  drop == NULL or p == 0 disables dropout.            */
+typedef struct {
+  const unsigned long long* rng_state;
+  float p;
+  unsigned int site;
+} b200_dropout_t;
+
 /* ---- lifecycle ------------------------------------------------------------------------------- */
 int b200_init(int device);
 const char* b200_last_error_string(void);
@@ -52,6 +63,13 @@ int b200_abi_version(void);
 /* kernels launched by this library since the last reset (host-side counter; bench.py's gpu_launches) */
 long long b200_launch_count(void);
 void b200_reset_launch_count(void);
+
+/* keep-scales (0 or 1/(1-p)) of elements [0,n) of a dropout site, as fp32 — test/debug aid that materialises the
+ * mask the fused kernels regenerate on the fly.                                                              */
+int b200_dropout_mask(const b200_dropout_t* drop, long long n, float* out, void* stream);
+/* out[i] = x[i] * keep_scale(i)  (element index i = row*ld + col of a dense [.., ld] tensor): backward of a dropout
+ * that was fused into a GEMM epilogue with a residual add.                                                     */
+int b200_dropout_apply(const void* x, void* out, long long n, int dtype, const b200_dropout_t* drop, void* stream);
 
 /* ---- elementwise ----------------------------------------------------------------------------- */
 /* dtype conversion (autocast's weight/activation casts; torch/amp/autocast_mode, called around every
@@ -69,10 +87,12 @@ int b200_colsum(const void* x, int dtype, int R, int N, const int32_t* tile_grou
  * a_layout/b_layout select [rows,K] (B200_LAYOUT_K) or [K,rows] (B200_LAYOUT_MN) storage, which gives
  * forward (K,K), dgrad (K,MN) and wgrad (MN,MN) from one kernel.  dtype BF16 -> tcgen05/TMEM/TMA kernel,
  * F32 -> SIMT fp32 kernel (validation mode).  out_dtype may be F32 for BF16 inputs (wgrad).
- * lda/ldb/ldo/ld_aux are row pitches in elements. bias is fp32 [N] or NULL.                        */
+ * lda/ldb/ldo/ld_aux are row pitches in elements. bias is fp32 [N] or NULL.  With `drop`, EPI_ACT applies
+ * dropout after the activation, EPI_DACT multiplies by the same mask, EPI_ADD computes dropout(acc+bias)+aux_in
+ * (element index = row*ldo + col).                                                                        */
 int b200_gemm(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, void* out,
               int ldo, int M, int N, int K, int dtype, int out_dtype, const float* bias, int epi,
-              int act, const void* aux_in, void* aux_out, int ld_aux, void* stream);
+              int act, const void* aux_in, void* aux_out, int ld_aux, const b200_dropout_t* drop, void* stream);
 
 /* Grouped GEMM over expert row segments (FeedForwardExpert fc1/fc2 fwd + dgrad, expert_types.py:79-83,
  * evaluated sparsely instead of moe_layer.py:151-168's dense loop).  A is [R, K] (permuted rows, each
@@ -81,7 +101,8 @@ int b200_gemm(const void* A, int lda, int a_layout, const void* B, int ldb, int 
  * bias is [G, N] fp32 or NULL.                                                                      */
 int b200_ggemm(const void* A, int lda, const void* B, int b_layout, void* out, int ldo, int R, int N,
                int K, int G, const int32_t* tile_group, int dtype, int out_dtype, const float* bias,
-               int epi, int act, const void* aux_in, void* aux_out, int ld_aux, void* stream);
+               int epi, int act, const void* aux_in, void* aux_out, int ld_aux, const b200_dropout_t* drop,
+               void* stream);
 
 /* Grouped weight gradient: out[g] (fp32 [Mo, No]) = A[rows of g, :Mo]^T * B[rows of g, :No], rows of g =
  * [group_off[g], group_off[g+1]) (device int32, multiples of 128; pad rows must be zero in A or B).  */
@@ -92,30 +113,32 @@ int b200_ggemm_wgrad(const void* A, int lda, const void* B, int ldb, float* out,
 /* y = LN(x + res) * gamma[g] + beta[g]   (res may be NULL).  nn.LayerNorm after the residual adds at
  * vqa_model.py:301,305,309, expert_types.py:85-90, moe_layer.py:171, fusion_approaches.py:268-279.
  * tile_group (may be NULL -> group 0) picks per-expert affine parameters gamma/beta [G, D].
- * Saves mean/rstd [R] for backward.                                                                */
+ * Saves mean/rstd [R] for backward.  drop_target: 0 none, 1 dropout on x, 2 dropout on res (the branch).  */
 int b200_add_ln_fwd(const void* x, const void* res, const float* gamma, const float* beta,
                     const int32_t* tile_group, float eps, void* y, float* mean, float* rstd, int R, int D,
-                    int dtype, void* stream);
-/* dsum = d(x+res); dgamma/dbeta [G, D] fp32 (overwritten).  workspace >= b200_add_ln_bwd_ws(R, D)   */
+                    int dtype, const b200_dropout_t* drop, int drop_target, void* stream);
+/* dsum = d(x+res); dgamma/dbeta [G, D] fp32 (overwritten).  With dropout, d_dropped receives the gradient of the
+ * dropped operand (dsum * mask / (1-p)).  workspace >= b200_add_ln_bwd_ws(R, D)                        */
 size_t b200_add_ln_bwd_ws(int R, int D);
 int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float* mean, const float* rstd,
                     const float* gamma, const int32_t* tile_group, int G, void* dsum, float* dgamma,
-                    float* dbeta, int R, int D, int dtype, void* workspace, size_t workspace_bytes,
-                    void* stream);
+                    float* dbeta, int R, int D, int dtype, const b200_dropout_t* drop, int drop_target,
+                    void* d_dropped, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- attention ------------------------------------------------------------------------------- */
 /* o[b,t,h,:] = softmax_s(scale * q[b,t,h,:].k[b,s,h,:] + mask) v[b,s,h,:]; nn.MultiheadAttention core
  * (vqa_model.py:300,304; fusion_approaches.py:262-277; TransformerEncoderLayer self-attn in
  * generative_vqa_model.py:203-214).  q/k/v are [B, T|S, H, dh] views with row pitches ldq/ldk/ldv
  * (elements; lets q,k,v alias one packed in-proj output).  key_pad [B,S] uint8, 1 = ignore, or NULL.
- * lse [B,H,T] fp32 is saved for backward.  The [B,H,T,S] score tensor never touches HBM.            */
+ * lse [B,H,T] fp32 is saved for backward.  The [B,H,T,S] score tensor never touches HBM.  `drop` applies
+ * attention-probability dropout (element index = ((b*H+h)*T+t)*S+s).                                 */
 int b200_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
                   const uint8_t* key_pad, void* o, int ldo, float* lse, int B, int H, int T, int S, int dh,
-                  float scale, int dtype, void* stream);
+                  float scale, int dtype, const b200_dropout_t* drop, void* stream);
 int b200_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
                   const uint8_t* key_pad, const void* o, int ldo, const void* d_o, int lddo,
                   const float* lse, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int B,
-                  int H, int T, int S, int dh, float scale, int dtype, void* stream);
+                  int H, int T, int S, int dh, float scale, int dtype, const b200_dropout_t* drop, void* stream);
 
 /* ---- MOE router ------------------------------------------------------------------------------ */
 /* TopKRouter / NoisyTopKRouter forward (router.py:105-178, 287-366): logits = x Wg^T in fp32,

@@ -31,17 +31,19 @@ SIGNATURES = {
     "b200_abi_version": ("i", ""),
     "b200_launch_count": ("l", ""),
     "b200_reset_launch_count": ("v", ""),
+    "b200_dropout_mask": ("i", "plpp"),
+    "b200_dropout_apply": ("i", "pplipp"),
     "b200_cast": ("i", "pipilp"),
     "b200_colsum_ws": ("z", "ii"),
     "b200_colsum": ("i", "piiipippzp"),
-    "b200_gemm": ("i", "piipiipiiiiiipiippip"),
-    "b200_ggemm": ("i", "pipipiiiiipiipiippip"),
+    "b200_gemm": ("i", "piipiipiiiiiipiippipp"),
+    "b200_ggemm": ("i", "pipipiiiiipiipiippipp"),
     "b200_ggemm_wgrad": ("i", "pipipiiiipip"),
-    "b200_add_ln_fwd": ("i", "pppppfpppiiip"),
+    "b200_add_ln_fwd": ("i", "pppppfpppiiipip"),
     "b200_add_ln_bwd_ws": ("z", "ii"),
-    "b200_add_ln_bwd": ("i", "pppppppipppiiipzp"),
-    "b200_attn_fwd": ("i", "pipipippipiiiiifip"),
-    "b200_attn_bwd": ("i", "pipipippipippipipiiiiiifip"),
+    "b200_add_ln_bwd": ("i", "pppppppipppiiipippzp"),
+    "b200_attn_fwd": ("i", "pipipippipiiiiifipp"),
+    "b200_attn_bwd": ("i", "pipipippipippipipiiiiiifipp"),
     "b200_router_ws": ("z", "ii"),
     "b200_router_fwd": ("i", "pipppffiiiippppppppppzp"),
     "b200_router_bwd_ws": ("z", "iii"),
@@ -56,6 +58,19 @@ SIGNATURES = {
     "b200_moe_combine_bwd_ws": ("z", "ii"),
     "b200_moe_combine_bwd": ("i", "ppppppppiiiiipppppzp"),
 }
+
+class DropoutT(ctypes.Structure):
+    """b200_dropout_t: device pointer to (seed, offset), probability, site id."""
+    _fields_ = [("rng_state", ctypes.c_void_p), ("p", ctypes.c_float), ("site", ctypes.c_uint)]
+
+
+def dropout_arg(drop):
+    """(state_tensor, p, site) or None -> ctypes struct or None."""
+    if drop is None:
+        return None
+    st, p, site = drop
+    return DropoutT(st.data_ptr(), float(p), int(site) & 0xFFFFFFFF)
+
 
 _lib = None
 _initialized_devices: set[int] = set()
@@ -102,6 +117,8 @@ def _ptr(x):
         return None
     if isinstance(x, torch.Tensor):
         return x.data_ptr()
+    if isinstance(x, DropoutT):
+        return ctypes.addressof(x)
     return x
 
 

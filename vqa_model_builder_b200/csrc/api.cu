@@ -112,11 +112,46 @@ __global__ void colsum_stage1_scalar(const T* __restrict__ x, int R, int N, floa
 int launch_partial_reduce(const float* part, int blocks, int rows_per_block, int width, const int* tile_group, int G,
                           float* out, cudaStream_t stream);
 
+__global__ void dropout_mask_kernel(const unsigned long long* st, float p, unsigned int site, long long n, float* out) {
+  const DropState d = drop_load(st, p, site);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = d.on ? drop_scale1(d, (unsigned long long)i) : 1.f;
+}
+
+template <typename T>
+__global__ void dropout_apply_kernel(const T* __restrict__ x, T* __restrict__ out, long long n,
+                                     const unsigned long long* st, float p, unsigned int site) {
+  const DropState d = drop_load(st, p, site);
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    float sc[4];
+    drop_scales4(d, (unsigned long long)i >> 2, sc);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (i + q < n) out[i + q] = from_f32<T>(to_f32<T>(x[i + q]) * sc[q]);
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
 
 extern "C" {
+
+int b200_dropout_apply(const void* x, void* out, long long n, int dtype, const b200_dropout_t* drop, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(drop != nullptr && n > 0, "dropout_apply: bad arguments");
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  if (dtype == B200_BF16)
+    dropout_apply_kernel<bf16><<<(int)blocks, 256, 0, stream>>>((const bf16*)x, (bf16*)out, n, drop->rng_state, drop->p, drop->site);
+  else
+    dropout_apply_kernel<float><<<(int)blocks, 256, 0, stream>>>((const float*)x, (float*)out, n, drop->rng_state, drop->p, drop->site);
+  B200_LAUNCH_CHECK("dropout_apply_kernel");
+  count_launch();
+  return 0;
+}
 
 int b200_init(int device) {
   B200_CUDA(cudaSetDevice(device));
@@ -159,6 +194,15 @@ int b200_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long lon
   return 0;
 }
 
+int b200_dropout_mask(const b200_dropout_t* drop, long long n, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(drop != nullptr && n > 0, "dropout_mask: bad arguments");
+  dropout_mask_kernel<<<256, 256, 0, stream>>>(drop->rng_state, drop->p, drop->site, n, out);
+  B200_LAUNCH_CHECK("dropout_mask_kernel");
+  count_launch();
+  return 0;
+}
+
 size_t b200_colsum_ws(int R, int N) {
   const size_t blocks = (size_t)(R + CS_ROWS - 1) / CS_ROWS;
   return blocks * (size_t)N * sizeof(float);
@@ -195,7 +239,7 @@ static int check_epi(int epi, int act, const void* aux_in, int out_dtype) {
 
 int b200_gemm(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, void* out, int ldo,
               int M, int N, int K, int dtype, int out_dtype, const float* bias, int epi, int act,
-              const void* aux_in, void* aux_out, int ld_aux, void* stream_) {
+              const void* aux_in, void* aux_out, int ld_aux, const b200_dropout_t* drop, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   B200_CHECK_ARG(dtype == B200_F32 || dtype == B200_BF16, "gemm: bad dtype %d", dtype);
@@ -205,6 +249,7 @@ int b200_gemm(const void* A, int lda, int a_layout, const void* B, int ldb, int 
   a.M = M; a.N = N; a.K = K; a.mode = GEMM_DENSE; a.epi = epi; a.act = act;
   a.out_f32 = (out_dtype == B200_F32); a.ldo = ldo; a.ld_aux = ld_aux; a.out = out; a.aux_in = aux_in;
   a.aux_out = aux_out; a.bias = bias; a.k_splits = 1;
+  if (drop != nullptr && drop->p > 0.f) { a.drop_state = drop->rng_state; a.drop_p = drop->p; a.drop_site = drop->site; }
   const int m_tiles = (M + B200_GROUP_TILE - 1) / B200_GROUP_TILE;
   if (epi == B200_EPI_ACCUM)  // accumulate into a zeroed buffer (split-K partial sums are added atomically)
     B200_CUDA(cudaMemsetAsync(out, 0, (size_t)M * ldo * sizeof(float), stream));
@@ -219,7 +264,7 @@ int b200_gemm(const void* A, int lda, int a_layout, const void* B, int ldb, int 
 
 int b200_ggemm(const void* A, int lda, const void* B, int b_layout, void* out, int ldo, int R, int N, int K, int G,
                const int32_t* tile_group, int dtype, int out_dtype, const float* bias, int epi, int act,
-               const void* aux_in, void* aux_out, int ld_aux, void* stream_) {
+               const void* aux_in, void* aux_out, int ld_aux, const b200_dropout_t* drop, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(R > 0 && R % B200_GROUP_TILE == 0, "ggemm: R=%d must be a positive multiple of %d", R,
                  B200_GROUP_TILE);
@@ -231,6 +276,7 @@ int b200_ggemm(const void* A, int lda, const void* B, int b_layout, void* out, i
   a.M = R; a.N = N; a.K = K; a.mode = GEMM_GROUP_ROWS; a.epi = epi; a.act = act;
   a.out_f32 = (out_dtype == B200_F32); a.ldo = ldo; a.ld_aux = ld_aux; a.out = out; a.aux_in = aux_in;
   a.aux_out = aux_out; a.bias = bias; a.tile_group = tile_group; a.k_splits = 1;
+  if (drop != nullptr && drop->p > 0.f) { a.drop_state = drop->rng_state; a.drop_p = drop->p; a.drop_site = drop->site; }
   a.b_group_rows = (b_layout == B200_LAYOUT_K) ? N : K;
   a.b_group_elems = (long long)N * K;
   const int m_tiles = R / B200_GROUP_TILE;

@@ -21,8 +21,10 @@ template <typename T>
 __global__ void __launch_bounds__(FA_WARPS * 32)
 attn_fwd_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int ldk, const T* __restrict__ v, int ldv,
                 const uint8_t* __restrict__ key_pad, T* __restrict__ o, int ldo, float* __restrict__ lse, int H, int Tq,
-                int S, int dh, float scale) {
+                int S, int dh, float scale, const unsigned long long* drop_state, float drop_p, unsigned int drop_site) {
   extern __shared__ float sm[];
+  const DropState ds = drop_load(drop_state, drop_p, drop_site);
+  const unsigned long long s_pad = (unsigned long long)((S + 127) / 128) * 128;   // attention dropout index pitch
   const int LD = dh + 1;
   float* Ks = sm;                          // [FA_SC][LD]
   float* Vs = Ks + FA_SC * LD;             // [FA_SC][LD]
@@ -84,7 +86,10 @@ attn_fwd_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int l
 #pragma unroll
       for (int jj = 0; jj < FA_SC / 32; ++jj) {
         const float p = (sj[jj] == -INFINITY) ? 0.f : __expf(sj[jj] - m_new);
-        ps[lane + 32 * jj] = p;
+        float keep = 1.f;
+        if (ds.on)
+          keep = drop_scale1(ds, ((unsigned long long)blockIdx.x * Tq + t) * s_pad + (unsigned long long)(s0 + lane + 32 * jj));
+        ps[lane + 32 * jj] = p * keep;   // dropped probabilities feed P.V; the normaliser uses the undropped sum
         psum += p;
       }
       psum = warp_sum(psum);
@@ -158,8 +163,11 @@ __global__ void __launch_bounds__(256)
 attn_bwd_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int ldk, const T* __restrict__ v, int ldv,
                 const uint8_t* __restrict__ key_pad, const T* __restrict__ o, int ldo, const T* __restrict__ d_o,
                 int lddo, const float* __restrict__ lse, T* __restrict__ dq, int lddq, T* __restrict__ dk, int lddk,
-                T* __restrict__ dv, int lddv, int H, int Tq, int S, int dh, float scale) {
+                T* __restrict__ dv, int lddv, int H, int Tq, int S, int dh, float scale,
+                const unsigned long long* drop_state, float drop_p, unsigned int drop_site) {
   extern __shared__ float sm[];
+  const DropState ds = drop_load(drop_state, drop_p, drop_site);
+  const unsigned long long s_pad = (unsigned long long)((S + 127) / 128) * 128;
   const int LD = dh + 1, LS = BT + 1;
   float* Qs = sm;                 // [BT][LD]
   float* dOs = Qs + BT * LD;      // [BT][LD]
@@ -242,9 +250,12 @@ attn_bwd_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int l
       float p = 0.f;
       if (t < Tq && s < S && !(key_pad != nullptr && key_pad[(long long)b * S + s]))
         p = __expf(Ps[r * LS + c] - lses[r]);
-      const float ds = p * (dPs[r * LS + c] - delta[r]);
-      Ps[r * LS + c] = p;
-      dPs[r * LS + c] = ds;
+      float keep = 1.f;
+      if (ds.on && p != 0.f)
+        keep = drop_scale1(ds, ((unsigned long long)blockIdx.x * Tq + t) * s_pad + (unsigned long long)s);
+      const float dsv = p * (dPs[r * LS + c] * keep - delta[r]);
+      Ps[r * LS + c] = p * keep;
+      dPs[r * LS + c] = dsv;
     }
     __syncthreads();
     if (PASS == 0) {
@@ -287,11 +298,11 @@ int set_smem(K kern, size_t bytes) {
 bool attn_tc_supported(int T, int S, int dh, int ldq, int ldk, int ldv, const void* q, const void* k, const void* v);
 int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
                        void* o, int ldo, float* lse, int B, int H, int T, int S, int dh, float scale,
-                       cudaStream_t stream);
+                       const unsigned long long* drop_state, float drop_p, unsigned int drop_site, cudaStream_t stream);
 int launch_attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
                        const void* o, int ldo, const void* d_o, int lddo, const float* lse, void* dq, int lddq, void* dk,
                        int lddk, void* dv, int lddv, int B, int H, int T, int S, int dh, float scale,
-                       cudaStream_t stream);
+                       const unsigned long long* drop_state, float drop_p, unsigned int drop_site, cudaStream_t stream);
 
 static bool use_tc_attention() {
   static int v = -1;
@@ -309,25 +320,30 @@ extern "C" {
 
 int b200_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
                   void* o, int ldo, float* lse, int B, int H, int T, int S, int dh, float scale, int dtype,
-                  void* stream_) {
+                  const b200_dropout_t* drop, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const bool don = drop != nullptr && drop->p > 0.f;
+  const unsigned long long* dst = don ? drop->rng_state : nullptr;
+  const float dpp = don ? drop->p : 0.f;
+  const unsigned int dsite = don ? drop->site : 0u;
   B200_CHECK_ARG(B > 0 && H > 0 && T > 0 && S > 0 && dh > 0 && dh <= 128 && dh % 4 == 0,
                  "attn_fwd: bad shape B=%d H=%d T=%d S=%d dh=%d (dh<=128, dh%%4==0)", B, H, T, S, dh);
   if (dtype == B200_BF16 && use_tc_attention() && attn_tc_supported(T, S, dh, ldq, ldk, ldv, q, k, v) &&
       ldo % 8 == 0 && ((uintptr_t)o & 15) == 0)
-    return launch_attn_fwd_tc(q, ldq, k, ldk, v, ldv, key_pad, o, ldo, lse, B, H, T, S, dh, scale, stream);
+    return launch_attn_fwd_tc(q, ldq, k, ldk, v, ldv, key_pad, o, ldo, lse, B, H, T, S, dh, scale, dst, dpp, dsite,
+                              stream);
   dim3 grid(B * H, (T + FA_TQ - 1) / FA_TQ);
   const size_t smem = fwd_smem(dh);
   if (dtype == B200_BF16) {
     if (int rc = set_smem(attn_fwd_kernel<bf16>, smem)) return rc;
     attn_fwd_kernel<bf16><<<grid, FA_WARPS * 32, smem, stream>>>((const bf16*)q, ldq, (const bf16*)k, ldk,
                                                                  (const bf16*)v, ldv, key_pad, (bf16*)o, ldo, lse, H, T,
-                                                                 S, dh, scale);
+                                                                 S, dh, scale, dst, dpp, dsite);
   } else {
     if (int rc = set_smem(attn_fwd_kernel<float>, smem)) return rc;
     attn_fwd_kernel<float><<<grid, FA_WARPS * 32, smem, stream>>>((const float*)q, ldq, (const float*)k, ldk,
                                                                   (const float*)v, ldv, key_pad, (float*)o, ldo, lse, H,
-                                                                  T, S, dh, scale);
+                                                                  T, S, dh, scale, dst, dpp, dsite);
   }
   B200_LAUNCH_CHECK("attn_fwd_kernel");
   count_launch();
@@ -337,15 +353,19 @@ int b200_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v,
 int b200_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
                   const void* o, int ldo, const void* d_o, int lddo, const float* lse, void* dq, int lddq, void* dk,
                   int lddk, void* dv, int lddv, int B, int H, int T, int S, int dh, float scale, int dtype,
-                  void* stream_) {
+                  const b200_dropout_t* drop, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const bool don = drop != nullptr && drop->p > 0.f;
+  const unsigned long long* dst = don ? drop->rng_state : nullptr;
+  const float dpp = don ? drop->p : 0.f;
+  const unsigned int dsite = don ? drop->site : 0u;
   B200_CHECK_ARG(B > 0 && H > 0 && T > 0 && S > 0 && dh > 0 && dh <= 128 && dh % 4 == 0,
                  "attn_bwd: bad shape B=%d H=%d T=%d S=%d dh=%d (dh<=128, dh%%4==0)", B, H, T, S, dh);
   if (dtype == B200_BF16 && use_tc_attention() && attn_tc_supported(T, S, dh, ldq, ldk, ldv, q, k, v) &&
       ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 &&
       (((uintptr_t)o | (uintptr_t)d_o | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0)
     return launch_attn_bwd_tc(q, ldq, k, ldk, v, ldv, key_pad, o, ldo, d_o, lddo, lse, dq, lddq, dk, lddk, dv, lddv, B,
-                              H, T, S, dh, scale, stream);
+                              H, T, S, dh, scale, dst, dpp, dsite, stream);
   const int bt = bwd_smem(dh, 64) <= 200 * 1024 ? 64 : 32;
   const size_t smem = bwd_smem(dh, bt);
   dim3 g0(B * H, (S + bt - 1) / bt), g1(B * H, (T + bt - 1) / bt);
@@ -355,11 +375,11 @@ int b200_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v,
     if (int rc = set_smem(attn_bwd_kernel<TT, 1, BTV>, smem)) return rc;                                         \
     attn_bwd_kernel<TT, 0, BTV><<<g0, 256, smem, stream>>>(                                                      \
         (const TT*)q, ldq, (const TT*)k, ldk, (const TT*)v, ldv, key_pad, (const TT*)o, ldo, (const TT*)d_o,     \
-        lddo, lse, (TT*)dq, lddq, (TT*)dk, lddk, (TT*)dv, lddv, H, T, S, dh, scale);                             \
+        lddo, lse, (TT*)dq, lddq, (TT*)dk, lddk, (TT*)dv, lddv, H, T, S, dh, scale, dst, dpp, dsite);          \
     B200_LAUNCH_CHECK("attn_bwd_kernel<0>");                                                                     \
     attn_bwd_kernel<TT, 1, BTV><<<g1, 256, smem, stream>>>(                                                      \
         (const TT*)q, ldq, (const TT*)k, ldk, (const TT*)v, ldv, key_pad, (const TT*)o, ldo, (const TT*)d_o,     \
-        lddo, lse, (TT*)dq, lddq, (TT*)dk, lddk, (TT*)dv, lddv, H, T, S, dh, scale);                             \
+        lddo, lse, (TT*)dq, lddq, (TT*)dk, lddk, (TT*)dv, lddv, H, T, S, dh, scale, dst, dpp, dsite);          \
     B200_LAUNCH_CHECK("attn_bwd_kernel<1>");                                                                     \
   } while (0)
   if (dtype == B200_BF16) {

@@ -33,6 +33,8 @@ struct AttnTcArgs {
   bf16* dq; int lddq;
   bf16* dk; int lddk;
   bf16* dv; int lddv;
+  // attention-probability dropout; element index = ((b*H+h)*T + t) * (ntiles*128) + s
+  const unsigned long long* drop_state; float drop_p; unsigned int drop_site;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -179,6 +181,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   }
   const float sl2 = a.scale * LOG2E;
   const float m_s = (m == -INFINITY) ? 0.f : m * sl2;
+  const DropState ds = drop_load(a.drop_state, a.drop_p, a.drop_site);
+  const unsigned long long drow = ((unsigned long long)blockIdx.x * a.T + r) * (unsigned long long)(((a.S + ROWS - 1) / ROWS) * ROWS);
   float l = 0.f;
   for (int j = 0; j < NT; ++j) {
     const int n_valid = min(ROWS, a.S - j * ROWS);
@@ -196,6 +200,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
         const float pr = __bfloat162float(__float2bfloat16_rn(p));
         l += pr;
         v[i] = pr;
+      }
+      if (ds.on) {   // dropped probabilities feed P.V; the normaliser keeps the undropped sum
+#pragma unroll
+        for (int i4 = 0; i4 < 32; i4 += 4) {
+          float sc[4];
+          drop_scales4(ds, (drow + (unsigned long long)(j * ROWS + c * 32 + i4)) >> 2, sc);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[i4 + q] *= sc[q];
+        }
       }
       store_row32(pP, r, c, v);
     }
@@ -312,6 +325,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   }
   const float sl2 = a.scale * LOG2E;
   const uint8_t* kp = a.key_pad ? a.key_pad + (long long)b * a.S : nullptr;
+  const DropState ds = drop_load(a.drop_state, a.drop_p, a.drop_site);
+  const unsigned long long drow = ((unsigned long long)blockIdx.x * a.T + r) * (unsigned long long)(ntiles * ROWS);
 
   for (int j = 0; j < ntiles; ++j) {
     const int n_valid = min(ROWS, a.S - j * ROWS);
@@ -344,13 +359,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
         ld32(lane_base + C_S + c * 32, s);
         ld32(lane_base + C_DP + c * 32, dp);
       }
+      float keep[32];
+#pragma unroll
+      for (int i4 = 0; i4 < 32; i4 += 4) {
+        float sc[4] = {1.f, 1.f, 1.f, 1.f};
+        if (ds.on) drop_scales4(ds, (drow + (unsigned long long)(j * ROWS + c * 32 + i4)) >> 2, sc);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) keep[i4 + q] = sc[q];
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int col = c * 32 + i;
         const bool ok = row_ok && col < n_valid && !(kp && kp[j * ROWS + col]);
         const float p = ok ? ex2(fmaf(s[i], sl2, -lse_l2)) : 0.f;
-        s[i] = p;
-        dp[i] = ok ? p * (dp[i] - delta) * a.scale : 0.f;
+        s[i] = p * keep[i];                                               // dropped P feeds dV = P^T dO
+        dp[i] = ok ? p * (dp[i] * keep[i] - delta) * a.scale : 0.f;       // dS = P (dP*mask/(1-p) - delta)
       }
       // columns >= n16 are written as zeros too: the dV/dK products read all 128 columns of these tiles (M dim)
       store_row32(pP, r, c, s);
@@ -438,7 +461,7 @@ bool attn_tc_supported(int T, int S, int dh, int ldq, int ldk, int ldv, const vo
 
 int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
                        void* o, int ldo, float* lse, int B, int H, int T, int S, int dh, float scale,
-                       cudaStream_t stream) {
+                       const unsigned long long* drop_state, float drop_p, unsigned int drop_site, cudaStream_t stream) {
   CUtensorMap qm, km, vm;
   const long long cols = (long long)H * dh;
   if (int rc = make_tma_map_bf16(&qm, q, cols, (long long)B * T, ldq, ROWS)) return rc;
@@ -447,6 +470,7 @@ int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
   AttnTcArgs a{};
   a.B = B; a.H = H; a.T = T; a.S = S; a.dh = dh; a.scale = scale; a.key_pad = key_pad;
   a.o = (bf16*)o; a.ldo = ldo; a.lse = lse;
+  a.drop_state = drop_state; a.drop_p = drop_p; a.drop_site = drop_site;
   const size_t smem = fwd_smem(dh);
   const int nt = (S + ROWS - 1) / ROWS;
   static bool configured = false;
@@ -465,7 +489,7 @@ int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
 int launch_attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
                        const void* o, int ldo, const void* d_o, int lddo, const float* lse, void* dq, int lddq, void* dk,
                        int lddk, void* dv, int lddv, int B, int H, int T, int S, int dh, float scale,
-                       cudaStream_t stream) {
+                       const unsigned long long* drop_state, float drop_p, unsigned int drop_site, cudaStream_t stream) {
   CUtensorMap qm, km, vm, dom;
   const long long cols = (long long)H * dh;
   if (int rc = make_tma_map_bf16(&qm, q, cols, (long long)B * T, ldq, ROWS)) return rc;
@@ -477,6 +501,7 @@ int launch_attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
   a.lse = const_cast<float*>(lse);
   a.o_in = (const bf16*)o; a.ldo_in = ldo; a.d_o = (const bf16*)d_o; a.lddo = lddo;
   a.dq = (bf16*)dq; a.lddq = lddq; a.dk = (bf16*)dk; a.lddk = lddk; a.dv = (bf16*)dv; a.lddv = lddv;
+  a.drop_state = drop_state; a.drop_p = drop_p; a.drop_site = drop_site;
   const size_t smem = bwd_smem(dh);
   static bool configured = false;
   if (!configured) {

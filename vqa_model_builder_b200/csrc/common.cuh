@@ -153,13 +153,38 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr, uint32_
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// keep-scale for element `idx`: 0 if dropped else 1/(1-p).  p == 0 -> 1.
-__device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t stream, uint64_t idx, float p) {
-  if (p <= 0.f) return 1.f;
-  uint4 r = philox4x32(seed, idx >> 2, stream);
-  uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
-  float u = (float)(w >> 8) * (1.0f / 16777216.0f);
-  return u < p ? 0.f : 1.0f / (1.0f - p);
+// Dropout state resolved once per kernel from the ABI struct (device memory read for seed / offset).
+struct DropState {
+  unsigned long long seed, off;
+  float p, inv_keep;
+  unsigned int site;
+  bool on;
+};
+__device__ __forceinline__ DropState drop_load(const unsigned long long* rng_state, float p, unsigned int site) {
+  DropState d;
+  d.on = (rng_state != nullptr) && (p > 0.f);
+  d.p = p;
+  d.inv_keep = d.on ? 1.0f / (1.0f - p) : 1.0f;
+  d.site = site;
+  d.seed = d.on ? rng_state[0] : 0ull;
+  d.off = d.on ? rng_state[1] : 0ull;
+  return d;
+}
+// keep-scales of the 4 elements 4*idx4 .. 4*idx4+3
+__device__ __forceinline__ void drop_scales4(const DropState& d, unsigned long long idx4, float (&s)[4]) {
+  const uint4 r = philox4x32(d.seed ^ (d.off * 0x9E3779B97F4A7C15ull), idx4, d.site);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float u = (float)(w[i] >> 8) * (1.0f / 16777216.0f);
+    s[i] = u < d.p ? 0.f : d.inv_keep;
+  }
+}
+__device__ __forceinline__ float drop_scale1(const DropState& d, unsigned long long idx) {
+  float s[4];
+  drop_scales4(d, idx >> 2, s);
+  const int k = (int)(idx & 3);
+  return k == 0 ? s[0] : k == 1 ? s[1] : k == 2 ? s[2] : s[3];
 }
 
 }  // namespace b200

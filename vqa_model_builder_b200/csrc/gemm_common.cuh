@@ -25,7 +25,27 @@ struct GemmArgs {
   const void* A; const void* B;
   long long sa_m, sa_k, sb_n, sb_k;  // element strides
   long long b_group_elems;           // GROUP_ROWS: elements per group in B
+  // dropout on the activation output (EPI_ACT) / its backward (EPI_DACT); element index = row*ldo + col
+  const unsigned long long* drop_state; float drop_p; unsigned int drop_site;
 };
+
+// multiply CNT consecutive columns (col0 % 4 == 0, CNT % 4 == 0) of one row by their keep-scales
+template <int CNT>
+__device__ __forceinline__ void apply_dropout_row(const DropState& d, long long row, int ldo, int col0, float (&v)[CNT]) {
+  const unsigned long long base = (unsigned long long)row * (unsigned long long)ldo + (unsigned long long)col0;
+  if ((base & 3ull) == 0) {
+#pragma unroll
+    for (int j = 0; j < CNT; j += 4) {
+      float sc[4];
+      drop_scales4(d, (base + j) >> 2, sc);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[j + q] *= sc[q];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) v[j] *= drop_scale1(d, base + j);
+  }
+}
 
 // Apply the epilogue to CNT consecutive columns [col0, col0+CNT) of one output row and store them.
 // T = activation storage type (bf16 or float) used for aux tensors and non-fp32 outputs.
@@ -66,6 +86,10 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& p, int group, lon
     }
 #pragma unroll
     for (int j = 0; j < CNT; ++j) acc[j] = act_fwd(acc[j], p.act);
+    if (p.drop_state != nullptr && p.drop_p > 0.f) {
+      const DropState ds = drop_load(p.drop_state, p.drop_p, p.drop_site);
+      apply_dropout_row<CNT>(ds, row, p.ldo, col0, acc);
+    }
   } else if (p.epi == B200_EPI_ADD || p.epi == B200_EPI_DACT) {
     const T* ai = reinterpret_cast<const T*>(p.aux_in) + abase;
     float aux[CNT];
@@ -82,11 +106,19 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& p, int group, lon
       for (int j = 0; j < CNT; ++j) aux[j] = (col0 + j < p.N) ? to_f32<T>(ai[j]) : 0.f;
     }
     if (p.epi == B200_EPI_ADD) {
+      if (p.drop_state != nullptr && p.drop_p > 0.f) {   // out = dropout(acc + bias) + residual
+        const DropState ds = drop_load(p.drop_state, p.drop_p, p.drop_site);
+        apply_dropout_row<CNT>(ds, row, p.ldo, col0, acc);
+      }
 #pragma unroll
       for (int j = 0; j < CNT; ++j) acc[j] += aux[j];
     } else {
 #pragma unroll
       for (int j = 0; j < CNT; ++j) acc[j] *= act_bwd(aux[j], p.act);
+      if (p.drop_state != nullptr && p.drop_p > 0.f) {
+        const DropState ds = drop_load(p.drop_state, p.drop_p, p.drop_site);
+        apply_dropout_row<CNT>(ds, row, p.ldo, col0, acc);
+      }
     }
   }
 

@@ -330,6 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         (p.ld_aux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0) &&
                         (p.mode != GEMM_GROUP_WGRAD || p.out_group_elems % 4 == 0);
+    const DropState drop = drop_load(p.drop_state, p.drop_p, p.drop_site);
     int acc_it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileInfo t = get_tile<BN, B_MN>(p, tile, m_tiles, n_tiles);
@@ -377,14 +378,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (p.epi == B200_EPI_ACT) {
             if (p.aux_out != nullptr) stage_store_tile<2>(stg, lane, v, p.aux_out, p.ld_aux, row0, rows_ok, col0);
             tile_act_fwd(v, p.act);
+            if (drop.on) apply_dropout_row<32>(drop, my_row, p.ldo, col0, v);
           } else if (p.epi == B200_EPI_ADD || p.epi == B200_EPI_DACT) {
             float aux[32];
             stage_load_tile_bf16(stg, lane, aux, p.aux_in, p.ld_aux, row0, rows_ok, col0);
             if (p.epi == B200_EPI_ADD) {
+              if (drop.on) apply_dropout_row<32>(drop, my_row, p.ldo, col0, v);   // dropout(acc+bias) + residual
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] += aux[j];
             } else {
               tile_act_bwd(v, aux, p.act);
+              if (drop.on) apply_dropout_row<32>(drop, my_row, p.ldo, col0, v);
             }
           }
           if (p.epi == B200_EPI_ACCUM)

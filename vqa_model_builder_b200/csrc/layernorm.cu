@@ -9,14 +9,58 @@ namespace {
 constexpr int LN_WARPS = 8;
 constexpr int LN_ROWS_PER_BLOCK = 8;  // workspace bound: the backward never uses fewer than 8 rows per block
 
+// multiply a register-resident row by its dropout keep-scales (element index = r*D + d)
+template <typename T, int NV>
+__device__ __forceinline__ void drop_row(RowRegs<T, NV>& row, const DropState& ds, int r, int D, int lane) {
+  constexpr int VT = Vec16<T>::N;
+  const int nv = D / VT;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int vi = lane + 32 * j;
+    if (vi < nv) {
+      const unsigned long long base = (unsigned long long)r * D + (unsigned long long)vi * VT;
+#pragma unroll
+      for (int u = 0; u < VT; u += 4) {
+        float sc[4];
+        drop_scales4(ds, (base + u) >> 2, sc);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) row.v[j][u + q] *= sc[q];
+      }
+    }
+  }
+}
+
+// row = drop?(x) + drop?(res)
+template <typename T, int NV>
+__device__ __forceinline__ void load_sum_row(RowRegs<T, NV>& row, const T* x, const T* res, const DropState& ds,
+                                             int drop_target, int r, int D, int lane) {
+  row.load(x + (long long)r * D, D, lane);
+  if (ds.on && drop_target == 1) drop_row<T, NV>(row, ds, r, D, lane);
+  if (res != nullptr) {
+    if (ds.on && drop_target == 2) {
+      RowRegs<T, NV> rr;
+      rr.load(res + (long long)r * D, D, lane);
+      drop_row<T, NV>(rr, ds, r, D, lane);
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int u = 0; u < Vec16<T>::N; ++u) row.v[j][u] += rr.v[j][u];
+    } else {
+      row.axpy(res + (long long)r * D, 1.f, D, lane);
+    }
+  }
+}
+
 template <typename T, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
                   const float* __restrict__ beta, const int* __restrict__ tile_group, float eps,
-                  T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int R, int D) {
+                  T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int R, int D,
+                  const unsigned long long* drop_state, float drop_p, unsigned int drop_site, int drop_target) {
   constexpr int VT = Vec16<T>::N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / VT;
+  const DropState ds = drop_load(drop_state, drop_p, drop_site);
   const int r = blockIdx.x * LN_WARPS + warp;
   if (r >= R) return;
   int g = 0;
@@ -25,8 +69,7 @@ add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const floa
     if (g < 0) return;
   }
   RowRegs<T, NV> row;
-  row.load(x + (long long)r * D, D, lane);
-  if (res != nullptr) row.axpy(res + (long long)r * D, 1.f, D, lane);
+  load_sum_row<T, NV>(row, x, res, ds, drop_target, r, D, lane);
   const float mean = row.sum(D, lane) / D;
   const float var = row.sumsq_centered(mean, D, lane) / D;
   const float rstd = rsqrtf(var + eps);
@@ -59,9 +102,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                   const float* __restrict__ gamma, const int* __restrict__ tile_group, T* __restrict__ dsum,
-                  float* __restrict__ part, int R, int D, int rpw) {
+                  float* __restrict__ part, int R, int D, int rpw, const unsigned long long* drop_state, float drop_p,
+                  unsigned int drop_site, int drop_target, T* __restrict__ d_dropped) {
   constexpr int VT = Vec16<T>::N;
   extern __shared__ float red[];  // [LN_WARPS][2][D]
+  const DropState ds = drop_load(drop_state, drop_p, drop_site);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / VT;
   // per-warp dgamma / dbeta accumulators live in shared memory (each lane owns its own 16-byte slots, so no
@@ -84,8 +129,7 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
     const int r = row0 + i * LN_WARPS + warp;   // interleaved so the 8 warps stream adjacent rows
     if (r >= R) break;
     RowRegs<T, NV> xr, gr;
-    xr.load(x + (long long)r * D, D, lane);
-    if (res != nullptr) xr.axpy(res + (long long)r * D, 1.f, D, lane);
+    load_sum_row<T, NV>(xr, x, res, ds, drop_target, r, D, lane);
     gr.load(dy + (long long)r * D, D, lane);
     const float mean = mean_in[r], rstd = rstd_in[r];
     float s1 = 0.f, s2 = 0.f;
@@ -126,6 +170,10 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
 #pragma unroll
       for (int u = 0; u < VT; ++u) gr.v[j][u] = rstd * (gr.v[j][u] - s1 - xr.v[j][u] * s2);
     gr.store(dsum + (long long)r * D, D, lane);
+    if (ds.on && d_dropped != nullptr) {   // gradient of the operand that went through dropout
+      drop_row<T, NV>(gr, ds, r, D, lane);
+      gr.store(d_dropped + (long long)r * D, D, lane);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
@@ -215,18 +263,22 @@ extern "C" {
 
 int b200_add_ln_fwd(const void* x, const void* res, const float* gamma, const float* beta,
                     const int32_t* tile_group, float eps, void* y, float* mean, float* rstd, int R, int D, int dtype,
-                    void* stream_) {
+                    const b200_dropout_t* drop, int drop_target, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(R > 0 && D > 0, "add_ln_fwd: bad shape R=%d D=%d", R, D);
+  const bool don = drop != nullptr && drop->p > 0.f && drop_target != 0;
+  const unsigned long long* dst = don ? drop->rng_state : nullptr;
+  const float dp = don ? drop->p : 0.f;
+  const unsigned int dsite = don ? drop->site : 0u;
   const int blocks = (R + LN_WARPS - 1) / LN_WARPS;
   if (dtype == B200_BF16) {
     B200_CHECK_ARG(RowRegs<bf16>::supported(D), "add_ln_fwd: D=%d unsupported for bf16 (need D%%8==0, D<=2048)", D);
     B200_NV_SWITCH(row_nv<bf16>(D), add_ln_fwd_kernel<bf16, NV><<<blocks, LN_WARPS * 32, 0, stream>>>(
-        (const bf16*)x, (const bf16*)res, gamma, beta, tile_group, eps, (bf16*)y, mean, rstd, R, D));
+        (const bf16*)x, (const bf16*)res, gamma, beta, tile_group, eps, (bf16*)y, mean, rstd, R, D, dst, dp, dsite, drop_target));
   } else {
     B200_CHECK_ARG(RowRegs<float>::supported(D), "add_ln_fwd: D=%d unsupported for fp32 (need D%%4==0, D<=1024)", D);
     B200_NV_SWITCH(row_nv<float>(D), add_ln_fwd_kernel<float, NV><<<blocks, LN_WARPS * 32, 0, stream>>>(
-        (const float*)x, (const float*)res, gamma, beta, tile_group, eps, (float*)y, mean, rstd, R, D));
+        (const float*)x, (const float*)res, gamma, beta, tile_group, eps, (float*)y, mean, rstd, R, D, dst, dp, dsite, drop_target));
   }
   B200_LAUNCH_CHECK("add_ln_fwd_kernel");
   count_launch();
@@ -240,9 +292,14 @@ size_t b200_add_ln_bwd_ws(int R, int D) {
 
 int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float* mean, const float* rstd,
                     const float* gamma, const int32_t* tile_group, int G, void* dsum, float* dgamma, float* dbeta,
-                    int R, int D, int dtype, void* workspace, size_t workspace_bytes, void* stream_) {
+                    int R, int D, int dtype, const b200_dropout_t* drop, int drop_target, void* d_dropped,
+                    void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(R > 0 && D > 0 && G > 0, "add_ln_bwd: bad shape R=%d D=%d G=%d", R, D, G);
+  const bool don = drop != nullptr && drop->p > 0.f && drop_target != 0;
+  const unsigned long long* dst = don ? drop->rng_state : nullptr;
+  const float dp = don ? drop->p : 0.f;
+  const unsigned int dsite = don ? drop->site : 0u;
   B200_CHECK_ARG(workspace_bytes >= b200_add_ln_bwd_ws(R, D), "add_ln_bwd: workspace too small");
   const int rpw = ln_bwd_rpw(R);
   const int rows_per_block = LN_WARPS * rpw;
@@ -256,7 +313,8 @@ int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float*
       if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<bf16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       add_ln_bwd_kernel<bf16, NV><<<blocks, LN_WARPS * 32, smem, stream>>>(
-          (const bf16*)dy, (const bf16*)x, (const bf16*)res, mean, rstd, gamma, tile_group, (bf16*)dsum, part, R, D, rpw);
+          (const bf16*)dy, (const bf16*)x, (const bf16*)res, mean, rstd, gamma, tile_group, (bf16*)dsum, part, R, D, rpw,
+          dst, dp, dsite, drop_target, (bf16*)d_dropped);
     });
   } else {
     B200_CHECK_ARG(RowRegs<float>::supported(D), "add_ln_bwd: D=%d unsupported for fp32", D);
@@ -264,7 +322,8 @@ int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float*
       if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<float, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       add_ln_bwd_kernel<float, NV><<<blocks, LN_WARPS * 32, smem, stream>>>(
-          (const float*)dy, (const float*)x, (const float*)res, mean, rstd, gamma, tile_group, (float*)dsum, part, R, D, rpw);
+          (const float*)dy, (const float*)x, (const float*)res, mean, rstd, gamma, tile_group, (float*)dsum, part, R, D, rpw,
+          dst, dp, dsite, drop_target, (float*)d_dropped);
     });
   }
   B200_LAUNCH_CHECK("add_ln_bwd_kernel");

@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..runtime import SlabOwner, resolve_compute_dtype
+from ..runtime import DropCtx, SlabOwner, alloc_sites, resolve_compute_dtype
 from . import blocks
 
 
@@ -49,13 +49,17 @@ class CrossAttentionBlock(nn.Module):
         self.t2v_norm2 = nn.LayerNorm(dim)
         self.t2v_ffn = mlp()
 
-    def _block(self, v2, t2, B, V, T, vpad_u8, tpad_u8, slab):
-        a = blocks.cross_attention(t2, v2, B, T, V, self.v2t_attention, slab, vpad_u8)
+    SITES = 6   # per direction: attention probabilities, ffn inner, ffn output
+
+    def _block(self, v2, t2, B, V, T, vpad_u8, tpad_u8, slab, dc, k0=0):
+        a = blocks.cross_attention(t2, v2, B, T, V, self.v2t_attention, slab, vpad_u8, drop_attn=dc.site(k0 + 0))
         t2 = blocks.add_ln(t2, a, self.v2t_norm1)
-        t2 = blocks.add_ln(t2, blocks.ffn(t2, self.v2t_ffn[0], self.v2t_ffn[3], slab), self.v2t_norm2)
-        a = blocks.cross_attention(v2, t2, B, V, T, self.t2v_attention, slab, tpad_u8)
+        f = blocks.ffn(t2, self.v2t_ffn[0], self.v2t_ffn[3], slab, drop_in=dc.site(k0 + 1))
+        t2 = blocks.add_ln(t2, f, self.v2t_norm2, dc.site(k0 + 2))
+        a = blocks.cross_attention(v2, t2, B, V, T, self.t2v_attention, slab, tpad_u8, drop_attn=dc.site(k0 + 3))
         v2 = blocks.add_ln(v2, a, self.t2v_norm1)
-        v2 = blocks.add_ln(v2, blocks.ffn(v2, self.t2v_ffn[0], self.t2v_ffn[3], slab), self.t2v_norm2)
+        f = blocks.ffn(v2, self.t2v_ffn[0], self.t2v_ffn[3], slab, drop_in=dc.site(k0 + 4))
+        v2 = blocks.add_ln(v2, f, self.t2v_norm2, dc.site(k0 + 5))
         return v2, t2
 
 
@@ -79,6 +83,8 @@ class CrossAttentionFusion(SlabOwner, BaseFusion):
                                           nn.Dropout(dropout), nn.Linear(output_dim, output_dim),
                                           nn.LayerNorm(output_dim))
         self.pooling = nn.AdaptiveAvgPool1d(1)
+        self.dropout_p = float(dropout)
+        self._sites = alloc_sites(CrossAttentionBlock.SITES * num_layers)
 
     def _slab_groups(self):
         return blocks.param_groups(self)
@@ -98,8 +104,9 @@ class CrossAttentionFusion(SlabOwner, BaseFusion):
             t2 = blocks.linear(t2, self.text_projection, slab)
         vpad = blocks.pad_mask_u8(~vision_mask.bool()) if vision_mask is not None else None
         tpad = blocks.pad_mask_u8(~text_mask.bool()) if text_mask is not None else None
-        for layer in self.cross_attention_layers:
-            v2, t2 = layer._block(v2, t2, B, V, T, vpad, tpad, slab)
+        dc = DropCtx(self.training, self.dropout_p, text_features.device, self._sites)
+        for li, layer in enumerate(self.cross_attention_layers):
+            v2, t2 = layer._block(v2, t2, B, V, T, vpad, tpad, slab, dc, li * CrossAttentionBlock.SITES)
         # mask-unaware mean pooling over tokens, as in the reference (:172-173)
         vp = v2.view(B, V, D).float().mean(dim=1)
         tp = t2.view(B, T, D).float().mean(dim=1)
@@ -114,7 +121,7 @@ class CrossAttentionFusion(SlabOwner, BaseFusion):
         fl = self.fusion_layer
         h = blocks.linear(ops.to_compute(fused.contiguous(), cdt), fl[0], slab)
         h = blocks.add_ln(h, None, fl[1])
-        h = torch.nn.functional.gelu(h)            # [B, D] elementwise between two LayerNorms
+        h = fl[3](torch.nn.functional.gelu(h))     # [B, D] elementwise (+ nn.Dropout) between two LayerNorms
         h = blocks.linear(h, fl[4], slab)
         h = blocks.add_ln(h, None, fl[5])
         return ops.to_compute(h, text_features.dtype)

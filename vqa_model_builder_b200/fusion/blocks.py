@@ -21,34 +21,38 @@ def pad_mask_u8(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return mask.to(torch.uint8).contiguous()
 
 
-def self_attention(x2, B, T, mha: nn.MultiheadAttention, slab: ParamSlab, key_pad_u8, residual=None):
-    """out_proj(softmax(q k^T / sqrt(dh) + mask) v) over x2 [B*T, D]; optional residual fused into out_proj."""
+def self_attention(x2, B, T, mha: nn.MultiheadAttention, slab: ParamSlab, key_pad_u8, residual=None, drop_attn=None,
+                   drop_out=None):
+    """out_proj(softmax(q k^T / sqrt(dh) + mask) v) over x2 [B*T, D]; optional (dropout +) residual fused into
+    out_proj."""
     cdt = x2.dtype
     qkv = ops.LinearFn.apply(x2, mha.in_proj_weight, mha.in_proj_bias, slab.compute_view(mha.in_proj_weight, cdt),
                              None)
-    ctx = ops.AttentionFn.apply(qkv, None, key_pad_u8, B, T, T, mha.num_heads, True)
+    ctx = ops.AttentionFn.apply(qkv, None, key_pad_u8, B, T, T, mha.num_heads, True, drop_attn)
     return ops.LinearFn.apply(ctx, mha.out_proj.weight, mha.out_proj.bias,
-                              slab.compute_view(mha.out_proj.weight, cdt), residual)
+                              slab.compute_view(mha.out_proj.weight, cdt), residual, drop_out)
 
 
-def cross_attention(x2, kv2, B, T, S, mha: nn.MultiheadAttention, slab: ParamSlab, key_pad_u8, residual=None):
+def cross_attention(x2, kv2, B, T, S, mha: nn.MultiheadAttention, slab: ParamSlab, key_pad_u8, residual=None,
+                    drop_attn=None):
     """Queries from x2 [B*T, D], keys/values from kv2 [B*S, D] (question -> image patches)."""
     cdt = x2.dtype
     q, kvp = ops.CrossProjFn.apply(x2, kv2, mha.in_proj_weight, mha.in_proj_bias,
                                    slab.compute_view(mha.in_proj_weight, cdt))
-    ctx = ops.AttentionFn.apply(q, kvp, key_pad_u8, B, T, S, mha.num_heads, False)
+    ctx = ops.AttentionFn.apply(q, kvp, key_pad_u8, B, T, S, mha.num_heads, False, drop_attn)
     return ops.LinearFn.apply(ctx, mha.out_proj.weight, mha.out_proj.bias,
                               slab.compute_view(mha.out_proj.weight, cdt), residual)
 
 
-def ffn(x2, lin1: nn.Linear, lin2: nn.Linear, slab: ParamSlab, act: int = ACT_GELU, residual=None):
+def ffn(x2, lin1: nn.Linear, lin2: nn.Linear, slab: ParamSlab, act: int = ACT_GELU, residual=None, drop_in=None,
+        drop_out=None):
     cdt = x2.dtype
     return ops.FFNFn.apply(x2, lin1.weight, lin1.bias, lin2.weight, lin2.bias, slab.compute_view(lin1.weight, cdt),
-                           slab.compute_view(lin2.weight, cdt), act, residual)
+                           slab.compute_view(lin2.weight, cdt), act, residual, drop_in, drop_out)
 
 
-def add_ln(x2, branch, ln: nn.LayerNorm):
-    return ops.AddLNFn.apply(x2, branch, ln.weight, ln.bias, ln.eps)
+def add_ln(x2, branch, ln: nn.LayerNorm, drop=None):
+    return ops.AddLNFn.apply(x2, branch, ln.weight, ln.bias, ln.eps, drop)
 
 
 def linear(x2, lin: nn.Linear, slab: ParamSlab, residual=None):

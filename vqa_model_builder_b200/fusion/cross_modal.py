@@ -10,7 +10,7 @@ from torch import nn
 
 from .. import ops
 from .._lib import ACT_RELU
-from ..runtime import SlabOwner, resolve_compute_dtype
+from ..runtime import DropCtx, SlabOwner, alloc_sites, resolve_compute_dtype
 from . import blocks
 
 
@@ -39,17 +39,21 @@ class CrossModalAttention(SlabOwner, nn.Module):
         self.norm2 = nn.LayerNorm(embed_dim)
         self.norm3 = nn.LayerNorm(embed_dim)
         self.dropout = nn.Dropout(dropout)
+        self.dropout_p = float(dropout)
+        self._sites = alloc_sites(self.SITES)
 
     def _slab_groups(self):
         return blocks.param_groups(self)
 
-    def _block(self, x2, kv2, B, T, S, qmask_u8, kvmask_u8, slab):
-        a = blocks.self_attention(x2, B, T, self.self_attn, slab, qmask_u8)
-        x2 = blocks.add_ln(x2, a, self.norm1)
-        c = blocks.cross_attention(x2, kv2, B, T, S, self.cross_attn, slab, kvmask_u8)
-        x2 = blocks.add_ln(x2, c, self.norm2)
-        f = blocks.ffn(x2, self.ffn[0], self.ffn[3], slab)
-        return blocks.add_ln(x2, f, self.norm3)
+    SITES = 6   # dropout sites: attn probs (self), attn out, attn probs (cross), cross out, ffn inner, ffn out
+
+    def _block(self, x2, kv2, B, T, S, qmask_u8, kvmask_u8, slab, dc: DropCtx, k0: int = 0):
+        a = blocks.self_attention(x2, B, T, self.self_attn, slab, qmask_u8, drop_attn=dc.site(k0 + 0))
+        x2 = blocks.add_ln(x2, a, self.norm1, dc.site(k0 + 1))
+        c = blocks.cross_attention(x2, kv2, B, T, S, self.cross_attn, slab, kvmask_u8, drop_attn=dc.site(k0 + 2))
+        x2 = blocks.add_ln(x2, c, self.norm2, dc.site(k0 + 3))
+        f = blocks.ffn(x2, self.ffn[0], self.ffn[3], slab, drop_in=dc.site(k0 + 4))
+        return blocks.add_ln(x2, f, self.norm3, dc.site(k0 + 5))
 
     def forward(self, query: torch.Tensor, key_value: torch.Tensor, query_mask: Optional[torch.Tensor] = None,
                 kv_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -59,7 +63,8 @@ class CrossModalAttention(SlabOwner, nn.Module):
         slab = self._get_slab(query.device, cdt)
         x2 = ops.to_compute(query.reshape(B * T, D), cdt)
         kv2 = ops.to_compute(key_value.reshape(B * S, D), cdt)
-        out = self._block(x2, kv2, B, T, S, blocks.pad_mask_u8(query_mask), blocks.pad_mask_u8(kv_mask), slab)
+        dc = DropCtx(self.training, self.dropout_p, query.device, self._sites)
+        out = self._block(x2, kv2, B, T, S, blocks.pad_mask_u8(query_mask), blocks.pad_mask_u8(kv_mask), slab, dc)
         return ops.to_compute(out, query.dtype).view(B, T, D)
 
 
@@ -84,6 +89,7 @@ class MultimodalFusion(SlabOwner, nn.Module):
         else:
             self.fusion_layer = nn.Linear(config.hidden_dim, config.output_dim)
         self.layer_norm = nn.LayerNorm(config.output_dim) if config.use_layer_norm else None
+        self._sites = alloc_sites(CrossModalAttention.SITES * max(1, getattr(config, "num_layers", 1)) + 2)
 
     def _slab_groups(self):
         return blocks.param_groups(self)
@@ -103,14 +109,16 @@ class MultimodalFusion(SlabOwner, nn.Module):
             x2 = ops.to_compute(text_features.reshape(B * T, D), cdt)
             kv2 = ops.to_compute(visual_features.reshape(B * S, D), cdt)
             qm, km = blocks.pad_mask_u8(text_mask), blocks.pad_mask_u8(visual_mask)
-            for layer in self.fusion_layers:
-                x2 = layer._block(x2, kv2, B, T, S, qm, km, slab)
+            dc = DropCtx(self.training, float(self.config.dropout), text_features.device, self._sites)
+            for li, layer in enumerate(self.fusion_layers):
+                x2 = layer._block(x2, kv2, B, T, S, qm, km, slab, dc, li * CrossModalAttention.SITES)
             cls = x2.view(B, T, D)[:, 0, :]                      # CLS position, strided rows (no copy)
             fused = blocks.linear(cls, self.output_proj, slab)
         elif ft == "concat":
             both = torch.cat([self._pool(visual_features), self._pool(text_features)], dim=-1)
+            dc = DropCtx(self.training, float(self.config.dropout), text_features.device, self._sites)
             fused = blocks.ffn(ops.to_compute(both.contiguous(), cdt), self.fusion_layer[0], self.fusion_layer[3],
-                               slab, act=ACT_RELU)
+                               slab, act=ACT_RELU, drop_in=dc.site(0))
         elif ft == "bilinear":
             # 768^3-parameter tensor contraction; not on the cross-attention path (left to torch)
             fused = self.bilinear(self._pool(visual_features), self._pool(text_features))

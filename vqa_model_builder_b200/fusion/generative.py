@@ -12,7 +12,7 @@ from torch import nn
 from .. import ops
 from ..moe.config import MOEConfig, RouterConfig
 from ..moe.layers import MOELayer, SparseMOELayer, VQAMOELayer
-from ..runtime import SlabOwner, resolve_compute_dtype
+from ..runtime import DropCtx, SlabOwner, alloc_sites, resolve_compute_dtype
 from . import blocks
 
 
@@ -57,6 +57,7 @@ class CrossModalFusion(SlabOwner, nn.Module):
         if self.use_moe:
             self._create_moe_layer(config)
         self.layer_norm = nn.LayerNorm(config.fusion_dim)
+        self._sites = alloc_sites(4 * config.fusion_num_layers)
 
     def _create_moe_layer(self, config):
         if self.moe_type == "vqa":
@@ -105,11 +106,14 @@ class CrossModalFusion(SlabOwner, nn.Module):
             pad = torch.cat([torch.zeros(B, V, dtype=torch.bool, device=fused.device), ~question_mask.bool()], dim=1)
         pad = blocks.pad_mask_u8(pad)
         x2 = ops.to_compute(fused.reshape(B * S, D), cdt)
-        for layer in self.layers:  # pre-LN: x += SA(LN1 x); x += FF(LN2 x)
+        dc = DropCtx(self.training, float(self.config.fusion_dropout), fused.device, self._sites)
+        for li, layer in enumerate(self.layers):  # pre-LN: x += drop(SA(LN1 x)); x += drop(FF(LN2 x))
             h = blocks.add_ln(x2, None, layer.norm1)
-            x2 = blocks.self_attention(h, B, S, layer.self_attn, slab, pad, residual=x2)
+            x2 = blocks.self_attention(h, B, S, layer.self_attn, slab, pad, residual=x2, drop_attn=dc.site(4 * li),
+                                       drop_out=dc.site(4 * li + 1))
             h = blocks.add_ln(x2, None, layer.norm2)
-            x2 = blocks.ffn(h, layer.linear1, layer.linear2, slab, residual=x2)
+            x2 = blocks.ffn(h, layer.linear1, layer.linear2, slab, residual=x2, drop_in=dc.site(4 * li + 2),
+                            drop_out=dc.site(4 * li + 3))
         aux: Union[float, torch.Tensor] = 0.0
         if self.moe_layer is not None:
             x3 = self.moe_layer(x2.view(B, S, D))

@@ -13,7 +13,7 @@ from torch import nn
 
 from .. import ops
 from .._lib import ACT_CODES
-from ..runtime import resolve_compute_dtype
+from ..runtime import DropCtx, alloc_sites, resolve_compute_dtype
 
 
 class BaseExpert(nn.Module):
@@ -79,6 +79,7 @@ class FeedForwardExpert(BaseExpert):
         self.fc2 = nn.Linear(hidden_dim, output_dim)
         self.dropout = nn.Dropout(dropout)
         self.layer_norm = nn.LayerNorm(output_dim)
+        self._sites = alloc_sites(2)
 
     @property
     def act_code(self) -> int:
@@ -91,9 +92,14 @@ class FeedForwardExpert(BaseExpert):
         w1, w2 = self.fc1.weight, self.fc2.weight
         w1c = w1.detach() if cdt == torch.float32 else ops.cast(w1.detach(), cdt)
         w2c = w2.detach() if cdt == torch.float32 else ops.cast(w2.detach(), cdt)
-        h = ops.FFNFn.apply(x2, w1, self.fc1.bias, w2, self.fc2.bias, w1c, w2c, self.act_code, None)
-        residual = x2 if x.shape[-1] == self.output_dim else None
-        y = ops.AddLNFn.apply(h, residual, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
+        dc = DropCtx(self.training, float(self.dropout_rate), x.device, self._sites)
+        h = ops.FFNFn.apply(x2, w1, self.fc1.bias, w2, self.fc2.bias, w1c, w2c, self.act_code, None, dc.site(0), None)
+        if x.shape[-1] == self.output_dim:   # LN(dropout(h) + x)
+            y = ops.AddLNFn.apply(x2, h, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps, dc.site(1))
+        else:
+            if dc.on:
+                h = ops.DropoutFn.apply(h, dc.site(1))
+            y = ops.AddLNFn.apply(h, None, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps, None)
         return ops.to_compute(y, x.dtype).view(*lead, self.output_dim)
 
 

@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..runtime import SlabOwner, resolve_compute_dtype
+from ..runtime import DropCtx, SlabOwner, alloc_sites, resolve_compute_dtype
 from .config import MOEConfig
 from .experts import FeedForwardExpert, create_expert
 from .router import NoisyTopKRouter, create_router
@@ -118,8 +118,11 @@ class MOELayer(SlabOwner, nn.Module):
             w2d = w2d * keep.view(N, K).to(w2d.dtype)
         params = self._expert_params()
         xp = ops.PermuteFn.apply(x2, plan.row_src, plan.pad_off, plan.dest_row, E, K, plan.Rmax)
+        if "_sites" not in self.__dict__:
+            self.__dict__["_sites"] = alloc_sites(2)
+        dc = DropCtx(self.training, float(ex[0].dropout_rate), x.device, self.__dict__["_sites"])
         z = ops.ExpertFFNFn.apply(xp, plan.tile_group, plan.pad_off, (w1s, b1s, w2s, b2s, lng, lnb), ex[0].act_code,
-                                  D == Do, ex[0].layer_norm.eps, *params)
+                                  D == Do, ex[0].layer_norm.eps, (dc.site(0), dc.site(1)) if dc.on else None, *params)
         out = ops.CombineFn.apply(z, w2d, plan.dest_row, plan.row_src, self.output_norm.weight, self.output_norm.bias,
                                   self.output_norm.eps)
         self.last_plan = plan

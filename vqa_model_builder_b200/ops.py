@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_CODES, ACT_NONE, EPI_ACCUM, EPI_ACT, EPI_ADD, EPI_DACT, EPI_NONE, GROUP_TILE, LAYOUT_K,
-                   LAYOUT_MN, call, dtype_code, query, stream_ptr)
+                   LAYOUT_MN, call, dropout_arg, dtype_code, query, stream_ptr)
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
@@ -48,6 +48,19 @@ class CastFn(torch.autograd.Function):
         return cast(g, ctx.src_dtype), None
 
 
+class DropoutFn(torch.autograd.Function):
+    """Stand-alone dropout with a regenerated mask (rarely needed: dropout is normally fused into a neighbour)."""
+
+    @staticmethod
+    def forward(ctx, x, drop):
+        ctx.drop = drop
+        return dropout_apply(x, drop)
+
+    @staticmethod
+    def backward(ctx, g):
+        return dropout_apply(g, ctx.drop), None
+
+
 def to_compute(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return x if x.dtype == dtype else CastFn.apply(x, dtype)
 
@@ -55,7 +68,7 @@ def to_compute(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 # ---- raw GEMM helpers (no autograd) ------------------------------------------------------------------
 def gemm(a: torch.Tensor, a_layout: int, b: torch.Tensor, b_layout: int, M: int, N: int, K: int, *,
          out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None, bias=None, epi=EPI_NONE,
-         act=ACT_NONE, aux_in=None, aux_out=None) -> torch.Tensor:
+         act=ACT_NONE, aux_in=None, aux_out=None, drop=None) -> torch.Tensor:
     lda, dt = _rows(a)
     ldb, _ = _rows(b)
     if out is None:
@@ -65,7 +78,15 @@ def gemm(a: torch.Tensor, a_layout: int, b: torch.Tensor, b_layout: int, M: int,
         if t is not None:
             ld_aux = t.stride(0)
     call("b200_gemm", a, lda, a_layout, b, ldb, b_layout, out, out.stride(0), M, N, K, dt, dtype_code(out.dtype),
-         bias, epi, act, aux_in, aux_out, ld_aux, stream_ptr())
+         bias, epi, act, aux_in, aux_out, ld_aux, dropout_arg(drop), stream_ptr())
+    return out
+
+
+def dropout_apply(x: torch.Tensor, drop) -> torch.Tensor:
+    """x * keep-mask of a site (element index = flat index of the dense tensor)."""
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    call("b200_dropout_apply", x, out, x.numel(), dtype_code(x.dtype), dropout_arg(drop), stream_ptr())
     return out
 
 
@@ -81,41 +102,46 @@ def colsum(x: torch.Tensor, tile_group=None, G: int = 1) -> torch.Tensor:
 
 # ---- Linear (+bias, + optional residual) ---------------------------------------------------------------
 class LinearFn(torch.autograd.Function):
-    """y = x W^T + b (+ residual).  nn.Linear / MHA in-proj / out-proj (vqa_model.py:258-263)."""
+    """y = x W^T + b, or y = dropout(x W^T + b) + residual.  nn.Linear / MHA in-proj / out-proj
+    (vqa_model.py:258-263; TransformerEncoderLayer's x + dropout1(sa(x)))."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, w_c, residual):
+    def forward(ctx, x, weight, bias, w_c, residual, drop=None):
         _lib.ensure_device(x)
         M, K = x.shape
         N = w_c.shape[0]
         epi = EPI_ADD if residual is not None else EPI_NONE
-        y = gemm(x, LAYOUT_K, w_c, LAYOUT_K, M, N, K, bias=bias, epi=epi, aux_in=residual)
+        if residual is None:
+            drop = None
+        y = gemm(x, LAYOUT_K, w_c, LAYOUT_K, M, N, K, bias=bias, epi=epi, aux_in=residual, drop=drop)
         ctx.save_for_backward(x, w_c)
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
+        ctx.drop = drop
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w_c = ctx.saved_tensors
         dy = dy.contiguous()
+        g = dropout_apply(dy, ctx.drop) if ctx.drop is not None else dy   # gradient of the pre-dropout GEMM output
         M, K = x.shape
         N = w_c.shape[0]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = gemm(dy, LAYOUT_K, w_c, LAYOUT_MN, M, K, N)
+            dx = gemm(g, LAYOUT_K, w_c, LAYOUT_MN, M, K, N)
         if ctx.needs_input_grad[1]:
             flat = torch.empty(N * K + (N if ctx.has_bias else 0), dtype=torch.float32, device=x.device)
             dw = flat[:N * K].view(N, K)
             # split-K accumulates atomically when the [N,K] tile grid cannot fill the machine
             epi = EPI_ACCUM if x.dtype == torch.bfloat16 else EPI_NONE
-            gemm(dy, LAYOUT_MN, x, LAYOUT_MN, N, K, M, out=dw, epi=epi)
+            gemm(g, LAYOUT_MN, x, LAYOUT_MN, N, K, M, out=dw, epi=epi)
             if ctx.has_bias:
                 db = flat[N * K:]
-                _colsum_into(dy, db)
+                _colsum_into(g, db)
         elif ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dy)
-        return dx, dw, db, None, (dy if ctx.has_res else None)
+            db = colsum(g)
+        return dx, dw, db, None, (dy if ctx.has_res else None), None
 
 
 def _colsum_into(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
@@ -128,28 +154,34 @@ def _colsum_into(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
 
 # ---- two-layer FFN with fused activation ----------------------------------------------------------------
 class FFNFn(torch.autograd.Function):
-    """y = act(x W1^T + b1) W2^T + b2   (ffn of vqa_model.py:265-271; TransformerEncoderLayer FF).
-    The activation runs in GEMM-1's epilogue; its derivative in the epilogue of GEMM-2's dgrad."""
+    """y = drop_in(act(x W1^T + b1)) W2^T + b2, optionally y = drop_out(...) + residual
+    (ffn of vqa_model.py:265-271; TransformerEncoderLayer FF).  The activation (+dropout) runs in GEMM-1's epilogue;
+    its derivative (x the same mask) in the epilogue of GEMM-2's dgrad."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, w1_c, w2_c, act, residual):
+    def forward(ctx, x, w1, b1, w2, b2, w1_c, w2_c, act, residual, drop_in=None, drop_out=None):
         _lib.ensure_device(x)
         M, D = x.shape
         F = w1_c.shape[0]
         Do = w2_c.shape[0]
         pre = torch.empty((M, F), dtype=x.dtype, device=x.device)
-        h = gemm(x, LAYOUT_K, w1_c, LAYOUT_K, M, F, D, bias=b1, epi=EPI_ACT, act=act, aux_out=pre)
+        h = gemm(x, LAYOUT_K, w1_c, LAYOUT_K, M, F, D, bias=b1, epi=EPI_ACT, act=act, aux_out=pre, drop=drop_in)
         epi = EPI_ADD if residual is not None else EPI_NONE
-        y = gemm(h, LAYOUT_K, w2_c, LAYOUT_K, M, Do, F, bias=b2, epi=epi, aux_in=residual)
+        if residual is None:
+            drop_out = None
+        y = gemm(h, LAYOUT_K, w2_c, LAYOUT_K, M, Do, F, bias=b2, epi=epi, aux_in=residual, drop=drop_out)
         ctx.save_for_backward(x, pre, h, w1_c, w2_c)
         ctx.act = act
         ctx.has_res = residual is not None
+        ctx.drops = (drop_in, drop_out)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, pre, h, w1_c, w2_c = ctx.saved_tensors
+        drop_in, drop_out = ctx.drops
         dy = dy.contiguous()
+        g = dropout_apply(dy, drop_out) if drop_out is not None else dy
         M, D = x.shape
         F = w1_c.shape[0]
         Do = w2_c.shape[0]
@@ -160,33 +192,36 @@ class FFNFn(torch.autograd.Function):
         db1 = flat[F * D:F * D + F]
         dw2 = flat[F * D + F:F * D + F + Do * F].view(Do, F)
         db2 = flat[F * D + F + Do * F:]
-        gemm(dy, LAYOUT_MN, h, LAYOUT_MN, Do, F, M, out=dw2, epi=wepi)
-        _colsum_into(dy, db2)
-        dpre = gemm(dy, LAYOUT_K, w2_c, LAYOUT_MN, M, F, Do, epi=EPI_DACT, act=ctx.act, aux_in=pre)
+        gemm(g, LAYOUT_MN, h, LAYOUT_MN, Do, F, M, out=dw2, epi=wepi)
+        _colsum_into(g, db2)
+        dpre = gemm(g, LAYOUT_K, w2_c, LAYOUT_MN, M, F, Do, epi=EPI_DACT, act=ctx.act, aux_in=pre, drop=drop_in)
         gemm(dpre, LAYOUT_MN, x, LAYOUT_MN, F, D, M, out=dw1, epi=wepi)
         _colsum_into(dpre, db1)
         dx = gemm(dpre, LAYOUT_K, w1_c, LAYOUT_MN, M, D, F) if ctx.needs_input_grad[0] else None
-        return dx, dw1, db1, dw2, db2, None, None, None, (dy if ctx.has_res else None)
+        return dx, dw1, db1, dw2, db2, None, None, None, (dy if ctx.has_res else None), None, None
 
 
 # ---- residual add + LayerNorm ------------------------------------------------------------------------------
 class AddLNFn(torch.autograd.Function):
-    """y = LayerNorm(x + branch)   (post-LN residual blocks, vqa_model.py:301,305,309); branch may be None."""
+    """y = LayerNorm(x + dropout(branch))   (post-LN residual blocks, vqa_model.py:301,305,309); branch may be None."""
 
     @staticmethod
-    def forward(ctx, x, branch, gamma, beta, eps):
+    def forward(ctx, x, branch, gamma, beta, eps, drop=None):
         _lib.ensure_device(x)
         x = x.contiguous()
         if branch is not None:
             branch = branch.contiguous()
+        else:
+            drop = None
         R, D = x.shape
         y = torch.empty_like(x)
         mean = torch.empty(R, dtype=torch.float32, device=x.device)
         rstd = torch.empty(R, dtype=torch.float32, device=x.device)
         call("b200_add_ln_fwd", x, branch, gamma, beta, None, float(eps), y, mean, rstd, R, D, dtype_code(x.dtype),
-             stream_ptr())
+             dropout_arg(drop), 2 if drop is not None else 0, stream_ptr())
         ctx.save_for_backward(x, branch, mean, rstd, gamma)
         ctx.has_branch = branch is not None
+        ctx.drop = drop
         return y
 
     @staticmethod
@@ -195,12 +230,16 @@ class AddLNFn(torch.autograd.Function):
         dy = dy.contiguous()
         R, D = x.shape
         dsum = torch.empty_like(x)
+        dbranch = torch.empty_like(x) if ctx.drop is not None else None
         flat = torch.empty(2 * D, dtype=torch.float32, device=x.device)
         nb = query("b200_add_ln_bwd_ws", R, D)
         ws = _ws(nb, x.device)
         call("b200_add_ln_bwd", dy, x, branch, mean, rstd, gamma, None, 1, dsum, flat[:D], flat[D:], R, D,
-             dtype_code(x.dtype), ws, nb, stream_ptr())
-        return dsum, (dsum if ctx.has_branch else None), flat[:D], flat[D:], None
+             dtype_code(x.dtype), dropout_arg(ctx.drop), 2 if ctx.drop is not None else 0, dbranch, ws, nb,
+             stream_ptr())
+        if not ctx.has_branch:
+            return dsum, None, flat[:D], flat[D:], None, None
+        return dsum, (dbranch if dbranch is not None else dsum), flat[:D], flat[D:], None, None
 
 
 # ---- attention -----------------------------------------------------------------------------------------------
@@ -210,7 +249,7 @@ class AttentionFn(torch.autograd.Function):
     cross-attention: q_src = q [B*T, D], kv_src = kv [B*S, 2D] (k | v column blocks)."""
 
     @staticmethod
-    def forward(ctx, q_src, kv_src, key_pad, B, T, S, H, self_attn):
+    def forward(ctx, q_src, kv_src, key_pad, B, T, S, H, self_attn, drop=None):
         _lib.ensure_device(q_src)
         es = q_src.element_size()
         if self_attn:
@@ -227,9 +266,10 @@ class AttentionFn(torch.autograd.Function):
         o = torch.empty((B * T, D), dtype=q_src.dtype, device=q_src.device)
         lse = torch.empty((B, H, T), dtype=torch.float32, device=q_src.device)
         call("b200_attn_fwd", qp, ldq, kp, ldk, vp, ldv, key_pad, o, D, lse, B, H, T, S, dh, scale,
-             dtype_code(q_src.dtype), stream_ptr())
+             dtype_code(q_src.dtype), dropout_arg(drop), stream_ptr())
         ctx.save_for_backward(q_src, kv_src if not self_attn else None, key_pad, o, lse)
         ctx.dims = (B, T, S, H, D, dh, scale, self_attn)
+        ctx.drop = drop
         return o
 
     @staticmethod
@@ -245,15 +285,15 @@ class AttentionFn(torch.autograd.Function):
             dqp, dkp, dvp = dqkv.data_ptr(), dqkv.data_ptr() + D * es, dqkv.data_ptr() + 2 * D * es
             ldd = 3 * D
             call("b200_attn_bwd", qp, ldq, kp, ldk, vp, ldv, key_pad, o, D, do, D, lse, dqp, ldd, dkp, ldd, dvp, ldd,
-                 B, H, T, S, dh, scale, dtype_code(q_src.dtype), stream_ptr())
-            return dqkv, None, None, None, None, None, None, None
+                 B, H, T, S, dh, scale, dtype_code(q_src.dtype), dropout_arg(ctx.drop), stream_ptr())
+            return dqkv, None, None, None, None, None, None, None, None
         dq = torch.empty((B * T, D), dtype=q_src.dtype, device=q_src.device)
         dkv = torch.empty((B * S, 2 * D), dtype=q_src.dtype, device=q_src.device)
         qp, kp, vp = q_src.data_ptr(), kv_src.data_ptr(), kv_src.data_ptr() + D * es
         call("b200_attn_bwd", qp, q_src.stride(0), kp, kv_src.stride(0), vp, kv_src.stride(0), key_pad, o, D, do, D,
              lse, dq, D, dkv.data_ptr(), 2 * D, dkv.data_ptr() + D * es, 2 * D, B, H, T, S, dh, scale,
-             dtype_code(q_src.dtype), stream_ptr())
-        return dq, dkv, None, None, None, None, None, None
+             dtype_code(q_src.dtype), dropout_arg(ctx.drop), stream_ptr())
+        return dq, dkv, None, None, None, None, None, None, None
 
 
 # ---- MOE router ----------------------------------------------------------------------------------------------
@@ -422,8 +462,9 @@ class ExpertFFNFn(torch.autograd.Function):
         fc1.weight x E, fc1.bias x E, fc2.weight x E, fc2.bias x E, ln.weight x E, ln.bias x E."""
 
     @staticmethod
-    def forward(ctx, xp, tile_group, pad_off, stacks, act, residual, eps, *expert_params):
+    def forward(ctx, xp, tile_group, pad_off, stacks, act, residual, eps, drops, *expert_params):
         _lib.ensure_device(xp)
+        drop_in, drop_out = drops if drops is not None else (None, None)
         R, D = xp.shape
         w1s, b1s, w2s, b2s, lng, lnb = stacks  # [E,F,D] c, [E,F] f32, [E,Do,F] c, [E,Do] f32, [E,Do] f32 x2
         E, F = w1s.shape[0], w1s.shape[1]
@@ -434,17 +475,18 @@ class ExpertFFNFn(torch.autograd.Function):
         pre = torch.empty((R, F), dtype=xp.dtype, device=dev)
         h = torch.empty((R, F), dtype=xp.dtype, device=dev)
         call("b200_ggemm", xp, D, w1s, LAYOUT_K, h, F, R, F, D, E, tile_group, dt, dt, b1s, EPI_ACT, act, None, pre, F,
-             st)
+             dropout_arg(drop_in), st)
         y2 = torch.empty((R, Do), dtype=xp.dtype, device=dev)
         call("b200_ggemm", h, F, w2s, LAYOUT_K, y2, Do, R, Do, F, E, tile_group, dt, dt, b2s, EPI_NONE, ACT_NONE, None,
-             None, 0, st)
+             None, 0, None, st)
         z = torch.empty((R, Do), dtype=xp.dtype, device=dev)
         mean_e = torch.empty(R, dtype=torch.float32, device=dev)
         rstd_e = torch.empty(R, dtype=torch.float32, device=dev)
         call("b200_add_ln_fwd", y2, xp if residual else None, lng, lnb, tile_group, float(eps), z, mean_e, rstd_e, R,
-             Do, dt, st)
+             Do, dt, dropout_arg(drop_out), 1 if drop_out is not None else 0, st)
         ctx.save_for_backward(xp, pre, h, y2, mean_e, rstd_e, w1s, w2s, lng, tile_group, pad_off)
         ctx.cfg = (R, D, E, F, Do, act, residual)
+        ctx.drops = (drop_in, drop_out)
         return z
 
     @staticmethod
@@ -462,18 +504,21 @@ class ExpertFFNFn(torch.autograd.Function):
         for sz in sizes:
             offs.append(offs[-1] + sz)
         dw1, db1, dw2, db2, dlng, dlnb = [flat[offs[i]:offs[i + 1]] for i in range(6)]
-        dr = torch.empty((R, Do), dtype=dz.dtype, device=dev)
+        drop_in, drop_out = ctx.drops
+        dsum = torch.empty((R, Do), dtype=dz.dtype, device=dev)            # grad of (drop(y2) + xp): residual path
+        dr = torch.empty((R, Do), dtype=dz.dtype, device=dev) if drop_out is not None else dsum   # grad of y2
         nb = query("b200_add_ln_bwd_ws", R, Do)
         ws = _ws(nb, dev)
-        call("b200_add_ln_bwd", dz, y2, xp if residual else None, mean_e, rstd_e, lng, tile_group, E, dr, dlng, dlnb, R,
-             Do, dt, ws, nb, st)
+        call("b200_add_ln_bwd", dz, y2, xp if residual else None, mean_e, rstd_e, lng, tile_group, E, dsum, dlng, dlnb,
+             R, Do, dt, dropout_arg(drop_out), 1 if drop_out is not None else 0,
+             dr if drop_out is not None else None, ws, nb, st)
         nb = query("b200_colsum_ws", R, max(F, Do))
         ws = _ws(nb, dev)
         call("b200_colsum", dr, dt, R, Do, tile_group, E, db2, ws, nb, st)
         call("b200_ggemm_wgrad", dr, Do, h, F, dw2, Do, F, R, E, pad_off, dt, st)
         dpre = torch.empty((R, F), dtype=dz.dtype, device=dev)
         call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, tile_group, dt, dt, None, EPI_DACT, act, pre,
-             None, F, st)
+             None, F, dropout_arg(drop_in), st)
         call("b200_colsum", dpre, dt, R, F, tile_group, E, db1, ws, nb, st)
         call("b200_ggemm_wgrad", dpre, F, xp, D, dw1, F, D, R, E, pad_off, dt, st)
         dxp = None
@@ -481,16 +526,16 @@ class ExpertFFNFn(torch.autograd.Function):
             dxp = torch.empty((R, D), dtype=dz.dtype, device=dev)
             if residual:
                 call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, tile_group, dt, dt, None, EPI_ADD,
-                     ACT_NONE, dr, None, Do, st)
+                     ACT_NONE, dsum, None, Do, None, st)
             else:
                 call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, tile_group, dt, dt, None, EPI_NONE,
-                     ACT_NONE, None, None, 0, st)
+                     ACT_NONE, None, None, 0, None, st)
         # hand every per-expert Parameter its slice of the flat buffer
         grads: List[torch.Tensor] = []
         for buf, shape in ((dw1, (F, D)), (db1, (F,)), (dw2, (Do, F)), (db2, (Do,)), (dlng, (Do,)), (dlnb, (Do,))):
             per = buf.view(E, *shape)
             grads.extend(per[e] for e in range(E))
-        return (dxp, None, None, None, None, None, None, *grads)
+        return (dxp, None, None, None, None, None, None, None, *grads)
 
 
 class CombineFn(torch.autograd.Function):

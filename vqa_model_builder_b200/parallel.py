@@ -194,8 +194,13 @@ class ExpertParallelMOELayer(torch.nn.Module):
             stacks = L._expert_stacks(x.device, cdt)
             ex0 = L.experts[0]
             xp2 = ops.PermuteFn.apply(got, plan2.row_src, plan2.pad_off, plan2.dest_row, El, 1, plan2.Rmax)
+            from .runtime import DropCtx, alloc_sites
+            if "_sites" not in self.__dict__:
+                self.__dict__["_sites"] = alloc_sites(2)
+            dc = DropCtx(self.training, float(ex0.dropout_rate), x.device, self.__dict__["_sites"])
             z2 = ops.ExpertFFNFn.apply(xp2, plan2.tile_group, plan2.pad_off, stacks, ex0.act_code,
-                                       D == ex0.output_dim, ex0.layer_norm.eps, *L._expert_params())
+                                       D == ex0.output_dim, ex0.layer_norm.eps,
+                                       (dc.site(0), dc.site(1)) if dc.on else None, *L._expert_params())
             zc = ops.GatherRowsFn.apply(z2, plan2.dest_row, plan2.row_src, plan2.pad_off, El)
         else:
             zc = got.new_zeros((0, self.output_dim))

@@ -63,3 +63,56 @@ class SlabOwner:
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         return new
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Dropout: counter-based masks regenerated inside the kernels (include/b200vqa.h: b200_dropout_t)
+# ---------------------------------------------------------------------------------------------------------
+_rng_states = {}
+_next_site = [1]
+_seed_override = [None]
+
+
+def alloc_sites(n: int) -> int:
+    """Reserve `n` consecutive dropout site ids (called once per module at construction)."""
+    base = _next_site[0]
+    _next_site[0] += n
+    return base
+
+
+def dropout_state(device: torch.device) -> torch.Tensor:
+    """Per-device int64 [2] = (seed, step offset)."""
+    key = (device.type, device.index)
+    st = _rng_states.get(key)
+    if st is None:
+        seed = _seed_override[0] if _seed_override[0] is not None else torch.initial_seed()
+        st = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
+        _rng_states[key] = st
+    return st
+
+
+def reseed_dropout(seed: int) -> None:
+    """Restart the dropout streams of every device (existing and future) from `seed`, step offset 0."""
+    _seed_override[0] = seed
+    for st in _rng_states.values():
+        st[0] = seed & 0x7FFFFFFFFFFFFFFF
+        st[1] = 0
+
+
+class DropCtx:
+    """Dropout context of one module forward: advances the device-side step offset (graph-capturable in-place add)
+    and snapshots (seed, offset) so the backward of this forward regenerates the same masks even if other forwards
+    ran in between (gradient accumulation)."""
+
+    def __init__(self, training: bool, p: float, device: torch.device, base_site: int):
+        self.on = bool(training) and p > 0.0
+        self.p = float(p)
+        self.base = base_site
+        self.snap = None
+        if self.on:
+            st = dropout_state(device)
+            st[1:].add_(1)
+            self.snap = st.clone()
+
+    def site(self, k: int):
+        return (self.snap, self.p, self.base + k) if self.on else None
