@@ -28,7 +28,7 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-CFG = dict(B=32, T=64, V=50, D=768, H=8, L=2, E=8, K=2, F=2048, dropout=0.0)
+CFG = dict(B=32, T=64, V=50, D=768, H=8, L=2, E=8, K=2, F=2048, dropout=0.1)
 METRIC = "fusion+MOE fwd+bwd samples/sec"
 
 
@@ -131,8 +131,9 @@ def cpu_reference_step_factory(c, threads: int):
     def step():
         for t in list(sd_f.values()) + list(sd_m.values()) + [vis, txt]:
             t.grad = None
-        fused = rp.multimodal_fusion(sd_f, "cross_attention", c["H"], c["L"], True, vis, txt, None, pad)
-        out, aux, _, _, _ = rp.moe_layer(sd_m, fused.unsqueeze(1), c["E"], c["K"])
+        fused = rp.multimodal_fusion(sd_f, "cross_attention", c["H"], c["L"], True, vis, txt, None, pad,
+                                     pdrop=c["dropout"])
+        out, aux, _, _, _ = rp.moe_layer(sd_m, fused.unsqueeze(1), c["E"], c["K"], pdrop=c["dropout"])
         (out.float().square().mean() + aux).backward()
 
     return step
@@ -164,7 +165,7 @@ def run_reference(args, c):
     ts = time_cpu(step, max(1, min(args.warmup, 2)), steps)
     ms = 1e3 * sum(ts) / len(ts)
     val = c["B"] / (ms / 1e3)
-    sample = f"{steps} full steps of the B={c['B']} workload, fp32, {threads} threads, dropout 0"
+    sample = f"{steps} full steps of the B={c['B']} workload, fp32, {threads} threads, train mode dropout {c['dropout']}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -370,7 +371,7 @@ def run_ours(args, c):
                          "launches_per_step": gemm_launches, "kernel_ms_per_step": gemm_ms,
                          "algorithmic_gflop_per_step": fl["gemm"] * c["B"] / 1e9},
             "cpu_baseline": {"value": cpu_val, "unit": "samples/s", "cores": threads, "kind": "port",
-                             "sample": "3 full fwd+bwd steps of the same B=32 workload (oracle port, fp32, dropout 0)"},
+                             "sample": f"3 full fwd+bwd steps of the same B=32 workload (oracle port, fp32, train mode dropout {c['dropout']})"},
             "kernels": per_kernel, "cuda_graph": graph is not None,
             "algorithmic_gflop_per_step_total": fl["total"] * c["B"] / 1e9,
         }

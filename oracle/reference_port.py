@@ -20,6 +20,11 @@ import torch
 SD = Dict[str, torch.Tensor]
 
 
+def drop(x: torch.Tensor, p: float) -> torch.Tensor:
+    """nn.Dropout in train mode (p = 0: identity).  Only the CPU baseline timing uses p > 0; parity runs use 0."""
+    return torch.nn.functional.dropout(x, p, training=True) if p > 0 else x
+
+
 def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     mu = x.mean(dim=-1, keepdim=True)
     var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)          # biased variance, as nn.LayerNorm
@@ -43,7 +48,7 @@ def activation(x: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def mha(sd: SD, p: str, q_in: torch.Tensor, kv_in: torch.Tensor, num_heads: int,
-        key_padding_mask: Optional[torch.Tensor]) -> torch.Tensor:
+        key_padding_mask: Optional[torch.Tensor], pdrop: float = 0.0) -> torch.Tensor:
     """torch.nn.functional.multi_head_attention_forward semantics as used at vqa_model.py:300,304 and
     fusion_approaches.py:262-277: packed in_proj rows q=[0:D], k=[D:2D], v=[2D:3D]; q scaled by 1/sqrt(dh);
     bool key_padding_mask (True = ignore) -> -inf before softmax; out_proj.  Attention weights are discarded."""
@@ -60,36 +65,37 @@ def mha(sd: SD, p: str, q_in: torch.Tensor, kv_in: torch.Tensor, num_heads: int,
     scores = q @ k.transpose(-1, -2)                            # [B,H,T,S]
     if key_padding_mask is not None:
         scores = scores.masked_fill(key_padding_mask.bool()[:, None, None, :], float("-inf"))
-    ctx = torch.softmax(scores, dim=-1) @ v
+    ctx = drop(torch.softmax(scores, dim=-1), pdrop) @ v            # attention-probability dropout
     ctx = ctx.transpose(1, 2).reshape(B, T, D)
     return ctx @ sd[p + "out_proj.weight"].t() + sd[p + "out_proj.bias"]
 
 
-def ffn(sd: SD, p1: str, p2: str, x: torch.Tensor, act: str = "gelu") -> torch.Tensor:
-    h = activation(x @ sd[p1 + "weight"].t() + sd[p1 + "bias"], act)
-    return h @ sd[p2 + "weight"].t() + sd[p2 + "bias"]
+def ffn(sd: SD, p1: str, p2: str, x: torch.Tensor, act: str = "gelu", pdrop: float = 0.0) -> torch.Tensor:
+    h = drop(activation(x @ sd[p1 + "weight"].t() + sd[p1 + "bias"], act), pdrop)
+    return drop(h @ sd[p2 + "weight"].t() + sd[p2 + "bias"], pdrop)
 
 
 # ---- A1: CrossModalAttention (vqa_model.py:279-311), dropout p = 0 -----------------------------------------
-def cross_modal_attention(sd: SD, p: str, query, key_value, query_mask, kv_mask, num_heads: int):
+def cross_modal_attention(sd: SD, p: str, query, key_value, query_mask, kv_mask, num_heads: int, pdrop: float = 0.0):
     x = query
-    x = layer_norm(x + mha(sd, p + "self_attn.", x, x, num_heads, query_mask), sd[p + "norm1.weight"],
-                   sd[p + "norm1.bias"])
-    x = layer_norm(x + mha(sd, p + "cross_attn.", x, key_value, num_heads, kv_mask), sd[p + "norm2.weight"],
-                   sd[p + "norm2.bias"])
-    x = layer_norm(x + ffn(sd, p + "ffn.0.", p + "ffn.3.", x), sd[p + "norm3.weight"], sd[p + "norm3.bias"])
+    x = layer_norm(x + drop(mha(sd, p + "self_attn.", x, x, num_heads, query_mask, pdrop), pdrop),
+                   sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+    x = layer_norm(x + drop(mha(sd, p + "cross_attn.", x, key_value, num_heads, kv_mask, pdrop), pdrop),
+                   sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+    x = layer_norm(x + ffn(sd, p + "ffn.0.", p + "ffn.3.", x, pdrop=pdrop), sd[p + "norm3.weight"],
+                   sd[p + "norm3.bias"])
     return x
 
 
 # ---- A2: MultimodalFusion (vqa_model.py:361-433) -------------------------------------------------------------
 def multimodal_fusion(sd: SD, fusion_type: str, num_heads: int, num_layers: int, use_layer_norm: bool, visual, text,
-                      visual_mask=None, text_mask=None):
+                      visual_mask=None, text_mask=None, pdrop: float = 0.0):
     def pool(t):
         return t[:, 0, :] if t.dim() == 3 else t
 
     if fusion_type == "cross_attention":
         for l in range(num_layers):
-            text = cross_modal_attention(sd, f"fusion_layers.{l}.", text, visual, text_mask, visual_mask, num_heads)
+            text = cross_modal_attention(sd, f"fusion_layers.{l}.", text, visual, text_mask, visual_mask, num_heads, pdrop)
         fused = text[:, 0, :] @ sd["output_proj.weight"].t() + sd["output_proj.bias"]
     elif fusion_type == "concat":
         both = torch.cat([pool(visual), pool(text)], dim=-1)
@@ -158,8 +164,8 @@ def topk_router(sd: SD, p: str, x: torch.Tensor, top_k: int, lb_weight: float = 
 
 
 # ---- A7: FeedForwardExpert (expert_types.py:75-92), dropout p = 0 ------------------------------------------------
-def feed_forward_expert(sd: SD, p: str, x: torch.Tensor, act: str = "gelu") -> torch.Tensor:
-    h = ffn(sd, p + "fc1.", p + "fc2.", x, act)
+def feed_forward_expert(sd: SD, p: str, x: torch.Tensor, act: str = "gelu", pdrop: float = 0.0) -> torch.Tensor:
+    h = ffn(sd, p + "fc1.", p + "fc2.", x, act, pdrop)
     if x.shape[-1] == h.shape[-1]:
         h = h + x
     return layer_norm(h, sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"])
@@ -167,7 +173,7 @@ def feed_forward_expert(sd: SD, p: str, x: torch.Tensor, act: str = "gelu") -> t
 
 # ---- A6: MOELayer dense combine (moe_layer.py:146-171) -------------------------------------------------------------
 def moe_layer(sd: SD, x: torch.Tensor, num_experts: int, top_k: int, lb_weight: float = 0.01, act: str = "gelu",
-              noise=None, noise_std: float = 1.0, weights_indices=None):
+              noise=None, noise_std: float = 1.0, weights_indices=None, pdrop: float = 0.0):
     """The reference's algorithm verbatim in structure: every selected expert is evaluated on ALL tokens and masked
     by its routing weight; accumulation in ascending expert order from a zero tensor; output_norm."""
     if weights_indices is None:
@@ -181,7 +187,7 @@ def moe_layer(sd: SD, x: torch.Tensor, num_experts: int, top_k: int, lb_weight: 
         if not bool(hit.any()):
             continue
         we = (w * hit.to(w.dtype)).sum(dim=-1)
-        out = out + feed_forward_expert(sd, f"experts.{e}.", x, act) * we.unsqueeze(-1)
+        out = out + feed_forward_expert(sd, f"experts.{e}.", x, act, pdrop) * we.unsqueeze(-1)
     return layer_norm(out, sd["output_norm.weight"], sd["output_norm.bias"]), loss, probs, w, idx
 
 
