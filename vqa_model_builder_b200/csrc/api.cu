@@ -1,5 +1,6 @@
 // C-ABI surface: lifecycle, error reporting, casts, column sums and the GEMM entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
