@@ -34,10 +34,20 @@ int num_sms() {
   return g_num_sms;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200VQA_PDL");
+    v = (e != nullptr && strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
 
 // ---- cast ---------------------------------------------------------------------------------------
 template <typename S, typename D>
 __global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, long long n) {
+  pdl_trigger();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 3 < n) {
@@ -70,6 +80,8 @@ constexpr int CS_ROWS = 64;  // rows per partial block; divides B200_GROUP_TILE
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VT = Vec16<T>::N;
   __shared__ float red[8][32 * VT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,6 +114,8 @@ colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part) {
 // scalar fallback for widths that are not a multiple of the vector length
 template <typename T>
 __global__ void colsum_stage1_scalar(const T* __restrict__ x, int R, int N, float* __restrict__ part) {
+  pdl_trigger();
+  pdl_wait();
   const int col = blockIdx.x * 128 + threadIdx.x;
   const int r0 = blockIdx.y * CS_ROWS, r1 = min(R, r0 + CS_ROWS);
   if (col >= N) return;
@@ -114,6 +128,8 @@ int launch_partial_reduce(const float* part, int blocks, int rows_per_block, int
                           float* out, cudaStream_t stream);
 
 __global__ void dropout_mask_kernel(const unsigned long long* st, float p, unsigned int site, long long n, float* out) {
+  pdl_trigger();
+  pdl_wait();
   const DropState d = drop_load(st, p, site);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = d.on ? drop_scale1(d, (unsigned long long)i) : 1.f;
@@ -122,6 +138,8 @@ __global__ void dropout_mask_kernel(const unsigned long long* st, float p, unsig
 template <typename T>
 __global__ void dropout_apply_kernel(const T* __restrict__ x, T* __restrict__ out, long long n,
                                      const unsigned long long* st, float p, unsigned int site) {
+  pdl_trigger();
+  pdl_wait();
   const DropState d = drop_load(st, p, site);
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
@@ -146,9 +164,9 @@ int b200_dropout_apply(const void* x, void* out, long long n, int dtype, const b
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   if (dtype == B200_BF16)
-    dropout_apply_kernel<bf16><<<(int)blocks, 256, 0, stream>>>((const bf16*)x, (bf16*)out, n, drop->rng_state, drop->p, drop->site);
+    launch_kernel(dropout_apply_kernel<bf16>, dim3((int)blocks), dim3(256), 0, stream, (const bf16*)x, (bf16*)out, n, drop->rng_state, drop->p, drop->site);
   else
-    dropout_apply_kernel<float><<<(int)blocks, 256, 0, stream>>>((const float*)x, (float*)out, n, drop->rng_state, drop->p, drop->site);
+    launch_kernel(dropout_apply_kernel<float>, dim3((int)blocks), dim3(256), 0, stream, (const float*)x, (float*)out, n, drop->rng_state, drop->p, drop->site);
   B200_LAUNCH_CHECK("dropout_apply_kernel");
   count_launch();
   return 0;
@@ -179,13 +197,13 @@ int b200_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long lon
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (src_dtype == B200_F32 && dst_dtype == B200_BF16)
-    cast_kernel<float, bf16><<<(int)blocks, threads, 0, stream>>>((const float*)src, (bf16*)dst, n);
+    launch_kernel(cast_kernel<float, bf16>, dim3((int)blocks), dim3(threads), 0, stream, (const float*)src, (bf16*)dst, n);
   else if (src_dtype == B200_BF16 && dst_dtype == B200_F32)
-    cast_kernel<bf16, float><<<(int)blocks, threads, 0, stream>>>((const bf16*)src, (float*)dst, n);
+    launch_kernel(cast_kernel<bf16, float>, dim3((int)blocks), dim3(threads), 0, stream, (const bf16*)src, (float*)dst, n);
   else if (src_dtype == B200_F32 && dst_dtype == B200_F32)
-    cast_kernel<float, float><<<(int)blocks, threads, 0, stream>>>((const float*)src, (float*)dst, n);
+    launch_kernel(cast_kernel<float, float>, dim3((int)blocks), dim3(threads), 0, stream, (const float*)src, (float*)dst, n);
   else if (src_dtype == B200_BF16 && dst_dtype == B200_BF16)
-    cast_kernel<bf16, bf16><<<(int)blocks, threads, 0, stream>>>((const bf16*)src, (bf16*)dst, n);
+    launch_kernel(cast_kernel<bf16, bf16>, dim3((int)blocks), dim3(threads), 0, stream, (const bf16*)src, (bf16*)dst, n);
   else {
     set_error("cast: bad dtypes %d -> %d", src_dtype, dst_dtype);
     return B200_ERR_INVALID;
@@ -198,7 +216,7 @@ int b200_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long lon
 int b200_dropout_mask(const b200_dropout_t* drop, long long n, float* out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(drop != nullptr && n > 0, "dropout_mask: bad arguments");
-  dropout_mask_kernel<<<256, 256, 0, stream>>>(drop->rng_state, drop->p, drop->site, n, out);
+  launch_kernel(dropout_mask_kernel, dim3(256), dim3(256), 0, stream, drop->rng_state, drop->p, drop->site, n, out);
   B200_LAUNCH_CHECK("dropout_mask_kernel");
   count_launch();
   return 0;
@@ -218,12 +236,12 @@ int b200_colsum(const void* x, int dtype, int R, int N, const int32_t* tile_grou
   const int vt = dtype == B200_F32 ? 4 : 8;
   if (N % vt == 0 && ((uintptr_t)x & 15) == 0) {
     dim3 g1((N + 32 * vt - 1) / (32 * vt), blocks);
-    if (dtype == B200_F32) colsum_stage1<float><<<g1, 256, 0, stream>>>((const float*)x, R, N, part);
-    else colsum_stage1<bf16><<<g1, 256, 0, stream>>>((const bf16*)x, R, N, part);
+    if (dtype == B200_F32) launch_kernel(colsum_stage1<float>, dim3(g1), dim3(256), 0, stream, (const float*)x, R, N, part);
+    else launch_kernel(colsum_stage1<bf16>, dim3(g1), dim3(256), 0, stream, (const bf16*)x, R, N, part);
   } else {
     dim3 g1((N + 127) / 128, blocks);
-    if (dtype == B200_F32) colsum_stage1_scalar<float><<<g1, 128, 0, stream>>>((const float*)x, R, N, part);
-    else colsum_stage1_scalar<bf16><<<g1, 128, 0, stream>>>((const bf16*)x, R, N, part);
+    if (dtype == B200_F32) launch_kernel(colsum_stage1_scalar<float>, dim3(g1), dim3(128), 0, stream, (const float*)x, R, N, part);
+    else launch_kernel(colsum_stage1_scalar<bf16>, dim3(g1), dim3(128), 0, stream, (const bf16*)x, R, N, part);
   }
   B200_LAUNCH_CHECK("colsum_stage1");
   count_launch();

@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(FA_WARPS * 32)
 attn_fwd_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int ldk, const T* __restrict__ v, int ldv,
                 const uint8_t* __restrict__ key_pad, T* __restrict__ o, int ldo, float* __restrict__ lse, int H, int Tq,
                 int S, int dh, float scale, const unsigned long long* drop_state, float drop_p, unsigned int drop_site) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const DropState ds = drop_load(drop_state, drop_p, drop_site);
   const unsigned long long s_pad = (unsigned long long)((S + 127) / 128) * 128;   // attention dropout index pitch
@@ -165,6 +167,8 @@ attn_bwd_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int l
                 int lddo, const float* __restrict__ lse, T* __restrict__ dq, int lddq, T* __restrict__ dk, int lddk,
                 T* __restrict__ dv, int lddv, int H, int Tq, int S, int dh, float scale,
                 const unsigned long long* drop_state, float drop_p, unsigned int drop_site) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const DropState ds = drop_load(drop_state, drop_p, drop_site);
   const unsigned long long s_pad = (unsigned long long)((S + 127) / 128) * 128;
@@ -336,12 +340,12 @@ int b200_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v,
   const size_t smem = fwd_smem(dh);
   if (dtype == B200_BF16) {
     if (int rc = set_smem(attn_fwd_kernel<bf16>, smem)) return rc;
-    attn_fwd_kernel<bf16><<<grid, FA_WARPS * 32, smem, stream>>>((const bf16*)q, ldq, (const bf16*)k, ldk,
+    launch_kernel(attn_fwd_kernel<bf16>, dim3(grid), dim3(FA_WARPS * 32), smem, stream, (const bf16*)q, ldq, (const bf16*)k, ldk,
                                                                  (const bf16*)v, ldv, key_pad, (bf16*)o, ldo, lse, H, T,
                                                                  S, dh, scale, dst, dpp, dsite);
   } else {
     if (int rc = set_smem(attn_fwd_kernel<float>, smem)) return rc;
-    attn_fwd_kernel<float><<<grid, FA_WARPS * 32, smem, stream>>>((const float*)q, ldq, (const float*)k, ldk,
+    launch_kernel(attn_fwd_kernel<float>, dim3(grid), dim3(FA_WARPS * 32), smem, stream, (const float*)q, ldq, (const float*)k, ldk,
                                                                   (const float*)v, ldv, key_pad, (float*)o, ldo, lse, H,
                                                                   T, S, dh, scale, dst, dpp, dsite);
   }
@@ -373,11 +377,11 @@ int b200_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v,
   do {                                                                                                           \
     if (int rc = set_smem(attn_bwd_kernel<TT, 0, BTV>, smem)) return rc;                                         \
     if (int rc = set_smem(attn_bwd_kernel<TT, 1, BTV>, smem)) return rc;                                         \
-    attn_bwd_kernel<TT, 0, BTV><<<g0, 256, smem, stream>>>(                                                      \
+    launch_kernel(attn_bwd_kernel<TT, 0, BTV>, dim3(g0), dim3(256), smem, stream,                                                       \
         (const TT*)q, ldq, (const TT*)k, ldk, (const TT*)v, ldv, key_pad, (const TT*)o, ldo, (const TT*)d_o,     \
         lddo, lse, (TT*)dq, lddq, (TT*)dk, lddk, (TT*)dv, lddv, H, T, S, dh, scale, dst, dpp, dsite);          \
     B200_LAUNCH_CHECK("attn_bwd_kernel<0>");                                                                     \
-    attn_bwd_kernel<TT, 1, BTV><<<g1, 256, smem, stream>>>(                                                      \
+    launch_kernel(attn_bwd_kernel<TT, 1, BTV>, dim3(g1), dim3(256), smem, stream,                                                       \
         (const TT*)q, ldq, (const TT*)k, ldk, (const TT*)v, ldv, key_pad, (const TT*)o, ldo, (const TT*)d_o,     \
         lddo, lse, (TT*)dq, lddq, (TT*)dk, lddk, (TT*)dv, lddv, H, T, S, dh, scale, dst, dpp, dsite);          \
     B200_LAUNCH_CHECK("attn_bwd_kernel<1>");                                                                     \

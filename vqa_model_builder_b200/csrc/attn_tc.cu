@@ -127,6 +127,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_trigger();   // setup above overlapped the previous kernel's tail; global traffic starts below
+  pdl_wait();
   uint32_t ph_k = 0, ph_v = 0, ph_mma = 0;
 
   // ---- S_j = Q K_j^T for every kv tile (K buffer reused serially; the tensor-core work here is tiny) ----
@@ -297,6 +299,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
   uint32_t ph_kv = 0, ph_mma = 0;
 
@@ -479,8 +483,8 @@ int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
     B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(128)));
     configured = true;
   }
-  if (nt == 1) attn_fwd_tc_kernel<1><<<B * H, 128, smem, stream>>>(qm, km, vm, a);
-  else attn_fwd_tc_kernel<3><<<B * H, 128, smem, stream>>>(qm, km, vm, a);
+  if (nt == 1) launch_kernel(attn_fwd_tc_kernel<1>, dim3(B * H), dim3(128), smem, stream, qm, km, vm, a);
+  else launch_kernel(attn_fwd_tc_kernel<3>, dim3(B * H), dim3(128), smem, stream, qm, km, vm, a);
   B200_LAUNCH_CHECK("attn_fwd_tc_kernel");
   count_launch();
   return 0;
@@ -508,7 +512,7 @@ int launch_attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
     B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem(128)));
     configured = true;
   }
-  attn_bwd_tc_kernel<<<B * H, 128, smem, stream>>>(qm, km, vm, dom, a);
+  launch_kernel(attn_bwd_tc_kernel, dim3(B * H), dim3(128), smem, stream, qm, km, vm, dom, a);
   B200_LAUNCH_CHECK("attn_bwd_tc_kernel");
   count_launch();
   return 0;

@@ -40,6 +40,33 @@ int num_sms();
 void count_launch(int n = 1);
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the library is launched with the programmatic-stream-
+// serialization attribute and starts with griddepcontrol.launch_dependents + griddepcontrol.wait, so the launch
+// latency and the prologue (barrier init, TMEM allocation, descriptor prefetch) of kernel N+1 overlap the tail of
+// kernel N.  All global-memory traffic stays behind the wait.  B200VQA_PDL=0 disables the attribute.
+// ---------------------------------------------------------------------------------------------
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KP, typename... A>
+inline cudaError_t launch_kernel(void (*kern)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KP>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // dtype helpers
 // ---------------------------------------------------------------------------------------------
 typedef __nv_bfloat16 bf16;

@@ -16,6 +16,8 @@ constexpr int MAX_E = 64;
 // ---- plan stage 1: per-chunk expert histogram ------------------------------------------------------
 __global__ void __launch_bounds__(PLAN_CHUNK)
 plan_count_kernel(const int* __restrict__ idx, int NK, int E, int* __restrict__ block_counts) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int hist[MAX_E];
   if (threadIdx.x < MAX_E) hist[threadIdx.x] = 0;
   __syncthreads();
@@ -33,6 +35,8 @@ __global__ void __launch_bounds__(1024)
 plan_scan_kernel(int* __restrict__ block_counts /* in: counts, out: exclusive bases */, int chunks, int E, int Rmax,
                  int* __restrict__ counts, int* __restrict__ cmp_off, int* __restrict__ pad_off,
                  int* __restrict__ tile_group) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int s_pad[MAX_E + 1];
   const int t = threadIdx.x;
   if (t < E) {
@@ -74,6 +78,8 @@ __global__ void __launch_bounds__(PLAN_CHUNK)
 plan_scatter_kernel(const int* __restrict__ idx, int NK, int E, const int* __restrict__ block_base,
                     const int* __restrict__ cmp_off, const int* __restrict__ pad_off, int* __restrict__ dest_row,
                     int* __restrict__ cmp_pos, int* __restrict__ row_src) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int warp_hist[PLAN_CHUNK / 32][MAX_E];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int j = threadIdx.x; j < (PLAN_CHUNK / 32) * MAX_E; j += blockDim.x) (&warp_hist[0][0])[j] = 0;
@@ -108,6 +114,8 @@ plan_scatter_kernel(const int* __restrict__ idx, int NK, int E, const int* __res
 // ---- capacity masking (SparseMOELayer) -----------------------------------------------------------------
 __global__ void capacity_init_kernel(const float* __restrict__ w, int NK, float* __restrict__ w_eff,
                                      uint8_t* __restrict__ keep) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < NK) {
     w_eff[i] = w[i];
@@ -117,6 +125,8 @@ __global__ void capacity_init_kernel(const float* __restrict__ w, int NK, float*
 __global__ void __launch_bounds__(1024)
 capacity_kernel(const float* __restrict__ w, const int* __restrict__ counts, const int* __restrict__ pad_off,
                 const int* __restrict__ row_src, int capacity, float* __restrict__ w_eff, uint8_t* __restrict__ keep) {
+  pdl_trigger();
+  pdl_wait();
   const int e = blockIdx.x;
   const int c = counts[e];
   if (c <= capacity) return;
@@ -141,6 +151,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 permute_kernel(const T* __restrict__ x, const int* __restrict__ row_src, const int* __restrict__ pad_off, int E, int K,
                int Rmax, int D, T* __restrict__ xp) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VT = Vec16<T>::N;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -163,6 +175,8 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(256)
 unpermute_kernel(const T* __restrict__ dxp, const int* __restrict__ dest_row, const T* __restrict__ add, int N, int K,
                  int D, T* __restrict__ dx) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int n = warp; n < N; n += nwarps) {
@@ -183,6 +197,8 @@ __global__ void __launch_bounds__(256)
 combine_fwd_kernel(const T* __restrict__ z, const int* __restrict__ dest_row, const float* __restrict__ w,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int N, int K, int D,
                    T* __restrict__ out, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VT = Vec16<T>::N;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -227,6 +243,8 @@ combine_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ z, const in
                    const float* __restrict__ w, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                    const float* __restrict__ gamma, int N, int K, int D, T* __restrict__ dz, float* __restrict__ d_w,
                    float* __restrict__ part, int tpw) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VT = Vec16<T>::N;
   extern __shared__ float red[];  // [CMB_WARPS][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -319,6 +337,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 zero_unwritten_rows_kernel(const int* __restrict__ row_src, const float* __restrict__ w, int Rmax, int D,
                            T* __restrict__ dz) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VT = Vec16<T>::N;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -370,11 +390,11 @@ int b200_moe_plan(const int32_t* idx, int NK, int E, int Rmax, int32_t* counts, 
   const int chunks = (NK + PLAN_CHUNK - 1) / PLAN_CHUNK;
   int* block_counts = (int*)workspace;
   B200_CUDA(cudaMemsetAsync(row_src, 0xFF, (size_t)Rmax * sizeof(int), stream));
-  plan_count_kernel<<<chunks, PLAN_CHUNK, 0, stream>>>(idx, NK, E, block_counts);
+  launch_kernel(plan_count_kernel, dim3(chunks), dim3(PLAN_CHUNK), 0, stream, idx, NK, E, block_counts);
   B200_LAUNCH_CHECK("plan_count_kernel");
-  plan_scan_kernel<<<1, 1024, 0, stream>>>(block_counts, chunks, E, Rmax, counts, cmp_off, pad_off, tile_group);
+  launch_kernel(plan_scan_kernel, dim3(1), dim3(1024), 0, stream, block_counts, chunks, E, Rmax, counts, cmp_off, pad_off, tile_group);
   B200_LAUNCH_CHECK("plan_scan_kernel");
-  plan_scatter_kernel<<<chunks, PLAN_CHUNK, 0, stream>>>(idx, NK, E, block_counts, cmp_off, pad_off, dest_row, cmp_pos,
+  launch_kernel(plan_scatter_kernel, dim3(chunks), dim3(PLAN_CHUNK), 0, stream, idx, NK, E, block_counts, cmp_off, pad_off, dest_row, cmp_pos,
                                                          row_src);
   B200_LAUNCH_CHECK("plan_scatter_kernel");
   count_launch(3);
@@ -386,9 +406,9 @@ int b200_moe_capacity(const int32_t* idx, const float* w, const int32_t* counts,
   cudaStream_t stream = (cudaStream_t)stream_;
   (void)idx;
   B200_CHECK_ARG(NK > 0 && E > 0 && capacity >= 0, "moe_capacity: bad arguments");
-  capacity_init_kernel<<<(NK + 255) / 256, 256, 0, stream>>>(w, NK, w_eff, keep);
+  launch_kernel(capacity_init_kernel, dim3((NK + 255) / 256), dim3(256), 0, stream, w, NK, w_eff, keep);
   B200_LAUNCH_CHECK("capacity_init_kernel");
-  capacity_kernel<<<E, 1024, 0, stream>>>(w, counts, pad_off, row_src, capacity, w_eff, keep);
+  launch_kernel(capacity_kernel, dim3(E), dim3(1024), 0, stream, w, counts, pad_off, row_src, capacity, w_eff, keep);
   B200_LAUNCH_CHECK("capacity_kernel");
   count_launch(2);
   return 0;
@@ -404,9 +424,9 @@ int b200_moe_permute(const void* x, const int32_t* row_src, const int32_t* pad_o
   B200_ROW_DISPATCH(dtype, D, "moe_permute");
   const int blocks = row_grid(Rmax);
   if (dtype == B200_BF16)
-    permute_kernel<bf16><<<blocks, 256, 0, stream>>>((const bf16*)x, row_src, pad_off, E, K, Rmax, D, (bf16*)xp);
+    launch_kernel(permute_kernel<bf16>, dim3(blocks), dim3(256), 0, stream, (const bf16*)x, row_src, pad_off, E, K, Rmax, D, (bf16*)xp);
   else
-    permute_kernel<float><<<blocks, 256, 0, stream>>>((const float*)x, row_src, pad_off, E, K, Rmax, D, (float*)xp);
+    launch_kernel(permute_kernel<float>, dim3(blocks), dim3(256), 0, stream, (const float*)x, row_src, pad_off, E, K, Rmax, D, (float*)xp);
   B200_LAUNCH_CHECK("permute_kernel");
   count_launch();
   return 0;
@@ -418,10 +438,10 @@ int b200_moe_unpermute(const void* dxp, const int32_t* dest_row, const void* add
   B200_ROW_DISPATCH(dtype, D, "moe_unpermute");
   const int blocks = row_grid(N);
   if (dtype == B200_BF16) {
-    B200_NV_SWITCH(row_nv<bf16>(D), unpermute_kernel<bf16, NV><<<blocks, 256, 0, stream>>>(
+    B200_NV_SWITCH(row_nv<bf16>(D), launch_kernel(unpermute_kernel<bf16, NV>, dim3(blocks), dim3(256), 0, stream, 
         (const bf16*)dxp, dest_row, (const bf16*)add, N, K, D, (bf16*)dx));
   } else {
-    B200_NV_SWITCH(row_nv<float>(D), unpermute_kernel<float, NV><<<blocks, 256, 0, stream>>>(
+    B200_NV_SWITCH(row_nv<float>(D), launch_kernel(unpermute_kernel<float, NV>, dim3(blocks), dim3(256), 0, stream, 
         (const float*)dxp, dest_row, (const float*)add, N, K, D, (float*)dx));
   }
   B200_LAUNCH_CHECK("unpermute_kernel");
@@ -436,10 +456,10 @@ int b200_moe_combine_fwd(const void* z, const int32_t* dest_row, const float* w,
   B200_ROW_DISPATCH(dtype, D, "moe_combine_fwd");
   const int blocks = row_grid(N);
   if (dtype == B200_BF16) {
-    B200_NV_SWITCH(row_nv<bf16>(D), combine_fwd_kernel<bf16, NV><<<blocks, 256, 0, stream>>>(
+    B200_NV_SWITCH(row_nv<bf16>(D), launch_kernel(combine_fwd_kernel<bf16, NV>, dim3(blocks), dim3(256), 0, stream, 
         (const bf16*)z, dest_row, w, gamma, beta, eps, N, K, D, (bf16*)out, mean, rstd));
   } else {
-    B200_NV_SWITCH(row_nv<float>(D), combine_fwd_kernel<float, NV><<<blocks, 256, 0, stream>>>(
+    B200_NV_SWITCH(row_nv<float>(D), launch_kernel(combine_fwd_kernel<float, NV>, dim3(blocks), dim3(256), 0, stream, 
         (const float*)z, dest_row, w, gamma, beta, eps, N, K, D, (float*)out, mean, rstd));
   }
   B200_LAUNCH_CHECK("combine_fwd_kernel");
@@ -468,19 +488,19 @@ int b200_moe_combine_bwd(const void* dout, const void* z, const int32_t* dest_ro
   float* part = (float*)workspace;
   const int zb = row_grid(Rmax);
   if (dtype == B200_BF16) {
-    zero_unwritten_rows_kernel<bf16><<<zb, 256, 0, stream>>>(row_src, w, Rmax, D, (bf16*)dz);
+    launch_kernel(zero_unwritten_rows_kernel<bf16>, dim3(zb), dim3(256), 0, stream, row_src, w, Rmax, D, (bf16*)dz);
     B200_NV_SWITCH(row_nv<bf16>(D), {
       if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(combine_bwd_kernel<bf16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      combine_bwd_kernel<bf16, NV><<<blocks, CMB_WARPS * 32, smem, stream>>>(
+      launch_kernel(combine_bwd_kernel<bf16, NV>, dim3(blocks), dim3(CMB_WARPS * 32), smem, stream, 
           (const bf16*)dout, (const bf16*)z, dest_row, w, mean, rstd, gamma, N, K, D, (bf16*)dz, d_w, part, tpw);
     });
   } else {
-    zero_unwritten_rows_kernel<float><<<zb, 256, 0, stream>>>(row_src, w, Rmax, D, (float*)dz);
+    launch_kernel(zero_unwritten_rows_kernel<float>, dim3(zb), dim3(256), 0, stream, row_src, w, Rmax, D, (float*)dz);
     B200_NV_SWITCH(row_nv<float>(D), {
       if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(combine_bwd_kernel<float, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      combine_bwd_kernel<float, NV><<<blocks, CMB_WARPS * 32, smem, stream>>>(
+      launch_kernel(combine_bwd_kernel<float, NV>, dim3(blocks), dim3(CMB_WARPS * 32), smem, stream, 
           (const float*)dout, (const float*)z, dest_row, w, mean, rstd, gamma, N, K, D, (float*)dz, d_w, part, tpw);
     });
   }

@@ -11,6 +11,8 @@ namespace {
 constexpr int TM = 64, TN = 64, TK = 16;
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
 
@@ -83,7 +85,7 @@ int launch_gemm_simt(GemmArgs args, int grid_m_tiles, int groups, cudaStream_t s
   dim3 grid((args.N + TN - 1) / TN, grid_m_tiles * (B200_GROUP_TILE / TM),
             args.mode == GEMM_GROUP_WGRAD ? groups : 1);
   args.k_splits = 1;
-  gemm_simt_kernel<<<grid, 256, 0, stream>>>(args);
+  launch_kernel(gemm_simt_kernel, dim3(grid), dim3(256), 0, stream, args);
   B200_LAUNCH_CHECK("gemm_simt_kernel");
   count_launch();
   return 0;

@@ -249,6 +249,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -473,7 +476,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
     configured = true;
   }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  kern<<<grid, NUM_THREADS, smem_bytes<BN>(), stream>>>(ta, tb, args, m_tiles, n_tiles, total_tiles);
+  launch_kernel(kern, dim3(grid), dim3(NUM_THREADS), smem_bytes<BN>(), stream, ta, tb, args, m_tiles, n_tiles, total_tiles);
   B200_LAUNCH_CHECK("gemm_tc_kernel");
   count_launch();
   return 0;

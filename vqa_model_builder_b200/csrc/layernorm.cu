@@ -57,6 +57,8 @@ add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const floa
                   const float* __restrict__ beta, const int* __restrict__ tile_group, float eps,
                   T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int R, int D,
                   const unsigned long long* drop_state, float drop_p, unsigned int drop_site, int drop_target) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VT = Vec16<T>::N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / VT;
@@ -104,6 +106,8 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
                   const float* __restrict__ gamma, const int* __restrict__ tile_group, T* __restrict__ dsum,
                   float* __restrict__ part, int R, int D, int rpw, const unsigned long long* drop_state, float drop_p,
                   unsigned int drop_site, int drop_target, T* __restrict__ d_dropped) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VT = Vec16<T>::N;
   extern __shared__ float red[];  // [LN_WARPS][2][D]
   const DropState ds = drop_load(drop_state, drop_p, drop_site);
@@ -201,6 +205,8 @@ __global__ void __launch_bounds__(256)
 partial_reduce_kernel(const float* __restrict__ part, int blocks, int rows_per_block, int width, int nz,
                       const int* __restrict__ tile_group, int tiles, float* __restrict__ out0,
                       float* __restrict__ out1) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][33];
   __shared__ int s_lo, s_hi;
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
@@ -238,7 +244,7 @@ int launch_ln_param_reduce(const float* part, int blocks, int rows_per_block, in
                            float* dgamma, float* dbeta, cudaStream_t stream) {
   dim3 grid((D + 31) / 32, G, 2);
   const int tiles = (int)(((long long)blocks * rows_per_block + B200_GROUP_TILE - 1) / B200_GROUP_TILE);
-  partial_reduce_kernel<<<grid, 256, 0, stream>>>(part, blocks, rows_per_block, D, 2, tile_group, tiles, dgamma, dbeta);
+  launch_kernel(partial_reduce_kernel, dim3(grid), dim3(256), 0, stream, part, blocks, rows_per_block, D, 2, tile_group, tiles, dgamma, dbeta);
   B200_LAUNCH_CHECK("partial_reduce_kernel");
   count_launch();
   return 0;
@@ -249,7 +255,7 @@ int launch_partial_reduce(const float* part, int blocks, int rows_per_block, int
                           float* out, cudaStream_t stream) {
   dim3 grid((width + 31) / 32, G, 1);
   const int tiles = (int)(((long long)blocks * rows_per_block + B200_GROUP_TILE - 1) / B200_GROUP_TILE);
-  partial_reduce_kernel<<<grid, 256, 0, stream>>>(part, blocks, rows_per_block, width, 1, tile_group, tiles, out, out);
+  launch_kernel(partial_reduce_kernel, dim3(grid), dim3(256), 0, stream, part, blocks, rows_per_block, width, 1, tile_group, tiles, out, out);
   B200_LAUNCH_CHECK("partial_reduce_kernel");
   count_launch();
   return 0;
@@ -273,11 +279,11 @@ int b200_add_ln_fwd(const void* x, const void* res, const float* gamma, const fl
   const int blocks = (R + LN_WARPS - 1) / LN_WARPS;
   if (dtype == B200_BF16) {
     B200_CHECK_ARG(RowRegs<bf16>::supported(D), "add_ln_fwd: D=%d unsupported for bf16 (need D%%8==0, D<=2048)", D);
-    B200_NV_SWITCH(row_nv<bf16>(D), add_ln_fwd_kernel<bf16, NV><<<blocks, LN_WARPS * 32, 0, stream>>>(
+    B200_NV_SWITCH(row_nv<bf16>(D), launch_kernel(add_ln_fwd_kernel<bf16, NV>, dim3(blocks), dim3(LN_WARPS * 32), 0, stream, 
         (const bf16*)x, (const bf16*)res, gamma, beta, tile_group, eps, (bf16*)y, mean, rstd, R, D, dst, dp, dsite, drop_target));
   } else {
     B200_CHECK_ARG(RowRegs<float>::supported(D), "add_ln_fwd: D=%d unsupported for fp32 (need D%%4==0, D<=1024)", D);
-    B200_NV_SWITCH(row_nv<float>(D), add_ln_fwd_kernel<float, NV><<<blocks, LN_WARPS * 32, 0, stream>>>(
+    B200_NV_SWITCH(row_nv<float>(D), launch_kernel(add_ln_fwd_kernel<float, NV>, dim3(blocks), dim3(LN_WARPS * 32), 0, stream, 
         (const float*)x, (const float*)res, gamma, beta, tile_group, eps, (float*)y, mean, rstd, R, D, dst, dp, dsite, drop_target));
   }
   B200_LAUNCH_CHECK("add_ln_fwd_kernel");
@@ -312,7 +318,7 @@ int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float*
     B200_NV_SWITCH(row_nv<bf16>(D), {
       if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<bf16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      add_ln_bwd_kernel<bf16, NV><<<blocks, LN_WARPS * 32, smem, stream>>>(
+      launch_kernel(add_ln_bwd_kernel<bf16, NV>, dim3(blocks), dim3(LN_WARPS * 32), smem, stream, 
           (const bf16*)dy, (const bf16*)x, (const bf16*)res, mean, rstd, gamma, tile_group, (bf16*)dsum, part, R, D, rpw,
           dst, dp, dsite, drop_target, (bf16*)d_dropped);
     });
@@ -321,7 +327,7 @@ int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float*
     B200_NV_SWITCH(row_nv<float>(D), {
       if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<float, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      add_ln_bwd_kernel<float, NV><<<blocks, LN_WARPS * 32, smem, stream>>>(
+      launch_kernel(add_ln_bwd_kernel<float, NV>, dim3(blocks), dim3(LN_WARPS * 32), smem, stream, 
           (const float*)dy, (const float*)x, (const float*)res, mean, rstd, gamma, tile_group, (float*)dsum, part, R, D, rpw,
           dst, dp, dsite, drop_target, (float*)d_dropped);
     });

@@ -76,6 +76,8 @@ router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
                   const float* __restrict__ eps, float noise_std, int N, int D, int E, int K, int* __restrict__ idx,
                   float* __restrict__ w, float* __restrict__ topk_sum, float* __restrict__ probs,
                   float* __restrict__ probs_noisy, float* __restrict__ part /* [grid][3][RT_MAX_E] */) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VT = Vec16<T>::N;
   constexpr int DP = NV * 32 * VT;
   extern __shared__ float smem[];
@@ -161,6 +163,8 @@ __global__ void __launch_bounds__(1024)
 router_finalize_kernel(const float* __restrict__ part, int blocks, int N, int E, float lb_weight,
                        float* __restrict__ counts, float* __restrict__ psum, float* __restrict__ loss,
                        float* __restrict__ noise_scale_mean) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_red[16][3][RT_MAX_E];
   __shared__ float s_cnt[RT_MAX_E], s_ps[RT_MAX_E], s_ns[RT_MAX_E];
   const int e = threadIdx.x & (RT_MAX_E - 1), y = threadIdx.x / RT_MAX_E;   // 64 experts x 16 partial lanes
@@ -205,6 +209,8 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
                   const float* __restrict__ probs, const float* __restrict__ probs_noisy,
                   const float* __restrict__ counts, const float* __restrict__ d_w, const float* __restrict__ d_loss,
                   T* __restrict__ dx, float* __restrict__ dl_out, float* __restrict__ du_out) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VT = Vec16<T>::N;
   constexpr int DP = NV * 32 * VT;
   extern __shared__ float smem[];
@@ -305,6 +311,8 @@ template <typename T, int EB>   // EB = expert-count bucket (8/16/32/64): a runt
 __global__ void __launch_bounds__(128)   // predicated FMAs per token even for E = 8
 router_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ dl, int N, int D, int E,
                     float* __restrict__ part) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_dl[32][EB];
   const int d = blockIdx.x * 128 + threadIdx.x;
   const int n0 = blockIdx.y * RW_CHUNK, n1 = min(N, n0 + RW_CHUNK);
@@ -344,6 +352,8 @@ router_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ dl, int N
   }
 }
 __global__ void router_wgrad_reduce_kernel(const float* __restrict__ part, int chunks, int ED, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ED) return;
   float s = 0.f;
@@ -397,18 +407,18 @@ int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* 
   if (dtype == B200_BF16) {
     B200_NV_SWITCH(nvb, {
       if (int rc = set_smem(router_fwd_kernel<bf16, NV>, smem)) return rc;
-      router_fwd_kernel<bf16, NV><<<blocks, RT_WARPS * 32, smem, stream>>>(
+      launch_kernel(router_fwd_kernel<bf16, NV>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream, 
           (const bf16*)x, w_gate, w_noise, eps, noise_std, N, D, E, K, idx, w, topk_sum, probs, probs_noisy, part);
     });
   } else {
     B200_NV_SWITCH(nvb, {
       if (int rc = set_smem(router_fwd_kernel<float, NV>, smem)) return rc;
-      router_fwd_kernel<float, NV><<<blocks, RT_WARPS * 32, smem, stream>>>(
+      launch_kernel(router_fwd_kernel<float, NV>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream, 
           (const float*)x, w_gate, w_noise, eps, noise_std, N, D, E, K, idx, w, topk_sum, probs, probs_noisy, part);
     });
   }
   B200_LAUNCH_CHECK("router_fwd_kernel");
-  router_finalize_kernel<<<1, 1024, 0, stream>>>(part, blocks, N, E, lb_weight, counts, psum, loss,
+  launch_kernel(router_finalize_kernel, dim3(1), dim3(1024), 0, stream, part, blocks, N, E, lb_weight, counts, psum, loss,
                                                      eps != nullptr ? noise_scale_mean : nullptr);
   B200_LAUNCH_CHECK("router_finalize_kernel");
   count_launch(2);
@@ -448,14 +458,14 @@ int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* 
   if (dtype == B200_BF16) {
     B200_NV_SWITCH(nvb, {
       if (int rc = set_smem(router_bwd_kernel<bf16, NV>, smem)) return rc;
-      router_bwd_kernel<bf16, NV><<<blocks, RT_WARPS * 32, smem, stream>>>(
+      launch_kernel(router_bwd_kernel<bf16, NV>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream, 
           (const bf16*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
           counts, d_w, d_loss, (bf16*)dx, dl, du);
     });
   } else {
     B200_NV_SWITCH(nvb, {
       if (int rc = set_smem(router_bwd_kernel<float, NV>, smem)) return rc;
-      router_bwd_kernel<float, NV><<<blocks, RT_WARPS * 32, smem, stream>>>(
+      launch_kernel(router_bwd_kernel<float, NV>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream, 
           (const float*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
           counts, d_w, d_loss, (float*)dx, dl, du);
     });
@@ -465,7 +475,7 @@ int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* 
   for (int pass = 0; pass < (noisy ? 2 : 1); ++pass) {
     const float* g = pass == 0 ? dl : du;
     float* out = pass == 0 ? d_w_gate : d_w_noise;
-#define B200_RW(TT, EBV) router_wgrad_kernel<TT, EBV><<<wg_grid, 128, 0, stream>>>((const TT*)x, g, N, D, E, part)
+#define B200_RW(TT, EBV) launch_kernel(router_wgrad_kernel<TT, EBV>, dim3(wg_grid), dim3(128), 0, stream, (const TT*)x, g, N, D, E, part)
     if (dtype == B200_BF16) {
       if (E <= 8) B200_RW(bf16, 8); else if (E <= 16) B200_RW(bf16, 16); else if (E <= 32) B200_RW(bf16, 32); else B200_RW(bf16, 64);
     } else {
