@@ -59,7 +59,10 @@ class SlabOwner:
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k == "_slab":
+            if k in ("_slab", "last_plan"):       # rebuilt lazily / per-forward scratch
+                continue
+            if k == "aux_outputs":                # holds autograd-tracked tensors of the last forward
+                new.__dict__[k] = {}
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         return new
