@@ -202,6 +202,23 @@ int b200_moe_combine_bwd(const void* dout, const void* z, const int32_t* dest_ro
                          float* d_w, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* ---- expert parallelism over NVLink peer memory ------------------------------------------------------
+ * Dispatch / return fused with their collective: rows are written straight into the destination rank's buffer
+ * through peer-mapped pointers (symmetric allocations; `peer_*` are DEVICE arrays of W device pointers, one per
+ * rank).  No host-side split sizes; phases are separated by a stream-ordered cross-rank barrier owned by the caller.
+ *   b200_ep_push_counts : counts[E] (pairs per GLOBAL expert on this rank) -> row `me` of every peer's table [W,E]
+ *   b200_ep_layout      : table -> send_off[E], seg_off[W*El+1], home_off[W*El], idx_recv[cap] (-1 beyond received)
+ *   b200_ep_dispatch    : compact (expert-sorted) row r of `src` (gathered as src[row_src_c[r]/K] when row_src_c is
+ *                         given) -> peer_bufs[owner(e)][send_off[e] + r - cmp_off[e]]
+ *   b200_ep_return      : received row i (rows[row_map[i]] or rows[i]) -> peer_rets[home][home_off[g] + i - seg_off[g]] */
+int b200_ep_push_counts(const int32_t* counts, void* const* peer_tabs, int me, int W, int E, void* stream);
+int b200_ep_layout(const int32_t* tab, int me, int W, int E, int cap, int32_t* send_off, int32_t* seg_off,
+                   int32_t* home_off, int32_t* idx_recv, void* stream);
+int b200_ep_dispatch(const void* src, const int32_t* row_src_c, const int32_t* cmp_off, const int32_t* send_off,
+                     void* const* peer_bufs, int K, int NK, int E, int El, int D, int cap, int dtype, void* stream);
+int b200_ep_return(const void* rows, const int32_t* row_map, const int32_t* seg_off, const int32_t* home_off,
+                   void* const* peer_rets, int W, int El, int D, int cap, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

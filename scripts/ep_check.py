@@ -30,7 +30,9 @@ def main():
     B, S, D, F, E, K = 4, 57, 256, 512, 8, 2
     torch.manual_seed(0)
     full = moe.MOELayer(input_dim=D, hidden_dim=F, output_dim=D, num_experts=E, top_k=K, dropout=0.0).to(dev).train()
-    ep = parallel.ExpertParallelMOELayer(copy.deepcopy(full))
+    transport = os.environ.get("EP_TRANSPORT", "nccl")
+    cls = parallel.P2PExpertParallelMOELayer if transport == "p2p" else parallel.ExpertParallelMOELayer
+    ep = cls(copy.deepcopy(full))
     g = torch.Generator(device="cpu").manual_seed(1)
     x_all = torch.randn(world * B, S, D, generator=g).to(dev)
     gout_all = torch.randn(world * B, S, D, generator=g).to(dev)
@@ -61,7 +63,7 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     print(f"[rank {rank}] aux ep={float(ep.get_aux_loss()):.8f} full={float(full.get_aux_loss()):.8f} "
           f"counts={ep.last_plan.counts.tolist()}", flush=True)
-    print(f"[rank {rank}] mode={mode} worst {worst_key}={errs[worst_key]:.3e} out={errs['out']:.3e} aux_abs={errs['aux']:.2e} "
+    print(f"[rank {rank}] transport={transport} mode={mode} worst {worst_key}={errs[worst_key]:.3e} out={errs['out']:.3e} aux_abs={errs['aux']:.2e} "
           f"dx={errs['dx']:.3e}", flush=True)
     if rank == 0:
         print("EP_CHECK", "PASS" if int(flag) == 1 else "FAIL", flush=True)

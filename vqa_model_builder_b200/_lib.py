@@ -57,6 +57,10 @@ SIGNATURES = {
     "b200_moe_combine_fwd": ("i", "pppppfiiiipppp"),
     "b200_moe_combine_bwd_ws": ("z", "ii"),
     "b200_moe_combine_bwd": ("i", "ppppppppiiiiipppppzp"),
+    "b200_ep_push_counts": ("i", "ppiiip"),
+    "b200_ep_layout": ("i", "piiiippppp"),
+    "b200_ep_dispatch": ("i", "pppppiiiiiiip"),
+    "b200_ep_return": ("i", "pppppiiiiip"),
 }
 
 class DropoutT(ctypes.Structure):

@@ -224,3 +224,169 @@ def finish_gradients(replicated, expert_sharded, group=None) -> None:
     for p in expert_sharded:
         if p.grad is not None:
             p.grad.div_(world)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Expert parallelism with dispatch/return FUSED with the collective: kernels store rows straight into peer GPUs'
+# buffers over NVLink (symmetric memory), no all_to_all call, no host-side split sizes, no host sync.
+# ---------------------------------------------------------------------------------------------------------
+class _P2PState:
+    """Symmetric buffers of one EP layer + the device arrays of peer pointers the kernels index."""
+
+    def __init__(self, group, world: int, rank: int, E: int, D: int, nk_cap: int, dtype: torch.dtype, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank, self.E, self.D, self.nk_cap, self.dtype = world, rank, E, D, nk_cap, dtype
+        self.cap = world * nk_cap                       # worst case: every pair of every rank lands here
+        es = torch.empty((), dtype=dtype).element_size()
+        al = lambda n: (n + 255) // 256 * 256
+        sizes = {"tab": al(world * E * 4), "recv_x": al(self.cap * D * es), "recv_g": al(self.cap * D * es),
+                 "ret_z": al(nk_cap * D * es), "ret_dx": al(nk_cap * D * es)}
+        self.offs, total = {}, 0
+        for k, v in sizes.items():
+            self.offs[k] = total
+            total += v
+        group = group if group is not None else dist.group.WORLD
+        if hasattr(symm_mem, "enable_symm_mem_for_group"):
+            try:
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        bases = list(self.hdl.buffer_ptrs)
+        self.ptrs = {k: torch.tensor([b + off for b in bases], dtype=torch.int64, device=device)
+                     for k, off in self.offs.items()}
+        self.buf.zero_()
+        self.barrier()
+
+    def local(self, key: str, rows: int = None):
+        off = self.offs[key]
+        if key == "tab":
+            return self.buf[off:off + self.world * self.E * 4].view(torch.int32)
+        rows = rows if rows is not None else (self.cap if key.startswith("recv") else self.nk_cap)
+        es = torch.empty((), dtype=self.dtype).element_size()
+        return self.buf[off:off + rows * self.D * es].view(self.dtype).view(rows, self.D)
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+
+class _P2PDispatchFn(torch.autograd.Function):
+    """x rows -> owners' receive buffers (peer stores); backward returns the received rows' gradients home."""
+
+    @staticmethod
+    def forward(ctx, x2, st, meta):
+        from . import _lib
+        plan, row_src_c, send_off, seg_off, home_off, K, El = meta
+        x2 = x2.contiguous()
+        _lib.call("b200_ep_dispatch", x2, row_src_c, plan.cmp_off, send_off, st.ptrs["recv_x"], K, plan.NK, plan.E, El,
+                  st.D, st.cap, _lib.dtype_code(x2.dtype), _lib.stream_ptr())
+        st.barrier()
+        ctx.st, ctx.meta, ctx.n = st, meta, x2.shape[0]
+        return st.local("recv_x")
+
+    @staticmethod
+    def backward(ctx, d_recv):
+        from . import _lib
+        st = ctx.st
+        plan, row_src_c, send_off, seg_off, home_off, K, El = ctx.meta
+        d_recv = d_recv.contiguous()
+        _lib.call("b200_ep_return", d_recv, None, seg_off, home_off, st.ptrs["ret_dx"], st.world, El, st.D, st.cap,
+                  _lib.dtype_code(d_recv.dtype), _lib.stream_ptr())
+        st.barrier()
+        dx = torch.empty((ctx.n, st.D), dtype=d_recv.dtype, device=d_recv.device)
+        _lib.call("b200_moe_unpermute", st.local("ret_dx"), plan.cmp_pos, None, ctx.n, K, st.D,
+                  _lib.dtype_code(d_recv.dtype), dx, _lib.stream_ptr())
+        return dx, None, None
+
+
+class _P2PReturnFn(torch.autograd.Function):
+    """expert outputs (padded layout on the owner) -> home ranks' buffers at the compact positions; backward sends the
+    combine gradients to the owners with the dispatch kernel."""
+
+    @staticmethod
+    def forward(ctx, z2, st, meta, plan2):
+        from . import _lib
+        plan, row_src_c, send_off, seg_off, home_off, K, El = meta
+        z2 = z2.contiguous()
+        _lib.call("b200_ep_return", z2, plan2.dest_row, seg_off, home_off, st.ptrs["ret_z"], st.world, El, st.D, st.cap,
+                  _lib.dtype_code(z2.dtype), _lib.stream_ptr())
+        st.barrier()
+        ctx.st, ctx.meta, ctx.plan2, ctx.rows = st, meta, plan2, z2.shape[0]
+        return st.local("ret_z", plan.NK).clone()
+
+    @staticmethod
+    def backward(ctx, d_back):
+        from . import _lib
+        st, plan2 = ctx.st, ctx.plan2
+        plan, row_src_c, send_off, seg_off, home_off, K, El = ctx.meta
+        d_back = d_back.contiguous()
+        _lib.call("b200_ep_dispatch", d_back, None, plan.cmp_off, send_off, st.ptrs["recv_g"], K, plan.NK, plan.E, El,
+                  st.D, st.cap, _lib.dtype_code(d_back.dtype), _lib.stream_ptr())
+        st.barrier()
+        dz2 = torch.empty((ctx.rows, st.D), dtype=d_back.dtype, device=d_back.device)
+        _lib.call("b200_moe_permute", st.local("recv_g"), plan2.row_src, plan2.pad_off, El, 1, ctx.rows, st.D,
+                  _lib.dtype_code(d_back.dtype), dz2, _lib.stream_ptr())
+        return dz2, None, None, None
+
+
+class P2PExpertParallelMOELayer(ExpertParallelMOELayer):
+    """ExpertParallelMOELayer whose dispatch / return are single kernels over NVLink peer memory (no NCCL all-to-all,
+    no host read of the routing counts: the whole layer is asynchronous on the stream)."""
+
+    def _state(self, NK: int, D: int, dtype, device) -> _P2PState:
+        st = self.__dict__.get("_p2p")
+        if st is None or st.nk_cap < NK or st.dtype != dtype or st.D != D:
+            st = _P2PState(self.group, self.world, self.rank, self.num_experts, D, NK, dtype, device)
+            self.__dict__["_p2p"] = st
+        return st
+
+    def forward(self, x: torch.Tensor, mask=None, **kwargs) -> torch.Tensor:
+        from . import _lib, ops
+        from .runtime import DropCtx, alloc_sites, resolve_compute_dtype
+        L = self.local
+        B, S, D = x.shape
+        N, K, E, W, El = B * S, self.top_k, self.num_experts, self.world, self.experts_per_rank
+        weights, indices, aux = L.router(x)
+        L.aux_outputs = self.aux_outputs = aux
+        cdt = resolve_compute_dtype(x)
+        x2 = ops.to_compute(x.reshape(N, D), cdt)
+        stash = aux.get("_b200_idx32")
+        idx32 = stash[1] if stash is not None and stash[0] is indices else indices.reshape(N, K).to(torch.int32)
+        plan = ops.RoutingPlan(idx32, E)
+        NK = plan.NK
+        dev = x.device
+        ar = torch.arange(NK, device=dev, dtype=torch.int32)
+        valid = plan.cmp_pos >= 0
+        row_src_c = torch.full((NK,), -1, dtype=torch.int32, device=dev)
+        row_src_c[plan.cmp_pos[valid].long()] = ar[valid]
+        st = self._state(NK, D, cdt, dev)
+        sp = _lib.stream_ptr()
+        # phase 1: publish my per-expert counts in every rank's table, then derive all offsets on the device
+        _lib.call("b200_ep_push_counts", plan.counts, st.ptrs["tab"], self.rank, W, E, sp)
+        st.barrier()
+        send_off = torch.empty(E, dtype=torch.int32, device=dev)
+        seg_off = torch.empty(W * El + 1, dtype=torch.int32, device=dev)
+        home_off = torch.empty(W * El, dtype=torch.int32, device=dev)
+        idx_recv = torch.empty(st.cap, dtype=torch.int32, device=dev)
+        _lib.call("b200_ep_layout", st.local("tab"), self.rank, W, E, st.cap, send_off, seg_off, home_off, idx_recv, sp)
+        meta = (plan, row_src_c, send_off, seg_off, home_off, K, El)
+        # phase 2: permute fused with the exchange
+        got = _P2PDispatchFn.apply(x2, st, meta)
+        plan2 = ops.RoutingPlan(idx_recv.view(st.cap, 1), El)
+        stacks = L._expert_stacks(dev, cdt)
+        ex0 = L.experts[0]
+        xp2 = ops.PermuteFn.apply(got, plan2.row_src, plan2.pad_off, plan2.dest_row, El, 1, plan2.Rmax)
+        if "_sites" not in self.__dict__:
+            self.__dict__["_sites"] = alloc_sites(2)
+        dc = DropCtx(self.training, float(ex0.dropout_rate), dev, self.__dict__["_sites"])
+        z2 = ops.ExpertFFNFn.apply(xp2, plan2.tile_group, plan2.pad_off, stacks, ex0.act_code, D == ex0.output_dim,
+                                   ex0.layer_norm.eps, (dc.site(0), dc.site(1)) if dc.on else None,
+                                   *L._expert_params())
+        # phase 3: expert outputs go straight back to the tokens' home ranks
+        back = _P2PReturnFn.apply(z2, st, meta, plan2)
+        w2d = weights.reshape(N, K).to(torch.float32)
+        out = ops.CombineFn.apply(back, w2d, plan.cmp_pos, row_src_c, L.output_norm.weight, L.output_norm.bias,
+                                  L.output_norm.eps)
+        self.last_plan = plan
+        return ops.to_compute(out, x.dtype).view(B, S, self.output_dim)
