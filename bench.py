@@ -211,19 +211,43 @@ def run_ours(args, c):
     loss_d = torch.zeros(1, dtype=torch.float32, device=dev)
 
     comm = {"on": True}
+    fus_params, moe_params = list(fus.parameters()), list(layer.parameters())
+    side_comm = torch.cuda.Stream() if world > 1 else None
 
-    def step():
+    # The step is split where the MOE layer's gradients are complete (MOE is last in forward, first in backward):
+    # under data parallelism their all-reduce then overlaps the backward pass of the fusion block.
+    def part1():
         for p in params:
             p.grad = None
         vis.grad = None
         txt.grad = None
         fused = fus(vis, txt, text_mask=pad)
-        out = layer(fused.unsqueeze(1))
+        fd = fused.detach().requires_grad_(True)
+        out = layer(fd.unsqueeze(1))
         loss = out.float().square().mean() + layer.get_aux_loss()
         loss.backward()
-        if world > 1 and comm["on"] and not torch.cuda.is_current_stream_capturing():
-            parallel.allreduce_gradients(params)
         loss_d.copy_(loss.detach().reshape(1))
+        return fused, fd
+
+    def part2(fused, fd):
+        fused.backward(fd.grad)
+
+    def reduce_overlapped(run_part2):
+        """MOE grads are reduced on a side stream while part 2 runs; fusion grads afterwards."""
+        cur = torch.cuda.current_stream()
+        side_comm.wait_stream(cur)
+        with torch.cuda.stream(side_comm):
+            parallel.allreduce_gradients(moe_params)
+        run_part2()
+        parallel.allreduce_gradients(fus_params)
+        cur.wait_stream(side_comm)
+
+    def step():
+        fused, fd = part1()
+        if world > 1 and comm["on"]:
+            reduce_overlapped(lambda: part2(fused, fd))
+        else:
+            part2(fused, fd)
 
     # ---- eager warm-up (also configures kernels), launch count per step ----
     side = torch.cuda.Stream()
@@ -233,30 +257,39 @@ def run_ours(args, c):
             step()
         torch.cuda.synchronize()
         _lib.reset_launch_count()
+        comm["on"] = False
         step()
+        comm["on"] = True
         torch.cuda.synchronize()
         launches_per_step = _lib.launch_count()
     torch.cuda.current_stream().wait_stream(side)
+    if world > 1:   # the un-reduced counting step must leave every rank with identical state: re-sync grads
+        dist.barrier()
 
     use_graph = not args.no_graph
-    graph = None
+    graph = graph2 = None
     if use_graph:
         try:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                step()
+                held = part1()
+            graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph2, pool=graph.pool()):
+                part2(*held)
         except Exception as e:  # capture unsupported for this configuration: time eagerly
             if rank == 0:
                 print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches",
                       file=sys.stderr)
-            graph = None
+            graph = graph2 = None
             torch.cuda.synchronize()
 
     def run_step():
         if graph is not None:
             graph.replay()
-            if world > 1:   # the gradient all-reduce stays outside the captured graph (NCCL launched eagerly)
-                parallel.allreduce_gradients(params)
+            if world > 1:   # NCCL launched eagerly between / after the two captured halves
+                reduce_overlapped(graph2.replay)
+            else:
+                graph2.replay()
         else:
             step()
 
@@ -304,13 +337,8 @@ def run_ours(args, c):
             vis.copy_(vis_h, non_blocking=True)
             txt.copy_(txt_h, non_blocking=True)
             pad.copy_(pad_h, non_blocking=True)
-            if graph is not None:
-                graph.replay()
-                if world > 1:
-                    parallel.allreduce_gradients(params)
-            else:
-                with torch.enable_grad():
-                    step()
+            with torch.enable_grad():
+                run_step()
             loss_h.copy_(loss_d, non_blocking=True)
             e2e_e[i].record()
             e2e_e[i].synchronize()          # the caller reads the loss every step (training_pipeline.py:484)
