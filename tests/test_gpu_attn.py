@@ -28,7 +28,10 @@ def ref_attn(q, k, v, pad, H):
 
 
 CASES = [(2, 4, 12, 7, 64), (32, 8, 64, 50, 768), (4, 8, 64, 257, 768), (3, 8, 114, 114, 768), (2, 8, 50, 64, 1024),
-         (2, 4, 70, 130, 128)]
+         (2, 4, 70, 130, 128),
+         # 64-row flavour (T, S <= 64): odd sizes, d_h = 64 / 96 / 128, a single query, many co-resident CTAs
+         (5, 8, 33, 17, 768), (3, 4, 64, 64, 256), (2, 8, 1, 50, 768), (3, 8, 64, 3, 1024), (200, 8, 64, 50, 768),
+         (2, 8, 65, 64, 768), (2, 8, 64, 65, 768)]
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

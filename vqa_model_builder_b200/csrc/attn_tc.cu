@@ -73,13 +73,24 @@ __device__ __forceinline__ uint32_t idesc(int M, int N, bool a_mn, bool b_mn) {
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // K-major operand: k-step kk covers columns 16kk..16kk+15 -> chunk kk/4, 32-byte step inside the 128-byte row
-__device__ __forceinline__ uint64_t desc_k(uint32_t tile, int kk) {
-  return ptx::umma_smem_desc(tile + (kk >> 2) * CHB + (kk & 3) * 32, 16, 1024);
+__device__ __forceinline__ uint64_t desc_k(uint32_t tile, int kk, int ch = CHB) {
+  return ptx::umma_smem_desc(tile + (kk >> 2) * ch + (kk & 3) * 32, 16, 1024);
 }
 // MN-major operand: k-step kk covers rows 16kk..16kk+15 (2048 bytes); 64-wide MN chunks are CHB apart
-__device__ __forceinline__ uint64_t desc_mn(uint32_t tile, int kk) {
-  return ptx::umma_smem_desc(tile + kk * 2048, CHB, 1024);
+__device__ __forceinline__ uint64_t desc_mn(uint32_t tile, int kk, int ch = CHB) {
+  return ptx::umma_smem_desc(tile + kk * 2048, ch, 1024);
 }
+
+// Geometry of the two kernel flavours.  R = 128: the general kernel (T <= 128, kv tiles of 128 rows, 128 threads).
+// R = 64: T <= 64 and S <= 64 (the question / image-patch shapes of the fusion block): TMA boxes of 64 rows, 64
+// threads, half the shared memory and a quarter of the TMEM, so 3 (forward) / 2 (backward) CTAs share an SM and
+// hide each other's TMA -> MMA -> softmax -> MMA latency chain.  The UMMAs keep M = 128: accumulator rows 64..127
+// are computed from whatever follows the 64-row operand in shared memory and are never read back.
+template <int R> struct Geo {
+  static constexpr int CH = R * 128;                 // bytes of one TMA-loaded [R rows x 64 bf16] chunk
+  static constexpr int PT = (R == 64) ? 8192 : 2 * CHB;   // bytes of a P / dS tile ([R x 64] or [128 x 128])
+  static constexpr int SLACK = (R == 64) ? 8192 : 0;      // readable bytes behind the last operand (M = 128 over-read)
+};
 
 struct Smem {
   uint32_t base;     // 1024-aligned shared address
@@ -93,20 +104,24 @@ __device__ __forceinline__ Smem align_smem(uint8_t* raw) {
 
 // ============================================ forward ==============================================
 // smem: Q[nch] | K[nch] | V[nch] | P[2] chunks, then barriers.  TMEM: S tiles at columns 128*j, O at 128*NT.
-template <int NT>
-__global__ void __launch_bounds__(128)
+template <int NT, int R>
+__global__ void __launch_bounds__(R)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                    const __grid_constant__ CUtensorMap vmap, const AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const Smem sm = align_smem(smem_raw);
   const int nch = (a.dh + 63) / 64;
-  const uint32_t sQ = sm.base, sK = sQ + nch * CHB, sV = sK + nch * CHB, sP = sV + nch * CHB;
-  uint8_t* pP = sm.ptr + 3 * nch * CHB;
-  const uint32_t bars = sP + 2 * CHB;
+  constexpr int CH = Geo<R>::CH;
+  constexpr bool SMALL = (R == 64);
+  static_assert(!SMALL || NT == 1, "the 64-row flavour handles a single kv tile");
+  const uint32_t sQ = sm.base, sK = sQ + nch * CH, sV = sK + nch * CH, sP = sV + nch * CH;
+  uint8_t* pP = sm.ptr + 3 * nch * CH;
+  const uint32_t bars = sP + Geo<R>::PT + Geo<R>::SLACK;
   const uint32_t bar_q = bars, bar_k = bars + 8, bar_v = bars + 16, bar_mma = bars + 24;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.ptr + 3 * nch * CHB + 2 * CHB + 32);
-  constexpr uint32_t TCOLS = NT == 1 ? 256 : 512;
-  constexpr uint32_t O_COL = NT * 128;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.ptr + 3 * nch * CH + Geo<R>::PT + Geo<R>::SLACK + 32);
+  // 64-row flavour: O overwrites S (S is dead once P sits in shared memory) -> 128 columns, 4 CTAs' worth per SM
+  constexpr uint32_t TCOLS = SMALL ? 128 : (NT == 1 ? 256 : 512);
+  constexpr uint32_t O_COL = SMALL ? 0 : NT * 128;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
@@ -133,23 +148,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 
   // ---- S_j = Q K_j^T for every kv tile (K buffer reused serially; the tensor-core work here is tiny) ----
   if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(bar_q, nch * CHB);
-    for (int c = 0; c < nch; ++c) ptx::tma_load_2d(sQ + c * CHB, &qmap, bar_q, h * a.dh + 64 * c, b * a.T);
+    ptx::mbar_arrive_expect_tx(bar_q, nch * CH);
+    for (int c = 0; c < nch; ++c) ptx::tma_load_2d(sQ + c * CH, &qmap, bar_q, h * a.dh + 64 * c, b * a.T);
   }
   for (int j = 0; j < NT; ++j) {
-    const int n_valid = min(ROWS, a.S - j * ROWS);
+    const int n_valid = min(R, a.S - j * R);
     if (n_valid <= 0) break;
     const int n16 = (n_valid + 15) & ~15;
     if (tid == 0) {
-      ptx::mbar_arrive_expect_tx(bar_k, nch * CHB);
+      ptx::mbar_arrive_expect_tx(bar_k, nch * CH);
       for (int c = 0; c < nch; ++c)
-        ptx::tma_load_2d(sK + c * CHB, &kmap, bar_k, h * a.dh + 64 * c, b * a.S + j * ROWS);
+        ptx::tma_load_2d(sK + c * CH, &kmap, bar_k, h * a.dh + 64 * c, b * a.S + j * R);
       if (j == 0) ptx::mbar_wait(bar_q, 0);
       ptx::mbar_wait(bar_k, ph_k);
       ptx::tc_fence_after();
       const uint32_t id = idesc(128, n16, false, false);
       for (int kk = 0; kk < ksteps_d; ++kk)
-        ptx::umma_bf16(tmem + j * 128, desc_k(sQ, kk), desc_k(sK, kk), id, kk > 0 ? 1u : 0u);
+        ptx::umma_bf16(tmem + j * 128, desc_k(sQ, kk, CH), desc_k(sK, kk, CH), id, kk > 0 ? 1u : 0u);
       ptx::umma_commit(bar_mma);
     }
     ph_k ^= 1;
@@ -158,8 +173,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   }
   ptx::tc_fence_after();
   if (tid == 0) {   // prefetch V_0 while the softmax statistics are computed
-    ptx::mbar_arrive_expect_tx(bar_v, nch * CHB);
-    for (int c = 0; c < nch; ++c) ptx::tma_load_2d(sV + c * CHB, &vmap, bar_v, h * a.dh + 64 * c, b * a.S);
+    ptx::mbar_arrive_expect_tx(bar_v, nch * CH);
+    for (int c = 0; c < nch; ++c) ptx::tma_load_2d(sV + c * CH, &vmap, bar_v, h * a.dh + 64 * c, b * a.S);
   }
 
   // ---- softmax: thread = query row -------------------------------------------------------------------
@@ -168,7 +183,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   const uint8_t* kp = a.key_pad ? a.key_pad + (long long)b * a.S : nullptr;
   float m = -INFINITY;
   for (int j = 0; j < NT; ++j) {
-    const int n_valid = min(ROWS, a.S - j * ROWS);
+    const int n_valid = min(R, a.S - j * R);
     if (n_valid <= 0) break;
     for (int c = 0; c * 32 < n_valid; ++c) {
       float v[32];
@@ -176,7 +191,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int col = c * 32 + i;
-        const bool ok = col < n_valid && !(kp && kp[j * ROWS + col]);
+        const bool ok = col < n_valid && !(kp && kp[j * R + col]);
         if (ok) m = fmaxf(m, v[i]);
       }
     }
@@ -187,7 +202,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   const unsigned long long drow = ((unsigned long long)blockIdx.x * a.T + r) * (unsigned long long)(((a.S + ROWS - 1) / ROWS) * ROWS);
   float l = 0.f;
   for (int j = 0; j < NT; ++j) {
-    const int n_valid = min(ROWS, a.S - j * ROWS);
+    const int n_valid = min(R, a.S - j * R);
     if (n_valid <= 0) break;
     const int n16 = (n_valid + 15) & ~15;
     for (int c = 0; c * 32 < n16; ++c) {
@@ -196,7 +211,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int col = c * 32 + i;
-        const bool ok = col < n_valid && !(kp && kp[j * ROWS + col]);
+        const bool ok = col < n_valid && !(kp && kp[j * R + col]);
         const float p = ok ? ex2(fmaf(v[i], sl2, -m_s)) : 0.f;
         // round to bf16 first so the normaliser matches the probabilities the tensor core actually sees
         const float pr = __bfloat162float(__float2bfloat16_rn(p));
@@ -222,16 +237,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
       ptx::mbar_wait(bar_v, ph_v);
       const uint32_t id = idesc(128, a.dh, false, true);
       for (int kk = 0; kk < n16 / 16; ++kk)
-        ptx::umma_bf16(tmem + O_COL, desc_k(sP, kk), desc_mn(sV, kk), id, (j > 0 || kk > 0) ? 1u : 0u);
+        ptx::umma_bf16(tmem + O_COL, desc_k(sP, kk), desc_mn(sV, kk, CH), id, (j > 0 || kk > 0) ? 1u : 0u);
       ptx::umma_commit(bar_mma);
     }
     ph_v ^= 1;
     ptx::mbar_wait(bar_mma, ph_mma);   // P and V buffers are free again
     ph_mma ^= 1;
-    if (tid == 0 && j + 1 < NT && a.S - (j + 1) * ROWS > 0) {
-      ptx::mbar_arrive_expect_tx(bar_v, nch * CHB);
+    if (tid == 0 && j + 1 < NT && a.S - (j + 1) * R > 0) {
+      ptx::mbar_arrive_expect_tx(bar_v, nch * CH);
       for (int c = 0; c < nch; ++c)
-        ptx::tma_load_2d(sV + c * CHB, &vmap, bar_v, h * a.dh + 64 * c, b * a.S + (j + 1) * ROWS);
+        ptx::tma_load_2d(sV + c * CH, &vmap, bar_v, h * a.dh + 64 * c, b * a.S + (j + 1) * R);
     }
   }
   ptx::tc_fence_after();
@@ -261,28 +276,35 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 }
 
 // ============================================ backward =============================================
-// smem: Q[nch] | dO[nch] | K[nch] | V[nch] | P[2] | dS[2].  TMEM: S/dV at 0, dP/dK at 128, dQ at 256.
-__global__ void __launch_bounds__(128)
+// smem: Q[nch] | dO[nch] | K[nch] | V[nch] | P | dS.  TMEM (R = 128): S/dV at 0, dP/dK at 128, dQ at 256.
+// R = 64: S at 0, dP at 64; dV at 0 and dK at 128 are drained first, then dQ reuses column 0 (256 columns in all,
+// two CTAs per SM).
+template <int R>
+__global__ void __launch_bounds__(R)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                    const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap domap,
                    const AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const Smem sm = align_smem(smem_raw);
   const int nch = (a.dh + 63) / 64;
-  const uint32_t sQ = sm.base, sdO = sQ + nch * CHB, sK = sdO + nch * CHB, sV = sK + nch * CHB;
-  const uint32_t sP = sV + nch * CHB, sdS = sP + 2 * CHB;
-  uint8_t* pP = sm.ptr + 4 * nch * CHB;
-  uint8_t* pdS = pP + 2 * CHB;
-  const uint32_t bars = sdS + 2 * CHB;
+  constexpr int CH = Geo<R>::CH, PT = Geo<R>::PT;
+  constexpr bool SMALL = (R == 64);
+  constexpr int PCH = SMALL ? PT : CHB;    // pitch between the 64-column chunks of the P / dS tiles
+  const uint32_t sQ = sm.base, sdO = sQ + nch * CH, sK = sdO + nch * CH, sV = sK + nch * CH;
+  const uint32_t sP = sV + nch * CH, sdS = sP + PT;
+  uint8_t* pP = sm.ptr + 4 * nch * CH;
+  uint8_t* pdS = pP + PT;
+  const uint32_t bars = sdS + PT + Geo<R>::SLACK;
   const uint32_t bar_q = bars, bar_kv = bars + 8, bar_mma = bars + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.ptr + 4 * nch * CHB + 4 * CHB + 32);
-  constexpr uint32_t TCOLS = 512, C_S = 0, C_DP = 128, C_DQ = 256;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.ptr + 4 * nch * CH + 2 * PT + Geo<R>::SLACK + 32);
+  constexpr uint32_t TCOLS = SMALL ? 256 : 512, C_S = 0, C_DP = SMALL ? 64 : 128, C_DV = 0, C_DK = 128,
+                     C_DQ = SMALL ? 0 : 256;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int ksteps_d = a.dh / 16;
-  const int ksteps_t = (min(a.T, ROWS) + 15) / 16;
-  const int ntiles = (a.S + ROWS - 1) / ROWS;
+  const int ksteps_t = (min(a.T, R) + 15) / 16;
+  const int ntiles = (a.S + R - 1) / R;
 
   if (tid == 0) {
     ptx::prefetch_tensormap(&qmap);
@@ -305,10 +327,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   uint32_t ph_kv = 0, ph_mma = 0;
 
   if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(bar_q, 2 * nch * CHB);
+    ptx::mbar_arrive_expect_tx(bar_q, 2 * nch * CH);
     for (int c = 0; c < nch; ++c) {
-      ptx::tma_load_2d(sQ + c * CHB, &qmap, bar_q, h * a.dh + 64 * c, b * a.T);
-      ptx::tma_load_2d(sdO + c * CHB, &domap, bar_q, h * a.dh + 64 * c, b * a.T);
+      ptx::tma_load_2d(sQ + c * CH, &qmap, bar_q, h * a.dh + 64 * c, b * a.T);
+      ptx::tma_load_2d(sdO + c * CH, &domap, bar_q, h * a.dh + 64 * c, b * a.T);
     }
   }
   // per-row statistics: delta = sum_d dO*O, lse
@@ -330,25 +352,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   const float sl2 = a.scale * LOG2E;
   const uint8_t* kp = a.key_pad ? a.key_pad + (long long)b * a.S : nullptr;
   const DropState ds = drop_load(a.drop_state, a.drop_p, a.drop_site);
-  const unsigned long long drow = ((unsigned long long)blockIdx.x * a.T + r) * (unsigned long long)(ntiles * ROWS);
+  const unsigned long long drow = ((unsigned long long)blockIdx.x * a.T + r) * (unsigned long long)(((a.S + ROWS - 1) / ROWS) * ROWS);
 
   for (int j = 0; j < ntiles; ++j) {
-    const int n_valid = min(ROWS, a.S - j * ROWS);
+    const int n_valid = min(R, a.S - j * R);
     const int n16 = (n_valid + 15) & ~15;
     if (tid == 0) {
-      ptx::mbar_arrive_expect_tx(bar_kv, 2 * nch * CHB);
+      ptx::mbar_arrive_expect_tx(bar_kv, 2 * nch * CH);
       for (int c = 0; c < nch; ++c) {
-        ptx::tma_load_2d(sK + c * CHB, &kmap, bar_kv, h * a.dh + 64 * c, b * a.S + j * ROWS);
-        ptx::tma_load_2d(sV + c * CHB, &vmap, bar_kv, h * a.dh + 64 * c, b * a.S + j * ROWS);
+        ptx::tma_load_2d(sK + c * CH, &kmap, bar_kv, h * a.dh + 64 * c, b * a.S + j * R);
+        ptx::tma_load_2d(sV + c * CH, &vmap, bar_kv, h * a.dh + 64 * c, b * a.S + j * R);
       }
       if (j == 0) ptx::mbar_wait(bar_q, 0);
       ptx::mbar_wait(bar_kv, ph_kv);
       ptx::tc_fence_after();
       const uint32_t id = idesc(128, n16, false, false);
       for (int kk = 0; kk < ksteps_d; ++kk)   // S = Q K^T
-        ptx::umma_bf16(tmem + C_S, desc_k(sQ, kk), desc_k(sK, kk), id, kk > 0 ? 1u : 0u);
+        ptx::umma_bf16(tmem + C_S, desc_k(sQ, kk, CH), desc_k(sK, kk, CH), id, kk > 0 ? 1u : 0u);
       for (int kk = 0; kk < ksteps_d; ++kk)   // dP = dO V^T
-        ptx::umma_bf16(tmem + C_DP, desc_k(sdO, kk), desc_k(sV, kk), id, kk > 0 ? 1u : 0u);
+        ptx::umma_bf16(tmem + C_DP, desc_k(sdO, kk, CH), desc_k(sV, kk, CH), id, kk > 0 ? 1u : 0u);
       ptx::umma_commit(bar_mma);
     }
     ph_kv ^= 1;
@@ -357,7 +379,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
     ptx::tc_fence_after();
 
     // P = exp(S*scale - lse), dS = P * (dP - delta) * scale  -> swizzled smem tiles (bf16)
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < R / 32; ++c) {
       float s[32], dp[32];
       if (c * 32 < n16) {
         ld32(lane_base + C_S + c * 32, s);
@@ -374,7 +396,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int col = c * 32 + i;
-        const bool ok = row_ok && col < n_valid && !(kp && kp[j * ROWS + col]);
+        const bool ok = row_ok && col < n_valid && !(kp && kp[j * R + col]);
         const float p = ok ? ex2(fmaf(s[i], sl2, -lse_l2)) : 0.f;
         s[i] = p * keep[i];                                               // dropped P feeds dV = P^T dO
         dp[i] = ok ? p * (dp[i] * keep[i] - delta) * a.scale : 0.f;       // dS = P (dP*mask/(1-p) - delta)
@@ -390,12 +412,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
       ptx::tc_fence_after();
       const uint32_t id_t = idesc(128, a.dh, true, true);    // A^T B with A = P / dS (MN-major), B = dO / Q (MN-major)
       for (int kk = 0; kk < ksteps_t; ++kk)   // dV = P^T dO
-        ptx::umma_bf16(tmem + C_S, desc_mn(sP, kk), desc_mn(sdO, kk), id_t, kk > 0 ? 1u : 0u);
+        ptx::umma_bf16(tmem + C_DV, desc_mn(sP, kk, PCH), desc_mn(sdO, kk, CH), id_t, kk > 0 ? 1u : 0u);
       for (int kk = 0; kk < ksteps_t; ++kk)   // dK = dS^T Q
-        ptx::umma_bf16(tmem + C_DP, desc_mn(sdS, kk), desc_mn(sQ, kk), id_t, kk > 0 ? 1u : 0u);
-      const uint32_t id_q = idesc(128, a.dh, false, true);   // dQ += dS K  (A = dS K-major, B = K MN-major)
-      for (int kk = 0; kk < n16 / 16; ++kk)
-        ptx::umma_bf16(tmem + C_DQ, desc_k(sdS, kk), desc_mn(sK, kk), id_q, (j > 0 || kk > 0) ? 1u : 0u);
+        ptx::umma_bf16(tmem + C_DK, desc_mn(sdS, kk, PCH), desc_mn(sQ, kk, CH), id_t, kk > 0 ? 1u : 0u);
+      if (!SMALL) {
+        const uint32_t id_q = idesc(128, a.dh, false, true);   // dQ += dS K  (A = dS K-major, B = K MN-major)
+        for (int kk = 0; kk < n16 / 16; ++kk)
+          ptx::umma_bf16(tmem + C_DQ, desc_k(sdS, kk, PCH), desc_mn(sK, kk, CH), id_q, (j > 0 || kk > 0) ? 1u : 0u);
+      }
       ptx::umma_commit(bar_mma);
     }
     ptx::mbar_wait(bar_mma, ph_mma);
@@ -403,14 +427,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
     ptx::tc_fence_after();
     // dV, dK rows of this tile: thread = kv row
     {
-      const int srow = j * ROWS + r;
+      const int srow = j * R + r;
       const bool ok = r < n_valid;
       bf16* dvrow = a.dv + ((long long)b * a.S + srow) * a.lddv + h * a.dh;
       bf16* dkrow = a.dk + ((long long)b * a.S + srow) * a.lddk + h * a.dh;
       for (int c = 0; c < a.dh / 32; ++c) {
         float v[32], k[32];
-        ld32(lane_base + C_S + c * 32, v);
-        ld32(lane_base + C_DP + c * 32, k);
+        ld32(lane_base + C_DV + c * 32, v);
+        ld32(lane_base + C_DK + c * 32, k);
         if (ok) {
 #pragma unroll
           for (int jv = 0; jv < 4; ++jv) {
@@ -429,6 +453,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
     __syncthreads();   // TMEM S/dP regions and the K/V/P/dS buffers may be overwritten by the next tile
   }
 
+  if (SMALL) {   // dV / dK are drained: dQ = dS K takes their columns (single kv tile in this flavour)
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      const int n16 = (min(R, a.S) + 15) & ~15;
+      const uint32_t id_q = idesc(128, a.dh, false, true);
+      for (int kk = 0; kk < n16 / 16; ++kk)
+        ptx::umma_bf16(tmem + C_DQ, desc_k(sdS, kk, PCH), desc_mn(sK, kk, CH), id_q, kk > 0 ? 1u : 0u);
+      ptx::umma_commit(bar_mma);
+    }
+    ptx::mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+  }
   // dQ rows
   ptx::tc_fence_after();
   {
@@ -452,8 +488,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   if (warp == 0) ptx::tmem_dealloc(tmem, TCOLS);
 }
 
-size_t fwd_smem(int dh) { return (size_t)(3 * ((dh + 63) / 64) + 2) * CHB + 1024 + 128; }
-size_t bwd_smem(int dh) { return (size_t)(4 * ((dh + 63) / 64) + 4) * CHB + 1024 + 128; }
+template <int R> size_t fwd_smem(int dh) {
+  return (size_t)3 * ((dh + 63) / 64) * Geo<R>::CH + Geo<R>::PT + Geo<R>::SLACK + 1024 + 128;
+}
+template <int R> size_t bwd_smem(int dh) {
+  return (size_t)4 * ((dh + 63) / 64) * Geo<R>::CH + 2 * Geo<R>::PT + Geo<R>::SLACK + 1024 + 128;
+}
+bool small_shape(int T, int S) { return T <= 64 && S <= 64; }
 
 }  // namespace
 
@@ -468,23 +509,27 @@ int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
                        const unsigned long long* drop_state, float drop_p, unsigned int drop_site, cudaStream_t stream) {
   CUtensorMap qm, km, vm;
   const long long cols = (long long)H * dh;
-  if (int rc = make_tma_map_bf16(&qm, q, cols, (long long)B * T, ldq, ROWS)) return rc;
-  if (int rc = make_tma_map_bf16(&km, k, cols, (long long)B * S, ldk, ROWS)) return rc;
-  if (int rc = make_tma_map_bf16(&vm, v, cols, (long long)B * S, ldv, ROWS)) return rc;
+  const bool small = small_shape(T, S);
+  const int box = small ? 64 : ROWS;
+  if (int rc = make_tma_map_bf16(&qm, q, cols, (long long)B * T, ldq, box)) return rc;
+  if (int rc = make_tma_map_bf16(&km, k, cols, (long long)B * S, ldk, box)) return rc;
+  if (int rc = make_tma_map_bf16(&vm, v, cols, (long long)B * S, ldv, box)) return rc;
   AttnTcArgs a{};
   a.B = B; a.H = H; a.T = T; a.S = S; a.dh = dh; a.scale = scale; a.key_pad = key_pad;
   a.o = (bf16*)o; a.ldo = ldo; a.lse = lse;
   a.drop_state = drop_state; a.drop_p = drop_p; a.drop_site = drop_site;
-  const size_t smem = fwd_smem(dh);
   const int nt = (S + ROWS - 1) / ROWS;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(128)));
-    B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(128)));
+    B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<128>(128)));
+    B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<128>(128)));
+    B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>(128)));
+    B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<1, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = true;
   }
-  if (nt == 1) launch_kernel(attn_fwd_tc_kernel<1>, dim3(B * H), dim3(128), smem, stream, qm, km, vm, a);
-  else launch_kernel(attn_fwd_tc_kernel<3>, dim3(B * H), dim3(128), smem, stream, qm, km, vm, a);
+  if (small) launch_kernel(attn_fwd_tc_kernel<1, 64>, dim3(B * H), dim3(64), fwd_smem<64>(dh), stream, qm, km, vm, a);
+  else if (nt == 1) launch_kernel(attn_fwd_tc_kernel<1, 128>, dim3(B * H), dim3(128), fwd_smem<128>(dh), stream, qm, km, vm, a);
+  else launch_kernel(attn_fwd_tc_kernel<3, 128>, dim3(B * H), dim3(128), fwd_smem<128>(dh), stream, qm, km, vm, a);
   B200_LAUNCH_CHECK("attn_fwd_tc_kernel");
   count_launch();
   return 0;
@@ -496,23 +541,27 @@ int launch_attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
                        const unsigned long long* drop_state, float drop_p, unsigned int drop_site, cudaStream_t stream) {
   CUtensorMap qm, km, vm, dom;
   const long long cols = (long long)H * dh;
-  if (int rc = make_tma_map_bf16(&qm, q, cols, (long long)B * T, ldq, ROWS)) return rc;
-  if (int rc = make_tma_map_bf16(&km, k, cols, (long long)B * S, ldk, ROWS)) return rc;
-  if (int rc = make_tma_map_bf16(&vm, v, cols, (long long)B * S, ldv, ROWS)) return rc;
-  if (int rc = make_tma_map_bf16(&dom, d_o, cols, (long long)B * T, lddo, ROWS)) return rc;
+  const bool small = small_shape(T, S);
+  const int box = small ? 64 : ROWS;
+  if (int rc = make_tma_map_bf16(&qm, q, cols, (long long)B * T, ldq, box)) return rc;
+  if (int rc = make_tma_map_bf16(&km, k, cols, (long long)B * S, ldk, box)) return rc;
+  if (int rc = make_tma_map_bf16(&vm, v, cols, (long long)B * S, ldv, box)) return rc;
+  if (int rc = make_tma_map_bf16(&dom, d_o, cols, (long long)B * T, lddo, box)) return rc;
   AttnTcArgs a{};
   a.B = B; a.H = H; a.T = T; a.S = S; a.dh = dh; a.scale = scale; a.key_pad = key_pad;
   a.lse = const_cast<float*>(lse);
   a.o_in = (const bf16*)o; a.ldo_in = ldo; a.d_o = (const bf16*)d_o; a.lddo = lddo;
   a.dq = (bf16*)dq; a.lddq = lddq; a.dk = (bf16*)dk; a.lddk = lddk; a.dv = (bf16*)dv; a.lddv = lddv;
   a.drop_state = drop_state; a.drop_p = drop_p; a.drop_site = drop_site;
-  const size_t smem = bwd_smem(dh);
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem(128)));
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<128>(128)));
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<64>(128)));
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = true;
   }
-  launch_kernel(attn_bwd_tc_kernel, dim3(B * H), dim3(128), smem, stream, qm, km, vm, dom, a);
+  if (small) launch_kernel(attn_bwd_tc_kernel<64>, dim3(B * H), dim3(64), bwd_smem<64>(dh), stream, qm, km, vm, dom, a);
+  else launch_kernel(attn_bwd_tc_kernel<128>, dim3(B * H), dim3(128), bwd_smem<128>(dh), stream, qm, km, vm, dom, a);
   B200_LAUNCH_CHECK("attn_bwd_tc_kernel");
   count_launch();
   return 0;

@@ -12,6 +12,7 @@ from typing import List, Optional, Tuple
 import torch
 
 from . import _lib
+from .runtime import aux_fork, aux_join, aux_on
 from ._lib import (ACT_CODES, ACT_NONE, EPI_ACCUM, EPI_ACT, EPI_ADD, EPI_DACT, EPI_NONE, GROUP_TILE, LAYOUT_K,
                    LAYOUT_MN, call, dropout_arg, dtype_code, query, stream_ptr)
 
@@ -128,19 +129,23 @@ class LinearFn(torch.autograd.Function):
         M, K = x.shape
         N = w_c.shape[0]
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = gemm(g, LAYOUT_K, w_c, LAYOUT_MN, M, K, N)
+        side = None
         if ctx.needs_input_grad[1]:
             flat = torch.empty(N * K + (N if ctx.has_bias else 0), dtype=torch.float32, device=x.device)
             dw = flat[:N * K].view(N, K)
             # split-K accumulates atomically when the [N,K] tile grid cannot fill the machine
             epi = EPI_ACCUM if x.dtype == torch.bfloat16 else EPI_NONE
-            gemm(g, LAYOUT_MN, x, LAYOUT_MN, N, K, M, out=dw, epi=epi)
-            if ctx.has_bias:
-                db = flat[N * K:]
-                _colsum_into(g, db)
+            side = aux_fork(x.device) if ctx.needs_input_grad[0] else None
+            with aux_on(side):          # parameter gradients run beside the dgrad GEMM
+                gemm(g, LAYOUT_MN, x, LAYOUT_MN, N, K, M, out=dw, epi=epi)
+                if ctx.has_bias:
+                    db = flat[N * K:]
+                    _colsum_into(g, db)
         elif ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(g)
+        if ctx.needs_input_grad[0]:
+            dx = gemm(g, LAYOUT_K, w_c, LAYOUT_MN, M, K, N)
+        aux_join(side)
         return dx, dw, db, None, (dy if ctx.has_res else None), None
 
 
@@ -192,12 +197,18 @@ class FFNFn(torch.autograd.Function):
         db1 = flat[F * D:F * D + F]
         dw2 = flat[F * D + F:F * D + F + Do * F].view(Do, F)
         db2 = flat[F * D + F + Do * F:]
-        gemm(g, LAYOUT_MN, h, LAYOUT_MN, Do, F, M, out=dw2, epi=wepi)
-        _colsum_into(g, db2)
+        # critical path (current stream): dpre -> dx;  auxiliary stream: dW2, db2, then (after dpre) dW1, db1
+        side = aux_fork(x.device)
+        with aux_on(side):
+            gemm(g, LAYOUT_MN, h, LAYOUT_MN, Do, F, M, out=dw2, epi=wepi)
+            _colsum_into(g, db2)
         dpre = gemm(g, LAYOUT_K, w2_c, LAYOUT_MN, M, F, Do, epi=EPI_DACT, act=ctx.act, aux_in=pre, drop=drop_in)
-        gemm(dpre, LAYOUT_MN, x, LAYOUT_MN, F, D, M, out=dw1, epi=wepi)
-        _colsum_into(dpre, db1)
+        side = aux_fork(x.device)       # dW1 / db1 read dpre
+        with aux_on(side):
+            gemm(dpre, LAYOUT_MN, x, LAYOUT_MN, F, D, M, out=dw1, epi=wepi)
+            _colsum_into(dpre, db1)
         dx = gemm(dpre, LAYOUT_K, w1_c, LAYOUT_MN, M, D, F) if ctx.needs_input_grad[0] else None
+        aux_join(side)
         return dx, dw1, db1, dw2, db2, None, None, None, (dy if ctx.has_res else None), None, None
 
 
@@ -514,13 +525,20 @@ class ExpertFFNFn(torch.autograd.Function):
              dr if drop_out is not None else None, ws, nb, st)
         nb = query("b200_colsum_ws", R, max(F, Do))
         ws = _ws(nb, dev)
-        call("b200_colsum", dr, dt, R, Do, tile_group, E, db2, ws, nb, st)
-        call("b200_ggemm_wgrad", dr, Do, h, F, dw2, Do, F, R, E, pad_off, dt, st)
+        # critical path (current stream): dpre -> dxp;  auxiliary stream: db2, dW2, then (after dpre) db1, dW1
+        side = aux_fork(dev)
+        with aux_on(side):
+            sa = stream_ptr()
+            call("b200_colsum", dr, dt, R, Do, tile_group, E, db2, ws, nb, sa)
+            call("b200_ggemm_wgrad", dr, Do, h, F, dw2, Do, F, R, E, pad_off, dt, sa)
         dpre = torch.empty((R, F), dtype=dz.dtype, device=dev)
         call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, tile_group, dt, dt, None, EPI_DACT, act, pre,
              None, F, dropout_arg(drop_in), st)
-        call("b200_colsum", dpre, dt, R, F, tile_group, E, db1, ws, nb, st)
-        call("b200_ggemm_wgrad", dpre, F, xp, D, dw1, F, D, R, E, pad_off, dt, st)
+        side = aux_fork(dev)
+        with aux_on(side):
+            sa = stream_ptr()
+            call("b200_colsum", dpre, dt, R, F, tile_group, E, db1, ws, nb, sa)
+            call("b200_ggemm_wgrad", dpre, F, xp, D, dw1, F, D, R, E, pad_off, dt, sa)
         dxp = None
         if ctx.needs_input_grad[0]:
             dxp = torch.empty((R, D), dtype=dz.dtype, device=dev)
@@ -530,6 +548,7 @@ class ExpertFFNFn(torch.autograd.Function):
             else:
                 call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, tile_group, dt, dt, None, EPI_NONE,
                      ACT_NONE, None, None, 0, None, st)
+        aux_join(side)
         # hand every per-expert Parameter its slice of the flat buffer
         grads: List[torch.Tensor] = []
         for buf, shape in ((dw1, (F, D)), (db1, (F,)), (dw2, (Do, F)), (db2, (Do,)), (dlng, (Do,)), (dlnb, (Do,))):
@@ -632,8 +651,12 @@ class CrossProjFn(torch.autograd.Function):
         Mk = kv.shape[0]
         bq = in_b[:D] if in_b is not None else None
         bkv = in_b[D:] if in_b is not None else None
+        kvp = torch.empty((Mk, 2 * D), dtype=kv.dtype, device=kv.device)
+        side = aux_fork(x.device)       # the image-patch projection is independent of the question stream
+        with aux_on(side):
+            gemm(kv, LAYOUT_K, in_w_c[D:], LAYOUT_K, Mk, 2 * D, D, bias=bkv, out=kvp)
         q = gemm(x, LAYOUT_K, in_w_c[:D], LAYOUT_K, M, D, D, bias=bq)
-        kvp = gemm(kv, LAYOUT_K, in_w_c[D:], LAYOUT_K, Mk, 2 * D, D, bias=bkv)
+        aux_join(side)
         ctx.save_for_backward(x, kv, in_w_c)
         ctx.has_bias = in_b is not None
         return q, kvp
@@ -650,10 +673,13 @@ class CrossProjFn(torch.autograd.Function):
         flat = torch.empty(3 * D * D + 3 * D, dtype=torch.float32, device=x.device)
         dw = flat[:3 * D * D].view(3 * D, D)
         db = flat[3 * D * D:]
-        gemm(dq, LAYOUT_MN, x, LAYOUT_MN, D, D, M, out=dw[:D], epi=wepi)
-        gemm(dkvp, LAYOUT_MN, kv, LAYOUT_MN, 2 * D, D, Mk, out=dw[D:], epi=wepi)
-        _colsum_into(dq, db[:D])
-        _colsum_into(dkvp, db[D:])
+        side = aux_fork(x.device)       # parameter gradients beside the two dgrad GEMMs
+        with aux_on(side):
+            gemm(dq, LAYOUT_MN, x, LAYOUT_MN, D, D, M, out=dw[:D], epi=wepi)
+            gemm(dkvp, LAYOUT_MN, kv, LAYOUT_MN, 2 * D, D, Mk, out=dw[D:], epi=wepi)
+            _colsum_into(dq, db[:D])
+            _colsum_into(dkvp, db[D:])
         dx = gemm(dq, LAYOUT_K, in_w_c[:D], LAYOUT_MN, M, D, D) if ctx.needs_input_grad[0] else None
         dkv = gemm(dkvp, LAYOUT_K, in_w_c[D:], LAYOUT_MN, Mk, D, 2 * D) if ctx.needs_input_grad[1] else None
+        aux_join(side)
         return dx, dkv, dw, (db if ctx.has_bias else None), None

@@ -1,7 +1,9 @@
 """Compute-dtype policy and small shared helpers for the drop-in modules."""
 from __future__ import annotations
 
+import contextlib
 import copy
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -34,6 +36,45 @@ def resolve_compute_dtype(x: torch.Tensor) -> torch.dtype:
     if torch.is_autocast_enabled() or x.dtype in (torch.bfloat16, torch.float16):
         return torch.bfloat16
     return torch.float32
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Auxiliary stream: work that is off the critical path of backward (weight / bias gradients) or independent of the
+# query stream (key/value projections of the image patches) is enqueued on a second stream so that it fills the SMs
+# a small dgrad GEMM leaves idle.  Fork = aux waits for everything enqueued so far on the current stream; join =
+# current stream waits for aux.  Every fork is joined before the enclosing autograd Function returns, so consumers
+# (autograd's accumulation, optimizers, collectives) never see an unfinished gradient and the pattern is
+# CUDA-graph capturable.  B200VQA_AUX_STREAM=0 (or set_aux_stream(False)) serialises everything on one stream.
+# ---------------------------------------------------------------------------------------------------------
+_AUX = [os.environ.get("B200VQA_AUX_STREAM", "1") != "0"]
+_aux_streams = {}
+
+
+def set_aux_stream(enabled: bool) -> None:
+    _AUX[0] = bool(enabled)
+
+
+def aux_fork(device: torch.device) -> Optional["torch.cuda.Stream"]:
+    """Order the device's auxiliary stream after the current stream and return it (None when disabled)."""
+    if not _AUX[0]:
+        return None
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    s = _aux_streams.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _aux_streams[key] = s
+    s.wait_stream(torch.cuda.current_stream(device))
+    return s
+
+
+def aux_on(s):
+    """Context: kernels launched inside go to the auxiliary stream `s` (no-op context when s is None)."""
+    return torch.cuda.stream(s) if s is not None else contextlib.nullcontext()
+
+
+def aux_join(s) -> None:
+    if s is not None:
+        torch.cuda.current_stream(s.device).wait_stream(s)
 
 
 class SlabOwner:
