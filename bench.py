@@ -367,6 +367,13 @@ def run_ours(args, c):
         torch.cuda.synchronize()
         for name, s, e, _ in _lib.PROFILE:
             kern.setdefault(name, []).append(s.elapsed_time(e))
+        if args.detail:     # per-call table of the dense GEMMs of the last profiled step (stderr)
+            calls = [(sc, s.elapsed_time(e)) for name, s, e, sc in _lib.PROFILE if name == "b200_gemm"]
+            calls = calls[-(len(calls) // 3):]
+            for sc, ms in calls:
+                lda, al, ldb, bl, ldo, M, N, K, dt, odt, epi, act = sc[:12]
+                print(f"[gemm] M={M:6d} N={N:5d} K={K:6d} layouts={al}{bl} epi={epi} out={'f32' if odt == 0 else 'bf16'} "
+                      f"{ms * 1e3:8.1f} us {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s", file=sys.stderr)
         _lib.PROFILE = None
         _rt.set_aux_stream(True)
     out = None
@@ -422,6 +429,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="print a per-call table of the dense GEMMs (stderr)")
     ap.add_argument("--batch", type=int, default=CFG["B"],
                     help="per-GPU batch; the default is the named configuration, larger values give the "
                          "saturating-batch roofline SURVEY 8(d) asks for beside it")

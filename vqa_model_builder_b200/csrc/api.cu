@@ -270,12 +270,11 @@ int b200_gemm(const void* A, int lda, int a_layout, const void* B, int ldb, int 
   a.aux_out = aux_out; a.bias = bias; a.k_splits = 1;
   if (drop != nullptr && drop->p > 0.f) { a.drop_state = drop->rng_state; a.drop_p = drop->p; a.drop_site = drop->site; }
   const int m_tiles = (M + B200_GROUP_TILE - 1) / B200_GROUP_TILE;
-  if (epi == B200_EPI_ACCUM)  // accumulate into a zeroed buffer (split-K partial sums are added atomically)
-    B200_CUDA(cudaMemsetAsync(out, 0, (size_t)M * ldo * sizeof(float), stream));
-  if (dtype == B200_BF16) {
+  if (dtype == B200_BF16) {   // (EPI_ACCUM: the launcher zeroes `out` when it decides to split K)
     return launch_gemm_tc(A, lda, a_layout, M, K, B, ldb, b_layout, N, K, a, m_tiles, 1, stream);
   }
   a.A = A; a.B = B;
+  if (epi == B200_EPI_ACCUM) a.epi = B200_EPI_NONE;   // the fp32 kernel never splits K: plain stores
   a.sa_m = a_layout == B200_LAYOUT_K ? lda : 1; a.sa_k = a_layout == B200_LAYOUT_K ? 1 : lda;
   a.sb_n = b_layout == B200_LAYOUT_K ? ldb : 1; a.sb_k = b_layout == B200_LAYOUT_K ? 1 : ldb;
   return launch_gemm_simt(a, m_tiles, 1, stream);

@@ -220,11 +220,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
       }
       if (ds.on) {   // dropped probabilities feed P.V; the normaliser keeps the undropped sum
 #pragma unroll
-        for (int i4 = 0; i4 < 32; i4 += 4) {
-          float sc[4];
-          drop_scales4(ds, (drow + (unsigned long long)(j * ROWS + c * 32 + i4)) >> 2, sc);
+        for (int i8 = 0; i8 < 32; i8 += 8) {
+          float sc[8];
+          drop_scales8(ds, (drow + (unsigned long long)(j * ROWS + c * 32 + i8)) >> 3, sc);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) v[i4 + q] *= sc[q];
+          for (int q = 0; q < 8; ++q) v[i8 + q] *= sc[q];
         }
       }
       store_row32(pP, r, c, v);
@@ -387,11 +387,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
       }
       float keep[32];
 #pragma unroll
-      for (int i4 = 0; i4 < 32; i4 += 4) {
-        float sc[4] = {1.f, 1.f, 1.f, 1.f};
-        if (ds.on) drop_scales4(ds, (drow + (unsigned long long)(j * ROWS + c * 32 + i4)) >> 2, sc);
+      for (int i8 = 0; i8 < 32; i8 += 8) {
+        float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (ds.on) drop_scales8(ds, (drow + (unsigned long long)(j * ROWS + c * 32 + i8)) >> 3, sc);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) keep[i4 + q] = sc[q];
+        for (int q = 0; q < 8; ++q) keep[i8 + q] = sc[q];
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) {

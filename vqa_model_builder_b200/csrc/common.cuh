@@ -164,7 +164,7 @@ __device__ __forceinline__ float act_bwd(float x, int act) {  // d act(x) / dx
 }
 
 // ---------------------------------------------------------------------------------------------
-// Counter-based RNG for dropout: Philox4x32-10 keyed by (seed, stream), counter = element index/4.
+// Counter-based RNG for dropout: Philox4x32-10 keyed by (seed, stream), counter = element index/8.
 // The same (seed, stream, index) reproduces the same keep-mask in backward without storing it.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr, uint32_t stream) {
@@ -182,9 +182,9 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr, uint32_
 }
 // Dropout state resolved once per kernel from the ABI struct (device memory read for seed / offset).
 struct DropState {
-  unsigned long long seed, off;
+  unsigned long long key;   // seed mixed with the step offset
   float p, inv_keep;
-  unsigned int site;
+  unsigned int site, thr;   // element dropped when its 16-bit uniform < thr  (thr = round(p * 65536))
   bool on;
 };
 __device__ __forceinline__ DropState drop_load(const unsigned long long* rng_state, float p, unsigned int site) {
@@ -193,19 +193,30 @@ __device__ __forceinline__ DropState drop_load(const unsigned long long* rng_sta
   d.p = p;
   d.inv_keep = d.on ? 1.0f / (1.0f - p) : 1.0f;
   d.site = site;
-  d.seed = d.on ? rng_state[0] : 0ull;
-  d.off = d.on ? rng_state[1] : 0ull;
+  d.thr = (unsigned int)fminf(p * 65536.0f + 0.5f, 65535.0f);
+  d.key = d.on ? (rng_state[0] ^ (rng_state[1] * 0x9E3779B97F4A7C15ull)) : 0ull;
   return d;
 }
-// keep-scales of the 4 elements 4*idx4 .. 4*idx4+3
-__device__ __forceinline__ void drop_scales4(const DropState& d, unsigned long long idx4, float (&s)[4]) {
-  const uint4 r = philox4x32(d.seed ^ (d.off * 0x9E3779B97F4A7C15ull), idx4, d.site);
+// One Philox4x32-10 call serves 8 consecutive elements (16 random bits each: p is resolved to 2^-16):
+// keep-scales of the elements 8*idx8 .. 8*idx8+7.
+__device__ __forceinline__ void drop_scales8(const DropState& d, unsigned long long idx8, float (&s)[8]) {
+  const uint4 r = philox4x32(d.key, idx8, d.site);
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float u = (float)(w[i] >> 8) * (1.0f / 16777216.0f);
-    s[i] = u < d.p ? 0.f : d.inv_keep;
+    s[2 * i] = (w[i] & 0xFFFFu) < d.thr ? 0.f : d.inv_keep;
+    s[2 * i + 1] = (w[i] >> 16) < d.thr ? 0.f : d.inv_keep;
   }
+}
+// keep-scales of the 4 elements 4*idx4 .. 4*idx4+3 (one half of the 8-element group)
+__device__ __forceinline__ void drop_scales4(const DropState& d, unsigned long long idx4, float (&s)[4]) {
+  const uint4 r = philox4x32(d.key, idx4 >> 1, d.site);
+  const bool hi = (idx4 & 1ull) != 0;
+  const uint32_t w0 = hi ? r.z : r.x, w1 = hi ? r.w : r.y;
+  s[0] = (w0 & 0xFFFFu) < d.thr ? 0.f : d.inv_keep;
+  s[1] = (w0 >> 16) < d.thr ? 0.f : d.inv_keep;
+  s[2] = (w1 & 0xFFFFu) < d.thr ? 0.f : d.inv_keep;
+  s[3] = (w1 >> 16) < d.thr ? 0.f : d.inv_keep;
 }
 __device__ __forceinline__ float drop_scale1(const DropState& d, unsigned long long idx) {
   float s[4];

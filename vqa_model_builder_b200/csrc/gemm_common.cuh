@@ -33,7 +33,15 @@ struct GemmArgs {
 template <int CNT>
 __device__ __forceinline__ void apply_dropout_row(const DropState& d, long long row, int ldo, int col0, float (&v)[CNT]) {
   const unsigned long long base = (unsigned long long)row * (unsigned long long)ldo + (unsigned long long)col0;
-  if ((base & 3ull) == 0) {
+  if ((base & 7ull) == 0 && CNT % 8 == 0) {
+#pragma unroll
+    for (int j = 0; j < CNT; j += 8) {
+      float sc[8];
+      drop_scales8(d, (base + j) >> 3, sc);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[j + q] *= sc[q];
+    }
+  } else if ((base & 3ull) == 0) {
 #pragma unroll
     for (int j = 0; j < CNT; j += 4) {
       float sc[4];

@@ -11,6 +11,7 @@
 //               tcgen05.ld -> bias / activation / residual in registers -> transpose through a padded
 //               shared-memory staging tile -> row-contiguous 16-byte global stores (full 32-byte sectors).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gemm_common.cuh"
 #include "tc_ptx.cuh"
@@ -502,20 +503,46 @@ int launch_gemm_tc(const void* A, int lda, int a_layout, long long a_mn_extent, 
   B200_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: bf16 operand pitches must be multiples of 8 (lda=%d ldb=%d)",
                  lda, ldb);
 
-  // tile-N selection: the largest tile that still gives (nearly) every SM a tile
+  // Tile-N / split-K selection by a small cost model (unit: the time of one 128x256x64 k-block, ~0.27 us):
+  //   time = fill + tiles_per_cta * max(k_blocks * c(BN), epilogue(BN)) + epilogue(BN)
+  // c(BN) is the per-k-block time of a tile (256: tensor-pipe bound; 128 / 64: bound by the shared-memory fill
+  // rate, 32 / 24 KB per k-block), the epilogue of tile i overlaps the main loop of tile i+1, the last one is
+  // exposed.  Split-K (atomic fp32 accumulation) is available to dense wgrad GEMMs only.
   const int sms = num_sms();
   const long long m_tiles = grid_m_tiles;
   const int zdim = args.mode == GEMM_GROUP_WGRAD ? groups : 1;
-  auto tiles = [&](int bn) { return m_tiles * ((args.N + bn - 1) / bn) * zdim; };
-  int bn = 64;
-  if (tiles(256) >= sms) bn = 256;
-  else if (tiles(128) >= (sms * 3) / 4) bn = 128;
-  int splits = 1;
-  if (args.mode == GEMM_DENSE && args.epi == B200_EPI_ACCUM) {
-    const int kblocks = (args.K + BK - 1) / BK;
-    while (tiles(bn) * splits * 2 <= sms && kblocks / (splits * 2) >= 4 && splits < 16) splits *= 2;
+  // grouped wgrad reduces over data-dependent row segments: use the mean segment length
+  const int kblocks = args.mode == GEMM_GROUP_WGRAD ? (int)((a_k_extent / (groups > 0 ? groups : 1) + BK - 1) / BK)
+                                                    : (args.K + BK - 1) / BK;
+  const bool can_split = args.mode == GEMM_DENSE && args.epi == B200_EPI_ACCUM;
+  const float epi256 = (args.epi == B200_EPI_ACT || args.epi == B200_EPI_DACT) ? 40.f
+                       : (args.epi == B200_EPI_ACCUM ? 8.f : (args.epi == B200_EPI_ADD ? 5.f : 3.f));
+  int bn = 64, splits = 1;
+  float best = 1e30f;
+  static const int forced_bn = []() { const char* e = getenv("B200VQA_GEMM_BN"); return e ? atoi(e) : 0; }();
+  for (int cand : {256, 128, 64}) {
+    if (forced_bn && cand != forced_bn) continue;
+    const float c = cand == 256 ? 1.0f : (cand == 128 ? 0.68f : 0.51f);
+    const float epi = epi256 * (float)cand / 256.f + 1.5f;   // + per-tile fixed cost (barrier waits, bias staging)
+    const long long tiles = m_tiles * ((args.N + cand - 1) / cand) * zdim;
+    for (int s_ = 1; s_ <= (can_split ? 16 : 1); ++s_) {
+      if (s_ > 1 && kblocks / s_ < 4) break;
+      const long long items = tiles * s_;
+      const long long ctas = items < sms ? items : sms;
+      const float tpc = (float)((items + ctas - 1) / ctas);
+      const float kb = (float)((kblocks + s_ - 1) / s_);
+      const float main_t = kb * c;
+      const float t = 6.f + tpc * (main_t > epi ? main_t : epi) + epi + (s_ > 1 ? 1.0f * s_ : 0.f);
+      if (t < best * 0.999f) { best = t; bn = cand; splits = s_; }
+    }
   }
   args.k_splits = splits;
+  if (args.epi == B200_EPI_ACCUM && args.mode == GEMM_DENSE) {
+    if (splits > 1)   // partial sums are added atomically into a zeroed buffer
+      B200_CUDA(cudaMemsetAsync(args.out, 0, (size_t)args.M * args.ldo * sizeof(float), stream));
+    else              // one CTA owns each output tile: plain fp32 stores
+      args.epi = B200_EPI_NONE;
+  }
 
   CUtensorMap ta, tb;
   int rc;

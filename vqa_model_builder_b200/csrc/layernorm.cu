@@ -19,12 +19,19 @@ __device__ __forceinline__ void drop_row(RowRegs<T, NV>& row, const DropState& d
     const int vi = lane + 32 * j;
     if (vi < nv) {
       const unsigned long long base = (unsigned long long)r * D + (unsigned long long)vi * VT;
+      if (VT == 8) {      // bf16 packets: 8 elements = one Philox call (D % 8 == 0, so base % 8 == 0)
+        float sc[8];
+        drop_scales8(ds, base >> 3, sc);
 #pragma unroll
-      for (int u = 0; u < VT; u += 4) {
-        float sc[4];
-        drop_scales4(ds, (base + u) >> 2, sc);
+        for (int q = 0; q < 8; ++q) row.v[j][q % VT] *= sc[q];
+      } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) row.v[j][u + q] *= sc[q];
+        for (int u = 0; u < VT; u += 4) {
+          float sc[4];
+          drop_scales4(ds, (base + u) >> 2, sc);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) row.v[j][u + q] *= sc[q];
+        }
       }
     }
   }
