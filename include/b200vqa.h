@@ -119,12 +119,14 @@ int b200_add_ln_fwd(const void* x, const void* res, const float* gamma, const fl
                     const int32_t* tile_group, float eps, void* y, float* mean, float* rstd, int R, int D,
                     int dtype, const b200_dropout_t* drop, int drop_target, void* stream);
 /* dsum = d(x+res); dgamma/dbeta [G, D] fp32 (overwritten).  With dropout, d_dropped receives the gradient of the
- * dropped operand (dsum * mask / (1-p)).  workspace >= b200_add_ln_bwd_ws(R, D)                        */
+ * dropped operand (dsum * mask / (1-p)).  d_colsum [G, D] (or NULL) receives the column sums of that gradient
+ * (d_dropped with dropout, else dsum): the bias gradient of the Linear that produced the operand, for free.
+ * workspace >= b200_add_ln_bwd_ws(R, D)                                                                  */
 size_t b200_add_ln_bwd_ws(int R, int D);
 int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float* mean, const float* rstd,
                     const float* gamma, const int32_t* tile_group, int G, void* dsum, float* dgamma,
-                    float* dbeta, int R, int D, int dtype, const b200_dropout_t* drop, int drop_target,
-                    void* d_dropped, void* workspace, size_t workspace_bytes, void* stream);
+                    float* dbeta, float* d_colsum, int R, int D, int dtype, const b200_dropout_t* drop,
+                    int drop_target, void* d_dropped, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- attention ------------------------------------------------------------------------------- */
 /* o[b,t,h,:] = softmax_s(scale * q[b,t,h,:].k[b,s,h,:] + mask) v[b,s,h,:]; nn.MultiheadAttention core

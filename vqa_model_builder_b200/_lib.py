@@ -41,7 +41,7 @@ SIGNATURES = {
     "b200_ggemm_wgrad": ("i", "pipipiiiipip"),
     "b200_add_ln_fwd": ("i", "pppppfpppiiipip"),
     "b200_add_ln_bwd_ws": ("z", "ii"),
-    "b200_add_ln_bwd": ("i", "pppppppipppiiipippzp"),
+    "b200_add_ln_bwd": ("i", "pppppppippppiiipippzp"),
     "b200_attn_fwd": ("i", "pipipippipiiiiifipp"),
     "b200_attn_bwd": ("i", "pipipippipippipipiiiiiifipp"),
     "b200_router_ws": ("z", "ii"),

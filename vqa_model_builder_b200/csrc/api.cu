@@ -74,12 +74,75 @@ __global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, long
   }
 }
 
-// ---- column sums (bias gradients), deterministic two-stage ---------------------------------------
+// ---- column sums (bias gradients): one launch, deterministic ------------------------------------------------
+// Every block writes the partial sums of its 64 rows; the block that finishes LAST within a column slab (ticket
+// counter, __threadfence reduction) folds the slab's partials in block order, so the result does not depend on
+// scheduling.  Tickets live in a device-global ring (zero at load, reset by the folding block): launches in flight
+// at the same time on different streams get different slots.
 constexpr int CS_ROWS = 64;  // rows per partial block; divides B200_GROUP_TILE
-// stage 1: 8 warps x 16-byte vectors: block (slab, rb) sums rows [rb*64, rb*64+64) of a 32*VT-column slab
+constexpr int TICKETS = 8192;
+__device__ unsigned int g_tickets[TICKETS];
+
+unsigned int ticket_slots(int n) {
+  static std::atomic<unsigned int> next{0};
+  unsigned int base = next.fetch_add((unsigned int)n) % TICKETS;
+  if (base + (unsigned int)n > TICKETS) base = 0;
+  return base;
+}
+
+// true in exactly one block per ticket: the last of `total` blocks to arrive (its reads see all partials)
+__device__ __forceinline__ bool last_arrival(unsigned int* ticket, unsigned int total) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == total - 1);
+    if (s_last) *ticket = 0u;       // ready for the next launch that is handed this slot
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
+// fold part[b][c] over the row blocks b: out[g][c] for every group g (groups are contiguous tile ranges of the
+// padded expert layout; tile_group == nullptr: one group)
+__device__ __forceinline__ void fold_partials(const float* __restrict__ part, int blocks, int N, int c,
+                                              const int* __restrict__ tile_group, int G, float* __restrict__ out) {
+  if (tile_group == nullptr) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int b = 0;
+    for (; b + 4 <= blocks; b += 4) {
+      s0 += __ldcg(part + (long long)b * N + c);
+      s1 += __ldcg(part + (long long)(b + 1) * N + c);
+      s2 += __ldcg(part + (long long)(b + 2) * N + c);
+      s3 += __ldcg(part + (long long)(b + 3) * N + c);
+    }
+    for (; b < blocks; ++b) s0 += __ldcg(part + (long long)b * N + c);
+    out[c] = (s0 + s1) + (s2 + s3);
+    return;
+  }
+  for (int g = 0; g < G; ++g) out[(long long)g * N + c] = 0.f;
+  constexpr int BPT = B200_GROUP_TILE / CS_ROWS;
+  int cur = -1;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) {
+    const int g = tile_group[b / BPT];
+    if (g != cur) {
+      if (cur >= 0) out[(long long)cur * N + c] = s;
+      cur = g;
+      s = 0.f;
+    }
+    if (g >= 0) s += __ldcg(part + (long long)b * N + c);
+  }
+  if (cur >= 0) out[(long long)cur * N + c] = s;
+}
+
+// 8 warps x 16-byte vectors: block (slab, rb) sums rows [rb*64, rb*64+64) of a 32*VT-column slab
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part) {
+colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part, const int* __restrict__ tile_group,
+              int G, float* __restrict__ out, unsigned int* __restrict__ tickets) {
   pdl_trigger();
   pdl_wait();
   constexpr int VT = Vec16<T>::N;
@@ -110,18 +173,28 @@ colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part) {
       part[(long long)blockIdx.y * N + gc] = s;
     }
   }
+  if (!last_arrival(tickets + blockIdx.x, gridDim.y)) return;
+  for (int c = threadIdx.x; c < 32 * VT; c += 256) {
+    const int gc = blockIdx.x * 32 * VT + c;
+    if (gc < N) fold_partials(part, gridDim.y, N, gc, tile_group, G, out);
+  }
 }
 // scalar fallback for widths that are not a multiple of the vector length
 template <typename T>
-__global__ void colsum_stage1_scalar(const T* __restrict__ x, int R, int N, float* __restrict__ part) {
+__global__ void colsum_stage1_scalar(const T* __restrict__ x, int R, int N, float* __restrict__ part,
+                                     const int* __restrict__ tile_group, int G, float* __restrict__ out,
+                                     unsigned int* __restrict__ tickets) {
   pdl_trigger();
   pdl_wait();
   const int col = blockIdx.x * 128 + threadIdx.x;
   const int r0 = blockIdx.y * CS_ROWS, r1 = min(R, r0 + CS_ROWS);
-  if (col >= N) return;
-  float s = 0.f;
-  for (int r = r0; r < r1; ++r) s += to_f32<T>(x[(long long)r * N + col]);
-  part[(long long)blockIdx.y * N + col] = s;
+  if (col < N) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += to_f32<T>(x[(long long)r * N + col]);
+    part[(long long)blockIdx.y * N + col] = s;
+  }
+  if (!last_arrival(tickets + blockIdx.x, gridDim.y)) return;
+  if (col < N) fold_partials(part, gridDim.y, N, col, tile_group, G, out);
 }
 
 int launch_partial_reduce(const float* part, int blocks, int rows_per_block, int width, const int* tile_group, int G,
@@ -236,16 +309,22 @@ int b200_colsum(const void* x, int dtype, int R, int N, const int32_t* tile_grou
   const int vt = dtype == B200_F32 ? 4 : 8;
   if (N % vt == 0 && ((uintptr_t)x & 15) == 0) {
     dim3 g1((N + 32 * vt - 1) / (32 * vt), blocks);
-    if (dtype == B200_F32) launch_kernel(colsum_stage1<float>, dim3(g1), dim3(256), 0, stream, (const float*)x, R, N, part);
-    else launch_kernel(colsum_stage1<bf16>, dim3(g1), dim3(256), 0, stream, (const bf16*)x, R, N, part);
+    unsigned int* tk = nullptr;
+    B200_CUDA(cudaGetSymbolAddress((void**)&tk, g_tickets));
+    tk += ticket_slots((int)g1.x);
+    if (dtype == B200_F32) launch_kernel(colsum_stage1<float>, dim3(g1), dim3(256), 0, stream, (const float*)x, R, N, part, tile_group, G, out, tk);
+    else launch_kernel(colsum_stage1<bf16>, dim3(g1), dim3(256), 0, stream, (const bf16*)x, R, N, part, tile_group, G, out, tk);
   } else {
     dim3 g1((N + 127) / 128, blocks);
-    if (dtype == B200_F32) launch_kernel(colsum_stage1_scalar<float>, dim3(g1), dim3(128), 0, stream, (const float*)x, R, N, part);
-    else launch_kernel(colsum_stage1_scalar<bf16>, dim3(g1), dim3(128), 0, stream, (const bf16*)x, R, N, part);
+    unsigned int* tk = nullptr;
+    B200_CUDA(cudaGetSymbolAddress((void**)&tk, g_tickets));
+    tk += ticket_slots((int)g1.x);
+    if (dtype == B200_F32) launch_kernel(colsum_stage1_scalar<float>, dim3(g1), dim3(128), 0, stream, (const float*)x, R, N, part, tile_group, G, out, tk);
+    else launch_kernel(colsum_stage1_scalar<bf16>, dim3(g1), dim3(128), 0, stream, (const bf16*)x, R, N, part, tile_group, G, out, tk);
   }
   B200_LAUNCH_CHECK("colsum_stage1");
   count_launch();
-  return launch_partial_reduce(part, blocks, CS_ROWS, N, tile_group, G, out, stream);
+  return 0;
 }
 
 static int check_epi(int epi, int act, const void* aux_in, int out_dtype) {

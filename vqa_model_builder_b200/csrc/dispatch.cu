@@ -6,7 +6,7 @@
 namespace b200 {
 
 int launch_ln_param_reduce(const float* part, int blocks, int rows_per_block, int D, const int* tile_group, int G,
-                           float* dgamma, float* dbeta, cudaStream_t stream);
+                           float* dgamma, float* dbeta, cudaStream_t stream, float* dcol = nullptr);
 
 namespace {
 

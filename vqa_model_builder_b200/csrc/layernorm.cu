@@ -112,19 +112,22 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                   const float* __restrict__ gamma, const int* __restrict__ tile_group, T* __restrict__ dsum,
                   float* __restrict__ part, int R, int D, int rpw, const unsigned long long* drop_state, float drop_p,
-                  unsigned int drop_site, int drop_target, T* __restrict__ d_dropped) {
+                  unsigned int drop_site, int drop_target, T* __restrict__ d_dropped, int nz) {
   pdl_trigger();
   pdl_wait();
   constexpr int VT = Vec16<T>::N;
-  extern __shared__ float red[];  // [LN_WARPS][2][D]
+  extern __shared__ float red[];  // [LN_WARPS][nz][D]; nz = 3 adds the column sums of the branch gradient
   const DropState ds = drop_load(drop_state, drop_p, drop_site);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / VT;
   // per-warp dgamma / dbeta accumulators live in shared memory (each lane owns its own 16-byte slots, so no
   // synchronisation is needed): keeping them in registers cost ~50 registers and left one block per SM
-  float* acc_g = red + (warp * 2 + 0) * D;
-  float* acc_b = red + (warp * 2 + 1) * D;
+  float* acc_g = red + (warp * nz + 0) * D;
+  float* acc_b = red + (warp * nz + 1) * D;
+  float* acc_c = red + (warp * nz + 2) * D;      // only touched when nz == 3
   for (int d = lane; d < D; d += 32) { acc_g[d] = 0.f; acc_b[d] = 0.f; }
+  if (nz == 3)
+    for (int d = lane; d < D; d += 32) acc_c[d] = 0.f;
   __syncwarp();
 
   const int row0 = blockIdx.x * (LN_WARPS * rpw);
@@ -185,14 +188,29 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
       drop_row<T, NV>(gr, ds, r, D, lane);
       gr.store(d_dropped + (long long)r * D, D, lane);
     }
+    if (nz == 3) {   // column sums of the branch gradient = bias gradient of the Linear that produced the branch
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int vi = lane + 32 * j;
+        if (vi < nv) {
+          float* ac = acc_c + vi * VT;
+#pragma unroll
+          for (int u = 0; u < VT; u += 4) {
+            float4 t = *reinterpret_cast<float4*>(ac + u);
+            t.x += gr.v[j][u]; t.y += gr.v[j][u + 1]; t.z += gr.v[j][u + 2]; t.w += gr.v[j][u + 3];
+            *reinterpret_cast<float4*>(ac + u) = t;
+          }
+        }
+      }
+    }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+  for (int c = threadIdx.x; c < nz * D; c += blockDim.x) {
     const int which = c / D, d = c % D;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < LN_WARPS; ++w) s += red[(w * 2 + which) * D + d];
-    part[((long long)blockIdx.x * 2 + which) * D + d] = s;
+    for (int w = 0; w < LN_WARPS; ++w) s += red[(w * nz + which) * D + d];
+    part[((long long)blockIdx.x * nz + which) * D + d] = s;
   }
 }
 
@@ -211,7 +229,7 @@ inline int ln_bwd_rpw(int R) {
 __global__ void __launch_bounds__(256)
 partial_reduce_kernel(const float* __restrict__ part, int blocks, int rows_per_block, int width, int nz,
                       const int* __restrict__ tile_group, int tiles, float* __restrict__ out0,
-                      float* __restrict__ out1) {
+                      float* __restrict__ out1, float* __restrict__ out2) {
   pdl_trigger();
   pdl_wait();
   __shared__ float red[8][33];
@@ -240,7 +258,7 @@ partial_reduce_kernel(const float* __restrict__ part, int blocks, int rows_per_b
     float t = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += red[j][x];
-    (z == 0 ? out0 : out1)[(long long)g * width + c] = t;
+    (z == 0 ? out0 : (z == 1 ? out1 : out2))[(long long)g * width + c] = t;
   }
 }
 
@@ -248,10 +266,11 @@ partial_reduce_kernel(const float* __restrict__ part, int blocks, int rows_per_b
 
 // shared with dispatch.cu (combine backward uses the same partial layout)
 int launch_ln_param_reduce(const float* part, int blocks, int rows_per_block, int D, const int* tile_group, int G,
-                           float* dgamma, float* dbeta, cudaStream_t stream) {
-  dim3 grid((D + 31) / 32, G, 2);
+                           float* dgamma, float* dbeta, cudaStream_t stream, float* dcol) {
+  const int nz = dcol != nullptr ? 3 : 2;
+  dim3 grid((D + 31) / 32, G, nz);
   const int tiles = (int)(((long long)blocks * rows_per_block + B200_GROUP_TILE - 1) / B200_GROUP_TILE);
-  launch_kernel(partial_reduce_kernel, dim3(grid), dim3(256), 0, stream, part, blocks, rows_per_block, D, 2, tile_group, tiles, dgamma, dbeta);
+  launch_kernel(partial_reduce_kernel, dim3(grid), dim3(256), 0, stream, part, blocks, rows_per_block, D, nz, tile_group, tiles, dgamma, dbeta, dcol);
   B200_LAUNCH_CHECK("partial_reduce_kernel");
   count_launch();
   return 0;
@@ -262,7 +281,7 @@ int launch_partial_reduce(const float* part, int blocks, int rows_per_block, int
                           float* out, cudaStream_t stream) {
   dim3 grid((width + 31) / 32, G, 1);
   const int tiles = (int)(((long long)blocks * rows_per_block + B200_GROUP_TILE - 1) / B200_GROUP_TILE);
-  launch_kernel(partial_reduce_kernel, dim3(grid), dim3(256), 0, stream, part, blocks, rows_per_block, width, 1, tile_group, tiles, out, out);
+  launch_kernel(partial_reduce_kernel, dim3(grid), dim3(256), 0, stream, part, blocks, rows_per_block, width, 1, tile_group, tiles, out, out, out);
   B200_LAUNCH_CHECK("partial_reduce_kernel");
   count_launch();
   return 0;
@@ -300,13 +319,13 @@ int b200_add_ln_fwd(const void* x, const void* res, const float* gamma, const fl
 
 size_t b200_add_ln_bwd_ws(int R, int D) {
   const size_t blocks = (size_t)(R + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK;
-  return blocks * 2 * (size_t)D * sizeof(float);
+  return blocks * 3 * (size_t)D * sizeof(float);
 }
 
 int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float* mean, const float* rstd,
                     const float* gamma, const int32_t* tile_group, int G, void* dsum, float* dgamma, float* dbeta,
-                    int R, int D, int dtype, const b200_dropout_t* drop, int drop_target, void* d_dropped,
-                    void* workspace, size_t workspace_bytes, void* stream_) {
+                    float* d_colsum, int R, int D, int dtype, const b200_dropout_t* drop, int drop_target,
+                    void* d_dropped, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(R > 0 && D > 0 && G > 0, "add_ln_bwd: bad shape R=%d D=%d G=%d", R, D, G);
   const bool don = drop != nullptr && drop->p > 0.f && drop_target != 0;
@@ -318,7 +337,8 @@ int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float*
   const int rows_per_block = LN_WARPS * rpw;
   const int blocks = (R + rows_per_block - 1) / rows_per_block;
   float* part = (float*)workspace;
-  const size_t smem = (size_t)LN_WARPS * 2 * D * sizeof(float);
+  const int nz = d_colsum != nullptr ? 3 : 2;
+  const size_t smem = (size_t)LN_WARPS * nz * D * sizeof(float);
   B200_CHECK_ARG(smem <= 160 * 1024, "add_ln_bwd: D=%d too large", D);
   if (dtype == B200_BF16) {
     B200_CHECK_ARG(RowRegs<bf16>::supported(D), "add_ln_bwd: D=%d unsupported for bf16", D);
@@ -327,7 +347,7 @@ int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float*
         B200_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<bf16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       launch_kernel(add_ln_bwd_kernel<bf16, NV>, dim3(blocks), dim3(LN_WARPS * 32), smem, stream, 
           (const bf16*)dy, (const bf16*)x, (const bf16*)res, mean, rstd, gamma, tile_group, (bf16*)dsum, part, R, D, rpw,
-          dst, dp, dsite, drop_target, (bf16*)d_dropped);
+          dst, dp, dsite, drop_target, (bf16*)d_dropped, nz);
     });
   } else {
     B200_CHECK_ARG(RowRegs<float>::supported(D), "add_ln_bwd: D=%d unsupported for fp32", D);
@@ -336,12 +356,12 @@ int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float*
         B200_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<float, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       launch_kernel(add_ln_bwd_kernel<float, NV>, dim3(blocks), dim3(LN_WARPS * 32), smem, stream, 
           (const float*)dy, (const float*)x, (const float*)res, mean, rstd, gamma, tile_group, (float*)dsum, part, R, D, rpw,
-          dst, dp, dsite, drop_target, (float*)d_dropped);
+          dst, dp, dsite, drop_target, (float*)d_dropped, nz);
     });
   }
   B200_LAUNCH_CHECK("add_ln_bwd_kernel");
   count_launch();
-  return launch_ln_param_reduce(part, blocks, rows_per_block, D, tile_group, G, dgamma, dbeta, stream);
+  return launch_ln_param_reduce(part, blocks, rows_per_block, D, tile_group, G, dgamma, dbeta, stream, d_colsum);
 }
 
 }  // extern "C"

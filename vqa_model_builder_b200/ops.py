@@ -101,6 +101,24 @@ def colsum(x: torch.Tensor, tile_group=None, G: int = 1) -> torch.Tensor:
     return out if tile_group is not None else out[0]
 
 
+# ---- bias gradients handed over by the kernel that produced dy -------------------------------------------------
+def _attach_colsum(t: torch.Tensor, cs: torch.Tensor) -> None:
+    """add_ln_bwd already summed the columns of the branch gradient it wrote; the Linear that produced the branch
+    picks the sums up from the gradient tensor instead of launching a column-sum kernel.  The tensor's version
+    counter is stored so an in-place accumulation by autograd invalidates the hand-over."""
+    t._b200_colsum = (cs, t._version)
+
+
+def _take_colsum(t: torch.Tensor, n: int) -> Optional[torch.Tensor]:
+    tag = getattr(t, "_b200_colsum", None)
+    if tag is None:
+        return None
+    cs, version = tag
+    if version != t._version or cs.numel() != n or cs.device != t.device:
+        return None
+    return cs
+
+
 # ---- Linear (+bias, + optional residual) ---------------------------------------------------------------
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b, or y = dropout(x W^T + b) + residual.  nn.Linear / MHA in-proj / out-proj
@@ -124,25 +142,29 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, w_c = ctx.saved_tensors
-        dy = dy.contiguous()
-        g = dropout_apply(dy, ctx.drop) if ctx.drop is not None else dy   # gradient of the pre-dropout GEMM output
         M, K = x.shape
         N = w_c.shape[0]
+        pre_db = _take_colsum(dy, N) if ctx.drop is None else None
+        dy = dy.contiguous()
+        g = dropout_apply(dy, ctx.drop) if ctx.drop is not None else dy   # gradient of the pre-dropout GEMM output
         dx = dw = db = None
         side = None
         if ctx.needs_input_grad[1]:
-            flat = torch.empty(N * K + (N if ctx.has_bias else 0), dtype=torch.float32, device=x.device)
+            need_db = ctx.has_bias and pre_db is None
+            flat = torch.empty(N * K + (N if need_db else 0), dtype=torch.float32, device=x.device)
             dw = flat[:N * K].view(N, K)
             # split-K accumulates atomically when the [N,K] tile grid cannot fill the machine
             epi = EPI_ACCUM if x.dtype == torch.bfloat16 else EPI_NONE
             side = aux_fork(x.device) if ctx.needs_input_grad[0] else None
             with aux_on(side):          # parameter gradients run beside the dgrad GEMM
                 gemm(g, LAYOUT_MN, x, LAYOUT_MN, N, K, M, out=dw, epi=epi)
-                if ctx.has_bias:
+                if need_db:
                     db = flat[N * K:]
                     _colsum_into(g, db)
+            if ctx.has_bias and pre_db is not None:
+                db = pre_db
         elif ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(g)
+            db = pre_db if pre_db is not None else colsum(g)
         if ctx.needs_input_grad[0]:
             dx = gemm(g, LAYOUT_K, w_c, LAYOUT_MN, M, K, N)
         aux_join(side)
@@ -185,11 +207,12 @@ class FFNFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, pre, h, w1_c, w2_c = ctx.saved_tensors
         drop_in, drop_out = ctx.drops
-        dy = dy.contiguous()
-        g = dropout_apply(dy, drop_out) if drop_out is not None else dy
         M, D = x.shape
         F = w1_c.shape[0]
         Do = w2_c.shape[0]
+        pre_db2 = _take_colsum(dy, Do) if drop_out is None else None
+        dy = dy.contiguous()
+        g = dropout_apply(dy, drop_out) if drop_out is not None else dy
         bf = x.dtype == torch.bfloat16
         wepi = EPI_ACCUM if bf else EPI_NONE
         flat = torch.empty(F * D + F + Do * F + Do, dtype=torch.float32, device=x.device)
@@ -201,7 +224,10 @@ class FFNFn(torch.autograd.Function):
         side = aux_fork(x.device)
         with aux_on(side):
             gemm(g, LAYOUT_MN, h, LAYOUT_MN, Do, F, M, out=dw2, epi=wepi)
-            _colsum_into(g, db2)
+            if pre_db2 is None:
+                _colsum_into(g, db2)
+            else:
+                db2 = pre_db2
         dpre = gemm(g, LAYOUT_K, w2_c, LAYOUT_MN, M, F, Do, epi=EPI_DACT, act=ctx.act, aux_in=pre, drop=drop_in)
         side = aux_fork(x.device)       # dW1 / db1 read dpre
         with aux_on(side):
@@ -242,15 +268,18 @@ class AddLNFn(torch.autograd.Function):
         R, D = x.shape
         dsum = torch.empty_like(x)
         dbranch = torch.empty_like(x) if ctx.drop is not None else None
-        flat = torch.empty(2 * D, dtype=torch.float32, device=x.device)
+        flat = torch.empty((3 if ctx.has_branch else 2) * D, dtype=torch.float32, device=x.device)
+        dcol = flat[2 * D:] if ctx.has_branch else None     # column sums of the branch gradient (its bias gradient)
         nb = query("b200_add_ln_bwd_ws", R, D)
         ws = _ws(nb, x.device)
-        call("b200_add_ln_bwd", dy, x, branch, mean, rstd, gamma, None, 1, dsum, flat[:D], flat[D:], R, D,
+        call("b200_add_ln_bwd", dy, x, branch, mean, rstd, gamma, None, 1, dsum, flat[:D], flat[D:2 * D], dcol, R, D,
              dtype_code(x.dtype), dropout_arg(ctx.drop), 2 if ctx.drop is not None else 0, dbranch, ws, nb,
              stream_ptr())
         if not ctx.has_branch:
-            return dsum, None, flat[:D], flat[D:], None, None
-        return dsum, (dbranch if dbranch is not None else dsum), flat[:D], flat[D:], None, None
+            return dsum, None, flat[:D], flat[D:2 * D], None, None
+        dbr = dbranch if dbranch is not None else dsum
+        _attach_colsum(dbr, dcol)
+        return dsum, dbr, flat[:D], flat[D:2 * D], None, None
 
 
 # ---- attention -----------------------------------------------------------------------------------------------
@@ -521,15 +550,14 @@ class ExpertFFNFn(torch.autograd.Function):
         nb = query("b200_add_ln_bwd_ws", R, Do)
         ws = _ws(nb, dev)
         call("b200_add_ln_bwd", dz, y2, xp if residual else None, mean_e, rstd_e, lng, tile_group, E, dsum, dlng, dlnb,
-             R, Do, dt, dropout_arg(drop_out), 1 if drop_out is not None else 0,
-             dr if drop_out is not None else None, ws, nb, st)
+             db2, R, Do, dt, dropout_arg(drop_out), 1 if drop_out is not None else 0,
+             dr if drop_out is not None else None, ws, nb, st)      # db2 = per-expert column sums of dr, fused
         nb = query("b200_colsum_ws", R, max(F, Do))
         ws = _ws(nb, dev)
         # critical path (current stream): dpre -> dxp;  auxiliary stream: db2, dW2, then (after dpre) db1, dW1
         side = aux_fork(dev)
         with aux_on(side):
             sa = stream_ptr()
-            call("b200_colsum", dr, dt, R, Do, tile_group, E, db2, ws, nb, sa)
             call("b200_ggemm_wgrad", dr, Do, h, F, dw2, Do, F, R, E, pad_off, dt, sa)
         dpre = torch.empty((R, F), dtype=dz.dtype, device=dev)
         call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, tile_group, dt, dt, None, EPI_DACT, act, pre,
