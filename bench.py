@@ -331,14 +331,37 @@ def run_ours(args, c):
     # ---- end-to-end through the module API with host buffers ("e2e") ----
     e2e_s = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e2e_e = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    # Input upload is software-pipelined: the pinned host batch of step i+1 is copied to a device staging buffer
+    # on a copy stream while step i computes (one H2D per step inside the timed intervals; step 0 pays for its own
+    # and the next one).  The step itself starts with a device-to-device copy staging -> the graph's input buffers.
+    copy_stream = torch.cuda.Stream()
+    vis_s, txt_s, pad_s = torch.empty_like(vis), torch.empty_like(txt), torch.empty_like(pad)
+    ready, free = torch.cuda.Event(), torch.cuda.Event()
+    main = torch.cuda.current_stream()
+
+    def upload():
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free)
+            vis_s.copy_(vis_h, non_blocking=True)
+            txt_s.copy_(txt_h, non_blocking=True)
+            pad_s.copy_(pad_h, non_blocking=True)
+            ready.record(copy_stream)
+
     barrier()
+    free.record(main)
     with torch.no_grad():
         for i in range(args.steps):
             flush.fill_(i & 0xFF)
             e2e_s[i].record()
-            vis.copy_(vis_h, non_blocking=True)
-            txt.copy_(txt_h, non_blocking=True)
-            pad.copy_(pad_h, non_blocking=True)
+            if i == 0:
+                upload()
+            main.wait_event(ready)
+            vis.copy_(vis_s, non_blocking=True)
+            txt.copy_(txt_s, non_blocking=True)
+            pad.copy_(pad_s, non_blocking=True)
+            free.record(main)
+            if i + 1 < args.steps:
+                upload()
             with torch.enable_grad():
                 run_step()
             loss_h.copy_(loss_d, non_blocking=True)
@@ -403,7 +426,8 @@ def run_ours(args, c):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(c, world),
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "pipeline": "pinned host batch i+1 uploaded on a copy stream during step i; loss read back every step"},
             "gpu_launches": int(launches_per_step) * args.steps,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (all dense + grouped GEMM launches of a step)",
                          "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",

@@ -26,6 +26,8 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-I", str(INCLUDE),
 ]
+if os.environ.get("B200VQA_EPI_WARPS"):     # experiment knob: epilogue warps of the tcgen05 GEMM (8 | 12 | 16)
+    NVCC_FLAGS.append("-DB200_EPI_WARPS=" + os.environ["B200VQA_EPI_WARPS"])
 
 
 def _nvcc() -> str:

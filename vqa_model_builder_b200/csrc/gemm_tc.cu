@@ -7,7 +7,7 @@
 //   warp 1      UMMA issuer (one elected lane); owns the TMEM allocation
 //   warps 2..9  epilogue: two 128 x BN fp32 accumulators live in TMEM, so the epilogue of tile i overlaps the
 //               main loop of tile i+1 (tmem_full / tmem_empty mbarriers).  Warp w reads TMEM lanes
-//               32*(w%4)..+31 (its hardware quadrant) and one half of the BN columns, 32 columns at a time:
+//               32*(w%4)..+31 (its hardware quadrant) and every PARTS-th 32-column chunk of the tile:
 //               tcgen05.ld -> bias / activation / residual in registers -> transpose through a padded
 //               shared-memory staging tile -> row-contiguous 16-byte global stores (full 32-byte sectors).
 #include <cuda.h>
@@ -25,11 +25,15 @@ constexpr int BK = 64;          // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int CHUNK_BYTES = 64 * BK * 2;  // one 64(MN) x 64(K) MN-major TMA box
-constexpr int NUM_EPI_WARPS = 8;
+#ifndef B200_EPI_WARPS
+#define B200_EPI_WARPS 8
+#endif
+constexpr int NUM_EPI_WARPS = B200_EPI_WARPS;      // multiple of 4: one warp per TMEM lane quadrant and column part
+constexpr int EPI_PARTS = NUM_EPI_WARPS / 4;
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
 constexpr int STG_PITCH = 144;                     // bytes per staged row: 128 B payload + 16 B pad (bank spread)
 constexpr int STG_BYTES = 32 * STG_PITCH;          // per epilogue warp
-constexpr int BIAS_FLOATS = 128;                   // per epilogue warp: its BN/2 columns
+constexpr int BIAS_FLOATS = 128;                   // per epilogue warp: the columns of its (at most 4) chunks
 
 template <int BN> constexpr int num_stages() { return BN == 256 ? 3 : (BN == 128 ? 5 : 6); }
 template <int BN> constexpr int stage_bytes() { return A_BYTES + BN * BK * 2; }
@@ -72,36 +76,55 @@ __device__ __forceinline__ TileInfo get_tile(const GemmArgs& p, int tile, int m_
   return t;
 }
 
-// erf with |error| < 1.5e-7 (Abramowitz & Stegun 7.1.26): far below bf16 resolution, ~half the cost of erff
-__device__ __forceinline__ float fast_erf(float x) {
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float r = 1.0f - poly * t * __expf(-ax * ax);
-  return copysignf(r, x);
+// GELU(x) = x * Phi(x), Phi(x) = 0.5 * (1 + erf(x / sqrt 2)), with erf from Abramowitz & Stegun 7.1.26
+// (|error| < 1.5e-7, far below bf16 resolution).  Written on the complementary tail so that no sign fix-up and no
+// IEEE reciprocal (whose slow path costs a branch per element) is needed:
+//   t = 1 / (1 + p |x| / sqrt 2),  q = 0.5 * poly(t) * t * exp(-x^2 / 2),  Phi = x >= 0 ? 1 - q : q
+// 16 instructions per element, two of them MUFU (rcp.approx, ex2.approx).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Phi(x) and e = exp(-x^2/2)
+__device__ __forceinline__ float gelu_cdf(float x, float& e) {
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
+  e = ex2_approx(x * x * (-0.5f * 1.4426950408889634f));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float q = poly * t * e;
+  return x >= 0.f ? 1.0f - q : q;
 }
 // Activation applied to a 32-value register tile with the activation kind resolved ONCE per tile (a per-element
 // runtime switch made every element pay for all branches: 100+ instructions per GELU).
 template <int ACT>
 __device__ __forceinline__ float act1_fwd(float x) {
-  if (ACT == B200_ACT_GELU) return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752440f));
+  if (ACT == B200_ACT_GELU) {
+    float e;
+    return x * gelu_cdf(x, e);
+  }
   if (ACT == B200_ACT_RELU) return fmaxf(x, 0.f);
-  if (ACT == B200_ACT_SILU) return x * __frcp_rn(1.0f + __expf(-x));
+  if (ACT == B200_ACT_SILU) return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
   if (ACT == B200_ACT_TANH) return tanhf(x);
   return x;
 }
 template <int ACT>
 __device__ __forceinline__ float act1_bwd(float x) {
-  if (ACT == B200_ACT_GELU) {
-    const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752440f));
-    return fmaf(x * 0.39894228040143267794f, __expf(-0.5f * x * x), cdf);
+  if (ACT == B200_ACT_GELU) {   // Phi(x) + x * phi(x), phi(x) = exp(-x^2/2) / sqrt(2 pi): the exponential is shared
+    float e;
+    const float cdf = gelu_cdf(x, e);
+    return fmaf(x * 0.39894228040143267794f, e, cdf);
   }
   if (ACT == B200_ACT_RELU) return x > 0.f ? 1.f : 0.f;
   if (ACT == B200_ACT_SILU) {
-    const float sg = __frcp_rn(1.0f + __expf(-x));
+    const float sg = rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
     return sg * (1.0f + x * (1.0f - sg));
   }
   if (ACT == B200_ACT_TANH) {
@@ -163,14 +186,15 @@ __device__ __forceinline__ void stage_store_tile(uint8_t* stg, int lane, const f
   }
   __syncwarp();
   const int sub = lane % LPR, rsel = lane / LPR;
+  // running pointers (one 64-bit add per row instead of a 64-bit multiply-add chain)
+  uint8_t* dst = reinterpret_cast<uint8_t*>(gbase) + ((row0 + rsel) * ld + col0) * ELEM_BYTES + 16 * sub;
+  const long long dstep = (long long)RPI * ld * ELEM_BYTES;
+  const uint8_t* src = stg + rsel * STG_PITCH + 16 * sub;
 #pragma unroll
   for (int i = 0; i < 32 / RPI; ++i) {
-    const int r = i * RPI + rsel;
-    if (r < rows_ok) {
-      const uint4 t = *reinterpret_cast<const uint4*>(stg + r * STG_PITCH + 16 * sub);
-      uint8_t* dst = reinterpret_cast<uint8_t*>(gbase) + ((row0 + r) * ld + col0) * ELEM_BYTES + 16 * sub;
-      *reinterpret_cast<uint4*>(dst) = t;
-    }
+    if (i * RPI + rsel < rows_ok) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+    dst += dstep;
+    src += RPI * STG_PITCH;
   }
   __syncwarp();
 }
@@ -190,15 +214,17 @@ __device__ __forceinline__ void stage_accum_tile(uint8_t* stg, int lane, const f
 __device__ __forceinline__ void stage_load_tile_bf16(uint8_t* stg, int lane, float (&v)[32], const void* gbase,
                                                      long long ld, long long row0, int rows_ok, int col0) {
   const int sub = lane % 4, rsel = lane / 4;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(gbase) + ((row0 + rsel) * ld + col0) * 2 + 16 * sub;
+  const long long sstep = 8ll * ld * 2;
+  uint4 t[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = i * 8 + rsel;
-    uint4 t = make_uint4(0, 0, 0, 0);
-    if (r < rows_ok)
-      t = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(gbase) +
-                                               ((row0 + r) * ld + col0) * 2 + 16 * sub));
-    *reinterpret_cast<uint4*>(stg + r * STG_PITCH + 16 * sub) = t;
+  for (int i = 0; i < 4; ++i) {      // four independent loads in flight
+    t[i] = make_uint4(0, 0, 0, 0);
+    if (i * 8 + rsel < rows_ok) t[i] = __ldg(reinterpret_cast<const uint4*>(src));
+    src += sstep;
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + (i * 8 + rsel) * STG_PITCH + 16 * sub) = t[i];
   __syncwarp();
   const uint8_t* mine = stg + lane * STG_PITCH;
 #pragma unroll
@@ -324,8 +350,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ================= epilogue warps =================
     const int ew = warp - 2;                 // 0..7
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;                // which half of the BN columns
-    constexpr int HALF_N = BN / 2;
+    const int part = ew >> 2;                // this warp handles chunks part, part + EPI_PARTS, ...
+    constexpr int NCHUNK = BN / 32;
     uint8_t* stg = stg_all + ew * STG_BYTES;
     float* bias_s = bias_all + ew * BIAS_FLOATS;
     const bool out_bf16 = !p.out_f32;
@@ -342,12 +368,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const bool have_acc = t.k_blocks > 0;
       const int acc = acc_it & 1;
       const uint32_t acc_ph = (acc_it >> 1) & 1;
-      const int ncol0 = t.n_tile * BN + half * HALF_N;         // first column of this warp
+      const int ncol0 = t.n_tile * BN;                          // first column of the tile
       // bias slice of this warp -> shared memory (broadcast reads later)
       const float* bias = p.bias;
       if (bias != nullptr) {
         if (p.mode == GEMM_GROUP_ROWS) bias += (long long)t.group * p.N;
-        for (int c = lane; c < HALF_N; c += 32) bias_s[c] = (ncol0 + c < p.N) ? __ldg(bias + ncol0 + c) : 0.f;
+        for (int c = part, k = 0; c < NCHUNK; c += EPI_PARTS, ++k) {
+          const int col = ncol0 + c * 32 + lane;
+          bias_s[k * 32 + lane] = (col < p.N) ? __ldg(bias + col) : 0.f;
+        }
         __syncwarp();
       }
       if (have_acc) {
@@ -360,12 +389,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int rows_ok = rows_left >= 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);
       const long long obase = (p.mode == GEMM_GROUP_WGRAD) ? (long long)t.group * p.out_group_elems : 0ll;
 #pragma unroll 1
-      for (int c = 0; c < HALF_N / 32; ++c) {
+      for (int c = part, k = 0; c < NCHUNK; c += EPI_PARTS, ++k) {
         const int col0 = ncol0 + c * 32;
         float v[32];
         if (have_acc) {
           uint32_t r[32];
-          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF_N + c * 32), r);
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -377,7 +406,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (vec_ok && col0 + 32 <= p.N) {
           if (bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += bias_s[c * 32 + j];
+            for (int j = 0; j < 32; ++j) v[j] += bias_s[k * 32 + j];
           }
           if (p.epi == B200_EPI_ACT) {
             if (p.aux_out != nullptr) stage_store_tile<2>(stg, lane, v, p.aux_out, p.ld_aux, row0, rows_ok, col0);
