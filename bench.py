@@ -28,6 +28,7 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+GEMM_DRAM_BYTES_PER_LAUNCH = 10.72e6   # measured, see roofline.traffic below
 CFG = dict(B=32, T=64, V=50, D=768, H=8, L=2, E=8, K=2, F=2048, dropout=0.1)
 METRIC = "fusion+MOE fwd+bwd samples/sec"
 
@@ -431,7 +432,12 @@ def run_ours(args, c):
             "gpu_launches": int(launches_per_step) * args.steps,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (all dense + grouped GEMM launches of a step)",
                          "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"],
+                         "frac": achieved / pk["tf_sustained"],
+                         # DRAM bytes (read + write) per GEMM launch, ncu, mean over the 51 launches of a step of
+                         # the default configuration (profiles/r01m_launches_dram_step_cfg2.md); null otherwise
+                         "traffic": GEMM_DRAM_BYTES_PER_LAUNCH if c["B"] == CFG["B"] else None,
+                         "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "peak_source": pk["source"],
                          "launches_per_step": gemm_launches, "kernel_ms_per_step": gemm_ms,
                          "algorithmic_gflop_per_step": fl["gemm"] * c["B"] / 1e9},
             "cpu_baseline": {"value": cpu_val, "unit": "samples/s", "cores": threads, "kind": "port",
