@@ -46,7 +46,9 @@ def _digest() -> str:
     for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [INCLUDE / "b200vqa.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    # flags without the include path: the digest must not depend on where the tree is checked out (the GPU box
+    # mounts the repo elsewhere; a path-dependent digest made every fresh box rebuild the prebuilt library)
+    h.update(" ".join(f for f in NVCC_FLAGS if f != str(INCLUDE)).encode())
     return h.hexdigest()
 
 
@@ -60,6 +62,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and is_fresh():
         return LIB_PATH
     OBJ_DIR.mkdir(exist_ok=True)
+    # one builder at a time (torchrun ranks import concurrently); late comers find a fresh library
+    import fcntl
+    with open(OBJ_DIR / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and is_fresh():
+            return LIB_PATH
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> Path:
     nvcc = _nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
 
@@ -75,11 +87,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH),
+    tmp = LIB_PATH.with_suffix(".so.tmp")
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp),
            *[str(o) for o in objs], "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)       # atomic: a concurrent dlopen sees the old or the new file, never a partial one
     (OBJ_DIR / "digest.txt").write_text(_digest())
     return LIB_PATH
 
