@@ -214,45 +214,32 @@ def run_ours(args, c):
     loss_d = torch.zeros(1, dtype=torch.float32, device=dev)
 
     comm = {"on": True}
-    fus_params, moe_params = list(fus.parameters()), list(layer.parameters())
-    side_comm = torch.cuda.Stream() if world > 1 else None
+    # Data parallel: gradients are all-reduced bucket by bucket on a communication stream as soon as backward has
+    # produced them (MOE layer first, then fusion layer 2, then layer 1), overlapped with the rest of backward.
+    reducer = None
+    if world > 1:
+        tail = [p for n, p in fus.named_parameters() if not n.startswith("fusion_layers.")]
+        buckets = [list(layer.parameters()), tail]
+        for blk in reversed(list(fus.fusion_layers)):     # backward order: FFN, cross-attention, self-attention
+            buckets.append(list(blk.ffn.parameters()) + list(blk.norm3.parameters()))
+            buckets.append(list(blk.cross_attn.parameters()) + list(blk.norm2.parameters()))
+            buckets.append(list(blk.self_attn.parameters()) + list(blk.norm1.parameters()))
+        reducer = parallel.OverlappedGradReducer(buckets)
 
-    # The step is split where the MOE layer's gradients are complete (MOE is last in forward, first in backward):
-    # under data parallelism their all-reduce then overlaps the backward pass of the fusion block.
-    def part1():
+    def step():
         for p in params:
             p.grad = None
         vis.grad = None
         txt.grad = None
         fused = fus(vis, txt, text_mask=pad)
-        fd = fused.detach().requires_grad_(True)
-        out = layer(fd.unsqueeze(1))
+        out = layer(fused.unsqueeze(1))
         loss = out.float().square().mean() + layer.get_aux_loss()
         loss.backward()
+        if reducer is not None:
+            reducer.finish()
         loss_d.copy_(loss.detach().reshape(1))
-        return fused, fd
 
-    def part2(fused, fd):
-        fused.backward(fd.grad)
-
-    def reduce_overlapped(run_part2):
-        """MOE grads are reduced on a side stream while part 2 runs; fusion grads afterwards."""
-        cur = torch.cuda.current_stream()
-        side_comm.wait_stream(cur)
-        with torch.cuda.stream(side_comm):
-            parallel.allreduce_gradients(moe_params)
-        run_part2()
-        parallel.allreduce_gradients(fus_params)
-        cur.wait_stream(side_comm)
-
-    def step():
-        fused, fd = part1()
-        if world > 1 and comm["on"]:
-            reduce_overlapped(lambda: part2(fused, fd))
-        else:
-            part2(fused, fd)
-
-    # ---- eager warm-up (also configures kernels), launch count per step ----
+    # ---- eager warm-up (also configures kernels, creates the NCCL communicator), launch count per step ----
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -260,39 +247,40 @@ def run_ours(args, c):
             step()
         torch.cuda.synchronize()
         _lib.reset_launch_count()
-        comm["on"] = False
+        if reducer is not None:
+            reducer.enabled = False
         step()
-        comm["on"] = True
+        if reducer is not None:
+            reducer.enabled = True
         torch.cuda.synchronize()
         launches_per_step = _lib.launch_count()
     torch.cuda.current_stream().wait_stream(side)
-    if world > 1:   # the un-reduced counting step must leave every rank with identical state: re-sync grads
+    if world > 1:
         dist.barrier()
 
+    # The whole step, collectives included (NCCL kernels are graph-capturable), is captured in one CUDA graph.
     use_graph = not args.no_graph
-    graph = graph2 = None
+    graph = None
     if use_graph:
         try:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                held = part1()
-            graph2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph2, pool=graph.pool()):
-                part2(*held)
+                step()
         except Exception as e:  # capture unsupported for this configuration: time eagerly
             if rank == 0:
                 print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches",
                       file=sys.stderr)
-            graph = graph2 = None
+            graph = None
             torch.cuda.synchronize()
+    if world > 1:   # every rank must take the same path (graph or eager): agree on the slower one
+        ok = torch.tensor([1 if graph is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            graph = None
 
     def run_step():
         if graph is not None:
             graph.replay()
-            if world > 1:   # NCCL launched eagerly between / after the two captured halves
-                reduce_overlapped(graph2.replay)
-            else:
-                graph2.replay()
         else:
             step()
 
@@ -381,7 +369,8 @@ def run_ours(args, c):
     kern = {}
     if rank == 0:
         _lib.PROFILE = []
-        comm["on"] = False          # rank-0-only pass: no collectives here
+        if reducer is not None:
+            reducer.enabled = False  # rank-0-only pass: no collectives here
         from vqa_model_builder_b200 import runtime as _rt
         _rt.set_aux_stream(False)   # one stream: per-kernel event times must not overlap each other
         for _ in range(3):
@@ -445,10 +434,16 @@ def run_ours(args, c):
             "kernels": per_kernel, "cuda_graph": graph is not None,
             "algorithmic_gflop_per_step_total": fl["total"] * c["B"] / 1e9,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        # The captured graph holds NCCL kernels; tearing the communicator down under a live graph was observed to
+        # block.  Drain the device, meet the other ranks, then leave without running destructors.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

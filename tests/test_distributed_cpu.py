@@ -97,3 +97,37 @@ def test_expert_owner_placement():
     assert parallel.expert_owner(7, 8, 8) == 7
     with pytest.raises(ValueError):
         parallel.expert_owner(0, 6, 4)
+
+
+def _overlapped_reducer(rank, world):
+    """Bucketed all-reduce driven by post-accumulate hooks: averaged gradients equal the full-batch gradients,
+    buckets fire in backward order, unused parameters are still reduced by finish(), counters re-arm."""
+    torch.manual_seed(0)
+    l1, l2 = torch.nn.Linear(6, 5), torch.nn.Linear(5, 3)
+    unused = torch.nn.Parameter(torch.ones(2))
+    fired = []
+    red = parallel.OverlappedGradReducer([list(l2.parameters()), list(l1.parameters()), [unused]])
+    orig = red._launch
+    red._launch = lambda bi: (fired.append(bi), orig(bi))[1]
+    x_all = torch.arange(4 * 6, dtype=torch.float32).view(4, 6) / 10.0
+    for it in range(2):
+        for p in list(l1.parameters()) + list(l2.parameters()) + [unused]:
+            p.grad = None
+        unused.grad = torch.full((2,), float(rank))          # a gradient no backward pass touches
+        x = x_all[rank * 2:(rank + 1) * 2]
+        l2(torch.tanh(l1(x))).square().mean().backward()
+        red.finish()
+        ref1, ref2 = torch.nn.Linear(6, 5), torch.nn.Linear(5, 3)
+        ref1.load_state_dict(l1.state_dict())
+        ref2.load_state_dict(l2.state_dict())
+        ref2(torch.tanh(ref1(x_all))).square().mean().backward()
+        for p, r in zip(list(l1.parameters()) + list(l2.parameters()), list(ref1.parameters()) + list(ref2.parameters())):
+            assert torch.allclose(p.grad, r.grad, atol=1e-6), (it, p.grad, r.grad)
+        assert torch.allclose(unused.grad, torch.full((2,), 0.5))
+        assert fired == [0, 1, 2], fired
+        fired.clear()
+    red.remove()
+
+
+def test_overlapped_grad_reducer_world2():
+    run2(_overlapped_reducer)

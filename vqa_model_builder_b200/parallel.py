@@ -81,6 +81,62 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], average: bool = Tr
     return len(grads)
 
 
+class OverlappedGradReducer:
+    """Data-parallel gradient all-reduce overlapped with backward (what DDP's buckets do, for these modules).
+
+    `buckets` lists parameters in the order their gradients become complete during backward (last layer first).
+    A post-accumulate hook counts the gradients of a bucket; when the last one has landed the bucket is all-reduced
+    on a communication stream ordered after the compute stream, while backward of the earlier layers continues.
+    `finish()` (after `backward()`) makes the compute stream wait for the communication stream.  The pattern holds no
+    host synchronisation, so a whole step including its collectives can be captured in one CUDA graph."""
+
+    def __init__(self, buckets, average: bool = True, group: Optional[dist.ProcessGroup] = None):
+        self.buckets = [[p for p in b if p.requires_grad] for b in buckets]
+        self.buckets = [b for b in self.buckets if b]
+        self.average = average
+        self.group = group
+        self.enabled = True
+        self.comm = torch.cuda.Stream() if torch.cuda.is_available() else None
+        self._left = [len(b) for b in self.buckets]
+        self._handles = []
+        for bi, bucket in enumerate(self.buckets):
+            for p in bucket:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._hook(bi)))
+
+    def _hook(self, bi: int):
+        def fire(_param):
+            if not self.enabled:
+                return
+            self._left[bi] -= 1
+            if self._left[bi] == 0:
+                self._launch(bi)
+        return fire
+
+    def _launch(self, bi: int) -> None:
+        if self.comm is None:                      # CPU / gloo: no streams, reduce in place
+            allreduce_gradients(self.buckets[bi], self.average, self.group)
+            return
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            allreduce_gradients(self.buckets[bi], self.average, self.group)
+
+    def finish(self) -> None:
+        """Call once after backward(): reduces buckets whose hooks did not all fire (unused parameters), joins the
+        communication stream and re-arms the counters."""
+        if self.enabled:
+            for bi, left in enumerate(self._left):
+                if left > 0:
+                    self._launch(bi)
+            if self.comm is not None:
+                torch.cuda.current_stream().wait_stream(self.comm)
+        self._left = [len(b) for b in self.buckets]
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
 def expert_owner(expert: int, num_experts: int, world: int) -> int:
     """Contiguous-block expert placement for expert parallelism: expert e lives on rank e // (E / W)."""
     if num_experts % world != 0:
