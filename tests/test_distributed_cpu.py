@@ -59,7 +59,7 @@ def _dp_buckets(rank, world):
     buckets = parallel.grad_buckets([a, b, c])
     assert len(buckets) == 2 and buckets[0].data_ptr() == flat.data_ptr()
     n = parallel.allreduce_gradients([a, b, c], average=True)
-    assert n == 3
+    assert n == 2          # a.grad and b.grad are views of one flat buffer: reduced once, as a whole
     assert torch.allclose(a.grad, (torch.arange(12, dtype=torch.float32) * 1.5).view(4, 3))
     assert torch.allclose(b.grad, torch.arange(12, 17, dtype=torch.float32) * 1.5)
     assert torch.allclose(c.grad, torch.full((2,), 1.5))

@@ -50,15 +50,35 @@ def grad_buckets(params: Iterable[torch.nn.Parameter]) -> List[torch.Tensor]:
     return order
 
 
+def _reduction_units(grads, seen: Optional[set] = None):
+    """Tensors to all-reduce for a list of gradients.  The autograd Functions of this package return the parameter
+    gradients of one stage as views of ONE flat fp32 buffer (all experts of a bank, weight + bias of a Linear, ...):
+    such gradients are replaced by their base buffer, reduced once.  Grouping follows the view structure (`_base`),
+    which is identical on every rank; storage addresses are only used to drop duplicates within this rank.  `seen`
+    carries the duplicates filter across calls (buckets of one backward pass)."""
+    units, local = [], set()
+    for g in grads:
+        base = g._base if g._base is not None else g
+        if base is not g and not (base.dim() == 1 and base.is_contiguous() and base.dtype == g.dtype):
+            base = g
+        key = (base.data_ptr(), base.numel())
+        if key in local or (seen is not None and key in seen):
+            continue
+        local.add(key)
+        if seen is not None:
+            seen.add(key)
+        units.append(base)
+    return units
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], average: bool = True,
-                        group: Optional[dist.ProcessGroup] = None) -> int:
-    """Sum (or average) gradients across ranks.  One all-reduce per parameter, issued inside a single NCCL group
-    (one fused launch) — the collective sequence depends only on the parameter list, never on how autograd happened
-    to alias gradient storage on a given rank.  Returns the number of tensors reduced."""
+                        group: Optional[dist.ProcessGroup] = None, seen: Optional[set] = None) -> int:
+    """Sum (or average) gradients across ranks: one all-reduce per flat gradient buffer (see `_reduction_units`),
+    issued inside a single NCCL group (one fused launch).  Returns the number of tensors reduced."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
     world = dist.get_world_size(group)
-    grads = [p.grad for p in params if p.grad is not None]
+    grads = _reduction_units([p.grad for p in params if p.grad is not None], seen)
     if not grads:
         return 0
     op = dist.ReduceOp.AVG if (average and grads[0].is_cuda) else dist.ReduceOp.SUM
@@ -98,6 +118,7 @@ class OverlappedGradReducer:
         self.enabled = True
         self.comm = torch.cuda.Stream() if torch.cuda.is_available() else None
         self._left = [len(b) for b in self.buckets]
+        self._seen = set()          # flat buffers already reduced in this backward pass (may span two buckets)
         self._handles = []
         for bi, bucket in enumerate(self.buckets):
             for p in bucket:
@@ -114,11 +135,11 @@ class OverlappedGradReducer:
 
     def _launch(self, bi: int) -> None:
         if self.comm is None:                      # CPU / gloo: no streams, reduce in place
-            allreduce_gradients(self.buckets[bi], self.average, self.group)
+            allreduce_gradients(self.buckets[bi], self.average, self.group, self._seen)
             return
         self.comm.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm):
-            allreduce_gradients(self.buckets[bi], self.average, self.group)
+            allreduce_gradients(self.buckets[bi], self.average, self.group, self._seen)
 
     def finish(self) -> None:
         """Call once after backward(): reduces buckets whose hooks did not all fire (unused parameters), joins the
@@ -130,6 +151,7 @@ class OverlappedGradReducer:
             if self.comm is not None:
                 torch.cuda.current_stream().wait_stream(self.comm)
         self._left = [len(b) for b in self.buckets]
+        self._seen = set()
 
     def remove(self) -> None:
         for h in self._handles:
