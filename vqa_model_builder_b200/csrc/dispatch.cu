@@ -276,16 +276,24 @@ combine_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ z, const in
         float* ag = acc_g + vi * VT;
         float* ab = acc_b + vi * VT;
 #pragma unroll
-        for (int u = 0; u < VT; ++u) {
-          const float xhat = (s.v[j][u] - mean) * rstd;
-          const float d = g.v[j][u];
-          ag[u] = fmaf(d, xhat, ag[u]);
-          ab[u] += d;
-          const float gg = d * gv[u];
-          s.v[j][u] = xhat;
-          g.v[j][u] = gg;
-          s1 += gg;
-          s2 = fmaf(gg, xhat, s2);
+        for (int u = 0; u < VT; u += 4) {      // 16-byte read-modify-write of the per-warp accumulators
+          float4 tg = *reinterpret_cast<float4*>(ag + u), tb = *reinterpret_cast<float4*>(ab + u);
+          float* pg = reinterpret_cast<float*>(&tg);
+          float* pb = reinterpret_cast<float*>(&tb);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float xhat = (s.v[j][u + q] - mean) * rstd;
+            const float d = g.v[j][u + q];
+            pg[q] = fmaf(d, xhat, pg[q]);
+            pb[q] += d;
+            const float gg = d * gv[u + q];
+            s.v[j][u + q] = xhat;
+            g.v[j][u + q] = gg;
+            s1 += gg;
+            s2 = fmaf(gg, xhat, s2);
+          }
+          *reinterpret_cast<float4*>(ag + u) = tg;
+          *reinterpret_cast<float4*>(ab + u) = tb;
         }
       }
     }

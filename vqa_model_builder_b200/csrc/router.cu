@@ -34,14 +34,42 @@ __device__ __forceinline__ void stage_gate_weights(const float* __restrict__ w, 
 }
 
 // dot products of one token row (held in registers, loaded once) with the E staged weight rows.
-// On return lane e (and slot 1: e+32) holds logit e.
-template <typename T, int NV>
+// On return lane e (and slot 1: e+32) holds logit e.  EB > 0: E <= EB is a compile-time bound, the expert loop is
+// unrolled and the EB warp reductions run interleaved (5 dependent shuffle rounds instead of 5 * E).
+template <typename T, int NV, int EB>
 __device__ __forceinline__ void gate_dots(const RowRegs<T, NV>& x, const float* __restrict__ ws, int E, int lane,
                                           float& l0, float& l1) {
   constexpr int VT = Vec16<T>::N;
   const float4* ws4 = reinterpret_cast<const float4*>(ws);
   l0 = 0.f;
   l1 = 0.f;
+  if (EB > 0) {
+    float s[EB > 0 ? EB : 1];
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      s[e] = 0.f;
+      if (e < E) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+          for (int q = 0; q < VT / 4; ++q) {
+            const float4 wv = ws4[((e * NV + j) * (VT / 4) + q) * 32 + lane];
+            s[e] = fmaf(x.v[j][4 * q + 0], wv.x, s[e]);
+            s[e] = fmaf(x.v[j][4 * q + 1], wv.y, s[e]);
+            s[e] = fmaf(x.v[j][4 * q + 2], wv.z, s[e]);
+            s[e] = fmaf(x.v[j][4 * q + 3], wv.w, s[e]);
+          }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int e = 0; e < EB; ++e) s[e] += __shfl_xor_sync(0xffffffffu, s[e], o);
+#pragma unroll
+    for (int e = 0; e < EB; ++e)
+      if (e == lane) l0 = s[e];
+    return;
+  }
   for (int e = 0; e < E; ++e) {
     float s = 0.f;
 #pragma unroll
@@ -70,7 +98,7 @@ __device__ __forceinline__ void warp_softmax(float& a, float& b) {
   b = eb / s;
 }
 
-template <typename T, int NV>
+template <typename T, int NV, int EB>
 __global__ void __launch_bounds__(RT_WARPS * 32)
 router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, const float* __restrict__ w_noise,
                   const float* __restrict__ eps, float noise_std, int N, int D, int E, int K, int* __restrict__ idx,
@@ -97,11 +125,11 @@ router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
     RowRegs<T, NV> xr;
     xr.load(x + (long long)n * D, D, lane);
     float c0, c1;  // clean logits -> clean probs
-    gate_dots<T, NV>(xr, wg, E, lane, c0, c1);
+    gate_dots<T, NV, EB>(xr, wg, E, lane, c0, c1);
     float q0 = c0, q1 = c1;  // logits used for selection
     if (noisy) {
       float u0, u1;
-      gate_dots<T, NV>(xr, wn, E, lane, u0, u1);
+      gate_dots<T, NV, EB>(xr, wn, E, lane, u0, u1);
       const float sp0 = softplus_f(u0), sp1 = softplus_f(u1);
       if (v0) { q0 = c0 + eps[(long long)n * E + lane] * sp0 * noise_std; ns0 += sp0; }
       if (v1) { q1 = c1 + eps[(long long)n * E + lane + 32] * sp1 * noise_std; ns1 += sp1; }
@@ -201,7 +229,7 @@ router_finalize_kernel(const float* __restrict__ part, int blocks, int N, int E,
 // ---- backward --------------------------------------------------------------------------------------------
 // per token: d logits (clean) and d noise-logits, then dx = dl Wg + du Wn.  dl/du are also written to the
 // workspace for the weight-gradient reduction.
-template <typename T, int NV>
+template <typename T, int NV, int EB>
 __global__ void __launch_bounds__(RT_WARPS * 32)
 router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, const float* __restrict__ w_noise,
                   const float* __restrict__ eps, float noise_std, float lb_weight, int N, int D, int E, int K,
@@ -259,7 +287,7 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
       RowRegs<T, NV> xr;
       xr.load(x + (long long)n * D, D, lane);
       float u0, u1;
-      gate_dots<T, NV>(xr, wn, E, lane, u0, u1);
+      gate_dots<T, NV, EB>(xr, wn, E, lane, u0, u1);
       if (v0) du0 = dsel0 * eps[(long long)n * E + lane] * noise_std * sigmoid_f(u0);
       if (v1) du1 = dsel1 * eps[(long long)n * E + lane + 32] * noise_std * sigmoid_f(u1);
     }
@@ -278,7 +306,9 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
     o.zero();
     const float4* wg4 = reinterpret_cast<const float4*>(wg);
     const float4* wn4 = reinterpret_cast<const float4*>(wn);
-    for (int e = 0; e < E; ++e) {
+#pragma unroll
+    for (int e = 0; e < (EB > 0 ? EB : RT_MAX_E); ++e) {
+      if (e >= E) break;
       const float a = s_dl[warp][e];
       const float bb = noisy ? s_du[warp][e] : 0.f;
 #pragma unroll
@@ -406,14 +436,20 @@ int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* 
   float* part = (float*)workspace;
   if (dtype == B200_BF16) {
     B200_NV_SWITCH(nvb, {
-      if (int rc = set_smem(router_fwd_kernel<bf16, NV>, smem)) return rc;
-      launch_kernel(router_fwd_kernel<bf16, NV>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream, 
-          (const bf16*)x, w_gate, w_noise, eps, noise_std, N, D, E, K, idx, w, topk_sum, probs, probs_noisy, part);
+      if (E <= 8) {
+        if (int rc = set_smem(router_fwd_kernel<bf16, NV, 8>, smem)) return rc;
+        launch_kernel(router_fwd_kernel<bf16, NV, 8>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream,
+            (const bf16*)x, w_gate, w_noise, eps, noise_std, N, D, E, K, idx, w, topk_sum, probs, probs_noisy, part);
+      } else {
+        if (int rc = set_smem(router_fwd_kernel<bf16, NV, 0>, smem)) return rc;
+        launch_kernel(router_fwd_kernel<bf16, NV, 0>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream,
+            (const bf16*)x, w_gate, w_noise, eps, noise_std, N, D, E, K, idx, w, topk_sum, probs, probs_noisy, part);
+      }
     });
   } else {
     B200_NV_SWITCH(nvb, {
-      if (int rc = set_smem(router_fwd_kernel<float, NV>, smem)) return rc;
-      launch_kernel(router_fwd_kernel<float, NV>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream, 
+      if (int rc = set_smem(router_fwd_kernel<float, NV, 0>, smem)) return rc;
+      launch_kernel(router_fwd_kernel<float, NV, 0>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream,
           (const float*)x, w_gate, w_noise, eps, noise_std, N, D, E, K, idx, w, topk_sum, probs, probs_noisy, part);
     });
   }
@@ -457,15 +493,22 @@ int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* 
   const int ED = E * D;
   if (dtype == B200_BF16) {
     B200_NV_SWITCH(nvb, {
-      if (int rc = set_smem(router_bwd_kernel<bf16, NV>, smem)) return rc;
-      launch_kernel(router_bwd_kernel<bf16, NV>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream, 
-          (const bf16*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
-          counts, d_w, d_loss, (bf16*)dx, dl, du);
+      if (E <= 8) {
+        if (int rc = set_smem(router_bwd_kernel<bf16, NV, 8>, smem)) return rc;
+        launch_kernel(router_bwd_kernel<bf16, NV, 8>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream,
+            (const bf16*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs,
+            probs_noisy, counts, d_w, d_loss, (bf16*)dx, dl, du);
+      } else {
+        if (int rc = set_smem(router_bwd_kernel<bf16, NV, 0>, smem)) return rc;
+        launch_kernel(router_bwd_kernel<bf16, NV, 0>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream,
+            (const bf16*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs,
+            probs_noisy, counts, d_w, d_loss, (bf16*)dx, dl, du);
+      }
     });
   } else {
     B200_NV_SWITCH(nvb, {
-      if (int rc = set_smem(router_bwd_kernel<float, NV>, smem)) return rc;
-      launch_kernel(router_bwd_kernel<float, NV>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream, 
+      if (int rc = set_smem(router_bwd_kernel<float, NV, 0>, smem)) return rc;
+      launch_kernel(router_bwd_kernel<float, NV, 0>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream, 
           (const float*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
           counts, d_w, d_loss, (float*)dx, dl, du);
     });

@@ -52,14 +52,16 @@ class CrossAttentionBlock(nn.Module):
     SITES = 6   # per direction: attention probabilities, ffn inner, ffn output
 
     def _block(self, v2, t2, B, V, T, vpad_u8, tpad_u8, slab, dc, k0=0):
-        a = blocks.cross_attention(t2, v2, B, T, V, self.v2t_attention, slab, vpad_u8, drop_attn=dc.site(k0 + 0))
-        t2 = blocks.add_ln(t2, a, self.v2t_norm1)
-        f = blocks.ffn(t2, self.v2t_ffn[0], self.v2t_ffn[3], slab, drop_in=dc.site(k0 + 1))
-        t2 = blocks.add_ln(t2, f, self.v2t_norm2, dc.site(k0 + 2))
-        a = blocks.cross_attention(v2, t2, B, V, T, self.t2v_attention, slab, tpad_u8, drop_attn=dc.site(k0 + 3))
-        v2 = blocks.add_ln(v2, a, self.t2v_norm1)
-        f = blocks.ffn(v2, self.t2v_ffn[0], self.t2v_ffn[3], slab, drop_in=dc.site(k0 + 4))
-        v2 = blocks.add_ln(v2, f, self.t2v_norm2, dc.site(k0 + 5))
+        a, r = blocks.cross_attention(t2, v2, B, T, V, self.v2t_attention, slab, vpad_u8, drop_attn=dc.site(k0 + 0),
+                                      passthrough=True)
+        t2 = blocks.add_ln(r, a, self.v2t_norm1)
+        f, r = blocks.ffn(t2, self.v2t_ffn[0], self.v2t_ffn[3], slab, drop_in=dc.site(k0 + 1), passthrough=True)
+        t2 = blocks.add_ln(r, f, self.v2t_norm2, dc.site(k0 + 2))
+        a, r = blocks.cross_attention(v2, t2, B, V, T, self.t2v_attention, slab, tpad_u8, drop_attn=dc.site(k0 + 3),
+                                      passthrough=True)
+        v2 = blocks.add_ln(r, a, self.t2v_norm1)
+        f, r = blocks.ffn(v2, self.t2v_ffn[0], self.t2v_ffn[3], slab, drop_in=dc.site(k0 + 4), passthrough=True)
+        v2 = blocks.add_ln(r, f, self.t2v_norm2, dc.site(k0 + 5))
         return v2, t2
 
 

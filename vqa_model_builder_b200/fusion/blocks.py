@@ -22,33 +22,52 @@ def pad_mask_u8(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 def self_attention(x2, B, T, mha: nn.MultiheadAttention, slab: ParamSlab, key_pad_u8, residual=None, drop_attn=None,
-                   drop_out=None):
+                   drop_out=None, passthrough=False):
     """out_proj(softmax(q k^T / sqrt(dh) + mask) v) over x2 [B*T, D]; optional (dropout +) residual fused into
-    out_proj."""
+    out_proj.  passthrough=True returns (out, alias of x2): use the alias for the residual connection around this
+    branch so the two gradients of x2 are summed in the in-projection's dgrad epilogue."""
     cdt = x2.dtype
-    qkv = ops.LinearFn.apply(x2, mha.in_proj_weight, mha.in_proj_bias, slab.compute_view(mha.in_proj_weight, cdt),
-                             None)
+    xr = None
+    if passthrough and x2.requires_grad:
+        qkv, xr = ops.LinearFn.apply(x2, mha.in_proj_weight, mha.in_proj_bias,
+                                     slab.compute_view(mha.in_proj_weight, cdt), None, None, True)
+    else:
+        qkv = ops.LinearFn.apply(x2, mha.in_proj_weight, mha.in_proj_bias,
+                                 slab.compute_view(mha.in_proj_weight, cdt), None)
     ctx = ops.AttentionFn.apply(qkv, None, key_pad_u8, B, T, T, mha.num_heads, True, drop_attn)
-    return ops.LinearFn.apply(ctx, mha.out_proj.weight, mha.out_proj.bias,
-                              slab.compute_view(mha.out_proj.weight, cdt), residual, drop_out)
+    out = ops.LinearFn.apply(ctx, mha.out_proj.weight, mha.out_proj.bias,
+                             slab.compute_view(mha.out_proj.weight, cdt), residual, drop_out)
+    return (out, xr if xr is not None else x2) if passthrough else out
 
 
 def cross_attention(x2, kv2, B, T, S, mha: nn.MultiheadAttention, slab: ParamSlab, key_pad_u8, residual=None,
-                    drop_attn=None):
-    """Queries from x2 [B*T, D], keys/values from kv2 [B*S, D] (question -> image patches)."""
+                    drop_attn=None, passthrough=False):
+    """Queries from x2 [B*T, D], keys/values from kv2 [B*S, D] (question -> image patches).  passthrough: see
+    self_attention."""
     cdt = x2.dtype
-    q, kvp = ops.CrossProjFn.apply(x2, kv2, mha.in_proj_weight, mha.in_proj_bias,
-                                   slab.compute_view(mha.in_proj_weight, cdt))
+    xr = None
+    if passthrough and x2.requires_grad:
+        q, kvp, xr = ops.CrossProjFn.apply(x2, kv2, mha.in_proj_weight, mha.in_proj_bias,
+                                           slab.compute_view(mha.in_proj_weight, cdt), True)
+    else:
+        q, kvp = ops.CrossProjFn.apply(x2, kv2, mha.in_proj_weight, mha.in_proj_bias,
+                                       slab.compute_view(mha.in_proj_weight, cdt))
     ctx = ops.AttentionFn.apply(q, kvp, key_pad_u8, B, T, S, mha.num_heads, False, drop_attn)
-    return ops.LinearFn.apply(ctx, mha.out_proj.weight, mha.out_proj.bias,
-                              slab.compute_view(mha.out_proj.weight, cdt), residual)
+    out = ops.LinearFn.apply(ctx, mha.out_proj.weight, mha.out_proj.bias,
+                             slab.compute_view(mha.out_proj.weight, cdt), residual)
+    return (out, xr if xr is not None else x2) if passthrough else out
 
 
 def ffn(x2, lin1: nn.Linear, lin2: nn.Linear, slab: ParamSlab, act: int = ACT_GELU, residual=None, drop_in=None,
-        drop_out=None):
+        drop_out=None, passthrough=False):
     cdt = x2.dtype
-    return ops.FFNFn.apply(x2, lin1.weight, lin1.bias, lin2.weight, lin2.bias, slab.compute_view(lin1.weight, cdt),
-                           slab.compute_view(lin2.weight, cdt), act, residual, drop_in, drop_out)
+    if passthrough and x2.requires_grad:
+        return ops.FFNFn.apply(x2, lin1.weight, lin1.bias, lin2.weight, lin2.bias,
+                               slab.compute_view(lin1.weight, cdt), slab.compute_view(lin2.weight, cdt), act, residual,
+                               drop_in, drop_out, True)
+    out = ops.FFNFn.apply(x2, lin1.weight, lin1.bias, lin2.weight, lin2.bias, slab.compute_view(lin1.weight, cdt),
+                          slab.compute_view(lin2.weight, cdt), act, residual, drop_in, drop_out)
+    return (out, x2) if passthrough else out
 
 
 def add_ln(x2, branch, ln: nn.LayerNorm, drop=None):

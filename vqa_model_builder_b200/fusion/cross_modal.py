@@ -48,12 +48,15 @@ class CrossModalAttention(SlabOwner, nn.Module):
     SITES = 6   # dropout sites: attn probs (self), attn out, attn probs (cross), cross out, ffn inner, ffn out
 
     def _block(self, x2, kv2, B, T, S, qmask_u8, kvmask_u8, slab, dc: DropCtx, k0: int = 0):
-        a = blocks.self_attention(x2, B, T, self.self_attn, slab, qmask_u8, drop_attn=dc.site(k0 + 0))
-        x2 = blocks.add_ln(x2, a, self.norm1, dc.site(k0 + 1))
-        c = blocks.cross_attention(x2, kv2, B, T, S, self.cross_attn, slab, kvmask_u8, drop_attn=dc.site(k0 + 2))
-        x2 = blocks.add_ln(x2, c, self.norm2, dc.site(k0 + 3))
-        f = blocks.ffn(x2, self.ffn[0], self.ffn[3], slab, drop_in=dc.site(k0 + 4))
-        return blocks.add_ln(x2, f, self.norm3, dc.site(k0 + 5))
+        # each branch returns an alias of its input for the residual connection (gradient sum fused into its dgrad)
+        a, xr = blocks.self_attention(x2, B, T, self.self_attn, slab, qmask_u8, drop_attn=dc.site(k0 + 0),
+                                      passthrough=True)
+        x2 = blocks.add_ln(xr, a, self.norm1, dc.site(k0 + 1))
+        c, xr = blocks.cross_attention(x2, kv2, B, T, S, self.cross_attn, slab, kvmask_u8, drop_attn=dc.site(k0 + 2),
+                                       passthrough=True)
+        x2 = blocks.add_ln(xr, c, self.norm2, dc.site(k0 + 3))
+        f, xr = blocks.ffn(x2, self.ffn[0], self.ffn[3], slab, drop_in=dc.site(k0 + 4), passthrough=True)
+        return blocks.add_ln(xr, f, self.norm3, dc.site(k0 + 5))
 
     def forward(self, query: torch.Tensor, key_value: torch.Tensor, query_mask: Optional[torch.Tensor] = None,
                 kv_mask: Optional[torch.Tensor] = None) -> torch.Tensor:

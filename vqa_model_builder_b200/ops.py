@@ -125,7 +125,10 @@ class LinearFn(torch.autograd.Function):
     (vqa_model.py:258-263; TransformerEncoderLayer's x + dropout1(sa(x)))."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, w_c, residual, drop=None):
+    def forward(ctx, x, weight, bias, w_c, residual, drop=None, passthrough=False):
+        """passthrough=True additionally returns x itself: a caller that also feeds x to a residual connection uses
+        the returned alias there, so both gradients of x arrive in this backward and the sum is fused into the
+        dgrad GEMM's epilogue instead of a separate accumulation kernel."""
         _lib.ensure_device(x)
         M, K = x.shape
         N = w_c.shape[0]
@@ -137,10 +140,11 @@ class LinearFn(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
         ctx.drop = drop
-        return y
+        ctx.passthrough = passthrough
+        return (y, x) if passthrough else y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dx_alias=None):
         x, w_c = ctx.saved_tensors
         M, K = x.shape
         N = w_c.shape[0]
@@ -166,9 +170,20 @@ class LinearFn(torch.autograd.Function):
         elif ctx.has_bias and ctx.needs_input_grad[2]:
             db = pre_db if pre_db is not None else colsum(g)
         if ctx.needs_input_grad[0]:
-            dx = gemm(g, LAYOUT_K, w_c, LAYOUT_MN, M, K, N)
+            if dx_alias is not None:
+                dx = gemm(g, LAYOUT_K, w_c, LAYOUT_MN, M, K, N, epi=EPI_ADD, aux_in=_as_rows(dx_alias, x))
+            else:
+                dx = gemm(g, LAYOUT_K, w_c, LAYOUT_MN, M, K, N)
         aux_join(side)
-        return dx, dw, db, None, (dy if ctx.has_res else None), None
+        return dx, dw, db, None, (dy if ctx.has_res else None), None, None
+
+
+def _as_rows(g: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """gradient of a pass-through alias as a contiguous [rows, features] tensor in the activation dtype"""
+    g = g.reshape(like.shape)
+    if g.dtype != like.dtype:
+        g = g.to(like.dtype)
+    return g.contiguous()
 
 
 def _colsum_into(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
@@ -186,7 +201,7 @@ class FFNFn(torch.autograd.Function):
     its derivative (x the same mask) in the epilogue of GEMM-2's dgrad."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, w1_c, w2_c, act, residual, drop_in=None, drop_out=None):
+    def forward(ctx, x, w1, b1, w2, b2, w1_c, w2_c, act, residual, drop_in=None, drop_out=None, passthrough=False):
         _lib.ensure_device(x)
         M, D = x.shape
         F = w1_c.shape[0]
@@ -201,10 +216,10 @@ class FFNFn(torch.autograd.Function):
         ctx.act = act
         ctx.has_res = residual is not None
         ctx.drops = (drop_in, drop_out)
-        return y
+        return (y, x) if passthrough else y     # see LinearFn: alias of x for the caller's residual connection
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dx_alias=None):
         x, pre, h, w1_c, w2_c = ctx.saved_tensors
         drop_in, drop_out = ctx.drops
         M, D = x.shape
@@ -233,9 +248,14 @@ class FFNFn(torch.autograd.Function):
         with aux_on(side):
             gemm(dpre, LAYOUT_MN, x, LAYOUT_MN, F, D, M, out=dw1, epi=wepi)
             _colsum_into(dpre, db1)
-        dx = gemm(dpre, LAYOUT_K, w1_c, LAYOUT_MN, M, D, F) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if dx_alias is not None:
+                dx = gemm(dpre, LAYOUT_K, w1_c, LAYOUT_MN, M, D, F, epi=EPI_ADD, aux_in=_as_rows(dx_alias, x))
+            else:
+                dx = gemm(dpre, LAYOUT_K, w1_c, LAYOUT_MN, M, D, F)
         aux_join(side)
-        return dx, dw1, db1, dw2, db2, None, None, None, (dy if ctx.has_res else None), None, None
+        return dx, dw1, db1, dw2, db2, None, None, None, (dy if ctx.has_res else None), None, None, None
 
 
 # ---- residual add + LayerNorm ------------------------------------------------------------------------------
@@ -673,7 +693,7 @@ class CrossProjFn(torch.autograd.Function):
     One Function so the packed parameter receives one gradient written in place (no slice/cat kernels)."""
 
     @staticmethod
-    def forward(ctx, x, kv, in_w, in_b, in_w_c):
+    def forward(ctx, x, kv, in_w, in_b, in_w_c, passthrough=False):
         _lib.ensure_device(x)
         M, D = x.shape
         Mk = kv.shape[0]
@@ -687,10 +707,10 @@ class CrossProjFn(torch.autograd.Function):
         aux_join(side)
         ctx.save_for_backward(x, kv, in_w_c)
         ctx.has_bias = in_b is not None
-        return q, kvp
+        return (q, kvp, x) if passthrough else (q, kvp)    # see LinearFn: alias of x for the residual connection
 
     @staticmethod
-    def backward(ctx, dq, dkvp):
+    def backward(ctx, dq, dkvp, dx_alias=None):
         x, kv, in_w_c = ctx.saved_tensors
         M, D = x.shape
         Mk = kv.shape[0]
@@ -707,7 +727,12 @@ class CrossProjFn(torch.autograd.Function):
             gemm(dkvp, LAYOUT_MN, kv, LAYOUT_MN, 2 * D, D, Mk, out=dw[D:], epi=wepi)
             _colsum_into(dq, db[:D])
             _colsum_into(dkvp, db[D:])
-        dx = gemm(dq, LAYOUT_K, in_w_c[:D], LAYOUT_MN, M, D, D) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if dx_alias is not None:
+                dx = gemm(dq, LAYOUT_K, in_w_c[:D], LAYOUT_MN, M, D, D, epi=EPI_ADD, aux_in=_as_rows(dx_alias, x))
+            else:
+                dx = gemm(dq, LAYOUT_K, in_w_c[:D], LAYOUT_MN, M, D, D)
         dkv = gemm(dkvp, LAYOUT_K, in_w_c[D:], LAYOUT_MN, Mk, D, 2 * D) if ctx.needs_input_grad[1] else None
         aux_join(side)
-        return dx, dkv, dw, (db if ctx.has_bias else None), None
+        return dx, dkv, dw, (db if ctx.has_bias else None), None, None
