@@ -59,6 +59,8 @@ def main():
         e.record()
         e.synchronize()
         ts.append(s.elapsed_time(e))
+    from vqa_model_builder_b200 import runtime as _rt
+    _rt.set_aux_stream(False)        # one stream: per-call event times must not overlap each other
     _lib.PROFILE = []
     for _ in range(args.iters):
         flush.fill_(0)

@@ -173,6 +173,7 @@ colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part, c
       part[(long long)blockIdx.y * N + gc] = s;
     }
   }
+  if (tickets == nullptr) return;                     // many row blocks / grouped: a second kernel folds in parallel
   if (!last_arrival(tickets + blockIdx.x, gridDim.y)) return;
   for (int c = threadIdx.x; c < 32 * VT; c += 256) {
     const int gc = blockIdx.x * 32 * VT + c;
@@ -193,6 +194,7 @@ __global__ void colsum_stage1_scalar(const T* __restrict__ x, int R, int N, floa
     for (int r = r0; r < r1; ++r) s += to_f32<T>(x[(long long)r * N + col]);
     part[(long long)blockIdx.y * N + col] = s;
   }
+  if (tickets == nullptr) return;
   if (!last_arrival(tickets + blockIdx.x, gridDim.y)) return;
   if (col < N) fold_partials(part, gridDim.y, N, col, tile_group, G, out);
 }
@@ -307,24 +309,27 @@ int b200_colsum(const void* x, int dtype, int R, int N, const int32_t* tile_grou
   const int blocks = (R + CS_ROWS - 1) / CS_ROWS;
   float* part = (float*)workspace;
   const int vt = dtype == B200_F32 ? 4 : 8;
-  if (N % vt == 0 && ((uintptr_t)x & 15) == 0) {
-    dim3 g1((N + 32 * vt - 1) / (32 * vt), blocks);
-    unsigned int* tk = nullptr;
+  // One launch when the fold is short (<= 64 row blocks, i.e. R <= 4096, ungrouped): the last-arriving block of a
+  // column slab adds the partials.  Otherwise the serial fold would dominate: a second kernel folds in parallel.
+  const bool single = (tile_group == nullptr) && blocks <= 64;
+  const bool vec = (N % vt == 0) && (((uintptr_t)x & 15) == 0);
+  dim3 g1(vec ? (N + 32 * vt - 1) / (32 * vt) : (N + 127) / 128, blocks);
+  unsigned int* tk = nullptr;
+  if (single) {
     B200_CUDA(cudaGetSymbolAddress((void**)&tk, g_tickets));
     tk += ticket_slots((int)g1.x);
+  }
+  if (vec) {
     if (dtype == B200_F32) launch_kernel(colsum_stage1<float>, dim3(g1), dim3(256), 0, stream, (const float*)x, R, N, part, tile_group, G, out, tk);
     else launch_kernel(colsum_stage1<bf16>, dim3(g1), dim3(256), 0, stream, (const bf16*)x, R, N, part, tile_group, G, out, tk);
   } else {
-    dim3 g1((N + 127) / 128, blocks);
-    unsigned int* tk = nullptr;
-    B200_CUDA(cudaGetSymbolAddress((void**)&tk, g_tickets));
-    tk += ticket_slots((int)g1.x);
     if (dtype == B200_F32) launch_kernel(colsum_stage1_scalar<float>, dim3(g1), dim3(128), 0, stream, (const float*)x, R, N, part, tile_group, G, out, tk);
     else launch_kernel(colsum_stage1_scalar<bf16>, dim3(g1), dim3(128), 0, stream, (const bf16*)x, R, N, part, tile_group, G, out, tk);
   }
   B200_LAUNCH_CHECK("colsum_stage1");
   count_launch();
-  return 0;
+  if (single) return 0;
+  return launch_partial_reduce(part, blocks, CS_ROWS, N, tile_group, G, out, stream);
 }
 
 static int check_epi(int epi, int act, const void* aux_in, int out_dtype) {

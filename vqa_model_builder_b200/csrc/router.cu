@@ -89,6 +89,120 @@ __device__ __forceinline__ void gate_dots(const RowRegs<T, NV>& x, const float* 
   }
 }
 
+// Token-blocked variants for the common case (bf16 rows, E <= 8, no noise): a warp handles TB consecutive tokens at
+// once so every staged weight vector read from shared memory feeds TB rows.  With one token per warp the kernel was
+// bound by shared-memory bandwidth (E * D * 4 bytes of weight reads per token: 35 % of HBM peak at best).  The
+// accumulation order per lane is the same as in gate_dots, so both paths give bit-identical logits.
+constexpr int RT_TB = 4;
+template <int NV, int EB, int TB>
+__device__ __forceinline__ void gate_dots_block(const bf16* __restrict__ x, const float* __restrict__ ws, int base,
+                                                int N, int D, int E, int lane, float (&out)[TB]) {
+  const float4* ws4 = reinterpret_cast<const float4*>(ws);
+  const int nv = D / 8;
+  uint4 raw[TB][NV];
+#pragma unroll
+  for (int t = 0; t < TB; ++t)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int vi = lane + 32 * j;
+      raw[t][j] = (base + t < N && vi < nv)
+                      ? __ldg(reinterpret_cast<const uint4*>(x + (long long)(base + t) * D + vi * 8))
+                      : make_uint4(0, 0, 0, 0);
+    }
+  float s[TB][EB];
+#pragma unroll
+  for (int t = 0; t < TB; ++t)
+#pragma unroll
+    for (int e = 0; e < EB; ++e) s[t][e] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float xv[TB][4];
+#pragma unroll
+      for (int t = 0; t < TB; ++t) {
+        const float2 a = unpack_bf16x2(q == 0 ? raw[t][j].x : raw[t][j].z);
+        const float2 b = unpack_bf16x2(q == 0 ? raw[t][j].y : raw[t][j].w);
+        xv[t][0] = a.x; xv[t][1] = a.y; xv[t][2] = b.x; xv[t][3] = b.y;
+      }
+#pragma unroll
+      for (int e = 0; e < EB; ++e) {
+        if (e < E) {
+          const float4 wv = ws4[((e * NV + j) * 2 + q) * 32 + lane];
+#pragma unroll
+          for (int t = 0; t < TB; ++t) {
+            s[t][e] = fmaf(xv[t][0], wv.x, s[t][e]);
+            s[t][e] = fmaf(xv[t][1], wv.y, s[t][e]);
+            s[t][e] = fmaf(xv[t][2], wv.z, s[t][e]);
+            s[t][e] = fmaf(xv[t][3], wv.w, s[t][e]);
+          }
+        }
+      }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int t = 0; t < TB; ++t)
+#pragma unroll
+      for (int e = 0; e < EB; ++e) s[t][e] += __shfl_xor_sync(0xffffffffu, s[t][e], o);
+#pragma unroll
+  for (int t = 0; t < TB; ++t) {
+    out[t] = 0.f;
+#pragma unroll
+    for (int e = 0; e < EB; ++e)
+      if (e == lane) out[t] = s[t][e];
+  }
+}
+
+// dx rows of TB consecutive tokens: dx[t] = sum_e dl[t][e] * Wg[e,:]  (dl from shared memory, same layout)
+template <int NV, int EB, int TB>
+__device__ __forceinline__ void gate_dx_block(const float* __restrict__ ws, const float (*dl_s)[RT_MAX_E], int base,
+                                              int N, int D, int E, int lane, bf16* __restrict__ dx) {
+  const float4* ws4 = reinterpret_cast<const float4*>(ws);
+  const int nv = D / 8;
+  float dl[TB][EB];
+#pragma unroll
+  for (int t = 0; t < TB; ++t)
+#pragma unroll
+    for (int e = 0; e < EB; ++e) dl[t][e] = (e < E) ? dl_s[t][e] : 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float o[TB][8];
+#pragma unroll
+    for (int t = 0; t < TB; ++t)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[t][u] = 0.f;
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      if (e < E) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float4 wv = ws4[((e * NV + j) * 2 + q) * 32 + lane];
+#pragma unroll
+          for (int t = 0; t < TB; ++t) {
+            o[t][4 * q + 0] = fmaf(dl[t][e], wv.x, o[t][4 * q + 0]);
+            o[t][4 * q + 1] = fmaf(dl[t][e], wv.y, o[t][4 * q + 1]);
+            o[t][4 * q + 2] = fmaf(dl[t][e], wv.z, o[t][4 * q + 2]);
+            o[t][4 * q + 3] = fmaf(dl[t][e], wv.w, o[t][4 * q + 3]);
+          }
+        }
+      }
+    }
+    const int vi = lane + 32 * j;
+    if (vi < nv) {
+#pragma unroll
+      for (int t = 0; t < TB; ++t) {
+        if (base + t < N) {
+          uint4 pk;
+          pk.x = pack_bf16x2(o[t][0], o[t][1]); pk.y = pack_bf16x2(o[t][2], o[t][3]);
+          pk.z = pack_bf16x2(o[t][4], o[t][5]); pk.w = pack_bf16x2(o[t][6], o[t][7]);
+          *reinterpret_cast<uint4*>(dx + (long long)(base + t) * D + vi * 8) = pk;
+        }
+      }
+    }
+  }
+}
+
 // softmax over the E logits spread as (lane, slot); invalid slots must hold -inf
 __device__ __forceinline__ void warp_softmax(float& a, float& b) {
   const float m = warp_max(fmaxf(a, b));
@@ -121,11 +235,26 @@ router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
   const bool v0 = lane < E, v1 = lane + 32 < E;
   float cnt0 = 0.f, cnt1 = 0.f, ps0 = 0.f, ps1 = 0.f, ns0 = 0.f, ns1 = 0.f;
 
-  for (int n = blockIdx.x * RT_WARPS + warp; n < N; n += gridDim.x * RT_WARPS) {
+  constexpr bool FAST = (EB == 8) && (sizeof(T) == 2);
+  constexpr int TBC = FAST ? RT_TB : 1;
+  const bool fast = FAST && !noisy;
+  const int tb = fast ? TBC : 1;
+  for (int base = (blockIdx.x * RT_WARPS + warp) * tb; base < N; base += gridDim.x * RT_WARPS * tb) {
+   float cl[TBC];
+   if (FAST && fast) gate_dots_block<NV, (FAST ? EB : 8), TBC>(reinterpret_cast<const bf16*>(x), wg, base, N, D, E, lane, cl);
+#pragma unroll
+   for (int t = 0; t < TBC; ++t) {
+    const int n = base + t;
+    if (t >= tb || n >= N) break;
     RowRegs<T, NV> xr;
-    xr.load(x + (long long)n * D, D, lane);
     float c0, c1;  // clean logits -> clean probs
-    gate_dots<T, NV, EB>(xr, wg, E, lane, c0, c1);
+    if (FAST && fast) {
+      c0 = cl[t];
+      c1 = 0.f;
+    } else {
+      xr.load(x + (long long)n * D, D, lane);
+      gate_dots<T, NV, EB>(xr, wg, E, lane, c0, c1);
+    }
     float q0 = c0, q1 = c1;  // logits used for selection
     if (noisy) {
       float u0, u1;
@@ -170,6 +299,7 @@ router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
       w[(long long)n * K + lane] = my_w / sel_sum;
     }
     if (lane == 0) topk_sum[n] = sel_sum;
+   }
   }
 
   // block partials: [0] counts, [1] sum of clean probs, [2] sum of softplus noise scales
@@ -244,7 +374,9 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
   extern __shared__ float smem[];
   float* wg = smem;
   float* wn = smem + (size_t)E * DP;
-  __shared__ float s_dl[RT_WARPS][RT_MAX_E], s_du[RT_WARPS][RT_MAX_E];
+  constexpr bool FAST = (EB == 8) && (sizeof(T) == 2);
+  constexpr int TBC = FAST ? RT_TB : 1;
+  __shared__ float s_dl[RT_WARPS][TBC][RT_MAX_E], s_du[RT_WARPS][RT_MAX_E];
   const bool noisy = (eps != nullptr);
   stage_gate_weights<VT, NV>(w_gate, wg, E, D);
   if (noisy) stage_gate_weights<VT, NV>(w_noise, wn, E, D);
@@ -253,7 +385,17 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
   const bool v0 = lane < E, v1 = lane + 32 < E;
   const float gl = (d_loss != nullptr) ? d_loss[0] : 0.f;
 
-  for (int n = blockIdx.x * RT_WARPS + warp; n < N; n += gridDim.x * RT_WARPS) {
+  const bool fast = FAST && !noisy;
+  const int tb = fast ? TBC : 1;
+  for (int base = (blockIdx.x * RT_WARPS + warp) * tb; base < N; base += gridDim.x * RT_WARPS * tb) {
+   if (FAST && fast) {      // rows beyond N contribute nothing
+#pragma unroll
+     for (int t = 0; t < TBC; ++t) { s_dl[warp][t][lane] = 0.f; s_dl[warp][t][lane + 32] = 0.f; }
+   }
+#pragma unroll
+   for (int t = 0; t < TBC; ++t) {
+    const int n = base + t;
+    if (t >= tb || n >= N) break;
     const float* qrow = (noisy ? probs_noisy : probs) + (long long)n * E;
     const float q0 = v0 ? qrow[lane] : 0.f, q1 = v1 ? qrow[lane + 32] : 0.f;
     // gradient wrt the selection probabilities q through w_k = q_{i_k} / sum_j q_{i_j}
@@ -292,7 +434,7 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
       if (v1) du1 = dsel1 * eps[(long long)n * E + lane + 32] * noise_std * sigmoid_f(u1);
     }
     const float dl0 = dsel0 + dc0, dl1 = dsel1 + dc1;
-    s_dl[warp][lane] = dl0; s_dl[warp][lane + 32] = dl1;
+    s_dl[warp][t][lane] = dl0; s_dl[warp][t][lane + 32] = dl1;
     s_du[warp][lane] = du0; s_du[warp][lane + 32] = du1;
     if (v0) dl_out[(long long)n * E + lane] = dl0;
     if (v1) dl_out[(long long)n * E + lane + 32] = dl1;
@@ -301,6 +443,7 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
       if (v1) du_out[(long long)n * E + lane + 32] = du1;
     }
     __syncwarp();
+    if (FAST && fast) continue;   // dx of the whole token block is produced below
     // dx = sum_e dl[e] Wg[e,:] + du[e] Wn[e,:]   (same conflict-free weight layout)
     RowRegs<T, NV> o;
     o.zero();
@@ -309,7 +452,7 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
 #pragma unroll
     for (int e = 0; e < (EB > 0 ? EB : RT_MAX_E); ++e) {
       if (e >= E) break;
-      const float a = s_dl[warp][e];
+      const float a = s_dl[warp][t][e];
       const float bb = noisy ? s_du[warp][e] : 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j)
@@ -332,6 +475,12 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
     }
     o.store(dx + (long long)n * D, D, lane);
     __syncwarp();
+   }
+   if (FAST && fast) {
+     __syncwarp();
+     gate_dx_block<NV, (FAST ? EB : 8), TBC>(wg, s_dl[warp], base, N, D, E, lane, reinterpret_cast<bf16*>(dx));
+     __syncwarp();
+   }
   }
 }
 
@@ -391,6 +540,14 @@ __global__ void router_wgrad_reduce_kernel(const float* __restrict__ part, int c
   out[i] = s;
 }
 
+// grid of the token-blocked path: RT_TB tokens per warp and pass, two resident blocks per SM
+inline int router_grid_blocked(int N) {
+  int blocks = (N + RT_WARPS * RT_TB - 1) / (RT_WARPS * RT_TB);
+  const int cap = num_sms() * 2;
+  if (blocks > cap) blocks = cap;
+  return blocks < 1 ? 1 : blocks;
+}
+
 inline int router_grid(int N) {
   int blocks = (N + RT_WARPS - 1) / RT_WARPS;
   const int cap = num_sms() * 6;   // ~2 tokens per warp at config-5 scale: more independent row loads in flight
@@ -432,7 +589,8 @@ int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* 
   const int nvb = dtype == B200_BF16 ? row_nv<bf16>(D) : row_nv<float>(D);
   const size_t smem = (size_t)E * nvb * 32 * (dtype == B200_BF16 ? 8 : 4) * sizeof(float) * (eps != nullptr ? 2 : 1);
   B200_CHECK_ARG(smem <= 200 * 1024, "router_fwd: gate weights (%zu B) do not fit in shared memory", smem);
-  const int blocks = router_grid(N);
+  int blocks = router_grid(N);
+  if (dtype == B200_BF16 && E <= 8 && eps == nullptr) blocks = router_grid_blocked(N);   // <= router_grid(N)
   float* part = (float*)workspace;
   if (dtype == B200_BF16) {
     B200_NV_SWITCH(nvb, {
@@ -487,7 +645,8 @@ int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* 
   float* dl = (float*)workspace;
   float* du = dl + (size_t)N * E;
   float* part = du + (size_t)N * E;
-  const int blocks = router_grid(N);
+  int blocks = router_grid(N);
+  if (dtype == B200_BF16 && E <= 8 && !noisy) blocks = router_grid_blocked(N);
   const int chunks = (N + RW_CHUNK - 1) / RW_CHUNK;
   dim3 wg_grid((D + 127) / 128, chunks);
   const int ED = E * D;
