@@ -224,7 +224,7 @@ def run_ours(args, c):
             buckets.append(list(blk.ffn.parameters()) + list(blk.norm3.parameters()))
             buckets.append(list(blk.cross_attn.parameters()) + list(blk.norm2.parameters()))
             buckets.append(list(blk.self_attn.parameters()) + list(blk.norm1.parameters()))
-        reducer = parallel.OverlappedGradReducer(buckets)
+        reducer = parallel.OverlappedGradReducer(buckets, transport=args.dp_transport)
 
     def step():
         for p in params:
@@ -454,6 +454,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp-transport", default="nccl", choices=["nccl", "p2p"],
+                    help="data-parallel gradient all-reduce: NCCL, or the peer-memory kernel over symmetric memory")
     ap.add_argument("--detail", action="store_true", help="print a per-call table of the dense GEMMs (stderr)")
     ap.add_argument("--batch", type=int, default=CFG["B"],
                     help="per-GPU batch; the default is the named configuration, larger values give the "

@@ -214,6 +214,12 @@ int b200_moe_combine_bwd(const void* dout, const void* z, const int32_t* dest_ro
  *   b200_ep_dispatch    : compact (expert-sorted) row r of `src` (gathered as src[row_src_c[r]/K] when row_src_c is
  *                         given) -> peer_bufs[owner(e)][send_off[e] + r - cmp_off[e]]
  *   b200_ep_return      : received row i (rows[row_map[i]] or rows[i]) -> peer_rets[home][home_off[g] + i - seg_off[g]] */
+/* Data-parallel gradient all-reduce over peer memory (SURVEY 8(e) collective 3, hand-rolled): peer_bufs is a HOST
+ * array of the W ranks' device addresses of one symmetric fp32 buffer; elements [offset, offset+count) are replaced
+ * on every rank by scale * (sum over ranks), summed in rank order (bit-identical on all ranks).  The caller places a
+ * cross-rank barrier on the stream before and after the call.                                            */
+int b200_p2p_allreduce_f32(const unsigned long long* peer_bufs, int me, int W, long long offset, long long count,
+                           float scale, void* stream);
 int b200_ep_push_counts(const int32_t* counts, void* const* peer_tabs, int me, int W, int E, void* stream);
 int b200_ep_layout(const int32_t* tab, int me, int W, int E, int cap, int32_t* send_off, int32_t* seg_off,
                    int32_t* home_off, int32_t* idx_recv, void* stream);

@@ -131,3 +131,33 @@ def _overlapped_reducer(rank, world):
 
 def test_overlapped_grad_reducer_world2():
     run2(_overlapped_reducer)
+
+
+def _staged_reducer(rank, world):
+    """transport='p2p' host logic (CPU stand-in for the symmetric buffer): gradients that are views of flat
+    per-stage buffers are staged once per buffer, reduced, and re-pointed with their offsets preserved — also when
+    a flat buffer is shared by parameters of two buckets."""
+    a = torch.nn.Parameter(torch.zeros(4, 3))
+    b = torch.nn.Parameter(torch.zeros(5))
+    c = torch.nn.Parameter(torch.zeros(2, 2))
+    d = torch.nn.Parameter(torch.zeros(3))
+    red = parallel.OverlappedGradReducer([[a, c], [b, d]], transport="p2p")
+    red.enabled = True
+    for it in range(2):
+        flat = torch.arange(17, dtype=torch.float32) * (rank + 1) + it      # a and b share one flat buffer
+        a.grad, b.grad = flat[:12].view(4, 3), flat[12:]
+        c.grad = torch.full((2, 2), float(rank + 1))
+        d.grad = torch.arange(3, dtype=torch.float32) * (rank + 2)
+        red._launch(0)
+        red._launch(1)
+        red.finish()
+        want = torch.arange(17, dtype=torch.float32) * 1.5 + it
+        assert torch.allclose(a.grad, want[:12].view(4, 3)), a.grad
+        assert torch.allclose(b.grad, want[12:]), b.grad
+        assert torch.allclose(c.grad, torch.full((2, 2), 1.5))
+        assert torch.allclose(d.grad, torch.arange(3, dtype=torch.float32) * 2.5)
+    red.remove()
+
+
+def test_staged_p2p_reducer_host_logic_world2():
+    run2(_staged_reducer)

@@ -61,6 +61,7 @@ SIGNATURES = {
     "b200_ep_layout": ("i", "piiiippppp"),
     "b200_ep_dispatch": ("i", "pppppiiiiiiip"),
     "b200_ep_return": ("i", "pppppiiiiip"),
+    "b200_p2p_allreduce_f32": ("i", "piillfp"),
 }
 
 class DropoutT(ctypes.Structure):

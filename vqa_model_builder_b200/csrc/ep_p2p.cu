@@ -132,6 +132,37 @@ inline int ep_grid(int rows) {
   return blocks < 1 ? 1 : blocks;
 }
 
+// ---- data-parallel gradient all-reduce over peer memory (two-shot: reduce-scatter + all-gather in one kernel) ----
+// Every rank owns a contiguous 1/W slice of the symmetric fp32 buffer: it loads that slice from all W ranks over
+// NVLink (ranks summed in a fixed order, so every rank ends up with bit-identical values), scales, and stores the
+// result into the same slice of every rank's buffer.  Cross-rank ordering is the caller's stream-ordered barrier
+// before (all contributions written) and after (all stores landed).
+constexpr int AR_MAX_W = 8;
+struct PeerPtrs { float* p[AR_MAX_W]; };
+
+__global__ void __launch_bounds__(512)
+p2p_allreduce_kernel(const PeerPtrs peers, int me, int W, long long nvec, float scale) {
+  pdl_trigger();
+  pdl_wait();
+  const long long per = (nvec + W - 1) / W;
+  const long long v0 = (long long)me * per, v1 = min(nvec, v0 + per);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = v0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; v < v1; v += stride) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < AR_MAX_W; ++r) {
+      if (r < W) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(peers.p[r]) + v);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+    }
+    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+#pragma unroll
+    for (int r = 0; r < AR_MAX_W; ++r)
+      if (r < W) __stcg(reinterpret_cast<float4*>(peers.p[r]) + v, acc);
+  }
+}
+
 }  // namespace
 }  // namespace b200
 
@@ -187,6 +218,29 @@ int b200_ep_return(const void* rows, const int32_t* row_map, const int32_t* seg_
     launch_kernel(ep_return_kernel<float>, dim3(ep_grid(cap)), dim3(256), 0, stream, (const float*)rows, row_map, seg_off,
                   home_off, (float* const*)peer_rets, W, El, D, cap);
   B200_LAUNCH_CHECK("ep_return_kernel");
+  count_launch();
+  return 0;
+}
+
+int b200_p2p_allreduce_f32(const unsigned long long* peer_bufs_host, int me, int W, long long offset,
+                           long long count, float scale, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(peer_bufs_host != nullptr && W >= 1 && W <= AR_MAX_W && me >= 0 && me < W,
+                 "p2p_allreduce: bad world (W=%d, me=%d; at most %d ranks)", W, me, AR_MAX_W);
+  B200_CHECK_ARG(count > 0 && count % 4 == 0 && offset >= 0 && offset % 4 == 0,
+                 "p2p_allreduce: offset / count must be multiples of 4 floats");
+  PeerPtrs pp{};
+  for (int r = 0; r < W; ++r) {
+    B200_CHECK_ARG((peer_bufs_host[r] & 15ull) == 0, "p2p_allreduce: peer buffers must be 16-byte aligned");
+    pp.p[r] = reinterpret_cast<float*>(peer_bufs_host[r]) + offset;
+  }
+  const long long nvec = count / 4;
+  long long blocks = (nvec / W + 511) / 512;
+  const long long cap = (long long)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  launch_kernel(p2p_allreduce_kernel, dim3((unsigned)blocks), dim3(512), 0, stream, pp, me, W, nvec, scale);
+  B200_LAUNCH_CHECK("p2p_allreduce_kernel");
   count_launch();
   return 0;
 }

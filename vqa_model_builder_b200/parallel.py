@@ -110,7 +110,19 @@ class OverlappedGradReducer:
     `finish()` (after `backward()`) makes the compute stream wait for the communication stream.  The pattern holds no
     host synchronisation, so a whole step including its collectives can be captured in one CUDA graph."""
 
-    def __init__(self, buckets, average: bool = True, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, buckets, average: bool = True, group: Optional[dist.ProcessGroup] = None,
+                 transport: str = "nccl"):
+        """transport='nccl' (default, verified): coalesced NCCL all-reduce per bucket.
+        transport='p2p' (EXPERIMENTAL — host logic is covered by the gloo test, but on 2xB200 `scripts/dp_check.py`
+        still reports one flat buffer reduced wrongly and one run hung; do not use it for training yet): the bucket's flat gradient
+        buffers are staged in a symmetric-memory buffer and reduced by `b200_p2p_allreduce_f32` (every rank reduces
+        its 1/W slice with loads from all peers over NVLink and stores the result into every peer's buffer); the
+        parameters' .grad are re-pointed at the reduced copies, so nothing is copied back."""
+        if transport not in ("nccl", "p2p"):
+            raise ValueError("transport must be 'nccl' or 'p2p'")
+        self.transport = transport
+        self._p2p = {}              # bucket index -> (symmetric buffer, handle, host pointer array, layout)
+        self._reduced = {}          # flat buffer key -> (symmetric buffer, offset) for this backward pass
         self.buckets = [[p for p in b if p.requires_grad] for b in buckets]
         self.buckets = [b for b in self.buckets if b]
         self.average = average
@@ -134,12 +146,94 @@ class OverlappedGradReducer:
         return fire
 
     def _launch(self, bi: int) -> None:
-        if self.comm is None:                      # CPU / gloo: no streams, reduce in place
-            allreduce_gradients(self.buckets[bi], self.average, self.group, self._seen)
+        if self.comm is None:                      # CPU / gloo: no streams
+            if self.transport == "p2p" and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                self._p2p_reduce(bi)               # staged path with a plain all-reduce (host-logic tests)
+            else:
+                allreduce_gradients(self.buckets[bi], self.average, self.group, self._seen)
             return
         self.comm.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm):
-            allreduce_gradients(self.buckets[bi], self.average, self.group, self._seen)
+            if self.transport == "p2p" and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                self._p2p_reduce(bi)
+            else:
+                allreduce_gradients(self.buckets[bi], self.average, self.group, self._seen)
+
+    def _p2p_reduce(self, bi: int) -> None:
+        import ctypes
+        from . import _lib
+        params = [p for p in self.buckets[bi] if p.grad is not None]
+        units = _reduction_units([p.grad for p in params], self._seen)
+        for u in units:
+            if u.dtype != torch.float32:
+                raise RuntimeError("p2p gradient all-reduce expects fp32 gradients")
+        if not units:
+            self._repoint(params)
+            return
+        group = self.group if self.group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        st = self._p2p.get(bi)
+        sizes = [(u.numel() + 3) // 4 * 4 for u in units]
+        on_gpu = units[0].is_cuda
+        if st is None or st["sizes"] != sizes:        # first use (eager warm-up): collective allocation
+            total = sum(sizes)
+            if on_gpu:
+                import torch.distributed._symmetric_memory as symm_mem
+                if hasattr(symm_mem, "enable_symm_mem_for_group"):
+                    try:
+                        symm_mem.enable_symm_mem_for_group(group.group_name)
+                    except Exception:
+                        pass
+                buf = symm_mem.empty(total, dtype=torch.float32, device=units[0].device)
+                hdl = symm_mem.rendezvous(buf, group)
+                # the tensor may sit at an offset inside its symmetric allocation: apply this rank's offset to all
+                delta = buf.data_ptr() - int(hdl.buffer_ptrs[rank])
+                host_ptrs = (ctypes.c_ulonglong * world)(*[int(a) + delta for a in hdl.buffer_ptrs])
+            else:                                     # CPU stand-in: same staging / re-pointing, library all-reduce
+                buf, hdl, host_ptrs = torch.empty(total, dtype=torch.float32), None, None
+            buf.zero_()
+            st = {"buf": buf, "hdl": hdl, "ptrs": host_ptrs, "sizes": sizes, "total": total}
+            self._p2p[bi] = st
+            if hdl is not None:
+                hdl.barrier(channel=0)
+        buf, hdl = st["buf"], st["hdl"]
+        offs, off = [], 0
+        for u, sz in zip(units, sizes):               # stage this rank's contribution
+            buf[off:off + u.numel()].copy_(u.reshape(-1))
+            if on_gpu:      # u is released when .grad is re-pointed below; its memory must outlive this copy
+                u.record_stream(torch.cuda.current_stream())
+            offs.append(off)
+            off += sz
+        if hdl is not None:
+            hdl.barrier(channel=0)                    # every rank's contribution is in place
+            _lib.call("b200_p2p_allreduce_f32", st["ptrs"], rank, world, 0, st["total"],
+                      (1.0 / world) if self.average else 1.0, _lib.stream_ptr())
+            hdl.barrier(channel=0)                    # every peer's stores into this rank's buffer have landed
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+            if self.average:
+                buf.div_(world)
+        for u, o in zip(units, offs):
+            self._reduced[(u.data_ptr(), u.numel())] = (buf, o)
+        self._repoint(params)
+
+    def _repoint(self, params) -> None:
+        """Point the gradients at the reduced copies in symmetric memory (same shapes, offsets inside their flat
+        buffer preserved); a flat buffer may have been reduced with an earlier bucket."""
+        for p in params:
+            g = p.grad
+            base = g._base if g._base is not None else g
+            if base is not g and not (base.dim() == 1 and base.is_contiguous() and base.dtype == g.dtype):
+                base = g
+            hit = self._reduced.get((base.data_ptr(), base.numel()))
+            if hit is None:
+                continue
+            buf, off = hit
+            if not g.is_contiguous():                  # odd view: copy the reduced values back instead
+                base.reshape(-1).copy_(buf[off:off + base.numel()])
+                continue
+            start = off + (g.data_ptr() - base.data_ptr()) // g.element_size()
+            p.grad = buf[start:start + g.numel()].view(g.shape)
 
     def finish(self) -> None:
         """Call once after backward(): reduces buckets whose hooks did not all fire (unused parameters), joins the
@@ -152,6 +246,7 @@ class OverlappedGradReducer:
                 torch.cuda.current_stream().wait_stream(self.comm)
         self._left = [len(b) for b in self.buckets]
         self._seen = set()
+        self._reduced = {}
 
     def remove(self) -> None:
         for h in self._handles:
