@@ -114,7 +114,8 @@ class OverlappedGradReducer:
                  transport: str = "nccl"):
         """transport='nccl' (default, verified): coalesced NCCL all-reduce per bucket.
         transport='p2p' (EXPERIMENTAL — host logic is covered by the gloo test, but on 2xB200 `scripts/dp_check.py`
-        still reports one flat buffer reduced wrongly and one run hung; do not use it for training yet): the bucket's flat gradient
+        reported one flat buffer reduced wrongly, and with the staged buffers' lifetime extended to the copy stream
+        (record_stream) the check hangs in the cross-rank barrier; do not use it for training yet): the bucket's flat gradient
         buffers are staged in a symmetric-memory buffer and reduced by `b200_p2p_allreduce_f32` (every rank reduces
         its 1/W slice with loads from all peers over NVLink and stores the result into every peer's buffer); the
         parameters' .grad are re-pointed at the reduced copies, so nothing is copied back."""
@@ -130,6 +131,7 @@ class OverlappedGradReducer:
         self.enabled = True
         self.comm = torch.cuda.Stream() if torch.cuda.is_available() else None
         self._left = [len(b) for b in self.buckets]
+        self._fired = [set() for _ in self.buckets]     # parameters whose gradient has landed in this pass
         self._seen = set()          # flat buffers already reduced in this backward pass (may span two buckets)
         self._handles = []
         for bi, bucket in enumerate(self.buckets):
@@ -137,9 +139,10 @@ class OverlappedGradReducer:
                 self._handles.append(p.register_post_accumulate_grad_hook(self._hook(bi)))
 
     def _hook(self, bi: int):
-        def fire(_param):
-            if not self.enabled:
-                return
+        def fire(param):
+            if not self.enabled or id(param) in self._fired[bi]:
+                return                      # a second accumulation into the same parameter must not count twice
+            self._fired[bi].add(id(param))
             self._left[bi] -= 1
             if self._left[bi] == 0:
                 self._launch(bi)
@@ -245,6 +248,7 @@ class OverlappedGradReducer:
             if self.comm is not None:
                 torch.cuda.current_stream().wait_stream(self.comm)
         self._left = [len(b) for b in self.buckets]
+        self._fired = [set() for _ in self.buckets]
         self._seen = set()
         self._reduced = {}
 
