@@ -213,7 +213,6 @@ def run_ours(args, c):
     loss_h = torch.zeros(1, dtype=torch.float32).pin_memory()
     loss_d = torch.zeros(1, dtype=torch.float32, device=dev)
 
-    comm = {"on": True}
     # Data parallel: gradients are all-reduced bucket by bucket on a communication stream as soon as backward has
     # produced them (MOE layer first, then fusion layer 2, then layer 1), overlapped with the rest of backward.
     reducer = None

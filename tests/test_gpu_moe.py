@@ -223,3 +223,30 @@ def test_heterogeneous_experts_dense_combine():
     gxr, = torch.autograd.grad((ref * gout).sum(), x)
     # reference-side router weights are constants in `ref` only through idx; both paths differentiate w
     assert rel_err(gx, gxr) < 1e-3, rel_err(gx, gxr)
+
+
+@pytest.mark.parametrize("N,E,K", [(37, 8, 2), (300, 5, 2), (1, 8, 1), (1000, 8, 3)])
+def test_router_token_blocked_path_matches_generic_path(N, E, K):
+    """bf16 rows with E <= 8 take the token-blocked kernels (4 tokens per warp), fp32 rows the generic ones (other
+    lane partition of the dot products, so logits agree to fp32 rounding, not bitwise).  On bf16-representable inputs
+    the two paths must pick the same experts (ties aside) and agree on weights, probabilities, aux loss and
+    gradients (the input gradient up to its bf16 rounding on the fast path)."""
+    g = torch.Generator(device=DEV).manual_seed(N * 10 + E)
+    D = 768
+    xb = torch.randn(N, D, generator=g, device=DEV).to(torch.bfloat16)
+    wg = (0.05 * torch.randn(E, D, generator=g, device=DEV))
+    dw_up = torch.randn(N, K, generator=g, device=DEV)
+    outs = []
+    for x in (xb.clone().requires_grad_(), xb.float().requires_grad_()):
+        w_gate = wg.clone().requires_grad_()
+        w, idx, loss, probs, _nsm, _ts, counts = ops.RouterFn.apply(x, w_gate, None, None, 0.0, 0.01, K)
+        ((w * dw_up).sum() + loss.sum()).backward()
+        outs.append((w, idx, loss, probs, counts, x.grad.float(), w_gate.grad))
+    fast, ref = outs
+    _, amb = routing_np.topk_with_ties(ref[3].cpu().numpy(), K)
+    assert not amb.any(), "random logits are not expected to tie"
+    assert torch.equal(fast[1], ref[1]) and torch.equal(fast[4], ref[4])        # indices, per-expert counts
+    assert rel_err(fast[3], ref[3]) < 1e-5 and rel_err(fast[0], ref[0]) < 1e-5
+    assert abs(float(fast[2]) - float(ref[2])) < 1e-7
+    assert rel_err(fast[5], ref[5]) < 6e-3                    # dx is stored in bf16 on the fast path
+    assert rel_err(fast[6], ref[6]) < 1e-5

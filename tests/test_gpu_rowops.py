@@ -45,3 +45,33 @@ def test_add_ln_fwd_bwd(R, D, dtype):
     # no-branch variant
     y2 = ops.AddLNFn.apply(x, None, gamma.detach(), beta.detach(), 1e-5)
     assert rel_err(y2, torch.nn.functional.layer_norm(x.double(), (D,), gr, btr, 1e-5)) < t
+
+
+@pytest.mark.parametrize("R", [1, 63, 64, 4096, 4097, 20000])
+@pytest.mark.parametrize("N", [768, 100])
+def test_colsum_single_launch_and_two_stage_paths(R, N):
+    """R <= 4096 folds the partials in the last-arriving block (one launch); larger R uses the second-stage kernel;
+    N = 100 exercises the scalar (non-vectorised) variant for bf16."""
+    g = torch.Generator(device=DEV).manual_seed(R + N)
+    x = torch.randn(R, N, generator=g, device=DEV)
+    for t in (x, x.to(torch.bfloat16)):
+        _lib.reset_launch_count()
+        got = ops.colsum(t.contiguous())
+        launches = _lib.launch_count()
+        assert rel_err(got, t.double().sum(0)) < 2e-6
+        assert launches == (1 if R <= 4096 else 2), launches
+    # repeated calls reuse (and re-arm) the ticket counters
+    for _ in range(3):
+        assert rel_err(ops.colsum(x), x.double().sum(0)) < 2e-6
+
+
+def test_colsum_grouped_by_expert_tiles():
+    g = torch.Generator(device=DEV).manual_seed(5)
+    tiles = torch.tensor([0, 0, 2, 3, 3, 3, -1, -1], dtype=torch.int32, device=DEV)   # expert 1 owns no tile
+    x = torch.randn(tiles.numel() * 128, 256, generator=g, device=DEV).to(torch.bfloat16)
+    got = ops.colsum(x, tile_group=tiles, G=4)
+    for e in range(4):
+        rows = torch.cat([x[t * 128:(t + 1) * 128] for t in range(tiles.numel()) if int(tiles[t]) == e] or
+                         [x[:0]])
+        assert rel_err(got[e], rows.double().sum(0)) < 2e-6 or float(rows.abs().sum()) == 0.0
+    assert float(got[1].abs().max()) == 0.0
