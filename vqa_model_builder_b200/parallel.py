@@ -121,6 +121,10 @@ class OverlappedGradReducer:
         parameters' .grad are re-pointed at the reduced copies, so nothing is copied back."""
         if transport not in ("nccl", "p2p"):
             raise ValueError("transport must be 'nccl' or 'p2p'")
+        if transport == "p2p" and torch.cuda.is_available() and \
+                os.environ.get("B200VQA_EXPERIMENTAL_P2P_ALLREDUCE") != "1":
+            raise RuntimeError("transport='p2p' is experimental and not verified on hardware yet (DESIGN.md section 6); "
+                               "set B200VQA_EXPERIMENTAL_P2P_ALLREDUCE=1 to try it")
         self.transport = transport
         self._p2p = {}              # bucket index -> (symmetric buffer, handle, host pointer array, layout)
         self._reduced = {}          # flat buffer key -> (symmetric buffer, offset) for this backward pass
