@@ -133,3 +133,16 @@ def test_compute_dtype_policy():
         pkg.set_compute_dtype("auto")
     with pytest.raises(ValueError):
         pkg.set_compute_dtype("fp8")
+
+
+def test_answer_head_state_dict_layout_matches_reference_sequential():
+    """AnswerHead keeps the reference's nn.Sequential layout (vqa_model.py:451-465): Linear / ReLU / Dropout triples,
+    so checkpoints keyed classifier.{0,3,6,...} load unchanged."""
+    from vqa_model_builder_b200 import heads
+    cfg = heads.AnswerHeadConfig(num_answers=3001, hidden_dims=[512, 256], dropout=0.3)
+    head = heads.AnswerHead(cfg, 768)
+    assert list(head.state_dict().keys()) == ["classifier.0.weight", "classifier.0.bias", "classifier.3.weight",
+                                              "classifier.3.bias", "classifier.6.weight", "classifier.6.bias"]
+    assert head.classifier[6].weight.shape == (3001, 256)
+    with pytest.raises(RuntimeError):          # CUDA-only product path: no silent CPU fallback
+        head(torch.randn(2, 768))

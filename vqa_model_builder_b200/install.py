@@ -13,6 +13,7 @@ import importlib
 from typing import Dict, List, Tuple
 
 from . import fusion as _fusion
+from . import heads as _heads
 from . import moe as _moe
 
 _saved: List[Tuple[object, str, object]] = []
@@ -64,7 +65,8 @@ def install(verbose: bool = False) -> Dict[str, str]:
     bind_all(ref_router, {k: moe_syms[k] for k in ("TopKRouter", "NoisyTopKRouter", "create_router")})
     bind_all(ref_experts, {k: moe_syms[k] for k in ("FeedForwardExpert", "create_expert")})
     bind_all(ref_vqa, {"MultimodalFusion": _fusion.MultimodalFusion,           # vqa_model.py:503
-                       "CrossModalAttention": _fusion.CrossModalAttention})    # vqa_model.py:331
+                       "CrossModalAttention": _fusion.CrossModalAttention,     # vqa_model.py:331
+                       "AnswerHead": _heads.AnswerHead})                       # vqa_model.py:436
     bind_all(ref_gen, {"MOELayer": _moe.MOELayer, "VQAMOELayer": _moe.VQAMOELayer,   # generative_vqa_model.py:23
                        "SparseMOELayer": _moe.SparseMOELayer, "CrossModalFusion": _fusion.CrossModalFusion})
     fus_syms = {"CrossAttentionFusion": _fusion.CrossAttentionFusion, "CrossAttentionBlock": _fusion.CrossAttentionBlock}

@@ -736,3 +736,80 @@ class CrossProjFn(torch.autograd.Function):
         dkv = gemm(dkvp, LAYOUT_K, in_w_c[D:], LAYOUT_MN, Mk, D, 2 * D) if ctx.needs_input_grad[1] else None
         aux_join(side)
         return dx, dkv, dw, (db if ctx.has_bias else None), None, None
+
+
+# ---- multi-layer perceptron with fused activations (answer head) -----------------------------------------------
+class MLPFn(torch.autograd.Function):
+    """h_{i+1} = dropout_i(act_i(h_i W_i^T + b_i)), last layer without activation (AnswerHead, vqa_model.py:451-477).
+    Every activation (+dropout) runs in its GEMM's epilogue; its derivative (x the regenerated mask) in the epilogue
+    of the next layer's dgrad GEMM, exactly as in FFNFn.  `params` = (w_0, b_0, wc_0, w_1, b_1, wc_1, ...): fp32
+    Parameters for autograd plus the compute-dtype copy the kernels read.  The output row pitch is padded to a
+    multiple of 8 elements so any number of classes satisfies the 16-byte operand rule of the tensor-core path; the
+    returned logits are the [:, :n_out] view."""
+
+    @staticmethod
+    def forward(ctx, x, acts, drops, *params):
+        _lib.ensure_device(x)
+        L = len(params) // 3
+        assert len(acts) == L and acts[-1] == ACT_NONE, "the last layer of the MLP must be linear"
+        h = x.contiguous()
+        saved = []
+        for i in range(L):
+            b, wc = params[3 * i + 1], params[3 * i + 2]
+            M, K = h.shape
+            N = wc.shape[0]
+            if i < L - 1:
+                pre = torch.empty((M, N), dtype=h.dtype, device=h.device)
+                nxt = gemm(h, LAYOUT_K, wc, LAYOUT_K, M, N, K, bias=b, epi=EPI_ACT, act=acts[i], aux_out=pre,
+                           drop=drops[i])
+                saved += [h, pre]
+                h = nxt
+            else:
+                npad = (N + 7) // 8 * 8
+                buf = torch.empty((M, npad), dtype=h.dtype, device=h.device)
+                gemm(h, LAYOUT_K, wc, LAYOUT_K, M, N, K, bias=b, out=buf[:, :N])
+                saved += [h]
+                out = buf[:, :N]
+        ctx.save_for_backward(*saved, *[params[3 * i + 2] for i in range(L)])
+        ctx.cfg = (L, tuple(acts), tuple(drops), [params[3 * i + 1] is not None for i in range(L)])
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        L, acts, drops, has_bias = ctx.cfg
+        saved = ctx.saved_tensors
+        wcs = saved[len(saved) - L:]
+        hs = [saved[2 * i] for i in range(L - 1)] + [saved[2 * (L - 1)]]
+        pres = [saved[2 * i + 1] for i in range(L - 1)]
+        dev = dy.device
+        bf = hs[0].dtype == torch.bfloat16
+        wepi = EPI_ACCUM if bf else EPI_NONE
+        M = dy.shape[0]
+        n_out = wcs[-1].shape[0]
+        npad = (n_out + 7) // 8 * 8
+        gbuf = torch.empty((M, npad), dtype=hs[0].dtype, device=dev)
+        gbuf[:, :n_out].copy_(dy)
+        g = gbuf[:, :n_out]                       # row pitch padded: a legal tensor-core operand for any n_out
+        g_dense = dy.to(hs[0].dtype).contiguous()  # for the column sums
+        grads = [None] * (3 * L)
+        dx = None
+        for i in range(L - 1, -1, -1):
+            h, wc = hs[i], wcs[i]
+            N, K = wc.shape
+            flat = torch.empty(N * K + (N if has_bias[i] else 0), dtype=torch.float32, device=dev)
+            dw = flat[:N * K].view(N, K)
+            side = aux_fork(dev)
+            with aux_on(side):                    # parameter gradients beside the dgrad GEMM
+                gemm(g, LAYOUT_MN, h, LAYOUT_MN, N, K, M, out=dw, epi=wepi)
+                if has_bias[i]:
+                    _colsum_into(g_dense, flat[N * K:])
+                    grads[3 * i + 1] = flat[N * K:]
+            grads[3 * i] = dw
+            if i > 0:      # gradient wrt the previous layer's pre-activation: act' and the dropout mask in the epilogue
+                g = gemm(g, LAYOUT_K, wc, LAYOUT_MN, M, K, N, epi=EPI_DACT, act=acts[i - 1], aux_in=pres[i - 1],
+                         drop=drops[i - 1])
+                g_dense = g
+            elif ctx.needs_input_grad[0]:
+                dx = gemm(g, LAYOUT_K, wc, LAYOUT_MN, M, K, N)
+            aux_join(side)
+        return (dx, None, None, *grads)
