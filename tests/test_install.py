@@ -45,6 +45,12 @@ def test_install_rebinds_and_reference_code_builds_our_modules(installed):
     cfg.fusion_dim, cfg.fusion_num_heads, cfg.decoder_ff_dim, cfg.use_moe, cfg.num_experts = 64, 4, 128, True, 4
     f = gen.CrossModalFusion(cfg)
     assert isinstance(f, fusion.CrossModalFusion) and isinstance(f.moe_layer, moe.MOELayer)
+    # answer head: the reference's AnswerHeadConfig drives ours; same state_dict keys as the reference's own class
+    from vqa_model_builder_b200 import heads
+    from src.modeling.meta_arch.vqa_config import AnswerHeadConfig
+    assert vqa.AnswerHead is heads.AnswerHead
+    head = vqa.AnswerHead(AnswerHeadConfig(num_answers=37), 64)
+    assert isinstance(head, heads.AnswerHead) and head.classifier[-1].out_features == 37
     # registry: cross_attention -> ours, others stay the reference's
     import src.modeling.fusion as ref_fusion
     assert isinstance(ref_fusion.create_fusion_model("cross_attention", vision_dim=64, text_dim=64, output_dim=64,
