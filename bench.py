@@ -454,8 +454,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dp-transport", default="nccl", choices=["nccl", "p2p"],
-                    help="data-parallel gradient all-reduce: NCCL (default, verified) or the experimental peer-memory "
-                         "kernel (needs B200VQA_EXPERIMENTAL_P2P_ALLREDUCE=1; not verified, see DESIGN.md section 6)")
+                    help="data-parallel gradient all-reduce: NCCL (default) or the peer-memory kernel over symmetric "
+                         "memory (correct, but slower at this size: DESIGN.md section 6)")
     ap.add_argument("--detail", action="store_true", help="print a per-call table of the dense GEMMs (stderr)")
     ap.add_argument("--batch", type=int, default=CFG["B"],
                     help="per-GPU batch; the default is the named configuration, larger values give the "

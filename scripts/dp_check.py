@@ -13,8 +13,6 @@ from vqa_model_builder_b200 import fusion, moe, parallel  # noqa: E402
 
 
 def main():
-    import os
-    os.environ.setdefault("B200VQA_EXPERIMENTAL_P2P_ALLREDUCE", "1")     # this script IS the verification harness
     rank, world, local = parallel.init_distributed()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -112,22 +112,19 @@ class OverlappedGradReducer:
 
     def __init__(self, buckets, average: bool = True, group: Optional[dist.ProcessGroup] = None,
                  transport: str = "nccl"):
-        """transport='nccl' (default, verified): coalesced NCCL all-reduce per bucket.
-        transport='p2p' (EXPERIMENTAL — host logic is covered by the gloo test, but on 2xB200 `scripts/dp_check.py`
-        reported one flat buffer reduced wrongly, and with the staged buffers' lifetime extended to the copy stream
-        (record_stream) the check hangs in the cross-rank barrier; do not use it for training yet): the bucket's flat gradient
-        buffers are staged in a symmetric-memory buffer and reduced by `b200_p2p_allreduce_f32` (every rank reduces
-        its 1/W slice with loads from all peers over NVLink and stores the result into every peer's buffer); the
-        parameters' .grad are re-pointed at the reduced copies, so nothing is copied back."""
+        """transport='nccl' (default): coalesced NCCL all-reduce per bucket.
+        transport='p2p': the bucket's gradient buffers are staged in a symmetric-memory buffer and reduced by
+        `b200_p2p_allreduce_f32` (every rank reduces its 1/W slice with loads from all peers over NVLink and stores
+        the result into every peer's buffer); the parameters' .grad are re-pointed at the reduced copies, so nothing
+        is copied back.  Verified on 2xB200 (`scripts/dp_check.py`: bit-identical to NCCL) and CUDA-graph capturable,
+        but at the benchmark's size it is slower than NCCL (1.66 vs 1.53 ms/step): one staging copy per gradient
+        buffer and two cross-rank barriers per bucket cost more than the kernel saves."""
         if transport not in ("nccl", "p2p"):
             raise ValueError("transport must be 'nccl' or 'p2p'")
-        if transport == "p2p" and torch.cuda.is_available() and \
-                os.environ.get("B200VQA_EXPERIMENTAL_P2P_ALLREDUCE") != "1":
-            raise RuntimeError("transport='p2p' is experimental and not verified on hardware yet (DESIGN.md section 6); "
-                               "set B200VQA_EXPERIMENTAL_P2P_ALLREDUCE=1 to try it")
         self.transport = transport
         self._p2p = {}              # bucket index -> (symmetric buffer, handle, host pointer array, layout)
         self._reduced = {}          # flat buffer key -> (symmetric buffer, offset) for this backward pass
+        self._keep = []             # staged gradient buffers of this pass (see _p2p_reduce)
         self.buckets = [[p for p in b if p.requires_grad] for b in buckets]
         self.buckets = [b for b in self.buckets if b]
         self.average = average
@@ -207,10 +204,13 @@ class OverlappedGradReducer:
         offs, off = [], 0
         for u, sz in zip(units, sizes):               # stage this rank's contribution
             buf[off:off + u.numel()].copy_(u.reshape(-1))
-            if on_gpu:      # u is released when .grad is re-pointed below; its memory must outlive this copy
-                u.record_stream(torch.cuda.current_stream())
             offs.append(off)
             off += sz
+        # The staged buffers are kept alive until finish(): re-pointing .grad below would free them, and (1) their
+        # memory must outlive the copy enqueued on the communication stream, (2) a later gradient allocated at the
+        # same address with the same size would collide with the (address, size) keys of this pass — it would be
+        # taken for "already reduced" and re-pointed at another parameter's data.
+        self._keep.extend(units)
         if hdl is not None:
             hdl.barrier(channel=0)                    # every rank's contribution is in place
             _lib.call("b200_p2p_allreduce_f32", st["ptrs"], rank, world, 0, st["total"],
@@ -255,6 +255,7 @@ class OverlappedGradReducer:
         self._fired = [set() for _ in self.buckets]
         self._seen = set()
         self._reduced = {}
+        self._keep = []
 
     def remove(self) -> None:
         for h in self._handles:
