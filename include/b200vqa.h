@@ -157,15 +157,17 @@ int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* 
                     float noise_std, float lb_weight, int N, int D, int E, int K, int32_t* idx, float* w,
                     float* topk_sum, float* probs, float* probs_noisy, float* counts, float* psum, float* loss,
                     float* noise_scale_mean, void* workspace, size_t workspace_bytes, void* stream);
-/* Backward of the above.  d_w [N,K] (may be NULL), d_loss device fp32 scalar (may be NULL).
+/* Backward of the above.  d_w [N,K] (may be NULL), d_loss device fp32 scalar (may be NULL), d_probs [N,E] fp32
+ * (may be NULL): gradient that reached the clean probabilities directly (aux_outputs['router_probs'] is
+ * differentiable in the reference, router.py:140,328; e.g. solvers/losses/vqa_losses.py:543-573).
  * Produces dx [N,D] (overwrite), d_w_gate [E,D] fp32, d_w_noise [E,D] fp32 (if noisy).
  * workspace >= b200_router_bwd_ws(N, D, E).                                                         */
 size_t b200_router_bwd_ws(int N, int D, int E);
 int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* w_noise, const float* eps,
                     float noise_std, float lb_weight, int N, int D, int E, int K, const int32_t* idx,
                     const float* w, const float* topk_sum, const float* probs, const float* probs_noisy,
-                    const float* counts, const float* d_w, const float* d_loss, void* dx, float* d_w_gate,
-                    float* d_w_noise, void* workspace, size_t workspace_bytes, void* stream);
+                    const float* counts, const float* d_w, const float* d_loss, const float* d_probs, void* dx,
+                    float* d_w_gate, float* d_w_noise, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- MOE dispatch / combine ------------------------------------------------------------------- */
 /* Upper bound of padded rows for NK (token,slot) pairs over E experts (host-side, no sync).        */
@@ -176,11 +178,13 @@ int b200_moe_max_rows(int NK, int E);
  * counts[E], cmp_off[E+1] (compact offsets), pad_off[E+1] (offsets with every segment padded to 128),
  * dest_row[NK] (row in the padded layout, -1 dropped), cmp_pos[NK] (position in the compact canonical
  * order, -1 dropped), row_src[Rmax] (flattened (n,k) of each padded row, -1 = padding),
- * tile_group[Rmax/128] (expert per 128-row tile, -1 unused).  workspace >= b200_moe_plan_ws(NK,E).  */
+ * tile_group[Rmax/128] (expert per 128-row tile, -1 unused), cmp_src[NK] (may be NULL: flattened (n,k) of each
+ * compact position, -1 beyond the routed pairs — the inverse of cmp_pos, used by the expert-parallel dispatch).
+ * workspace >= b200_moe_plan_ws(NK,E).                                                              */
 size_t b200_moe_plan_ws(int NK, int E);
 int b200_moe_plan(const int32_t* idx, int NK, int E, int Rmax, int32_t* counts, int32_t* cmp_off,
                   int32_t* pad_off, int32_t* dest_row, int32_t* cmp_pos, int32_t* row_src,
-                  int32_t* tile_group, void* workspace, size_t workspace_bytes, void* stream);
+                  int32_t* tile_group, int32_t* cmp_src, void* workspace, size_t workspace_bytes, void* stream);
 /* SparseMOELayer capacity (moe_layer.py:329-337): for experts with count > capacity keep the `capacity`
  * largest combine weights (ties: lower token first); others get w_eff = 0 and keep[...] = 0.        */
 int b200_moe_capacity(const int32_t* idx, const float* w, const int32_t* counts, const int32_t* pad_off,

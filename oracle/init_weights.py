@@ -39,3 +39,29 @@ def moe_layer_sd(D: int, F: int, E: int, noisy: bool = False) -> dict:
         sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"] = torch.ones(D), torch.zeros(D)
     sd["output_norm.weight"], sd["output_norm.bias"] = torch.ones(D), torch.zeros(D)
     return {k: v.detach().clone() for k, v in sd.items()}
+
+
+def seeded_state_dict(template: dict, seed: int, keys=None) -> dict:
+    """Deterministic weights for the golden vectors / fingerprints: values come from numpy's PCG64 stream (stable
+    across torch versions), drawn in the order of `keys` (default: the template's own order).  LayerNorm scales are
+    1 + 0.1 n, matrices n / sqrt(fan_in), vectors 0.1 n; integer tensors and 0-d buffers are copied.
+    `template` maps names to tensors of the right shape (a module's state_dict())."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for k in (list(template) if keys is None else list(keys)):
+        v = template[k]
+        if not v.dtype.is_floating_point or v.dim() == 0:
+            sd[k] = v.clone()
+            continue
+        parts = k.split(".")
+        is_norm_w = k.endswith("weight") and (k.endswith("norm.weight") or ".norm" in k or
+                                              (len(parts) >= 2 and parts[-2].startswith("norm")))
+        if is_norm_w:
+            a = 1.0 + 0.1 * rng.standard_normal(tuple(v.shape))
+        elif v.dim() >= 2:
+            a = rng.standard_normal(tuple(v.shape)) / np.sqrt(v.shape[-1])
+        else:
+            a = 0.1 * rng.standard_normal(tuple(v.shape))
+        sd[k] = torch.tensor(a, dtype=torch.float32)
+    return sd

@@ -16,26 +16,14 @@ import torch
 
 REF = os.environ.get("B200VQA_REFERENCE", "/root/reference")
 sys.path.insert(0, REF)
+sys.path.insert(1, str(Path(__file__).resolve().parent.parent))
 sys.dont_write_bytecode = True
 OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
 
 
 def rnd_state_dict(module: torch.nn.Module, seed: int) -> dict:
-    rng = np.random.default_rng(seed)
-    sd = {}
-    for k, v in module.state_dict().items():
-        if not v.dtype.is_floating_point or v.dim() == 0:
-            sd[k] = v.clone()
-            continue
-        if k.endswith("norm.weight") or ".norm" in k and k.endswith("weight") or k.endswith("layer_norm.weight") \
-                or k.split(".")[-2].startswith("norm") and k.endswith("weight"):
-            a = 1.0 + 0.1 * rng.standard_normal(v.shape)
-        elif v.dim() >= 2:
-            a = rng.standard_normal(v.shape) / np.sqrt(v.shape[-1])
-        else:
-            a = 0.1 * rng.standard_normal(v.shape)
-        sd[k] = torch.tensor(a, dtype=torch.float32)
-    return sd
+    from oracle.init_weights import seeded_state_dict
+    return seeded_state_dict(module.state_dict(), seed)
 
 
 def save(name: str, **arrays):
@@ -194,5 +182,182 @@ def main():
          grads=grads_of(m))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--r2" not in sys.argv:
     main()
+
+
+# =====================================================================================================================
+# Round-2 fixtures (own RNG stream, so the fixtures above stay byte-identical when this file is re-run):
+#   sparse_moe_layer_train : A8 in TRAIN mode — injected router noise, active capacity limit, forward + backward
+#   vqa_moe_layer          : A9 — the reference's own VQAMOELayer (heterogeneous experts): router outputs, every
+#                            expert's output, combined output, and the gradients that flow through router + combine
+#   fp_*                   : fingerprints at the BENCHMARK dimensions (D=768, H=8, d_h=96, F=2048): full outputs,
+#                            sha256 of the routing indices, gradient norms + seeded probes.  Weights and inputs are
+#                            regenerated from numpy seeds by the tests (tests/fingerprint_util.py), not stored.
+# =====================================================================================================================
+def seeded_inputs(seed: int, *shapes):
+    rng = np.random.default_rng(seed)
+    return [torch.tensor(rng.standard_normal(s), dtype=torch.float32) for s in shapes]
+
+
+from oracle.fingerprint import fingerprint, sha_int  # noqa: E402
+
+
+def main_r2():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    from src.modeling.meta_arch.vqa_model import MultimodalFusion
+    from src.modeling.meta_arch.vqa_config import FusionConfig
+    from src.modeling.moe.moe_layer import MOELayer, SparseMOELayer, VQAMOELayer
+    from src.modeling.meta_arch.generative_vqa_model import CrossModalFusion, GenerativeVQAConfig
+
+    rng = np.random.default_rng(20261019)
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+
+    # ---- A8: SparseMOELayer, train mode, noise injected, capacity active, fwd + bwd ------------------------------
+    Bm, Sm, Dm, Fm, Em, Km = 4, 24, 64, 128, 4, 2
+    m = SparseMOELayer(input_dim=Dm, hidden_dim=Fm, output_dim=Dm, num_experts=Em, top_k=Km, capacity_factor=0.7,
+                       dropout=0.0)
+    sd = rnd_state_dict(m, 21)
+    m.load_state_dict(sd)
+    m.train()
+    xs = f32(rng.standard_normal((Bm, Sm, Dm))).requires_grad_()
+    eps = f32(rng.standard_normal((Bm, Sm, Em)))
+    gs = f32(rng.standard_normal((Bm, Sm, Dm)))
+    orig = torch.randn_like
+    torch.randn_like = lambda t, **kw: eps.to(t.dtype)       # router.py:308
+    try:
+        out = m(xs)
+    finally:
+        torch.randn_like = orig
+    ((out * gs).sum() + 2.0 * m.get_aux_loss()).backward()
+    save("sparse_moe_layer_train", cfg=np.array([Bm, Sm, Dm, Fm, Em, Km]), capacity_factor=np.array(0.7), sd=sd,
+         x=xs, eps=eps, gout=gs, out=out, loss=m.get_aux_loss(), probs=m.aux_outputs["router_probs"], d_x=xs.grad,
+         grads=grads_of(m))
+
+    # ---- A9: the reference's VQAMOELayer (2/2/2/2 heterogeneous experts, NoisyTopK), train mode, injected noise --
+    Bv, Sv, Dv, Fv, Kv = 3, 5, 64, 128, 2
+    m = VQAMOELayer(input_dim=Dv, hidden_dim=Fv, output_dim=Dv, num_vision_experts=2, num_text_experts=2,
+                    num_multimodal_experts=2, num_specialized_experts=2, top_k=Kv, dropout=0.0)
+    Ev = m.num_experts
+    torch.manual_seed(5)
+    for p in m.parameters():                                 # the experts keep their own initialisers' structure;
+        if p.dim() >= 2:                                     # the values only need to be deterministic here
+            torch.nn.init.normal_(p, std=1.0 / np.sqrt(p.shape[-1]))
+    m.router.load_state_dict(rnd_state_dict(m.router, 22))
+    rn = np.random.default_rng(23)
+    m.output_norm.load_state_dict({"weight": torch.tensor(1.0 + 0.1 * rn.standard_normal(Dv), dtype=torch.float32),
+                                   "bias": torch.tensor(0.1 * rn.standard_normal(Dv), dtype=torch.float32)})
+    m.train()
+    xv = f32(rng.standard_normal((Bv, Sv, Dv))).requires_grad_()
+    epsv = f32(rng.standard_normal((Bv, Sv, Ev)))
+    gv = f32(rng.standard_normal((Bv, Sv, Dv)))
+    ys, kinds = {}, []
+    hooks = []
+    for e, ex in enumerate(m.experts):
+        kinds.append(type(ex).__name__)
+
+        def hook(mod, inp, outp, e=e):
+            outp.retain_grad()
+            ys[e] = outp
+        hooks.append(ex.register_forward_hook(hook))
+    torch.randn_like = lambda t, **kw: epsv.to(t.dtype) if t.shape == epsv.shape else orig(t, **kw)
+    try:
+        out = m(xv)
+        w_v, idx_v, _ = m.router(xv)                         # same noise -> same routing as inside forward
+    finally:
+        torch.randn_like = orig
+    ((out * gv).sum() + 2.0 * m.get_aux_loss()).backward()
+    N = Bv * Sv
+    ys_all = torch.zeros(Ev, N, Dv)
+    d_ys = torch.zeros(Ev, N, Dv)
+    used = np.zeros(Ev, dtype=np.int64)
+    for e, t in ys.items():
+        ys_all[e] = t.detach().reshape(N, Dv)
+        d_ys[e] = t.grad.reshape(N, Dv)
+        used[e] = 1
+    # router-path-only input gradient: experts fed a detached copy of x (their outputs do not depend on the router)
+    for h in hooks:
+        h.remove()
+    m.zero_grad()
+    xv2 = xv.detach().clone().requires_grad_()
+    restore = []
+    for ex in m.experts:
+        f = ex.forward
+        restore.append((ex, f))
+        ex.forward = (lambda f: (lambda t, **kw: f(t.detach(), **kw)))(f)
+    torch.randn_like = lambda t, **kw: epsv.to(t.dtype) if t.shape == epsv.shape else orig(t, **kw)
+    try:
+        out2 = m(xv2)
+    finally:
+        torch.randn_like = orig
+    ((out2 * gv).sum() + 2.0 * m.get_aux_loss()).backward()
+    for ex, f in restore:
+        ex.forward = f
+    g = grads_of(m)
+    save("vqa_moe_layer", cfg=np.array([Bv, Sv, Dv, Fv, Ev, Kv]), expert_kinds=np.array(kinds), used=used,
+         router_sd=m.router.state_dict(), norm_sd=m.output_norm.state_dict(), x=xv, eps=epsv, gout=gv, w=w_v,
+         idx=idx_v, probs=m.aux_outputs["router_probs"], loss=m.get_aux_loss(), ys=ys_all, d_ys=d_ys, out=out,
+         d_x_router=xv2.grad,
+         grads={k: v for k, v in g.items() if k.startswith("router.") or k.startswith("output_norm.")})
+
+    # ---- fingerprints at the benchmark dimensions -----------------------------------------------------------------
+    D, H, F = 768, 8, 2048
+    # A2: MultimodalFusion cross_attention, cfg1/2 shapes (T=64, V=50, L=2), 8 samples
+    B, T, V, L = 8, 64, 50, 2
+    m = MultimodalFusion(FusionConfig(fusion_type="cross_attention", hidden_dim=D, output_dim=D, num_heads=H,
+                                      num_layers=L, dropout=0.0, use_layer_norm=True))
+    sd = rnd_state_dict(m, 31)
+    m.load_state_dict(sd)
+    m.train()
+    vis, txt, gout = seeded_inputs(32, (B, V, D), (B, T, D), (B, D))
+    lens = np.random.default_rng(33).integers(8, T + 1, size=B)
+    valid = torch.arange(T)[None, :] < torch.tensor(lens)[:, None]
+    vis.requires_grad_(); txt.requires_grad_()
+    out = m(vis, txt, text_mask=~valid)
+    (out * gout).sum().backward()
+    tensors = {"d_visual": vis.grad, "d_text": txt.grad}
+    tensors.update({f"grads/{k}": v for k, v in grads_of(m).items()})
+    save("fp_multimodal_fusion_d768", cfg=np.array([B, T, V, D, H, L]), lens=lens, out=out, sd_keys=np.array(list(sd)),
+         **fingerprint(tensors))
+
+    # A6/A7: MOELayer on [32,114,768] (the cfg5 token layout), E=8, top-2, F=2048
+    B, S, E, K = 32, 114, 8, 2
+    m = MOELayer(input_dim=D, hidden_dim=F, output_dim=D, num_experts=E, top_k=K, dropout=0.0)
+    sd = rnd_state_dict(m, 41)
+    m.load_state_dict(sd)
+    m.train()
+    x, gout = seeded_inputs(42, (B, S, D), (B, S, D))
+    x.requires_grad_()
+    out = m(x)
+    ((out * gout).sum() + 2.0 * m.get_aux_loss()).backward()
+    _, idx, _ = m.router(x.detach())
+    tensors = {"out": out, "d_x": x.grad, "probs": m.aux_outputs["router_probs"]}
+    tensors.update({f"grads/{k}": v for k, v in grads_of(m).items()})
+    save("fp_moe_layer_d768", cfg=np.array([B, S, D, F, E, K]), loss=m.get_aux_loss(), idx_sha256=sha_int(idx),
+         idx_head=idx.reshape(-1, K)[:64], sd_keys=np.array(list(sd)), **fingerprint(tensors))
+
+    # A4: CrossModalFusion + standard MOE layer, cfg5 shapes (V=50, Tq=64 -> 114 tokens), 4 samples
+    B, V, Tq, E = 4, 50, 64, 8
+    cfg = GenerativeVQAConfig()
+    cfg.fusion_dim, cfg.fusion_num_heads, cfg.fusion_num_layers, cfg.fusion_dropout = D, H, 2, 0.0
+    cfg.decoder_ff_dim, cfg.use_moe, cfg.moe_type, cfg.moe_position = F, True, "standard", "fusion"
+    cfg.num_experts, cfg.num_experts_per_token = E, 2
+    m = CrossModalFusion(cfg)
+    sd = rnd_state_dict(m, 51)
+    m.load_state_dict(sd)
+    m.train()
+    vis, q, gout = seeded_inputs(52, (B, V, D), (B, Tq, D), (B, V + Tq, D))
+    lens = np.random.default_rng(53).integers(8, Tq + 1, size=B)
+    qvalid = torch.arange(Tq)[None, :] < torch.tensor(lens)[:, None]
+    vis.requires_grad_(); q.requires_grad_()
+    out, aux = m(vis, q, qvalid.long())
+    (out * gout).sum().backward()
+    tensors = {"out": out, "d_visual": vis.grad, "d_question": q.grad}
+    tensors.update({f"grads/{k}": v for k, v in grads_of(m).items()})
+    save("fp_cross_modal_fusion_d768", cfg=np.array([B, V, Tq, D, H, F, E]), lens=lens, aux=np.array(aux),
+         sd_keys=np.array(list(sd)), **fingerprint(tensors))
+
+
+if __name__ == "__main__" and "--r2" in sys.argv:
+    main_r2()

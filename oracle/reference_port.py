@@ -191,6 +191,23 @@ def moe_layer(sd: SD, x: torch.Tensor, num_experts: int, top_k: int, lb_weight: 
     return layer_norm(out, sd["output_norm.weight"], sd["output_norm.bias"]), loss, probs, w, idx
 
 
+# ---- A9: VQAMOELayer = MOELayer.forward over heterogeneous experts (moe_layer.py:146-171, 551-692) ----------------
+def moe_combine_dense(ys: torch.Tensor, w: torch.Tensor, idx: torch.Tensor, norm_w: torch.Tensor,
+                      norm_b: torch.Tensor) -> torch.Tensor:
+    """The combine of MOELayer.forward given every expert's output on the whole input: ys [E, B, S, D] (the
+    heterogeneous expert bodies are outside the hot path, so they enter as data); experts no token selected are
+    skipped; accumulation in ascending expert order; output_norm."""
+    E = ys.shape[0]
+    out = torch.zeros_like(ys[0])
+    for e in range(E):
+        hit = (idx == e)
+        if not bool(hit.any()):
+            continue
+        we = (w * hit.to(w.dtype)).sum(dim=-1)
+        out = out + ys[e] * we.unsqueeze(-1)
+    return layer_norm(out, norm_w, norm_b)
+
+
 # ---- A8: SparseMOELayer token dispatch with capacity (moe_layer.py:281-352) ---------------------------------------
 def sparse_moe_layer(sd: SD, x: torch.Tensor, num_experts: int, top_k: int, capacity_factor: float = 1.25,
                      lb_weight: float = 0.01, act: str = "gelu", noise=None, noise_std: float = 1.0):

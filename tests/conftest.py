@@ -30,7 +30,8 @@ def load_golden(name: str) -> dict:
     raw = np.load(GOLDEN / f"{name}.npz")
     out: dict = {}
     for k in raw.files:
-        v = torch.from_numpy(np.array(raw[k]))
+        a = np.array(raw[k])
+        v = torch.from_numpy(a) if a.dtype.kind in "fiub" else a      # string arrays (key lists) stay numpy
         if "/" in k:
             head, tail = k.split("/", 1)
             out.setdefault(head, {})[tail] = v
@@ -60,3 +61,18 @@ def round_sd_for_bf16(sd: dict) -> dict:
 
 def leafs(sd: dict) -> dict:
     return {k: v.clone().requires_grad_(v.dtype.is_floating_point and v.dim() > 0) for k, v in sd.items()}
+
+
+def seeded_normal(seed: int, *shapes):
+    """The input generator of oracle/make_golden.py's fingerprint fixtures (numpy PCG64, stable across versions)."""
+    rng = np.random.default_rng(seed)
+    return [torch.tensor(rng.standard_normal(s), dtype=torch.float32) for s in shapes]
+
+
+def fp_flat(g: dict) -> dict:
+    """load_golden() nests 'norm/<k>' and 'probe/<k>' one level; oracle.fingerprint.compare wants them flat."""
+    out = {}
+    for head in ("norm", "probe"):
+        for k, v in g[head].items():
+            out[f"{head}/{k}"] = v.numpy() if isinstance(v, torch.Tensor) else v
+    return out

@@ -156,3 +156,123 @@ def test_capacity_keep():
     w = np.array([[0.2], [0.9], [0.5], [1.0]], dtype=np.float32)
     keep = routing_np.capacity_keep(idx, w, 2, capacity=2)
     assert keep.tolist() == [0, 1, 1, 1]
+
+
+# ---- round-2 fixtures ---------------------------------------------------------------------------------------------
+def test_sparse_moe_layer_train_mode_noise_capacity_backward():
+    """A8 in train mode: injected router noise, active capacity limit, forward + backward."""
+    g = load_golden("sparse_moe_layer_train")
+    B, S, D, F, E, K = [int(v) for v in g["cfg"]]
+    sd = _leafs(g["sd"])
+    x = g["x"].clone().requires_grad_()
+    out, loss, probs, w, idx = rp.sparse_moe_layer(sd, x, E, K, capacity_factor=float(g["capacity_factor"]),
+                                                   noise=g["eps"], noise_std=1.0)
+    counts = np.bincount(idx.reshape(-1).numpy(), minlength=E)
+    assert counts.max() > int(float(g["capacity_factor"]) * B * S * K / E), "capacity limit must be active"
+    assert rel_err(out, g["out"]) < TOL
+    assert abs(float(loss) - float(g["loss"])) < 1e-7
+    ((out * g["gout"]).sum() + 2.0 * loss).backward()
+    assert rel_err(x.grad, g["d_x"]) < TOL
+    _check_grads(sd, g["grads"])
+
+
+def test_vqa_moe_layer_router_and_combine():
+    """A9: the reference's VQAMOELayer.  Its expert bodies are data here (recorded outputs); router (noisy, train mode)
+    and the dense combine + output_norm are restated and must reproduce the layer output and every gradient that flows
+    through them."""
+    g = load_golden("vqa_moe_layer")
+    B, S, D, F, E, K = [int(v) for v in g["cfg"]]
+    assert list(g["expert_kinds"]) == ["VisionExpert"] * 2 + ["TextExpert"] * 2 + ["MultimodalExpert"] * 2 + \
+        ["SegmentationExpert", "ObjectDetectionExpert"]
+    sd = _leafs({"gate.weight": g["router_sd"]["gate.weight"], "w_noise.weight": g["router_sd"]["w_noise.weight"],
+                 "nw": g["norm_sd"]["weight"], "nb": g["norm_sd"]["bias"]})
+    x = g["x"].clone().requires_grad_()
+    ys = g["ys"].view(E, B, S, D).clone().requires_grad_()
+    w, idx, loss, probs, _ = rp.topk_router(sd, "", x, K, 0.01, noise=g["eps"], noise_std=1.0)
+    assert torch.equal(idx, g["idx"])
+    assert rel_err(w, g["w"]) < TOL and rel_err(probs, g["probs"]) < TOL
+    out = rp.moe_combine_dense(ys, w, idx, sd["nw"], sd["nb"])
+    assert rel_err(out, g["out"]) < TOL
+    ((out * g["gout"]).sum() + 2.0 * loss).backward()
+    assert rel_err(x.grad, g["d_x_router"]) < TOL
+    used = g["used"].bool()
+    assert rel_err(ys.grad.view(E, B * S, D)[used], g["d_ys"][used]) < TOL
+    for k_ref, k in (("router.gate.weight", "gate.weight"), ("router.w_noise.weight", "w_noise.weight"),
+                     ("output_norm.weight", "nw"), ("output_norm.bias", "nb")):
+        assert rel_err(sd[k].grad, g["grads"][k_ref]) < TOL, k_ref
+
+
+def _fp_check(tensors, g, tol):
+    from oracle.fingerprint import compare
+    from conftest import fp_flat
+    errs = compare(tensors, fp_flat(g))
+    worst = max((v, k) for k, v in errs.items())
+    assert worst[0] < tol, worst
+
+
+def test_fingerprint_multimodal_fusion_d768():
+    """A2 at the benchmark dimensions (D=768, H=8, d_h=96, T=64, V=50): oracle vs the reference's fingerprint."""
+    from conftest import seeded_normal
+    from oracle.init_weights import multimodal_fusion_sd, seeded_state_dict
+    g = load_golden("fp_multimodal_fusion_d768")
+    B, T, V, D, H, L = [int(v) for v in g["cfg"]]
+    sd = _leafs(seeded_state_dict(multimodal_fusion_sd(D, H, L), 31, keys=list(g["sd_keys"])))
+    vis, txt, gout = seeded_normal(32, (B, V, D), (B, T, D), (B, D))
+    valid = torch.arange(T)[None, :] < g["lens"][:, None]
+    vis.requires_grad_(); txt.requires_grad_()
+    out = rp.multimodal_fusion(sd, "cross_attention", H, L, True, vis, txt, None, ~valid)
+    assert rel_err(out, g["out"]) < TOL
+    (out * gout).sum().backward()
+    tensors = {"d_visual": vis.grad, "d_text": txt.grad}
+    tensors.update({f"grads/{k}": v.grad for k, v in sd.items()})
+    _fp_check(tensors, g, 5e-5)
+
+
+def test_fingerprint_moe_layer_d768():
+    """A5-A7 at D=768 / F=2048 on [32,114,768]: routing indices by sha256, outputs and ALL gradients by probes."""
+    from conftest import seeded_normal
+    from oracle.fingerprint import sha_int
+    from oracle.init_weights import moe_layer_sd, seeded_state_dict
+    g = load_golden("fp_moe_layer_d768")
+    B, S, D, F, E, K = [int(v) for v in g["cfg"]]
+    tmpl = moe_layer_sd(D, F, E)
+    for e in range(E):      # buffers of BaseExpert (base_expert.py:50-51) are part of the reference's key order
+        tmpl[f"experts.{e}.usage_count"] = torch.tensor(0.0)
+        tmpl[f"experts.{e}.total_tokens"] = torch.tensor(0.0)
+    keys = list(g["sd_keys"])
+    assert set(keys) == set(tmpl)
+    sd = _leafs(seeded_state_dict(tmpl, 41, keys=keys))
+    x, gout = seeded_normal(42, (B, S, D), (B, S, D))
+    x.requires_grad_()
+    out, loss, probs, w, idx = rp.moe_layer(sd, x, E, K)
+    assert np.array_equal(sha_int(idx), g["idx_sha256"].numpy())
+    assert abs(float(loss) - float(g["loss"])) < 1e-7
+    ((out * gout).sum() + 2.0 * loss).backward()
+    tensors = {"out": out, "d_x": x.grad, "probs": probs}
+    tensors.update({f"grads/{k}": v.grad for k, v in sd.items() if v.requires_grad})
+    _fp_check(tensors, g, 5e-5)
+
+
+def test_fingerprint_cross_modal_fusion_d768():
+    """A4 at the cfg5 shapes (V=50, Tq=64 -> 114 tokens, D=768, F=2048, 8 experts): oracle vs the reference."""
+    from conftest import seeded_normal
+    from oracle.init_weights import seeded_state_dict
+    from vqa_model_builder_b200 import fusion       # parameter shapes only (construction needs no GPU)
+    g = load_golden("fp_cross_modal_fusion_d768")
+    B, V, Tq, D, H, F, E = [int(v) for v in g["cfg"]]
+    cfg = fusion.GenerativeFusionConfig(fusion_dim=D, fusion_num_heads=H, fusion_num_layers=2, fusion_dropout=0.0,
+                                        decoder_ff_dim=F, use_moe=True, moe_type="standard", num_experts=E,
+                                        num_experts_per_token=2)
+    tmpl = fusion.CrossModalFusion(cfg).state_dict()
+    keys = list(g["sd_keys"])
+    assert set(keys) == set(tmpl)
+    sd = _leafs(seeded_state_dict(tmpl, 51, keys=keys))
+    vis, q, gout = seeded_normal(52, (B, V, D), (B, Tq, D), (B, V + Tq, D))
+    qvalid = torch.arange(Tq)[None, :] < g["lens"][:, None]
+    vis.requires_grad_(); q.requires_grad_()
+    out, aux = rp.cross_modal_fusion(sd, H, 2, vis, q, qvalid, moe=dict(num_experts=E, top_k=2))
+    assert abs(float(aux) - float(g["aux"])) < 1e-6
+    (out * gout).sum().backward()
+    tensors = {"out": out, "d_visual": vis.grad, "d_question": q.grad}
+    tensors.update({f"grads/{k}": v.grad for k, v in sd.items() if v.requires_grad})
+    _fp_check(tensors, g, 5e-5)

@@ -47,10 +47,10 @@ SIGNATURES = {
     "b200_router_ws": ("z", "ii"),
     "b200_router_fwd": ("i", "pipppffiiiippppppppppzp"),
     "b200_router_bwd_ws": ("z", "iii"),
-    "b200_router_bwd": ("i", "pipppffiiiippppppppppppzp"),
+    "b200_router_bwd": ("i", "pipppffiiiipppppppppppppzp"),
     "b200_moe_max_rows": ("i", "ii"),
     "b200_moe_plan_ws": ("z", "ii"),
-    "b200_moe_plan": ("i", "piiippppppppzp"),
+    "b200_moe_plan": ("i", "piiipppppppppzp"),
     "b200_moe_capacity": ("i", "pppppiiippp"),
     "b200_moe_permute": ("i", "pppiiiiipp"),
     "b200_moe_unpermute": ("i", "pppiiiipp"),

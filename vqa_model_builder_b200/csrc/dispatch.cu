@@ -77,7 +77,7 @@ plan_scan_kernel(int* __restrict__ block_counts /* in: counts, out: exclusive ba
 __global__ void __launch_bounds__(PLAN_CHUNK)
 plan_scatter_kernel(const int* __restrict__ idx, int NK, int E, const int* __restrict__ block_base,
                     const int* __restrict__ cmp_off, const int* __restrict__ pad_off, int* __restrict__ dest_row,
-                    int* __restrict__ cmp_pos, int* __restrict__ row_src) {
+                    int* __restrict__ cmp_pos, int* __restrict__ row_src, int* __restrict__ cmp_src) {
   pdl_trigger();
   pdl_wait();
   __shared__ int warp_hist[PLAN_CHUNK / 32][MAX_E];
@@ -104,6 +104,7 @@ plan_scatter_kernel(const int* __restrict__ idx, int NK, int E, const int* __res
       dest_row[i] = d;
       cmp_pos[i] = cmp_off[e] + k;
       row_src[d] = i;
+      if (cmp_src != nullptr) cmp_src[cmp_off[e] + k] = i;
     } else {
       dest_row[i] = -1;
       cmp_pos[i] = -1;
@@ -388,8 +389,8 @@ size_t b200_moe_plan_ws(int NK, int E) {
 }
 
 int b200_moe_plan(const int32_t* idx, int NK, int E, int Rmax, int32_t* counts, int32_t* cmp_off, int32_t* pad_off,
-                  int32_t* dest_row, int32_t* cmp_pos, int32_t* row_src, int32_t* tile_group, void* workspace,
-                  size_t workspace_bytes, void* stream_) {
+                  int32_t* dest_row, int32_t* cmp_pos, int32_t* row_src, int32_t* tile_group, int32_t* cmp_src,
+                  void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(NK > 0 && E > 0 && E <= MAX_E, "moe_plan: need NK>0 and 0<E<=%d (NK=%d E=%d)", MAX_E, NK, E);
   B200_CHECK_ARG(Rmax % B200_GROUP_TILE == 0 && Rmax >= b200_moe_max_rows(NK, E),
@@ -398,12 +399,13 @@ int b200_moe_plan(const int32_t* idx, int NK, int E, int Rmax, int32_t* counts, 
   const int chunks = (NK + PLAN_CHUNK - 1) / PLAN_CHUNK;
   int* block_counts = (int*)workspace;
   B200_CUDA(cudaMemsetAsync(row_src, 0xFF, (size_t)Rmax * sizeof(int), stream));
+  if (cmp_src != nullptr) B200_CUDA(cudaMemsetAsync(cmp_src, 0xFF, (size_t)NK * sizeof(int), stream));
   launch_kernel(plan_count_kernel, dim3(chunks), dim3(PLAN_CHUNK), 0, stream, idx, NK, E, block_counts);
   B200_LAUNCH_CHECK("plan_count_kernel");
   launch_kernel(plan_scan_kernel, dim3(1), dim3(1024), 0, stream, block_counts, chunks, E, Rmax, counts, cmp_off, pad_off, tile_group);
   B200_LAUNCH_CHECK("plan_scan_kernel");
   launch_kernel(plan_scatter_kernel, dim3(chunks), dim3(PLAN_CHUNK), 0, stream, idx, NK, E, block_counts, cmp_off, pad_off, dest_row, cmp_pos,
-                                                         row_src);
+                                                         row_src, cmp_src);
   B200_LAUNCH_CHECK("plan_scatter_kernel");
   count_launch(3);
   return 0;

@@ -371,7 +371,8 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
                   const int* __restrict__ idx, const float* __restrict__ w, const float* __restrict__ topk_sum,
                   const float* __restrict__ probs, const float* __restrict__ probs_noisy,
                   const float* __restrict__ counts, const float* __restrict__ d_w, const float* __restrict__ d_loss,
-                  T* __restrict__ dx, float* __restrict__ dl_out, float* __restrict__ du_out) {
+                  const float* __restrict__ d_probs, T* __restrict__ dx, float* __restrict__ dl_out,
+                  float* __restrict__ du_out) {
   pdl_trigger();
   pdl_wait();
   constexpr int VT = Vec16<T>::N;
@@ -418,13 +419,18 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
     }
     float qdq = warp_sum(q0 * dq0 + q1 * dq1);
     float dsel0 = q0 * (dq0 - qdq), dsel1 = q1 * (dq1 - qdq);  // d (selection logits)
-    // aux loss: d loss / d p_clean[n,e] = lb_weight * E * (counts[e]/N) / N
+    // aux loss: d loss / d p_clean[n,e] = lb_weight * E * (counts[e]/N) / N; plus any gradient that reached
+    // router_probs directly (aux_outputs['router_probs'] is differentiable in the reference, router.py:140)
     float dc0 = 0.f, dc1 = 0.f;
-    if (gl != 0.f) {
+    if (gl != 0.f || d_probs != nullptr) {
       const float* prow = probs + (long long)n * E;
       const float p0 = v0 ? prow[lane] : 0.f, p1 = v1 ? prow[lane + 32] : 0.f;
       const float sc = gl * lb_weight * (float)E / ((float)N * (float)N);
-      const float dp0 = v0 ? sc * counts[lane] : 0.f, dp1 = v1 ? sc * counts[lane + 32] : 0.f;
+      float dp0 = v0 ? sc * counts[lane] : 0.f, dp1 = v1 ? sc * counts[lane + 32] : 0.f;
+      if (d_probs != nullptr) {
+        if (v0) dp0 += d_probs[(long long)n * E + lane];
+        if (v1) dp1 += d_probs[(long long)n * E + lane + 32];
+      }
       const float pdp = warp_sum(p0 * dp0 + p1 * dp1);
       dc0 = p0 * (dp0 - pdp);
       dc1 = p1 * (dp1 - pdp);
@@ -635,8 +641,8 @@ size_t b200_router_bwd_ws(int N, int D, int E) {
 int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* w_noise, const float* eps,
                     float noise_std, float lb_weight, int N, int D, int E, int K, const int32_t* idx, const float* w,
                     const float* topk_sum, const float* probs, const float* probs_noisy, const float* counts,
-                    const float* d_w, const float* d_loss, void* dx, float* d_w_gate, float* d_w_noise, void* workspace,
-                    size_t workspace_bytes, void* stream_) {
+                    const float* d_w, const float* d_loss, const float* d_probs, void* dx, float* d_w_gate,
+                    float* d_w_noise, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(N > 0 && D > 0 && E > 0 && E <= RT_MAX_E && K > 0 && K <= E, "router_bwd: bad shape");
   B200_CHECK_ARG(workspace_bytes >= b200_router_bwd_ws(N, D, E), "router_bwd: workspace too small");
@@ -665,12 +671,12 @@ int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* 
         if (int rc = set_smem(router_bwd_kernel<bf16, NV, 8>, smem)) return rc;
         launch_kernel(router_bwd_kernel<bf16, NV, 8>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream,
             (const bf16*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs,
-            probs_noisy, counts, d_w, d_loss, (bf16*)dx, dl, du);
+            probs_noisy, counts, d_w, d_loss, d_probs, (bf16*)dx, dl, du);
       } else {
         if (int rc = set_smem(router_bwd_kernel<bf16, NV, 0>, smem)) return rc;
         launch_kernel(router_bwd_kernel<bf16, NV, 0>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream,
             (const bf16*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs,
-            probs_noisy, counts, d_w, d_loss, (bf16*)dx, dl, du);
+            probs_noisy, counts, d_w, d_loss, d_probs, (bf16*)dx, dl, du);
       }
     });
   } else {
@@ -678,7 +684,7 @@ int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* 
       if (int rc = set_smem(router_bwd_kernel<float, NV, 0>, smem)) return rc;
       launch_kernel(router_bwd_kernel<float, NV, 0>, dim3(blocks), dim3(RT_WARPS * 32), smem, stream, 
           (const float*)x, w_gate, w_noise, eps, noise_std, lb_weight, N, D, E, K, idx, w, topk_sum, probs, probs_noisy,
-          counts, d_w, d_loss, (float*)dx, dl, du);
+          counts, d_w, d_loss, d_probs, (float*)dx, dl, du);
     });
   }
   B200_LAUNCH_CHECK("router_bwd_kernel");

@@ -17,6 +17,9 @@ from ._lib import (ACT_CODES, ACT_NONE, EPI_ACCUM, EPI_ACT, EPI_ADD, EPI_DACT, E
                    LAYOUT_MN, call, dropout_arg, dtype_code, query, stream_ptr)
 
 
+_LIB_DTYPES = (torch.float32, torch.bfloat16)
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -28,10 +31,14 @@ def _rows(x: torch.Tensor) -> Tuple[int, int]:
 
 
 def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """dtype conversion with the library's kernel (no autograd)."""
+    """dtype conversion with the library's kernel (no autograd).  float16 (the reference trains under fp16 autocast,
+    training_pipeline.py:457) is not a compute type of the library: fp16 tensors are converted by torch at the module
+    boundary, on entry to the bf16 compute type and on exit back to the caller's dtype."""
     if x.dtype == dtype:
         return x
     _lib.ensure_device(x)
+    if x.dtype not in _LIB_DTYPES or dtype not in _LIB_DTYPES:
+        return x.to(dtype)
     x = x.contiguous()
     out = torch.empty_like(x, dtype=dtype)
     call("b200_cast", x, dtype_code(x.dtype), out, dtype_code(dtype), x.numel(), stream_ptr())
@@ -404,11 +411,11 @@ class RouterFn(torch.autograd.Function):
                 counts = local_counts
         ctx.save_for_backward(x, wg, wn, eps, idx, w, topk_sum, probs, probs_noisy, counts_bwd.contiguous())
         ctx.cfg = (float(noise_std), float(lb_weight), N, D, E, K, noisy)
-        ctx.mark_non_differentiable(idx, probs, nsm, topk_sum, counts)
+        ctx.mark_non_differentiable(idx, nsm, topk_sum, counts)
         return w, idx, loss, probs, nsm, topk_sum, counts
 
     @staticmethod
-    def backward(ctx, d_w, _d_idx, d_loss, _d_probs, _d_nsm, _d_ts, _d_counts):
+    def backward(ctx, d_w, _d_idx, d_loss, d_probs, _d_nsm, _d_ts, _d_counts):
         x, wg, wn, eps, idx, w, topk_sum, probs, probs_noisy, counts = ctx.saved_tensors
         noise_std, lb_weight, N, D, E, K, noisy = ctx.cfg
         dev = x.device
@@ -422,8 +429,10 @@ class RouterFn(torch.autograd.Function):
             d_w = d_w.contiguous().float()
         if d_loss is not None:
             d_loss = d_loss.contiguous().float()
+        if d_probs is not None:      # a loss built on aux_outputs['router_probs'] (router.py:140 is differentiable)
+            d_probs = d_probs.contiguous().float()
         call("b200_router_bwd", x, dtype_code(x.dtype), wg, wn, eps, noise_std, lb_weight, N, D, E, K, idx, w,
-             topk_sum, probs, probs_noisy, counts, d_w, d_loss, dx, dwg, dwn, ws, nb, stream_ptr())
+             topk_sum, probs, probs_noisy, counts, d_w, d_loss, d_probs, dx, dwg, dwn, ws, nb, stream_ptr())
         return dx, dwg, dwn, None, None, None, None, None
 
 
@@ -431,7 +440,7 @@ class RouterFn(torch.autograd.Function):
 class RoutingPlan:
     """Device-resident maps produced by b200_moe_plan (no host reads)."""
 
-    def __init__(self, idx: torch.Tensor, E: int):
+    def __init__(self, idx: torch.Tensor, E: int, with_cmp_src: bool = False):
         _lib.ensure_device(idx)
         idx = idx.contiguous()
         if idx.dtype != torch.int32:
@@ -449,10 +458,11 @@ class RoutingPlan:
         self.cmp_pos = torch.empty(self.NK, **i32)
         self.row_src = torch.empty(self.Rmax, **i32)
         self.tile_group = torch.empty(self.Rmax // GROUP_TILE, **i32)
+        self.cmp_src = torch.empty(self.NK, **i32) if with_cmp_src else None    # inverse of cmp_pos (EP dispatch)
         nb = query("b200_moe_plan_ws", self.NK, E)
         ws = _ws(nb, dev)
         call("b200_moe_plan", idx, self.NK, E, self.Rmax, self.counts, self.cmp_off, self.pad_off, self.dest_row,
-             self.cmp_pos, self.row_src, self.tile_group, ws, nb, stream_ptr())
+             self.cmp_pos, self.row_src, self.tile_group, self.cmp_src, ws, nb, stream_ptr())
 
     def apply_capacity(self, w: torch.Tensor, capacity: int) -> Tuple[torch.Tensor, torch.Tensor]:
         w = w.contiguous()

@@ -94,6 +94,19 @@ class SlabOwner:
         slab.refresh(device, dtype)
         return slab
 
+    def invalidate(self) -> None:
+        """Mark the bf16 compute copy of the weights stale.  Staleness is normally detected through the parameters'
+        version counters; writes through `p.data` (EMA swap-in for evaluation, Lookahead's `p.data.copy_(slow)`,
+        solvers/optimizers/vqa_optimizers.py:312) do not bump them, so such code calls this (or `invalidate_all`)."""
+        slab = self.__dict__.get("_slab")
+        if slab is not None:
+            slab.dirty = True
+
+    def train(self, mode: bool = True):
+        # train()/eval() switches are where weight swaps (EMA, checkpoint averaging) usually happen: re-cast once
+        self.invalidate()
+        return super().train(mode)
+
     def __deepcopy__(self, memo):
         # drop the slab (it is rebuilt on first use) so deepcopy does not duplicate the flat buffers
         cls = self.__class__
@@ -107,6 +120,13 @@ class SlabOwner:
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         return new
+
+
+def invalidate_all(model: nn.Module) -> None:
+    """invalidate() on every drop-in module of `model` (call after editing weights through `.data`)."""
+    for m in model.modules():
+        if isinstance(m, SlabOwner):
+            m.invalidate()
 
 
 # ---------------------------------------------------------------------------------------------------------

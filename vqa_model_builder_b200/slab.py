@@ -50,6 +50,9 @@ class ParamSlab:
         self.master: torch.Tensor | None = None   # fp32 [total]
         self.shadow: torch.Tensor | None = None   # bf16 [total]
         self._versions: List[int] = []
+        #: set by SlabOwner.invalidate(): forces the next refresh to re-cast (writes through `p.data`, e.g. an EMA
+        #: weight swap or Lookahead's slow-weight copy, do not bump the version counters checked below)
+        self.dirty = False
 
     # -- packing --------------------------------------------------------------------------------------
     def _packed(self) -> bool:
@@ -118,6 +121,7 @@ class ParamSlab:
         if self.shadow is None:
             self.shadow = torch.empty(self.total, dtype=torch.bfloat16, device=device)
             self._versions = []
-        if capturing or ALWAYS_REFRESH or versions != self._versions:
+        if capturing or ALWAYS_REFRESH or self.dirty or versions != self._versions:
             _lib.call("b200_cast", self.master, _lib.F32, self.shadow, _lib.BF16, self.total, _lib.stream_ptr())
             self._versions = versions
+            self.dirty = False
