@@ -99,11 +99,12 @@ int b200_gemm(const void* A, int lda, int a_layout, const void* B, int ldb, int 
  * evaluated sparsely instead of moe_layer.py:151-168's dense loop).  A is [R, K] (permuted rows, each
  * expert's segment padded to B200_GROUP_TILE rows); tile_group[R/128] gives the expert of every 128-row
  * tile (-1 = unused tile).  B is the stacked expert weight [G, N, K] (b_layout K) or [G, K, N] (MN).
- * bias is [G, N] fp32 or NULL.                                                                      */
+ * bias is [G, N] fp32 or NULL.  rows_used (device int32, may be NULL) bounds the rows in use: 128-row tiles at or
+ * beyond it are not visited (expert-parallel receive buffers are sized for the worst case).          */
 int b200_ggemm(const void* A, int lda, const void* B, int b_layout, void* out, int ldo, int R, int N,
-               int K, int G, const int32_t* tile_group, int dtype, int out_dtype, const float* bias,
-               int epi, int act, const void* aux_in, void* aux_out, int ld_aux, const b200_dropout_t* drop,
-               void* stream);
+               int K, int G, const int32_t* tile_group, const int32_t* rows_used, int dtype, int out_dtype,
+               const float* bias, int epi, int act, const void* aux_in, void* aux_out, int ld_aux,
+               const b200_dropout_t* drop, void* stream);
 
 /* Grouped weight gradient: out[g] (fp32 [Mo, No]) = A[rows of g, :Mo]^T * B[rows of g, :No], rows of g =
  * [group_off[g], group_off[g+1]) (device int32, multiples of 128; pad rows must be zero in A or B).  */
@@ -210,27 +211,41 @@ int b200_moe_combine_bwd(const void* dout, const void* z, const int32_t* dest_ro
                          void* stream);
 
 /* ---- expert parallelism over NVLink peer memory ------------------------------------------------------
- * Dispatch / return fused with their collective: rows are written straight into the destination rank's buffer
- * through peer-mapped pointers (symmetric allocations; `peer_*` are DEVICE arrays of W device pointers, one per
- * rank).  No host-side split sizes; phases are separated by a stream-ordered cross-rank barrier owned by the caller.
+ * Dispatch / return fused with their collective (north star: "experts sharded expert-parallel ... all-to-all over
+ * NVLink"; the reference only has the placeholder moe_utils.py:194-254): token rows are written straight into the
+ * owner rank's grouped-GEMM input through peer-mapped pointers (symmetric allocations; `peer_*` are DEVICE arrays
+ * of W device pointers, one per rank).  No host-side split sizes, no staging buffer, no second permute; phases are
+ * separated by a stream-ordered cross-rank barrier owned by the caller:
+ *   push counts | barrier | layout, dispatch | barrier | grouped FFN, return | barrier | combine.
  *   b200_ep_push_counts : counts[E] (pairs per GLOBAL expert on this rank) -> row `me` of every peer's table [W,E]
- *   b200_ep_layout      : table -> send_off[E], seg_off[W*El+1], home_off[W*El], idx_recv[cap] (-1 beyond received)
- *   b200_ep_dispatch    : compact (expert-sorted) row r of `src` (gathered as src[row_src_c[r]/K] when row_src_c is
- *                         given) -> peer_bufs[owner(e)][send_off[e] + r - cmp_off[e]]
- *   b200_ep_return      : received row i (rows[row_map[i]] or rows[i]) -> peer_rets[home][home_off[g] + i - seg_off[g]] */
-/* Data-parallel gradient all-reduce over peer memory (SURVEY 8(e) collective 3, hand-rolled): peer_bufs is a HOST
- * array of the W ranks' device addresses of one symmetric fp32 buffer; elements [offset, offset+count) are replaced
- * on every rank by scale * (sum over ranks), summed in rank order (bit-identical on all ranks).  The caller places a
- * cross-rank barrier on the stream before and after the call.                                            */
+ *   b200_ep_layout      : table -> send_base[E] (row in owner(e)'s padded buffer where my rows for expert e start),
+ *                         pad_off2[2*El+1] (my padded segment offsets [El+1], then routed rows per local expert [El]),
+ *                         tile_group2[Rcap/128] (local expert per tile, -1 unused), row_home[Rcap]
+ *                         (home_rank * nk_cap + compact position at home of my padded row, -1 padding).
+ *                         Segment order = (expert, source rank, token) = the canonical order of the unsharded layer on
+ *                         the concatenated batch.
+ *   b200_ep_dispatch    : compact (expert-sorted) row r of `src` (src[cmp_src[r]/K] when cmp_src is given, else src[r])
+ *                         -> peer_bufs[owner(e)][send_base[e] + r - cmp_off[e]]; also zeroes my own padding rows
+ *   b200_ep_return      : my padded row i -> peer_rets[home_rank][home position]   (rows_hint sizes the grid)      */
+int b200_ep_push_counts(const int32_t* counts, void* const* peer_tabs, int me, int W, int E, void* stream);
+int b200_ep_layout(const int32_t* tab, int me, int W, int E, int Rcap, int nk_cap, int32_t* send_base,
+                   int32_t* pad_off2, int32_t* tile_group2, int32_t* row_home, void* stream);
+int b200_ep_dispatch(const void* src, const int32_t* cmp_src, const int32_t* cmp_off, const int32_t* send_base,
+                     const int32_t* pad_off2, void* const* peer_bufs, int me, int K, int NK, int E, int El, int D,
+                     int Rcap, int dtype, void* stream);
+int b200_ep_return(const void* rows, const int32_t* row_home, const int32_t* pad_off2, void* const* peer_rets,
+                   int El, int D, int Rcap, int nk_cap, int rows_hint, int dtype, void* stream);
+/* Data-parallel gradient all-reduce over peer memory (SURVEY 8(e) collective 3, hand-rolled).
+ * b200_p2p_allreduce_f32: peer_bufs is a HOST array of the W ranks' device addresses of one symmetric fp32 buffer;
+ * elements [offset, offset+count) are replaced on every rank by scale * (sum over ranks), summed in rank order
+ * (two-shot: every rank reduces 1/W of the range with peer loads and stores the result to every peer).
+ * b200_nvls_allreduce_f32: the same through the NVSwitch: multicast_ptr is the MULTICAST mapping of the buffer;
+ * multimem.ld_reduce sums the W copies inside the switch, multimem.st broadcasts the result (max_blocks <= 0: 64).
+ * The caller places a cross-rank barrier on the stream before and after either call.                          */
 int b200_p2p_allreduce_f32(const unsigned long long* peer_bufs, int me, int W, long long offset, long long count,
                            float scale, void* stream);
-int b200_ep_push_counts(const int32_t* counts, void* const* peer_tabs, int me, int W, int E, void* stream);
-int b200_ep_layout(const int32_t* tab, int me, int W, int E, int cap, int32_t* send_off, int32_t* seg_off,
-                   int32_t* home_off, int32_t* idx_recv, void* stream);
-int b200_ep_dispatch(const void* src, const int32_t* row_src_c, const int32_t* cmp_off, const int32_t* send_off,
-                     void* const* peer_bufs, int K, int NK, int E, int El, int D, int cap, int dtype, void* stream);
-int b200_ep_return(const void* rows, const int32_t* row_map, const int32_t* seg_off, const int32_t* home_off,
-                   void* const* peer_rets, int W, int El, int D, int cap, int dtype, void* stream);
+int b200_nvls_allreduce_f32(void* multicast_ptr, int me, int W, long long offset, long long count, float scale,
+                            int max_blocks, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,24 @@ def multimodal_fusion_sd(D: int, H: int, L: int, out_dim: int | None = None) -> 
     return {k: v.detach().clone() for k, v in sd.items()}
 
 
+def cross_modal_fusion_sd(D: int, H: int, L: int, F: int) -> dict:
+    """CrossModalFusion without its MOE layer (generative_vqa_model.py:196-222): L pre-LN TransformerEncoderLayers
+    (state_dict keys of nn.TransformerEncoderLayer) + the final LayerNorm."""
+    sd = {}
+    for l in range(L):
+        p = f"layers.{l}."
+        m = nn.MultiheadAttention(D, H, batch_first=True)
+        for k, v in m.state_dict().items():
+            sd[p + "self_attn." + k] = v
+        l1, l2 = nn.Linear(D, F), nn.Linear(F, D)
+        sd[p + "linear1.weight"], sd[p + "linear1.bias"] = l1.weight.detach(), l1.bias.detach()
+        sd[p + "linear2.weight"], sd[p + "linear2.bias"] = l2.weight.detach(), l2.bias.detach()
+        for n in ("norm1", "norm2"):
+            sd[p + n + ".weight"], sd[p + n + ".bias"] = torch.ones(D), torch.zeros(D)
+    sd["layer_norm.weight"], sd["layer_norm.bias"] = torch.ones(D), torch.zeros(D)
+    return {k: v.detach().clone() for k, v in sd.items()}
+
+
 def moe_layer_sd(D: int, F: int, E: int, noisy: bool = False) -> dict:
     sd = {"router.gate.weight": nn.Linear(D, E, bias=False).weight.detach()}
     if noisy:

@@ -234,16 +234,17 @@ def sparse_moe_layer(sd: SD, x: torch.Tensor, num_experts: int, top_k: int, capa
 
 
 # ---- A4: CrossModalFusion (generative_vqa_model.py:286-339) -----------------------------------------------------------
-def transformer_encoder_layer_prenorm(sd: SD, p: str, x, num_heads: int, key_padding_mask):
-    """nn.TransformerEncoderLayer(norm_first=True, activation='gelu'): x += SA(LN1 x); x += FF(LN2 x)."""
+def transformer_encoder_layer_prenorm(sd: SD, p: str, x, num_heads: int, key_padding_mask, pdrop: float = 0.0):
+    """nn.TransformerEncoderLayer(norm_first=True, activation='gelu'): x += drop(SA(LN1 x)); x += drop(FF(LN2 x))
+    (ffn() applies the inner and the outer dropout of the feed-forward block)."""
     h = layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
-    x = x + mha(sd, p + "self_attn.", h, h, num_heads, key_padding_mask)
+    x = x + drop(mha(sd, p + "self_attn.", h, h, num_heads, key_padding_mask, pdrop), pdrop)
     h = layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
-    return x + ffn(sd, p + "linear1.", p + "linear2.", h)
+    return x + ffn(sd, p + "linear1.", p + "linear2.", h, pdrop=pdrop)
 
 
 def cross_modal_fusion(sd: SD, num_heads: int, num_layers: int, visual, question, question_mask=None,
-                       moe: Optional[dict] = None):
+                       moe: Optional[dict] = None, pdrop: float = 0.0):
     """`moe`: None or dict(num_experts, top_k, lb_weight) for the standard MOELayer variant (moe_layer.* keys)."""
     B, V, _ = visual.shape
     fused = torch.cat([visual, question], dim=1)
@@ -251,9 +252,10 @@ def cross_modal_fusion(sd: SD, num_heads: int, num_layers: int, visual, question
     if question_mask is not None:
         pad = torch.cat([torch.zeros(B, V, dtype=torch.bool), ~question_mask.bool()], dim=1)
     for l in range(num_layers):
-        fused = transformer_encoder_layer_prenorm(sd, f"layers.{l}.", fused, num_heads, pad)
+        fused = transformer_encoder_layer_prenorm(sd, f"layers.{l}.", fused, num_heads, pad, pdrop)
     aux = None
     if moe is not None:
         sub = {k[len("moe_layer."):]: v for k, v in sd.items() if k.startswith("moe_layer.")}
-        fused, aux, _, _, _ = moe_layer(sub, fused, moe["num_experts"], moe["top_k"], moe.get("lb_weight", 0.01))
+        fused, aux, _, _, _ = moe_layer(sub, fused, moe["num_experts"], moe["top_k"], moe.get("lb_weight", 0.01),
+                                        pdrop=pdrop)
     return layer_norm(fused, sd["layer_norm.weight"], sd["layer_norm.bias"]), aux

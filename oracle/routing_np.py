@@ -72,3 +72,39 @@ def topk_with_ties(probs: np.ndarray, k: int, tol: float = 1e-6):
     gaps = sorted_p[..., :k] - sorted_p[..., 1:k + 1] if p.shape[-1] > k else sorted_p[..., :k - 1] - sorted_p[..., 1:k]
     ambiguous = (np.abs(gaps) < tol).any(axis=-1)
     return top, ambiguous
+
+
+def ep_layout(tab: np.ndarray, me: int, rcap: int, nk_cap: int):
+    """Expert-parallel layout derived from the table tab[s][e] = (token, slot) pairs rank s routes to global expert e
+    (experts sharded contiguous-block, expert e on rank e // (E / W)).  On the owner, expert segments lie in ascending
+    expert order, each padded to 128 rows, rows inside a segment ordered by (source rank, canonical position at the
+    source) — the canonical (expert, token) order of the unsharded layer on the concatenated batch.
+    Returns what rank `me` needs: send_base[E], pad_off2[2*El+1] (offsets, then routed rows per local expert),
+    tile_group2[rcap/128], row_home[rcap] (home_rank * nk_cap + compact position at home, -1 padding)."""
+    tab = np.asarray(tab, dtype=np.int64)
+    W, E = tab.shape
+    El = E // W
+    tot = tab.sum(axis=0)
+    padded = (tot + GROUP_TILE - 1) // GROUP_TILE * GROUP_TILE
+    pad = np.zeros(E, np.int64)                      # padded offset of expert e inside its owner's buffer
+    for e in range(E):
+        r = e // El
+        pad[e] = padded[r * El:e].sum()
+    send_base = (pad + tab[:me].sum(axis=0)).astype(np.int32)
+    pad_off2 = np.zeros(2 * El + 1, np.int32)
+    for le in range(El):
+        pad_off2[le] = pad[me * El + le]
+        pad_off2[El + 1 + le] = tot[me * El + le]
+    pad_off2[El] = pad[me * El + El - 1] + padded[me * El + El - 1]
+    tile_group2 = np.full(rcap // GROUP_TILE, -1, np.int32)
+    row_home = np.full(rcap, -1, np.int32)
+    cmp_off = np.concatenate([np.zeros((W, 1), np.int64), np.cumsum(tab, axis=1)], axis=1)   # per source rank
+    for le in range(El):
+        e = me * El + le
+        tile_group2[pad_off2[le] // GROUP_TILE:pad_off2[le + 1] // GROUP_TILE] = le
+        row = pad_off2[le]
+        for s in range(W):
+            n = int(tab[s, e])
+            row_home[row:row + n] = s * nk_cap + cmp_off[s, e] + np.arange(n)
+            row += n
+    return dict(send_base=send_base, pad_off2=pad_off2, tile_group2=tile_group2, row_home=row_home)

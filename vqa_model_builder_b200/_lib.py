@@ -37,7 +37,7 @@ SIGNATURES = {
     "b200_colsum_ws": ("z", "ii"),
     "b200_colsum": ("i", "piiipippzp"),
     "b200_gemm": ("i", "piipiipiiiiiipiippipp"),
-    "b200_ggemm": ("i", "pipipiiiiipiipiippipp"),
+    "b200_ggemm": ("i", "pipipiiiiippiipiippipp"),
     "b200_ggemm_wgrad": ("i", "pipipiiiipip"),
     "b200_add_ln_fwd": ("i", "pppppfpppiiipip"),
     "b200_add_ln_bwd_ws": ("z", "ii"),
@@ -58,10 +58,11 @@ SIGNATURES = {
     "b200_moe_combine_bwd_ws": ("z", "ii"),
     "b200_moe_combine_bwd": ("i", "ppppppppiiiiipppppzp"),
     "b200_ep_push_counts": ("i", "ppiiip"),
-    "b200_ep_layout": ("i", "piiiippppp"),
-    "b200_ep_dispatch": ("i", "pppppiiiiiiip"),
-    "b200_ep_return": ("i", "pppppiiiiip"),
+    "b200_ep_layout": ("i", "piiiiippppp"),
+    "b200_ep_dispatch": ("i", "ppppppiiiiiiiip"),
+    "b200_ep_return": ("i", "ppppiiiiiip"),
     "b200_p2p_allreduce_f32": ("i", "piillfp"),
+    "b200_nvls_allreduce_f32": ("i", "piillfip"),
 }
 
 class DropoutT(ctypes.Structure):

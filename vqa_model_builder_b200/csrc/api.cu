@@ -153,7 +153,9 @@ colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part, c
   float acc[VT];
 #pragma unroll
   for (int u = 0; u < VT; ++u) acc[u] = 0.f;
-  if (col < N) {
+  // rows of unused 128-row tiles (expert-parallel buffers are sized for the worst case) are never read
+  const bool live = tile_group == nullptr || tile_group[r0 / B200_GROUP_TILE] >= 0;
+  if (col < N && live) {
     for (int r = r0 + warp; r < r1; r += 8) {
       Vec16<T> v;
       v.load(x + (long long)r * N + col);
@@ -365,8 +367,8 @@ int b200_gemm(const void* A, int lda, int a_layout, const void* B, int ldb, int 
 }
 
 int b200_ggemm(const void* A, int lda, const void* B, int b_layout, void* out, int ldo, int R, int N, int K, int G,
-               const int32_t* tile_group, int dtype, int out_dtype, const float* bias, int epi, int act,
-               const void* aux_in, void* aux_out, int ld_aux, const b200_dropout_t* drop, void* stream_) {
+               const int32_t* tile_group, const int32_t* rows_used, int dtype, int out_dtype, const float* bias, int epi,
+               int act, const void* aux_in, void* aux_out, int ld_aux, const b200_dropout_t* drop, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(R > 0 && R % B200_GROUP_TILE == 0, "ggemm: R=%d must be a positive multiple of %d", R,
                  B200_GROUP_TILE);
@@ -377,7 +379,7 @@ int b200_ggemm(const void* A, int lda, const void* B, int b_layout, void* out, i
   GemmArgs a{};
   a.M = R; a.N = N; a.K = K; a.mode = GEMM_GROUP_ROWS; a.epi = epi; a.act = act;
   a.out_f32 = (out_dtype == B200_F32); a.ldo = ldo; a.ld_aux = ld_aux; a.out = out; a.aux_in = aux_in;
-  a.aux_out = aux_out; a.bias = bias; a.tile_group = tile_group; a.k_splits = 1;
+  a.aux_out = aux_out; a.bias = bias; a.tile_group = tile_group; a.rows_used = rows_used; a.k_splits = 1;
   if (drop != nullptr && drop->p > 0.f) { a.drop_state = drop->rng_state; a.drop_p = drop->p; a.drop_site = drop->site; }
   a.b_group_rows = (b_layout == B200_LAYOUT_K) ? N : K;
   a.b_group_elems = (long long)N * K;

@@ -17,6 +17,7 @@ struct GemmArgs {
   void* aux_out;
   const float* bias;
   const int* tile_group;      // GROUP_ROWS: expert of each 128-row tile
+  const int* rows_used;       // GROUP_ROWS (optional, device): rows in use; 128-row tiles beyond it are not visited
   const int* group_off;       // GROUP_WGRAD: padded row offsets [G+1]
   int b_group_rows;           // GROUP_ROWS: per-group coordinate offset in B (N for K-layout, K for MN-layout)
   long long out_group_elems;  // GROUP_WGRAD: output elements per group

@@ -240,7 +240,7 @@ __device__ __forceinline__ void stage_load_tile_bf16(uint8_t* stg, int lane, flo
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const GemmArgs p, const int m_tiles, const int n_tiles, const int total_tiles) {
+               const GemmArgs p, const int m_tiles_arg, const int n_tiles, const int total_tiles_arg) {
   constexpr int STAGES = num_stages<BN>();
   constexpr int STAGE = stage_bytes<BN>();
   extern __shared__ uint8_t smem_raw[];
@@ -279,6 +279,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
   pdl_trigger();
   pdl_wait();
+  // Expert-parallel receive buffers are sized for the worst case; the rows actually in use are only known on the
+  // device (tiles are numbered m-major, so bounding m_tiles bounds the tile walk).
+  int m_tiles = m_tiles_arg, total_tiles = total_tiles_arg;
+  if (p.rows_used != nullptr) {
+    const int used_tiles = (__ldg(p.rows_used) + BM - 1) / BM;
+    if (used_tiles < m_tiles) { m_tiles = used_tiles; total_tiles = used_tiles * n_tiles; }
+  }
 
   if (warp == 0) {
     // ================= TMA producer =================

@@ -24,6 +24,39 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+# ---- parameter-gradient buffers ----------------------------------------------------------------------------------
+# Every backward below writes the parameter gradients of its stage into ONE flat fp32 buffer.  Under data parallelism
+# the buffers come from a gradient arena in symmetric memory (parallel.GradArena): the wgrad GEMMs then write straight
+# into the buffer the peer-memory / NVLS all-reduce works on — no staging copy, no re-pointing of .grad.
+_ARENA = [None]
+_LOCAL = [False]
+
+
+def set_grad_arena(arena) -> None:
+    _ARENA[0] = arena
+
+
+class local_grads:
+    """Context: gradients of Functions whose FORWARD runs inside are rank-local (expert-parallel shards) and must not
+    be placed in the all-reduce arena."""
+
+    def __enter__(self):
+        self.prev = _LOCAL[0]
+        _LOCAL[0] = True
+
+    def __exit__(self, *a):
+        _LOCAL[0] = self.prev
+
+
+def grad_buffer(n: int, device, local: bool = False) -> torch.Tensor:
+    arena = _ARENA[0]
+    if arena is not None and not local:
+        t = arena.take(int(n), device)
+        if t is not None:
+            return t
+    return torch.empty(int(n), dtype=torch.float32, device=device)
+
+
 def _rows(x: torch.Tensor) -> Tuple[int, int]:
     """(row pitch, dtype code) of a 2-D activation whose last dim is contiguous."""
     assert x.dim() == 2 and x.stride(1) == 1, "activations must be 2-D with a contiguous last dim"
@@ -162,7 +195,7 @@ class LinearFn(torch.autograd.Function):
         side = None
         if ctx.needs_input_grad[1]:
             need_db = ctx.has_bias and pre_db is None
-            flat = torch.empty(N * K + (N if need_db else 0), dtype=torch.float32, device=x.device)
+            flat = grad_buffer(N * K + (N if need_db else 0), x.device)
             dw = flat[:N * K].view(N, K)
             # split-K accumulates atomically when the [N,K] tile grid cannot fill the machine
             epi = EPI_ACCUM if x.dtype == torch.bfloat16 else EPI_NONE
@@ -237,7 +270,7 @@ class FFNFn(torch.autograd.Function):
         g = dropout_apply(dy, drop_out) if drop_out is not None else dy
         bf = x.dtype == torch.bfloat16
         wepi = EPI_ACCUM if bf else EPI_NONE
-        flat = torch.empty(F * D + F + Do * F + Do, dtype=torch.float32, device=x.device)
+        flat = grad_buffer(F * D + F + Do * F + Do, x.device)
         dw1 = flat[:F * D].view(F, D)
         db1 = flat[F * D:F * D + F]
         dw2 = flat[F * D + F:F * D + F + Do * F].view(Do, F)
@@ -295,7 +328,7 @@ class AddLNFn(torch.autograd.Function):
         R, D = x.shape
         dsum = torch.empty_like(x)
         dbranch = torch.empty_like(x) if ctx.drop is not None else None
-        flat = torch.empty((3 if ctx.has_branch else 2) * D, dtype=torch.float32, device=x.device)
+        flat = grad_buffer((3 if ctx.has_branch else 2) * D, x.device)
         dcol = flat[2 * D:] if ctx.has_branch else None     # column sums of the branch gradient (its bias gradient)
         nb = query("b200_add_ln_bwd_ws", R, D)
         ws = _ws(nb, x.device)
@@ -420,7 +453,7 @@ class RouterFn(torch.autograd.Function):
         noise_std, lb_weight, N, D, E, K, noisy = ctx.cfg
         dev = x.device
         dx = torch.empty_like(x)
-        flat = torch.empty((2 if noisy else 1) * E * D, dtype=torch.float32, device=dev)
+        flat = grad_buffer((2 if noisy else 1) * E * D, dev)
         dwg = flat[:E * D].view(E, D)
         dwn = flat[E * D:].view(E, D) if noisy else None
         nb = query("b200_router_bwd_ws", N, D, E)
@@ -542,12 +575,14 @@ class ExpertFFNFn(torch.autograd.Function):
         dt = dtype_code(xp.dtype)
         st = stream_ptr()
         dev = xp.device
+        rows_used = pad_off[E:E + 1]          # rows in use (device): tiles beyond are never visited
+        ctx.local = _LOCAL[0]
         pre = torch.empty((R, F), dtype=xp.dtype, device=dev)
         h = torch.empty((R, F), dtype=xp.dtype, device=dev)
-        call("b200_ggemm", xp, D, w1s, LAYOUT_K, h, F, R, F, D, E, tile_group, dt, dt, b1s, EPI_ACT, act, None, pre, F,
+        call("b200_ggemm", xp, D, w1s, LAYOUT_K, h, F, R, F, D, E, tile_group, rows_used, dt, dt, b1s, EPI_ACT, act, None, pre, F,
              dropout_arg(drop_in), st)
         y2 = torch.empty((R, Do), dtype=xp.dtype, device=dev)
-        call("b200_ggemm", h, F, w2s, LAYOUT_K, y2, Do, R, Do, F, E, tile_group, dt, dt, b2s, EPI_NONE, ACT_NONE, None,
+        call("b200_ggemm", h, F, w2s, LAYOUT_K, y2, Do, R, Do, F, E, tile_group, rows_used, dt, dt, b2s, EPI_NONE, ACT_NONE, None,
              None, 0, None, st)
         z = torch.empty((R, Do), dtype=xp.dtype, device=dev)
         mean_e = torch.empty(R, dtype=torch.float32, device=dev)
@@ -567,9 +602,10 @@ class ExpertFFNFn(torch.autograd.Function):
         dev = dz.device
         dt = dtype_code(dz.dtype)
         st = stream_ptr()
+        rows_used = pad_off[E:E + 1]
         # one flat fp32 buffer for every parameter gradient of the expert bank (one DP all-reduce bucket)
         sizes = [E * F * D, E * F, E * Do * F, E * Do, E * Do, E * Do]
-        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        flat = grad_buffer(sum(sizes), dev, local=ctx.local)
         offs = [0]
         for sz in sizes:
             offs.append(offs[-1] + sz)
@@ -590,7 +626,7 @@ class ExpertFFNFn(torch.autograd.Function):
             sa = stream_ptr()
             call("b200_ggemm_wgrad", dr, Do, h, F, dw2, Do, F, R, E, pad_off, dt, sa)
         dpre = torch.empty((R, F), dtype=dz.dtype, device=dev)
-        call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, tile_group, dt, dt, None, EPI_DACT, act, pre,
+        call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, tile_group, rows_used, dt, dt, None, EPI_DACT, act, pre,
              None, F, dropout_arg(drop_in), st)
         side = aux_fork(dev)
         with aux_on(side):
@@ -601,10 +637,10 @@ class ExpertFFNFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dxp = torch.empty((R, D), dtype=dz.dtype, device=dev)
             if residual:
-                call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, tile_group, dt, dt, None, EPI_ADD,
+                call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, tile_group, rows_used, dt, dt, None, EPI_ADD,
                      ACT_NONE, dsum, None, Do, None, st)
             else:
-                call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, tile_group, dt, dt, None, EPI_NONE,
+                call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, tile_group, rows_used, dt, dt, None, EPI_NONE,
                      ACT_NONE, None, None, 0, None, st)
         aux_join(side)
         # hand every per-expert Parameter its slice of the flat buffer
@@ -643,7 +679,7 @@ class CombineFn(torch.autograd.Function):
         dev = dout.device
         dz = torch.empty((R, Do), dtype=dout.dtype, device=dev)
         d_w = torch.empty((N, K), dtype=torch.float32, device=dev)
-        flat = torch.empty(2 * Do, dtype=torch.float32, device=dev)
+        flat = grad_buffer(2 * Do, dev)
         nb = query("b200_moe_combine_bwd_ws", N, Do)
         ws = _ws(nb, dev)
         call("b200_moe_combine_bwd", dout, z, dest, w, mean_o, rstd_o, out_gamma, row_src, N, K, Do, R,
@@ -688,7 +724,7 @@ class DenseCombineFn(torch.autograd.Function):
         row_src[flat_dest[ok]] = torch.arange(N * K, device=dev, dtype=torch.int32)[ok]
         dys = torch.empty_like(ys)
         d_w = torch.empty((N, K), dtype=torch.float32, device=dev)
-        flat = torch.empty(2 * D, dtype=torch.float32, device=dev)
+        flat = grad_buffer(2 * D, dev)
         nb = query("b200_moe_combine_bwd_ws", N, D)
         ws = _ws(nb, dev)
         call("b200_moe_combine_bwd", dout, ys, dest, w, mean, rstd, out_gamma, row_src, N, K, D, E * N,
@@ -728,7 +764,7 @@ class CrossProjFn(torch.autograd.Function):
         dkvp = dkvp.contiguous()
         bf = x.dtype == torch.bfloat16
         wepi = EPI_ACCUM if bf else EPI_NONE
-        flat = torch.empty(3 * D * D + 3 * D, dtype=torch.float32, device=x.device)
+        flat = grad_buffer(3 * D * D + 3 * D, x.device)
         dw = flat[:3 * D * D].view(3 * D, D)
         db = flat[3 * D * D:]
         side = aux_fork(x.device)       # parameter gradients beside the two dgrad GEMMs
@@ -806,7 +842,7 @@ class MLPFn(torch.autograd.Function):
         for i in range(L - 1, -1, -1):
             h, wc = hs[i], wcs[i]
             N, K = wc.shape
-            flat = torch.empty(N * K + (N if has_bias[i] else 0), dtype=torch.float32, device=dev)
+            flat = grad_buffer(N * K + (N if has_bias[i] else 0), dev)
             dw = flat[:N * K].view(N, K)
             side = aux_fork(dev)
             with aux_on(side):                    # parameter gradients beside the dgrad GEMM

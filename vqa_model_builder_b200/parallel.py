@@ -317,6 +317,9 @@ class ExpertParallelMOELayer(torch.nn.Module):
         super().__init__()
         from .moe.layers import MOELayer
         assert isinstance(full_layer, MOELayer) and full_layer._homogeneous(), "needs homogeneous FeedForwardExperts"
+        if getattr(full_layer, "capacity_factor", None) is not None:
+            raise ValueError("expert parallelism does not implement SparseMOELayer's capacity_factor (the per-expert "
+                             "top-C selection needs the weights of every rank's tokens); use MOELayer")
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -385,7 +388,9 @@ class ExpertParallelMOELayer(torch.nn.Module):
                                        (dc.site(0), dc.site(1)) if dc.on else None, *L._expert_params())
             zc = ops.GatherRowsFn.apply(z2, plan2.dest_row, plan2.row_src, plan2.pad_off, El)
         else:
-            zc = got.new_zeros((0, self.output_dim))
+            # no row reached this rank's experts: keep BOTH all-to-alls in the autograd graph (a detached tensor here
+            # would skip their backward collectives on this rank while the peers block in theirs)
+            zc = got.sum(dim=1, keepdim=True).expand(0, self.output_dim).contiguous()
         back = AllToAllRows.apply(zc, out_splits, in_splits, self.group)
         w2d = weights.reshape(N, K).to(torch.float32)
         out = ops.CombineFn.apply(back, w2d, plan.cmp_pos, row_src_c[:max(n_send, 1)], L.output_norm.weight,
@@ -409,43 +414,56 @@ def finish_gradients(replicated, expert_sharded, group=None) -> None:
 
 
 # ---------------------------------------------------------------------------------------------------------
-# Expert parallelism with dispatch/return FUSED with the collective: kernels store rows straight into peer GPUs'
-# buffers over NVLink (symmetric memory), no all_to_all call, no host-side split sizes, no host sync.
+# Expert parallelism with dispatch/return FUSED with the collective: kernels store rows straight into the owner GPU's
+# grouped-GEMM input over NVLink (symmetric memory) — no all_to_all call, no send/receive staging, no second permute,
+# no host-side split sizes, no host sync: the layer is asynchronous on the stream and CUDA-graph capturable.
 # ---------------------------------------------------------------------------------------------------------
+def _symm_alloc(nbytes: int, group, device):
+    """(uint8 tensor in symmetric memory, handle, list of the W ranks' addresses of this tensor)."""
+    import torch.distributed._symmetric_memory as symm_mem
+    group = group if group is not None else dist.group.WORLD
+    if hasattr(symm_mem, "enable_symm_mem_for_group"):
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+    buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+    hdl = symm_mem.rendezvous(buf, group)
+    rank = dist.get_rank(group)
+    # the tensor may sit at an offset inside its symmetric allocation: the offset is the same on every rank
+    delta = buf.data_ptr() - int(hdl.buffer_ptrs[rank])
+    return buf, hdl, [int(a) + delta for a in hdl.buffer_ptrs], delta
+
+
 class _P2PState:
     """Symmetric buffers of one EP layer + the device arrays of peer pointers the kernels index."""
 
     def __init__(self, group, world: int, rank: int, E: int, D: int, nk_cap: int, dtype: torch.dtype, device):
-        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
         self.world, self.rank, self.E, self.D, self.nk_cap, self.dtype = world, rank, E, D, nk_cap, dtype
-        self.cap = world * nk_cap                       # worst case: every pair of every rank lands here
+        self.El = E // world
+        # worst case: every pair of every rank lands on this rank (exact routing, nothing is ever dropped)
+        self.Rcap = _lib.query("b200_moe_max_rows", world * nk_cap, self.El)
         es = torch.empty((), dtype=dtype).element_size()
         al = lambda n: (n + 255) // 256 * 256
-        sizes = {"tab": al(world * E * 4), "recv_x": al(self.cap * D * es), "recv_g": al(self.cap * D * es),
+        sizes = {"tab": al(world * E * 4), "recv_x": al(self.Rcap * D * es), "recv_g": al(self.Rcap * D * es),
                  "ret_z": al(nk_cap * D * es), "ret_dx": al(nk_cap * D * es)}
         self.offs, total = {}, 0
         for k, v in sizes.items():
             self.offs[k] = total
             total += v
-        group = group if group is not None else dist.group.WORLD
-        if hasattr(symm_mem, "enable_symm_mem_for_group"):
-            try:
-                symm_mem.enable_symm_mem_for_group(group.group_name)
-            except Exception:
-                pass
-        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
-        self.hdl = symm_mem.rendezvous(self.buf, group)
-        bases = list(self.hdl.buffer_ptrs)
+        self.buf, self.hdl, bases, _ = _symm_alloc(total, group, device)
         self.ptrs = {k: torch.tensor([b + off for b in bases], dtype=torch.int64, device=device)
                      for k, off in self.offs.items()}
         self.buf.zero_()
+        self.live = 0           # forwards whose backward has not run yet (their saved tensors alias the buffers)
         self.barrier()
 
-    def local(self, key: str, rows: int = None):
+    def local(self, key: str):
         off = self.offs[key]
         if key == "tab":
             return self.buf[off:off + self.world * self.E * 4].view(torch.int32)
-        rows = rows if rows is not None else (self.cap if key.startswith("recv") else self.nk_cap)
+        rows = self.Rcap if key.startswith("recv") else self.nk_cap
         es = torch.empty((), dtype=self.dtype).element_size()
         return self.buf[off:off + rows * self.D * es].view(self.dtype).view(rows, self.D)
 
@@ -453,74 +471,98 @@ class _P2PState:
         self.hdl.barrier(channel=0)
 
 
+class _EPMeta:
+    __slots__ = ("plan", "send_base", "pad_off2", "tile_group2", "row_home", "K", "El", "N", "zero_copy")
+
+
 class _P2PDispatchFn(torch.autograd.Function):
-    """x rows -> owners' receive buffers (peer stores); backward returns the received rows' gradients home."""
+    """token rows -> the owners' grouped-GEMM inputs (peer stores into the padded layout); backward brings the input
+    gradients of those rows home and sums the K copies per token."""
 
     @staticmethod
     def forward(ctx, x2, st, meta):
         from . import _lib
-        plan, row_src_c, send_off, seg_off, home_off, K, El = meta
+        plan = meta.plan
         x2 = x2.contiguous()
-        _lib.call("b200_ep_dispatch", x2, row_src_c, plan.cmp_off, send_off, st.ptrs["recv_x"], K, plan.NK, plan.E, El,
-                  st.D, st.cap, _lib.dtype_code(x2.dtype), _lib.stream_ptr())
+        _lib.call("b200_ep_dispatch", x2, plan.cmp_src, plan.cmp_off, meta.send_base, meta.pad_off2, st.ptrs["recv_x"],
+                  st.rank, meta.K, plan.NK, plan.E, meta.El, st.D, st.Rcap, _lib.dtype_code(x2.dtype), _lib.stream_ptr())
         st.barrier()
-        ctx.st, ctx.meta, ctx.n = st, meta, x2.shape[0]
-        return st.local("recv_x")
+        ctx.st, ctx.meta = st, meta
+        out = st.local("recv_x")
+        return out if meta.zero_copy else out.clone()
 
     @staticmethod
     def backward(ctx, d_recv):
         from . import _lib
-        st = ctx.st
-        plan, row_src_c, send_off, seg_off, home_off, K, El = ctx.meta
+        st, meta = ctx.st, ctx.meta
         d_recv = d_recv.contiguous()
-        _lib.call("b200_ep_return", d_recv, None, seg_off, home_off, st.ptrs["ret_dx"], st.world, El, st.D, st.cap,
-                  _lib.dtype_code(d_recv.dtype), _lib.stream_ptr())
+        _lib.call("b200_ep_return", d_recv, meta.row_home, meta.pad_off2, st.ptrs["ret_dx"], meta.El, st.D, st.Rcap,
+                  st.nk_cap, meta.plan.NK, _lib.dtype_code(d_recv.dtype), _lib.stream_ptr())
         st.barrier()
-        dx = torch.empty((ctx.n, st.D), dtype=d_recv.dtype, device=d_recv.device)
-        _lib.call("b200_moe_unpermute", st.local("ret_dx"), plan.cmp_pos, None, ctx.n, K, st.D,
+        dx = torch.empty((meta.N, st.D), dtype=d_recv.dtype, device=d_recv.device)
+        _lib.call("b200_moe_unpermute", st.local("ret_dx"), meta.plan.cmp_pos, None, meta.N, meta.K, st.D,
                   _lib.dtype_code(d_recv.dtype), dx, _lib.stream_ptr())
+        st.live = max(0, st.live - 1)
         return dx, None, None
 
 
 class _P2PReturnFn(torch.autograd.Function):
-    """expert outputs (padded layout on the owner) -> home ranks' buffers at the compact positions; backward sends the
-    combine gradients to the owners with the dispatch kernel."""
+    """expert outputs (padded layout on the owner) -> the tokens' home ranks at their compact positions; backward
+    sends the combine gradients to the owners with the dispatch kernel."""
 
     @staticmethod
-    def forward(ctx, z2, st, meta, plan2):
+    def forward(ctx, z2, st, meta):
         from . import _lib
-        plan, row_src_c, send_off, seg_off, home_off, K, El = meta
         z2 = z2.contiguous()
-        _lib.call("b200_ep_return", z2, plan2.dest_row, seg_off, home_off, st.ptrs["ret_z"], st.world, El, st.D, st.cap,
-                  _lib.dtype_code(z2.dtype), _lib.stream_ptr())
+        _lib.call("b200_ep_return", z2, meta.row_home, meta.pad_off2, st.ptrs["ret_z"], meta.El, st.D, st.Rcap,
+                  st.nk_cap, meta.plan.NK, _lib.dtype_code(z2.dtype), _lib.stream_ptr())
         st.barrier()
-        ctx.st, ctx.meta, ctx.plan2, ctx.rows = st, meta, plan2, z2.shape[0]
-        return st.local("ret_z", plan.NK).clone()
+        ctx.st, ctx.meta = st, meta
+        out = st.local("ret_z")[:meta.plan.NK]
+        return out if meta.zero_copy else out.clone()
 
     @staticmethod
     def backward(ctx, d_back):
         from . import _lib
-        st, plan2 = ctx.st, ctx.plan2
-        plan, row_src_c, send_off, seg_off, home_off, K, El = ctx.meta
+        st, meta = ctx.st, ctx.meta
+        plan = meta.plan
         d_back = d_back.contiguous()
-        _lib.call("b200_ep_dispatch", d_back, None, plan.cmp_off, send_off, st.ptrs["recv_g"], K, plan.NK, plan.E, El,
-                  st.D, st.cap, _lib.dtype_code(d_back.dtype), _lib.stream_ptr())
+        _lib.call("b200_ep_dispatch", d_back, None, plan.cmp_off, meta.send_base, meta.pad_off2, st.ptrs["recv_g"],
+                  st.rank, meta.K, plan.NK, plan.E, meta.El, st.D, st.Rcap, _lib.dtype_code(d_back.dtype),
+                  _lib.stream_ptr())
         st.barrier()
-        dz2 = torch.empty((ctx.rows, st.D), dtype=d_back.dtype, device=d_back.device)
-        _lib.call("b200_moe_permute", st.local("recv_g"), plan2.row_src, plan2.pad_off, El, 1, ctx.rows, st.D,
-                  _lib.dtype_code(d_back.dtype), dz2, _lib.stream_ptr())
-        return dz2, None, None, None
+        return st.local("recv_g"), None, None
 
 
 class P2PExpertParallelMOELayer(ExpertParallelMOELayer):
-    """ExpertParallelMOELayer whose dispatch / return are single kernels over NVLink peer memory (no NCCL all-to-all,
-    no host read of the routing counts: the whole layer is asynchronous on the stream)."""
+    """ExpertParallelMOELayer whose dispatch / return are single kernels over NVLink peer memory.
 
-    def _state(self, NK: int, D: int, dtype, device) -> _P2PState:
+    forward : router -> plan -> push counts | barrier | layout, dispatch (rows land in the owner's 128-row-padded
+              grouped-GEMM input) | barrier | grouped expert FFN | return | barrier | combine + output_norm
+    backward: the same two kernels in the opposite direction (2 barriers).
+    `max_tokens` (tokens per rank and forward, identical on all ranks) sizes the symmetric buffers; without it they are
+    sized from the first forward, agreed across ranks by one all-reduce.  With `zero_copy` (default) the tensors saved
+    for backward alias the symmetric buffers: a second forward before the backward of the first raises."""
+
+    def __init__(self, full_layer, group=None, max_tokens: Optional[int] = None, zero_copy: bool = True):
+        super().__init__(full_layer, group)
+        self.max_tokens = max_tokens
+        self.zero_copy = zero_copy
+
+    def _state(self, N: int, K: int, D: int, dtype, device) -> _P2PState:
         st = self.__dict__.get("_p2p")
-        if st is None or st.nk_cap < NK or st.dtype != dtype or st.D != D:
-            st = _P2PState(self.group, self.world, self.rank, self.num_experts, D, NK, dtype, device)
-            self.__dict__["_p2p"] = st
+        if st is not None and st.dtype == dtype and st.D == D:
+            if N * K > st.nk_cap:
+                raise RuntimeError(f"P2PExpertParallelMOELayer: {N} tokens exceed the buffers sized for "
+                                   f"{st.nk_cap // K}; construct the layer with max_tokens=")
+            return st
+        n_cap = self.max_tokens if self.max_tokens is not None else N
+        if self.max_tokens is None and self.world > 1:     # every rank must size the same: agree on the maximum once
+            t = torch.tensor([n_cap], dtype=torch.int64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            n_cap = int(t.item())
+        st = _P2PState(self.group, self.world, self.rank, self.num_experts, D, n_cap * K, dtype, device)
+        self.__dict__["_p2p"] = st
         return st
 
     def forward(self, x: torch.Tensor, mask=None, **kwargs) -> torch.Tensor:
@@ -535,40 +577,196 @@ class P2PExpertParallelMOELayer(ExpertParallelMOELayer):
         x2 = ops.to_compute(x.reshape(N, D), cdt)
         stash = aux.get("_b200_idx32")
         idx32 = stash[1] if stash is not None and stash[0] is indices else indices.reshape(N, K).to(torch.int32)
-        plan = ops.RoutingPlan(idx32, E)
-        NK = plan.NK
+        plan = ops.RoutingPlan(idx32, E, with_cmp_src=True)
         dev = x.device
-        ar = torch.arange(NK, device=dev, dtype=torch.int32)
-        valid = plan.cmp_pos >= 0
-        row_src_c = torch.full((NK,), -1, dtype=torch.int32, device=dev)
-        row_src_c[plan.cmp_pos[valid].long()] = ar[valid]
-        st = self._state(NK, D, cdt, dev)
+        st = self._state(N, K, D, cdt, dev)
+        if self.zero_copy and torch.is_grad_enabled() and x2.requires_grad:
+            if st.live > 0:
+                raise RuntimeError("P2PExpertParallelMOELayer(zero_copy=True): forward called again before the backward "
+                                   "of the previous forward; use zero_copy=False for such schedules")
+            st.live += 1
         sp = _lib.stream_ptr()
-        # phase 1: publish my per-expert counts in every rank's table, then derive all offsets on the device
+        # phase 1: publish my per-expert counts in every rank's table, then derive every layout on the device
         _lib.call("b200_ep_push_counts", plan.counts, st.ptrs["tab"], self.rank, W, E, sp)
         st.barrier()
-        send_off = torch.empty(E, dtype=torch.int32, device=dev)
-        seg_off = torch.empty(W * El + 1, dtype=torch.int32, device=dev)
-        home_off = torch.empty(W * El, dtype=torch.int32, device=dev)
-        idx_recv = torch.empty(st.cap, dtype=torch.int32, device=dev)
-        _lib.call("b200_ep_layout", st.local("tab"), self.rank, W, E, st.cap, send_off, seg_off, home_off, idx_recv, sp)
-        meta = (plan, row_src_c, send_off, seg_off, home_off, K, El)
-        # phase 2: permute fused with the exchange
-        got = _P2PDispatchFn.apply(x2, st, meta)
-        plan2 = ops.RoutingPlan(idx_recv.view(st.cap, 1), El)
+        i32 = dict(dtype=torch.int32, device=dev)
+        meta = _EPMeta()
+        meta.plan, meta.K, meta.El, meta.N, meta.zero_copy = plan, K, El, N, self.zero_copy
+        meta.send_base = torch.empty(E, **i32)
+        meta.pad_off2 = torch.empty(2 * El + 1, **i32)
+        meta.tile_group2 = torch.empty(st.Rcap // 128, **i32)
+        meta.row_home = torch.empty(st.Rcap, **i32)
+        _lib.call("b200_ep_layout", st.local("tab"), self.rank, W, E, st.Rcap, st.nk_cap, meta.send_base, meta.pad_off2,
+                  meta.tile_group2, meta.row_home, sp)
+        # phase 2: permute fused with the exchange: rows land in the owners' grouped-GEMM inputs
+        xp2 = _P2PDispatchFn.apply(x2, st, meta)
         stacks = L._expert_stacks(dev, cdt)
         ex0 = L.experts[0]
-        xp2 = ops.PermuteFn.apply(got, plan2.row_src, plan2.pad_off, plan2.dest_row, El, 1, plan2.Rmax)
         if "_sites" not in self.__dict__:
             self.__dict__["_sites"] = alloc_sites(2)
         dc = DropCtx(self.training, float(ex0.dropout_rate), dev, self.__dict__["_sites"])
-        z2 = ops.ExpertFFNFn.apply(xp2, plan2.tile_group, plan2.pad_off, stacks, ex0.act_code, D == ex0.output_dim,
-                                   ex0.layer_norm.eps, (dc.site(0), dc.site(1)) if dc.on else None,
-                                   *L._expert_params())
-        # phase 3: expert outputs go straight back to the tokens' home ranks
-        back = _P2PReturnFn.apply(z2, st, meta, plan2)
+        with ops.local_grads():          # the shard's gradients are complete locally: keep them out of the DP arena
+            z2 = ops.ExpertFFNFn.apply(xp2, meta.tile_group2, meta.pad_off2, stacks, ex0.act_code,
+                                       D == ex0.output_dim, ex0.layer_norm.eps,
+                                       (dc.site(0), dc.site(1)) if dc.on else None, *L._expert_params())
+        # phase 3: expert outputs go straight back to the tokens' home ranks (compact canonical positions)
+        back = _P2PReturnFn.apply(z2, st, meta)
         w2d = weights.reshape(N, K).to(torch.float32)
-        out = ops.CombineFn.apply(back, w2d, plan.cmp_pos, row_src_c, L.output_norm.weight, L.output_norm.bias,
+        out = ops.CombineFn.apply(back, w2d, plan.cmp_pos, plan.cmp_src, L.output_norm.weight, L.output_norm.bias,
                                   L.output_norm.eps)
         self.last_plan = plan
+        self.last_meta = meta
         return ops.to_compute(out, x.dtype).view(B, S, self.output_dim)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Data-parallel gradients in symmetric memory: the wgrad kernels write into the buffer the all-reduce works on
+# ---------------------------------------------------------------------------------------------------------
+class GradArena:
+    """Bump allocator over one fp32 buffer in symmetric memory.  While installed (`ops.set_grad_arena`), every backward
+    of this package takes its flat parameter-gradient buffer from here, so the gradients of a step lie back to back in
+    backward order at offsets that are identical on every rank and in every step (`reset()` at the start of a step).
+    `ArenaGradReducer` then all-reduces ranges of the arena in place — through the NVSwitch (multimem.ld_reduce /
+    multimem.st on the multicast mapping) when the allocation has one, else with peer loads — without any staging
+    copy and without touching `.grad`."""
+
+    ALIGN = 32      # floats: ranges stay 128-byte aligned
+
+    def __init__(self, numel: int, group=None, device=None):
+        self.numel = (int(numel) + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        raw, self.hdl, bases, delta = _symm_alloc(self.numel * 4, self.group, device)
+        self.buf = raw.view(torch.float32)
+        self.device = self.buf.device
+        self.peer_ptrs = bases
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self.multicast_ptr = mc + delta if mc else 0
+        self.off = 0
+        self.overflow = 0
+        self.buf.zero_()
+        self.hdl.barrier(channel=0)
+
+    def reset(self) -> None:
+        self.off = 0
+
+    def take(self, n: int, device) -> Optional[torch.Tensor]:
+        n_al = (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if torch.device(device) != self.device or self.off + n_al > self.numel:
+            self.overflow += n_al
+            return None
+        t = self.buf[self.off:self.off + n]
+        self.off += n_al
+        return t
+
+    def offset_of(self, t: torch.Tensor) -> int:
+        """element offset of a tensor inside the arena, or -1"""
+        d = t.data_ptr() - self.buf.data_ptr()
+        return d // 4 if 0 <= d < self.numel * 4 else -1
+
+
+class ArenaMeter:
+    """Stand-in arena that only measures: install it for one eager step to learn how many floats a step needs."""
+
+    def __init__(self):
+        self.total = 0
+        self.device = None
+
+    def reset(self):
+        self.total = 0
+
+    def take(self, n: int, device):
+        self.total += (n + GradArena.ALIGN - 1) // GradArena.ALIGN * GradArena.ALIGN
+        return None
+
+
+class ArenaGradReducer:
+    """Overlapped data-parallel all-reduce over a GradArena.  `buckets` lists parameters in backward order; when the
+    gradients of a bucket have landed, the arena range [cursor, end of the bucket's last gradient) is all-reduced in
+    place on the communication stream (the sweep covers every allocated float exactly once, whatever the bucket
+    boundaries), while backward continues.  Gradients that are not in the arena (produced by torch, or taken after an
+    overflow) fall back to NCCL.  No host synchronisation: the step stays CUDA-graph capturable."""
+
+    def __init__(self, arena: GradArena, buckets, average: bool = True, max_blocks: int = 0):
+        self.arena = arena
+        self.buckets = [[p for p in b if p.requires_grad] for b in buckets]
+        self.buckets = [b for b in self.buckets if b]
+        self.average = average
+        self.max_blocks = max_blocks
+        self.enabled = True
+        self.comm = torch.cuda.Stream()
+        self.cursor = 0
+        self._left = [len(b) for b in self.buckets]
+        self._fired = [set() for _ in self.buckets]
+        self._handles = []
+        for bi, bucket in enumerate(self.buckets):
+            for p in bucket:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._hook(bi)))
+        import ctypes
+        self._host_ptrs = (ctypes.c_ulonglong * arena.world)(*arena.peer_ptrs)
+
+    def _hook(self, bi: int):
+        def fire(param):
+            if not self.enabled or id(param) in self._fired[bi]:
+                return
+            self._fired[bi].add(id(param))
+            self._left[bi] -= 1
+            if self._left[bi] == 0:
+                self._launch(self.buckets[bi])
+        return fire
+
+    def _reduce_range(self, lo: int, hi: int) -> None:
+        from . import _lib
+        a = self.arena
+        if hi <= lo:
+            return
+        scale = (1.0 / a.world) if self.average else 1.0
+        a.hdl.barrier(channel=1)                # every rank's gradients of this range are written
+        if a.multicast_ptr:
+            _lib.call("b200_nvls_allreduce_f32", a.multicast_ptr, a.rank, a.world, lo, hi - lo, scale,
+                      self.max_blocks, _lib.stream_ptr())
+        else:
+            _lib.call("b200_p2p_allreduce_f32", self._host_ptrs, a.rank, a.world, lo, hi - lo, scale,
+                      _lib.stream_ptr())
+        a.hdl.barrier(channel=1)                # every rank's stores into this rank's copy have landed
+
+    def _launch(self, params) -> None:
+        a = self.arena
+        hi, outside = self.cursor, []
+        for p in params:
+            g = p.grad
+            if g is None:
+                continue
+            off = a.offset_of(g)
+            if off < 0:
+                outside.append(p)
+                continue
+            end = (off + g.numel() + a.ALIGN - 1) // a.ALIGN * a.ALIGN
+            hi = max(hi, end)
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            self._reduce_range(self.cursor, hi)
+            if outside:
+                allreduce_gradients(outside, self.average, a.group)
+        self.cursor = max(self.cursor, hi)
+
+    def finish(self) -> None:
+        """Call once after backward(): reduces what the hooks did not cover, joins the communication stream."""
+        if self.enabled:
+            pending = [p for bi, b in enumerate(self.buckets) if self._left[bi] > 0 for p in b
+                       if id(p) not in self._fired[bi]]
+            self.comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm):
+                self._reduce_range(self.cursor, self.arena.off)
+                outside = [p for p in pending if p.grad is not None and self.arena.offset_of(p.grad) < 0]
+                if outside:
+                    allreduce_gradients(outside, self.average, self.arena.group)
+            torch.cuda.current_stream().wait_stream(self.comm)
+        self.cursor = 0
+        self._left = [len(b) for b in self.buckets]
+        self._fired = [set() for _ in self.buckets]
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
