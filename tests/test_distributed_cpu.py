@@ -161,3 +161,87 @@ def _staged_reducer(rank, world):
 
 def test_staged_p2p_reducer_host_logic_world2():
     run2(_staged_reducer)
+
+
+class _ToyLinearFn(torch.autograd.Function):
+    """Mimics the package's Functions: parameter gradients are views of ONE flat buffer taken from ops.grad_buffer
+    (the gradient arena when one is installed)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return x @ w.t() + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        from vqa_model_builder_b200 import ops
+        x, w = ctx.saved_tensors
+        flat = ops.grad_buffer(w.numel() + b_numel(w), x.device)
+        dw = flat[:w.numel()].view_as(w)
+        db = flat[w.numel():]
+        dw.copy_(dy.t() @ x)
+        db.copy_(dy.sum(0))
+        return dy @ w, dw, db
+
+
+def b_numel(w):
+    return w.shape[0]
+
+
+def _arena_reducer(rank, world):
+    """Gradient arena + sweep reducer (CPU stand-in for the symmetric buffer): gradients are allocated back to back
+    in backward order at identical offsets on both ranks; every float is reduced exactly once whatever the bucket
+    boundaries; parameters whose gradients live outside the arena fall back to the library all-reduce; the arena is
+    re-used from offset 0 in the next step."""
+    from vqa_model_builder_b200 import ops
+    torch.manual_seed(0)
+    l1, l2, l3 = torch.nn.Linear(6, 5), torch.nn.Linear(5, 4), torch.nn.Linear(4, 3)
+    outside = torch.nn.Parameter(torch.ones(3))                  # gradient produced by torch, not in the arena
+    meter = parallel.ArenaMeter()
+    ops.set_grad_arena(meter)
+    x_all = torch.arange(4 * 6, dtype=torch.float32).view(4, 6) / 10.0
+
+    def fwd(x):
+        h = torch.tanh(_ToyLinearFn.apply(x, l1.weight, l1.bias))
+        h = torch.tanh(_ToyLinearFn.apply(h, l2.weight, l2.bias))
+        return (_ToyLinearFn.apply(h, l3.weight, l3.bias) * outside).square().mean()
+
+    x = x_all[rank * 2:(rank + 1) * 2]
+    fwd(x).backward()
+    assert meter.total == 3 * 32 + 0 or meter.total % 32 == 0     # three flat buffers, each padded to 32 floats
+    arena = parallel.GradArena(meter.total, device=torch.device("cpu"))
+    ops.set_grad_arena(arena)
+    # bucket boundaries deliberately cut across the flat buffers: (l3.weight) | (l3.bias, l2.*) | (l1.*, outside)
+    red = parallel.ArenaGradReducer(arena, [[l3.weight], [l3.bias, l2.weight, l2.bias],
+                                            [l1.weight, l1.bias, outside]], average=True)
+    ps = list(l1.parameters()) + list(l2.parameters()) + list(l3.parameters()) + [outside]
+    for it in range(2):
+        for p in ps:
+            p.grad = None
+        arena.reset()
+        fwd(x).backward()
+        assert all(arena.offset_of(p.grad) >= 0 for p in ps[:-1]) and arena.offset_of(outside.grad) < 0
+        ranges = list(red.ranges)
+        red.finish()
+        # the sweep is monotone and covers [0, arena.off) without overlap
+        covered = sorted(ranges)
+        assert covered[0][0] == 0 and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+        assert covered[-1][1] == arena.off or arena.off == covered[-1][1]
+        r1, r2, r3 = torch.nn.Linear(6, 5), torch.nn.Linear(5, 4), torch.nn.Linear(4, 3)
+        for a, b in ((r1, l1), (r2, l2), (r3, l3)):
+            a.load_state_dict(b.state_dict())
+        ro = torch.ones(3, requires_grad=True)
+        # mean over ranks of the local losses
+        tot = 0.0
+        for r in range(world):
+            xr = x_all[r * 2:(r + 1) * 2]
+            tot = tot + (r3(torch.tanh(r2(torch.tanh(r1(xr))))) * ro).square().mean() / world
+        tot.backward()
+        for p, q in zip(ps, list(r1.parameters()) + list(r2.parameters()) + list(r3.parameters()) + [ro]):
+            assert torch.allclose(p.grad, q.grad, atol=1e-6), (it, p.grad, q.grad)
+    red.remove()
+    ops.set_grad_arena(None)
+
+
+def test_gradient_arena_sweep_reducer_world2():
+    run2(_arena_reducer)

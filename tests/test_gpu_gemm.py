@@ -118,7 +118,7 @@ def test_grouped_gemm_and_wgrad(dtype):
     dt = _lib.dtype_code(dtype)
     h = torch.empty((R, F), dtype=dtype, device=DEV)
     pre = torch.empty((R, F), dtype=dtype, device=DEV)
-    _lib.call("b200_ggemm", xp, D, w1, LAYOUT_K, h, F, R, F, D, E, plan.tile_group, dt, dt, b1, EPI_ACT, ACT_GELU, None,
+    _lib.call("b200_ggemm", xp, D, w1, LAYOUT_K, h, F, R, F, D, E, plan.tile_group, None, dt, dt, b1, EPI_ACT, ACT_GELU, None,
               pre, F, None, _lib.stream_ptr())
     for e in range(E):
         r0, r1 = pad_off[e], pad_off[e + 1]
@@ -129,7 +129,7 @@ def test_grouped_gemm_and_wgrad(dtype):
         assert rel_err(h[r0:r1], torch.nn.functional.gelu(ref)) < tol(dtype), ("h", e)
     # dgrad layout: B = w1 read as [F(k), D(n)] per expert
     dx = torch.empty((R, D), dtype=dtype, device=DEV)
-    _lib.call("b200_ggemm", h, F, w1, LAYOUT_MN, dx, D, R, D, F, E, plan.tile_group, dt, dt, None, EPI_NONE, ACT_NONE,
+    _lib.call("b200_ggemm", h, F, w1, LAYOUT_MN, dx, D, R, D, F, E, plan.tile_group, plan.pad_off[E:E + 1], dt, dt, None, EPI_NONE, ACT_NONE,
               None, None, 0, None, _lib.stream_ptr())
     for e in range(E):
         r0, r1 = pad_off[e], pad_off[e + 1]

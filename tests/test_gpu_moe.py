@@ -243,7 +243,7 @@ def test_router_token_blocked_path_matches_generic_path(N, E, K):
         ((w * dw_up).sum() + loss.sum()).backward()
         outs.append((w, idx, loss, probs, counts, x.grad.float(), w_gate.grad))
     fast, ref = outs
-    _, amb = routing_np.topk_with_ties(ref[3].cpu().numpy(), K)
+    _, amb = routing_np.topk_with_ties(ref[3].detach().cpu().numpy(), K)
     assert not amb.any(), "random logits are not expected to tie"
     assert torch.equal(fast[1], ref[1]) and torch.equal(fast[4], ref[4])        # indices, per-expert counts
     assert rel_err(fast[3], ref[3]) < 1e-5 and rel_err(fast[0], ref[0]) < 1e-5

@@ -103,7 +103,10 @@ __device__ __forceinline__ Smem align_smem(uint8_t* raw) {
 }
 
 // ============================================ forward ==============================================
-// smem: Q[nch] | K[nch] | V[nch] | P[2] chunks, then barriers.  TMEM: S tiles at columns 128*j, O at 128*NT.
+// smem: Q[nch] | K/V[nch] (one buffer: every K tile is consumed by its S = Q K^T product before the first V tile is
+// loaded, and the V loads are issued behind the MMA that frees the buffer) | P[2] chunks, then barriers.  The shared
+// buffer is what lets two 128-row CTAs (four 64-row ones) share an SM and hide each other's TMA -> MMA -> softmax ->
+// MMA chain.  TMEM: S tiles at columns 128*j, O at 128*NT.
 template <int NT, int R>
 __global__ void __launch_bounds__(R)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
@@ -114,11 +117,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   constexpr int CH = Geo<R>::CH;
   constexpr bool SMALL = (R == 64);
   static_assert(!SMALL || NT == 1, "the 64-row flavour handles a single kv tile");
-  const uint32_t sQ = sm.base, sK = sQ + nch * CH, sV = sK + nch * CH, sP = sV + nch * CH;
-  uint8_t* pP = sm.ptr + 3 * nch * CH;
+  const uint32_t sQ = sm.base, sK = sQ + nch * CH, sV = sK, sP = sK + nch * CH;
+  uint8_t* pP = sm.ptr + 2 * nch * CH;
   const uint32_t bars = sP + Geo<R>::PT + Geo<R>::SLACK;
   const uint32_t bar_q = bars, bar_k = bars + 8, bar_v = bars + 16, bar_mma = bars + 24;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.ptr + 3 * nch * CH + Geo<R>::PT + Geo<R>::SLACK + 32);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.ptr + 2 * nch * CH + Geo<R>::PT + Geo<R>::SLACK + 32);
   // 64-row flavour: O overwrites S (S is dead once P sits in shared memory) -> 128 columns, 4 CTAs' worth per SM
   constexpr uint32_t TCOLS = SMALL ? 128 : (NT == 1 ? 256 : 512);
   constexpr uint32_t O_COL = SMALL ? 0 : NT * 128;
@@ -489,7 +492,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 }
 
 template <int R> size_t fwd_smem(int dh) {
-  return (size_t)3 * ((dh + 63) / 64) * Geo<R>::CH + Geo<R>::PT + Geo<R>::SLACK + 1024 + 128;
+  return (size_t)2 * ((dh + 63) / 64) * Geo<R>::CH + Geo<R>::PT + Geo<R>::SLACK + 1024 + 128;
 }
 template <int R> size_t bwd_smem(int dh) {
   return (size_t)4 * ((dh + 63) / 64) * Geo<R>::CH + 2 * Geo<R>::PT + Geo<R>::SLACK + 1024 + 128;
@@ -525,6 +528,7 @@ int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
     B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<128>(128)));
     B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>(128)));
     B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<1, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<1, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = true;
   }
   if (small) launch_kernel(attn_fwd_tc_kernel<1, 64>, dim3(B * H), dim3(64), fwd_smem<64>(dh), stream, qm, km, vm, a);

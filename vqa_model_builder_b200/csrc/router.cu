@@ -568,7 +568,8 @@ inline int router_grid(int N) {
 
 template <typename K>
 int set_smem(K kern, size_t bytes) {
-  if (bytes > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // the kernels also hold a few KB of static shared memory: opt in well before the 48 KB default limit is reached
+  if (bytes > 32 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 0;
 }
 

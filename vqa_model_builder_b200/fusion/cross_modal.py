@@ -2,6 +2,7 @@
 CrossModalAttention :237-311 and MultimodalFusion :314-433)."""
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
 
@@ -12,6 +13,13 @@ from .. import ops
 from .._lib import ACT_RELU
 from ..runtime import DropCtx, SlabOwner, alloc_sites, resolve_compute_dtype
 from . import blocks
+
+
+#: MultimodalFusion consumes only the CLS row of its last layer (vqa_model.py:386-387), so that layer's query
+#: projections, output projections, FFN and LayerNorms are evaluated for ONE row per sample; its self-attention still
+#: projects keys / values from all T rows and its cross-attention from all image patches (SURVEY 8(a) A2:
+#: 1.48 instead of 2.40 GFLOP forward per sample at config 1).  Results for the consumed row are unchanged.
+DEAD_ROW_ELIMINATION = os.environ.get("B200VQA_DEAD_ROWS", "1") != "0"
 
 
 @dataclass
@@ -56,6 +64,20 @@ class CrossModalAttention(SlabOwner, nn.Module):
                                        passthrough=True)
         x2 = blocks.add_ln(xr, c, self.norm2, dc.site(k0 + 3))
         f, xr = blocks.ffn(x2, self.ffn[0], self.ffn[3], slab, drop_in=dc.site(k0 + 4), passthrough=True)
+        return blocks.add_ln(xr, f, self.norm3, dc.site(k0 + 5))
+
+    def _block_cls(self, x2, kv2, B, T, S, qmask_u8, kvmask_u8, slab, dc: DropCtx, k0: int = 0):
+        """The block for the CLS row only: returns row 0 of every sample's block output, [B, D].  Queries come from
+        that row; the self-attention keys / values from all T rows of x2, the cross-attention ones from kv2."""
+        D = x2.shape[1]
+        x0 = x2.view(B, T, D)[:, 0, :].contiguous()
+        a, xr = blocks.cross_attention(x0, x2, B, 1, T, self.self_attn, slab, qmask_u8, drop_attn=dc.site(k0 + 0),
+                                       passthrough=True)
+        x0 = blocks.add_ln(xr, a, self.norm1, dc.site(k0 + 1))
+        c, xr = blocks.cross_attention(x0, kv2, B, 1, S, self.cross_attn, slab, kvmask_u8, drop_attn=dc.site(k0 + 2),
+                                       passthrough=True)
+        x0 = blocks.add_ln(xr, c, self.norm2, dc.site(k0 + 3))
+        f, xr = blocks.ffn(x0, self.ffn[0], self.ffn[3], slab, drop_in=dc.site(k0 + 4), passthrough=True)
         return blocks.add_ln(xr, f, self.norm3, dc.site(k0 + 5))
 
     def forward(self, query: torch.Tensor, key_value: torch.Tensor, query_mask: Optional[torch.Tensor] = None,
@@ -113,9 +135,15 @@ class MultimodalFusion(SlabOwner, nn.Module):
             kv2 = ops.to_compute(visual_features.reshape(B * S, D), cdt)
             qm, km = blocks.pad_mask_u8(text_mask), blocks.pad_mask_u8(visual_mask)
             dc = DropCtx(self.training, float(self.config.dropout), text_features.device, self._sites)
+            last = len(self.fusion_layers) - 1
+            cls = None
             for li, layer in enumerate(self.fusion_layers):
-                x2 = layer._block(x2, kv2, B, T, S, qm, km, slab, dc, li * CrossModalAttention.SITES)
-            cls = x2.view(B, T, D)[:, 0, :]                      # CLS position, strided rows (no copy)
+                if li == last and DEAD_ROW_ELIMINATION:          # only the CLS row of the last layer is consumed
+                    cls = layer._block_cls(x2, kv2, B, T, S, qm, km, slab, dc, li * CrossModalAttention.SITES)
+                else:
+                    x2 = layer._block(x2, kv2, B, T, S, qm, km, slab, dc, li * CrossModalAttention.SITES)
+            if cls is None:
+                cls = x2.view(B, T, D)[:, 0, :]                  # CLS position, strided rows (no copy)
             fused = blocks.linear(cls, self.output_proj, slab)
         elif ft == "concat":
             both = torch.cat([self._pool(visual_features), self._pool(text_features)], dim=-1)

@@ -7,6 +7,7 @@ handful of large buckets (one per fused stage) instead of one message per parame
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Dict, Iterable, List, Optional
 
@@ -636,16 +637,20 @@ class GradArena:
         self.numel = (int(numel) + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        raw, self.hdl, bases, delta = _symm_alloc(self.numel * 4, self.group, device)
-        self.buf = raw.view(torch.float32)
+        if device is not None and torch.device(device).type == "cuda":
+            raw, self.hdl, bases, delta = _symm_alloc(self.numel * 4, self.group, device)
+            self.buf = raw.view(torch.float32)
+            self.peer_ptrs = bases
+            mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+            self.multicast_ptr = mc + delta if mc else 0
+        else:       # CPU stand-in for the gloo host-logic tests: same bump allocation, library all-reduce on ranges
+            self.buf, self.hdl, self.peer_ptrs, self.multicast_ptr = torch.empty(self.numel), None, [], 0
         self.device = self.buf.device
-        self.peer_ptrs = bases
-        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
-        self.multicast_ptr = mc + delta if mc else 0
         self.off = 0
         self.overflow = 0
         self.buf.zero_()
-        self.hdl.barrier(channel=0)
+        if self.hdl is not None:
+            self.hdl.barrier(channel=0)
 
     def reset(self) -> None:
         self.off = 0
@@ -694,8 +699,9 @@ class ArenaGradReducer:
         self.average = average
         self.max_blocks = max_blocks
         self.enabled = True
-        self.comm = torch.cuda.Stream()
+        self.comm = torch.cuda.Stream() if arena.hdl is not None else None
         self.cursor = 0
+        self.ranges = []            # (lo, hi) reduced in the current pass (diagnostics / tests)
         self._left = [len(b) for b in self.buckets]
         self._fired = [set() for _ in self.buckets]
         self._handles = []
@@ -703,7 +709,7 @@ class ArenaGradReducer:
             for p in bucket:
                 self._handles.append(p.register_post_accumulate_grad_hook(self._hook(bi)))
         import ctypes
-        self._host_ptrs = (ctypes.c_ulonglong * arena.world)(*arena.peer_ptrs)
+        self._host_ptrs = (ctypes.c_ulonglong * arena.world)(*arena.peer_ptrs) if arena.peer_ptrs else None
 
     def _hook(self, bi: int):
         def fire(param):
@@ -720,7 +726,13 @@ class ArenaGradReducer:
         a = self.arena
         if hi <= lo:
             return
+        self.ranges.append((lo, hi))
         scale = (1.0 / a.world) if self.average else 1.0
+        if a.hdl is None:                       # CPU stand-in
+            dist.all_reduce(a.buf[lo:hi], op=dist.ReduceOp.SUM, group=a.group)
+            if self.average:
+                a.buf[lo:hi].div_(a.world)
+            return
         a.hdl.barrier(channel=1)                # every rank's gradients of this range are written
         if a.multicast_ptr:
             _lib.call("b200_nvls_allreduce_f32", a.multicast_ptr, a.rank, a.world, lo, hi - lo, scale,
@@ -743,8 +755,9 @@ class ArenaGradReducer:
                 continue
             end = (off + g.numel() + a.ALIGN - 1) // a.ALIGN * a.ALIGN
             hi = max(hi, end)
-        self.comm.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.comm):
+        if self.comm is not None:
+            self.comm.wait_stream(torch.cuda.current_stream())
+        with (torch.cuda.stream(self.comm) if self.comm is not None else contextlib.nullcontext()):
             self._reduce_range(self.cursor, hi)
             if outside:
                 allreduce_gradients(outside, self.average, a.group)
@@ -755,14 +768,17 @@ class ArenaGradReducer:
         if self.enabled:
             pending = [p for bi, b in enumerate(self.buckets) if self._left[bi] > 0 for p in b
                        if id(p) not in self._fired[bi]]
-            self.comm.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.comm):
+            if self.comm is not None:
+                self.comm.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(self.comm) if self.comm is not None else contextlib.nullcontext()):
                 self._reduce_range(self.cursor, self.arena.off)
                 outside = [p for p in pending if p.grad is not None and self.arena.offset_of(p.grad) < 0]
                 if outside:
                     allreduce_gradients(outside, self.average, self.arena.group)
-            torch.cuda.current_stream().wait_stream(self.comm)
+            if self.comm is not None:
+                torch.cuda.current_stream().wait_stream(self.comm)
         self.cursor = 0
+        self.ranges = []
         self._left = [len(b) for b in self.buckets]
         self._fired = [set() for _ in self.buckets]
 
