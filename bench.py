@@ -108,9 +108,12 @@ def algorithmic_flops(c) -> dict:
 
 
 def synth_inputs(c, rank: int):
+    """Encoder output features.  Under the configuration's bf16 AMP the encoders' projection Linears
+    (vqa_model.py:128-129, 231-232) hand the fusion bf16 tensors, so the synthetic features are bf16 (the CPU arm
+    computes in fp32 on the same bf16-representable values)."""
     g = torch.Generator().manual_seed(1234 + rank)
-    vis = torch.randn(c["B"], c["V"], c["D"], generator=g)
-    txt = torch.randn(c["B"], c["T"], c["D"], generator=g)
+    vis = torch.randn(c["B"], c["V"], c["D"], generator=g).to(torch.bfloat16)
+    txt = torch.randn(c["B"], c["T"], c["D"], generator=g).to(torch.bfloat16)
     lens = torch.randint(8, c["T"] + 1, (c["B"],), generator=torch.Generator().manual_seed(4321 + rank))
     pad = ~(torch.arange(c["T"])[None, :] < lens[:, None])       # True = PAD; position 0 always valid
     return vis, txt, pad
@@ -191,8 +194,7 @@ def cpu_reference_step_factory(c, threads: int, batch: int):
     D, H, L, E, K, F = c["D"], c["H"], c["L"], c["E"], c["K"], c["F"]
     cb = dict(c, B=batch)
     vis, txt, pad = synth_inputs(cb, 0)
-    vis.requires_grad_()
-    txt.requires_grad_()
+    vis, txt = vis.float().requires_grad_(), txt.float().requires_grad_()
     sd_m = {k: v.requires_grad_() for k, v in init_weights.moe_layer_sd(D, F, E).items()}
     if c["kind"] == "generative":
         sd_f = {k: v.requires_grad_() for k, v in init_weights.cross_modal_fusion_sd(D, H, L, F).items()}
@@ -438,17 +440,13 @@ def measure(wl: Workload, args, steps: int, warm_iters: int, want_e2e: bool, wan
     dev, world, rank, c = wl.dev, wl.world, wl.rank, wl.c
 
     # ---- eager warm-up (configures kernels, sizes the symmetric buffers), launch count per step ----
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            wl.step()
-        torch.cuda.synchronize()
-        _lib.reset_launch_count()
+    for _ in range(3):
         wl.step()
-        torch.cuda.synchronize()
-        launches_per_step = _lib.launch_count()
-    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    _lib.reset_launch_count()
+    wl.step()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count()
     if world > 1:
         dist.barrier()
 
@@ -551,7 +549,7 @@ def measure(wl: Workload, args, steps: int, warm_iters: int, want_e2e: bool, wan
         if world > 1:
             dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
         res["e2e_value"] = c["B"] * world * steps / (float(e2e_ms.item()) / 1e3)
-        res["h2d"] = vis_h.numel() * 4 + txt_h.numel() * 4 + pad_h.numel()
+        res["h2d"] = vis_h.numel() * vis_h.element_size() + txt_h.numel() * txt_h.element_size() + pad_h.numel()
         assert torch.isfinite(loss_h).all(), "non-finite loss"
 
     # ---- per-kernel timing pass (eager, CUDA events around every library call) for the roofline ----
@@ -640,6 +638,10 @@ def run_ours(args, c):
     dev = torch.device("cuda", local)
     pkg.set_compute_dtype("bf16")
     slab.ALWAYS_REFRESH = True       # pay autocast's per-step weight cast even without an optimizer update
+    # Nothing below runs on the legacy default stream: autograd's AccumulateGrad nodes remember the stream they were
+    # created on (the gradient hooks and aux_outputs keep them alive across steps), and a node created on the default
+    # stream would synchronise with it inside the CUDA-graph capture, which invalidates the capture.
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
 
     wl = Workload(c, dev, rank, world, args)
     ep_res = wl.check_expert_parallel() if world > 1 else None

@@ -101,11 +101,7 @@ def ep_check(rank, world, dev, mode, graph):
 
     step()
     if graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            step()
-        torch.cuda.current_stream().wait_stream(side)
+        step()
         torch.cuda.synchronize()
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr):
@@ -134,6 +130,9 @@ def main():
     rank, world, local = parallel.init_distributed("nccl")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    # never the legacy default stream: AccumulateGrad nodes created on it (and kept alive by aux_outputs / gradient
+    # hooks) would synchronise with it inside a CUDA-graph capture and invalidate the capture
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     results = {}
     for name, fn in (("dp_arena", lambda: dp_check(rank, world, dev)),
                      ("ep_fp32", lambda: ep_check(rank, world, dev, "fp32", False)),

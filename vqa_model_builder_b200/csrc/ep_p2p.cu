@@ -54,7 +54,7 @@ ep_layout_kernel(const int* __restrict__ tab, int me, int W, int E, int El, int 
     s_pad[t] = p;
     int before = 0;
     for (int s = 0; s < me; ++s) before += tab[s * E + t];
-    send_base[t] = p + before;
+    if (blockIdx.x == 0) send_base[t] = p + before;
   }
   __syncthreads();
   if (t <= El) {
@@ -65,8 +65,10 @@ ep_layout_kernel(const int* __restrict__ tab, int me, int W, int E, int El, int 
       p = s_pad[last] + (s_tot[last] + B200_GROUP_TILE - 1) / B200_GROUP_TILE * B200_GROUP_TILE;
     }
     s_poff[t] = p;
-    pad_off2[t] = p;
-    if (t < El) pad_off2[El + 1 + t] = s_tot[me * El + t];      // routed rows of local expert t (behind the offsets)
+    if (blockIdx.x == 0) {
+      pad_off2[t] = p;
+      if (t < El) pad_off2[El + 1 + t] = s_tot[me * El + t];    // routed rows of local expert t (behind the offsets)
+    }
   }
   for (int i = t; i < El * W; i += blockDim.x) {      // (le, s): prefix of sources inside the segment, home position
     const int le = i / W, s = i % W, e = me * El + le;
@@ -81,7 +83,9 @@ ep_layout_kernel(const int* __restrict__ tab, int me, int W, int E, int El, int 
   __syncthreads();
   const int used = s_poff[El];
   const int tiles = Rcap / B200_GROUP_TILE;
-  for (int tile = t; tile < tiles; tile += blockDim.x) {
+  // every block derives the (tiny) tables above; the per-row maps are spread over the grid
+  const int gt = blockIdx.x * blockDim.x + t, gstride = gridDim.x * blockDim.x;
+  for (int tile = gt; tile < tiles; tile += gstride) {
     const int r = tile * B200_GROUP_TILE;
     int g = -1;
     if (r < used)
@@ -89,7 +93,7 @@ ep_layout_kernel(const int* __restrict__ tab, int me, int W, int E, int El, int 
         if (r >= s_poff[le] && r < s_poff[le + 1]) g = le;
     tile_group2[tile] = g;
   }
-  for (int i = t; i < Rcap; i += blockDim.x) {
+  for (int i = gt; i < Rcap; i += gstride) {
     int v = -1;
     if (i < used) {
       int le = 0;
@@ -269,7 +273,9 @@ int b200_ep_layout(const int32_t* tab, int me, int W, int E, int Rcap, int nk_ca
                      nk_cap > 0 && (long long)W * nk_cap < 2147483647ll,
                  "ep_layout: bad arguments (W=%d E=%d Rcap=%d nk_cap=%d; W<=8, E<=%d, E %% W == 0)", W, E, Rcap,
                  nk_cap, EP_MAX_E);
-  launch_kernel(ep_layout_kernel, dim3(1), dim3(1024), 0, stream, tab, me, W, E, E / W, Rcap, nk_cap, send_base,
+  int blocks = (Rcap + 4095) / 4096;        // ~4 rows per thread
+  if (blocks > 64) blocks = 64;
+  launch_kernel(ep_layout_kernel, dim3(blocks), dim3(1024), 0, stream, tab, me, W, E, E / W, Rcap, nk_cap, send_base,
                 pad_off2, tile_group2, row_home);
   B200_LAUNCH_CHECK("ep_layout_kernel");
   count_launch();

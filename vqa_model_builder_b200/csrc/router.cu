@@ -101,7 +101,7 @@ __device__ __forceinline__ void gate_dots(const RowRegs<T, NV>& x, const float* 
 constexpr int RT_TB = 4;
 template <int NV, int EB, int TB>
 __device__ __forceinline__ void gate_dots_block(const bf16* __restrict__ x, const float* __restrict__ ws, int base,
-                                                int N, int D, int E, int lane, float (&out)[TB]) {
+                                                int N, int D, int E, int lane, float& out) {
   const float4* ws4 = reinterpret_cast<const float4*>(ws);
   const int nv = D / 8;
   uint4 raw[TB][NV];
@@ -144,19 +144,26 @@ __device__ __forceinline__ void gate_dots_block(const bf16* __restrict__ x, cons
         }
       }
     }
+  // Transpose-reduce: 32 partial sums per lane (index i = t * EB + e) -> lane l ends up with the FULL sum of index l.
+  // Round with offset o: the lane keeps the half of its values whose index has bit o equal to its own lane bit and
+  // receives the partner's partial sums of that half: 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 5 * 32.
+  static_assert(TB * EB == 32, "one value per lane");
+  float v[32];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
+  for (int t = 0; t < TB; ++t)
 #pragma unroll
-    for (int t = 0; t < TB; ++t)
+    for (int e = 0; e < EB; ++e) v[t * EB + e] = s[t][e];
 #pragma unroll
-      for (int e = 0; e < EB; ++e) s[t][e] += __shfl_xor_sync(0xffffffffu, s[t][e], o);
+  for (int o = 16; o > 0; o >>= 1) {
+    const bool up = (lane & o) != 0;
 #pragma unroll
-  for (int t = 0; t < TB; ++t) {
-    out[t] = 0.f;
-#pragma unroll
-    for (int e = 0; e < EB; ++e)
-      if (e == lane) out[t] = s[t][e];
+    for (int i = 0; i < o; ++i) {
+      const float keep = up ? v[i + o] : v[i];
+      const float send = up ? v[i] : v[i + o];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
   }
+  out = v[0];
 }
 
 // dx rows of TB consecutive tokens: dx[t] = sum_e dl[t][e] * Wg[e,:]  (dl from shared memory, same layout)
@@ -245,21 +252,50 @@ router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
   const bool fast = FAST && !noisy;
   const int tb = fast ? TBC : 1;
   for (int base = (blockIdx.x * RT_WARPS + warp) * tb; base < N; base += gridDim.x * RT_WARPS * tb) {
-   float cl[TBC];
-   if (FAST && fast) gate_dots_block<NV, (FAST ? EB : 8), TBC>(reinterpret_cast<const bf16*>(x), wg, base, N, D, E, lane, cl);
+   if constexpr (FAST) if (fast) {
+     // Token-blocked path: after the transpose-reduce lane l holds the logit of (token base + l / 8, expert l % 8),
+     // so softmax, top-k and the statistics of the 4 tokens run at once in 8-lane groups (3 shuffle rounds each).
+     float logit;
+     gate_dots_block<NV, EB, TBC>(reinterpret_cast<const bf16*>(x), wg, base, N, D, E, lane, logit);
+     const int e = lane & 7, n = base + (lane >> 3);
+     const bool tok_ok = n < N, ve = e < E;
+     float m = ve ? logit : -INFINITY;
 #pragma unroll
-   for (int t = 0; t < TBC; ++t) {
-    const int n = base + t;
-    if (t >= tb || n >= N) break;
+     for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+     const float ex = ve ? __expf(logit - m) : 0.f;
+     float sum = ex;
+#pragma unroll
+     for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+     const float p = ex / sum;
+     if (tok_ok && ve) { probs[(long long)n * E + e] = p; ps0 += p; }
+     float a = ve ? p : -1.f, sel_sum = 0.f, my_w = 0.f;
+     int my_i = 0;
+     for (int k = 0; k < K; ++k) {       // descending; exact ties -> lowest expert index
+       float bv = a;
+       int bi = e;
+#pragma unroll
+       for (int o = 4; o > 0; o >>= 1) {
+         const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+       }
+       sel_sum += bv;
+       if (e == k) { my_w = bv; my_i = bi; }
+       if (bi == e) { a = -2.f; if (tok_ok) cnt0 += 1.f; }
+     }
+     if (tok_ok && e < K) {
+       idx[(long long)n * K + e] = my_i;
+       w[(long long)n * K + e] = my_w / sel_sum;
+     }
+     if (tok_ok && e == 0) topk_sum[n] = sel_sum;
+     continue;
+   }
+   {
+    const int n = base;
     RowRegs<T, NV> xr;
     float c0, c1;  // clean logits -> clean probs
-    if (FAST && fast) {
-      c0 = cl[t];
-      c1 = 0.f;
-    } else {
-      xr.load(x + (long long)n * D, D, lane);
-      gate_dots<T, NV, EB>(xr, wg, E, lane, c0, c1);
-    }
+    xr.load(x + (long long)n * D, D, lane);
+    gate_dots<T, NV, EB>(xr, wg, E, lane, c0, c1);
     float q0 = c0, q1 = c1;  // logits used for selection
     if (noisy) {
       float u0, u1;
@@ -305,6 +341,13 @@ router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
     }
     if (lane == 0) topk_sum[n] = sel_sum;
    }
+  }
+  if (FAST && fast) {   // the 4 token groups of a warp each counted expert (lane & 7): fold them onto lanes 0..7
+    cnt0 += __shfl_xor_sync(0xffffffffu, cnt0, 8);
+    cnt0 += __shfl_xor_sync(0xffffffffu, cnt0, 16);
+    ps0 += __shfl_xor_sync(0xffffffffu, ps0, 8);
+    ps0 += __shfl_xor_sync(0xffffffffu, ps0, 16);
+    if (lane >= 8) { cnt0 = 0.f; ps0 = 0.f; }
   }
 
   // block partials: [0] counts, [1] sum of clean probs, [2] sum of softplus noise scales
