@@ -81,6 +81,11 @@ int b200_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long lon
 size_t b200_colsum_ws(int R, int N);
 int b200_colsum(const void* x, int dtype, int R, int N, const int32_t* tile_group, int G, float* out,
                 void* workspace, size_t workspace_bytes, void* stream);
+/* out[r,c] = x[r,c] * keep_scale(r*N + c) and colsum[c] = sum_r out[r,c] in one pass: the backward of
+ * "dropout(x W^T + b) + residual" (nn.TransformerEncoderLayer's dropout1/dropout2, generative_vqa_model.py:203-214)
+ * needs dropout(dy) as GEMM operand and its column sums as the bias gradient.  workspace >= b200_colsum_ws(R,N). */
+int b200_dropout_colsum(const void* x, void* out, int dtype, int R, int N, const b200_dropout_t* drop, float* colsum,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- GEMM ------------------------------------------------------------------------------------ */
 /* out[M,N] = A[M,K] * B[N,K]^T with epilogue.  Replaces nn.Linear fwd/bwd (vqa_model.py:258-271,

@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200_cast": ("i", "pipilp"),
     "b200_colsum_ws": ("z", "ii"),
     "b200_colsum": ("i", "piiipippzp"),
+    "b200_dropout_colsum": ("i", "ppiiipppzp"),
     "b200_gemm": ("i", "piipiipiiiiiipiippipp"),
     "b200_ggemm": ("i", "pipipiiiiippiipiippipp"),
     "b200_ggemm_wgrad": ("i", "pipipiiiipip"),

@@ -138,29 +138,59 @@ __device__ __forceinline__ void fold_partials(const float* __restrict__ part, in
   if (cur >= 0) out[(long long)cur * N + c] = s;
 }
 
-// 8 warps x 16-byte vectors: block (slab, rb) sums rows [rb*64, rb*64+64) of a 32*VT-column slab
+// 8 warps x 16-byte vectors: block (slab, rb) sums rows [rb*rpb, rb*rpb+rpb) of a 32*VT-column slab; four row loads per
+// warp are in flight at a time.  With `drop` the kernel first applies the dropout keep-scales of the site (element
+// index = row * N + col), stores the scaled rows to `gout` and sums THOSE: the backward of "dropout(x W^T + b) +
+// residual" needs both dropout(dy) (operand of the dgrad / wgrad GEMMs) and its column sums (the bias gradient).
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part, const int* __restrict__ tile_group,
-              int G, float* __restrict__ out, unsigned int* __restrict__ tickets) {
+colsum_stage1(const T* __restrict__ x, int R, int N, int rpb, float* __restrict__ part,
+              const int* __restrict__ tile_group, int G, float* __restrict__ out, unsigned int* __restrict__ tickets,
+              T* __restrict__ gout, const unsigned long long* drop_state, float drop_p, unsigned int drop_site) {
   pdl_trigger();
   pdl_wait();
   constexpr int VT = Vec16<T>::N;
   __shared__ float red[8][32 * VT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = (blockIdx.x * 32 + lane) * VT;
-  const int r0 = blockIdx.y * CS_ROWS, r1 = min(R, r0 + CS_ROWS);
+  const int r0 = blockIdx.y * rpb, r1 = min(R, r0 + rpb);
+  const DropState ds = drop_load(drop_state, drop_p, drop_site);
   float acc[VT];
 #pragma unroll
   for (int u = 0; u < VT; ++u) acc[u] = 0.f;
   // rows of unused 128-row tiles (expert-parallel buffers are sized for the worst case) are never read
   const bool live = tile_group == nullptr || tile_group[r0 / B200_GROUP_TILE] >= 0;
   if (col < N && live) {
-    for (int r = r0 + warp; r < r1; r += 8) {
-      Vec16<T> v;
-      v.load(x + (long long)r * N + col);
+    for (int rb = r0 + warp; rb < r1; rb += 32) {
+      Vec16<T> v[4];
 #pragma unroll
-      for (int u = 0; u < VT; ++u) acc[u] += v.v[u];
+      for (int q = 0; q < 4; ++q) {
+        const int r = rb + 8 * q;
+        if (r < r1) v[q].load(x + (long long)r * N + col);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = rb + 8 * q;
+        if (r < r1) {
+          if (ds.on) {
+            const unsigned long long base = (unsigned long long)r * N + col;
+            if (VT == 8) {
+              float sc[8];
+              drop_scales8(ds, base >> 3, sc);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[q].v[u % VT] *= sc[u];
+            } else {
+              float sc[4];
+              drop_scales4(ds, base >> 2, sc);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) v[q].v[u % VT] *= sc[u];
+            }
+            v[q].store(gout + (long long)r * N + col);
+          }
+#pragma unroll
+          for (int u = 0; u < VT; ++u) acc[u] += v[q].v[u];
+        }
+      }
     }
   }
 #pragma unroll
@@ -175,7 +205,7 @@ colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part, c
       part[(long long)blockIdx.y * N + gc] = s;
     }
   }
-  if (tickets == nullptr) return;                     // many row blocks / grouped: a second kernel folds in parallel
+  if (tickets == nullptr) return;                     // grouped: a second kernel folds per expert in parallel
   if (!last_arrival(tickets + blockIdx.x, gridDim.y)) return;
   for (int c = threadIdx.x; c < 32 * VT; c += 256) {
     const int gc = blockIdx.x * 32 * VT + c;
@@ -184,13 +214,13 @@ colsum_stage1(const T* __restrict__ x, int R, int N, float* __restrict__ part, c
 }
 // scalar fallback for widths that are not a multiple of the vector length
 template <typename T>
-__global__ void colsum_stage1_scalar(const T* __restrict__ x, int R, int N, float* __restrict__ part,
+__global__ void colsum_stage1_scalar(const T* __restrict__ x, int R, int N, int rpb, float* __restrict__ part,
                                      const int* __restrict__ tile_group, int G, float* __restrict__ out,
                                      unsigned int* __restrict__ tickets) {
   pdl_trigger();
   pdl_wait();
   const int col = blockIdx.x * 128 + threadIdx.x;
-  const int r0 = blockIdx.y * CS_ROWS, r1 = min(R, r0 + CS_ROWS);
+  const int r0 = blockIdx.y * rpb, r1 = min(R, r0 + rpb);
   if (col < N) {
     float s = 0.f;
     for (int r = r0; r < r1; ++r) s += to_f32<T>(x[(long long)r * N + col]);
@@ -303,35 +333,56 @@ size_t b200_colsum_ws(int R, int N) {
   const size_t blocks = (size_t)(R + CS_ROWS - 1) / CS_ROWS;
   return blocks * (size_t)N * sizeof(float);
 }
-int b200_colsum(const void* x, int dtype, int R, int N, const int32_t* tile_group, int G, float* out,
-                void* workspace, size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int launch_colsum(const void* x, void* gout, const b200_dropout_t* drop, int dtype, int R, int N,
+                         const int32_t* tile_group, int G, float* out, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream) {
   B200_CHECK_ARG(R > 0 && N > 0 && G > 0, "colsum: bad shape R=%d N=%d G=%d", R, N, G);
   B200_CHECK_ARG(workspace_bytes >= b200_colsum_ws(R, N), "colsum: workspace too small");
-  const int blocks = (R + CS_ROWS - 1) / CS_ROWS;
-  float* part = (float*)workspace;
+  const bool don = drop != nullptr && drop->p > 0.f && gout != nullptr;
   const int vt = dtype == B200_F32 ? 4 : 8;
-  // One launch when the fold is short (<= 64 row blocks, i.e. R <= 4096, ungrouped): the last-arriving block of a
-  // column slab adds the partials.  Otherwise the serial fold would dominate: a second kernel folds in parallel.
-  const bool single = (tile_group == nullptr) && blocks <= 64;
-  const bool vec = (N % vt == 0) && (((uintptr_t)x & 15) == 0);
+  const bool vec = (N % vt == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)gout & 15) == 0);
+  B200_CHECK_ARG(!don || vec, "dropout_colsum: needs 16-byte aligned rows (N %% %d == 0)", vt);
+  // Ungrouped: ONE launch — at most 64 row blocks (rows per block grows with R), the last-arriving block of a column
+  // slab folds the partials in block order (deterministic).  Grouped (per-expert sums): 64-row blocks, which never
+  // straddle a 128-row expert tile, and a second kernel folds per expert in parallel.
+  int rpb = CS_ROWS;
+  const bool single = tile_group == nullptr;
+  if (single)
+    while ((R + rpb - 1) / rpb > 64) rpb *= 2;
+  const int blocks = (R + rpb - 1) / rpb;
+  float* part = (float*)workspace;
   dim3 g1(vec ? (N + 32 * vt - 1) / (32 * vt) : (N + 127) / 128, blocks);
   unsigned int* tk = nullptr;
   if (single) {
     B200_CUDA(cudaGetSymbolAddress((void**)&tk, g_tickets));
     tk += ticket_slots((int)g1.x);
   }
+  const unsigned long long* dst = don ? drop->rng_state : nullptr;
+  const float dp = don ? drop->p : 0.f;
+  const unsigned int dsite = don ? drop->site : 0u;
   if (vec) {
-    if (dtype == B200_F32) launch_kernel(colsum_stage1<float>, dim3(g1), dim3(256), 0, stream, (const float*)x, R, N, part, tile_group, G, out, tk);
-    else launch_kernel(colsum_stage1<bf16>, dim3(g1), dim3(256), 0, stream, (const bf16*)x, R, N, part, tile_group, G, out, tk);
+    if (dtype == B200_F32) launch_kernel(colsum_stage1<float>, dim3(g1), dim3(256), 0, stream, (const float*)x, R, N, rpb, part, tile_group, G, out, tk, (float*)gout, dst, dp, dsite);
+    else launch_kernel(colsum_stage1<bf16>, dim3(g1), dim3(256), 0, stream, (const bf16*)x, R, N, rpb, part, tile_group, G, out, tk, (bf16*)gout, dst, dp, dsite);
   } else {
-    if (dtype == B200_F32) launch_kernel(colsum_stage1_scalar<float>, dim3(g1), dim3(128), 0, stream, (const float*)x, R, N, part, tile_group, G, out, tk);
-    else launch_kernel(colsum_stage1_scalar<bf16>, dim3(g1), dim3(128), 0, stream, (const bf16*)x, R, N, part, tile_group, G, out, tk);
+    if (dtype == B200_F32) launch_kernel(colsum_stage1_scalar<float>, dim3(g1), dim3(128), 0, stream, (const float*)x, R, N, rpb, part, tile_group, G, out, tk);
+    else launch_kernel(colsum_stage1_scalar<bf16>, dim3(g1), dim3(128), 0, stream, (const bf16*)x, R, N, rpb, part, tile_group, G, out, tk);
   }
   B200_LAUNCH_CHECK("colsum_stage1");
   count_launch();
   if (single) return 0;
   return launch_partial_reduce(part, blocks, CS_ROWS, N, tile_group, G, out, stream);
+}
+
+int b200_colsum(const void* x, int dtype, int R, int N, const int32_t* tile_group, int G, float* out,
+                void* workspace, size_t workspace_bytes, void* stream_) {
+  return launch_colsum(x, nullptr, nullptr, dtype, R, N, tile_group, G, out, workspace, workspace_bytes,
+                       (cudaStream_t)stream_);
+}
+
+int b200_dropout_colsum(const void* x, void* out, int dtype, int R, int N, const b200_dropout_t* drop, float* colsum,
+                        void* workspace, size_t workspace_bytes, void* stream_) {
+  B200_CHECK_ARG(drop != nullptr && out != nullptr && colsum != nullptr, "dropout_colsum: bad arguments");
+  return launch_colsum(x, out, drop, dtype, R, N, nullptr, 1, colsum, workspace, workspace_bytes, (cudaStream_t)stream_);
 }
 
 static int check_epi(int epi, int act, const void* aux_in, int out_dtype) {

@@ -131,6 +131,17 @@ def dropout_apply(x: torch.Tensor, drop) -> torch.Tensor:
     return out
 
 
+def dropout_colsum(x: torch.Tensor, drop, out_sum: torch.Tensor) -> torch.Tensor:
+    """(x * keep-mask of the site, column sums of that product written to out_sum) in one pass."""
+    x = x.contiguous()
+    R, N = x.shape
+    out = torch.empty_like(x)
+    nb = query("b200_colsum_ws", R, N)
+    ws = _ws(nb, x.device)
+    call("b200_dropout_colsum", x, out, dtype_code(x.dtype), R, N, dropout_arg(drop), out_sum, ws, nb, stream_ptr())
+    return out
+
+
 def colsum(x: torch.Tensor, tile_group=None, G: int = 1) -> torch.Tensor:
     R, N = x.shape
     assert x.is_contiguous()
@@ -190,24 +201,31 @@ class LinearFn(torch.autograd.Function):
         N = w_c.shape[0]
         pre_db = _take_colsum(dy, N) if ctx.drop is None else None
         dy = dy.contiguous()
-        g = dropout_apply(dy, ctx.drop) if ctx.drop is not None else dy   # gradient of the pre-dropout GEMM output
         dx = dw = db = None
         side = None
+        g = None
         if ctx.needs_input_grad[1]:
             need_db = ctx.has_bias and pre_db is None
             flat = grad_buffer(N * K + (N if need_db else 0), x.device)
             dw = flat[:N * K].view(N, K)
+            if need_db:
+                db = flat[N * K:]
+            if ctx.drop is not None:       # gradient of the pre-dropout GEMM output (+ its column sums, same pass)
+                g = dropout_colsum(dy, ctx.drop, db) if need_db else dropout_apply(dy, ctx.drop)
+            else:
+                g = dy
             # split-K accumulates atomically when the [N,K] tile grid cannot fill the machine
             epi = EPI_ACCUM if x.dtype == torch.bfloat16 else EPI_NONE
             side = aux_fork(x.device) if ctx.needs_input_grad[0] else None
             with aux_on(side):          # parameter gradients run beside the dgrad GEMM
                 gemm(g, LAYOUT_MN, x, LAYOUT_MN, N, K, M, out=dw, epi=epi)
-                if need_db:
-                    db = flat[N * K:]
+                if need_db and ctx.drop is None:
                     _colsum_into(g, db)
             if ctx.has_bias and pre_db is not None:
                 db = pre_db
-        elif ctx.has_bias and ctx.needs_input_grad[2]:
+        if g is None:
+            g = dropout_apply(dy, ctx.drop) if ctx.drop is not None else dy
+        if dw is None and ctx.has_bias and ctx.needs_input_grad[2]:
             db = pre_db if pre_db is not None else colsum(g)
         if ctx.needs_input_grad[0]:
             if dx_alias is not None:
@@ -267,7 +285,6 @@ class FFNFn(torch.autograd.Function):
         Do = w2_c.shape[0]
         pre_db2 = _take_colsum(dy, Do) if drop_out is None else None
         dy = dy.contiguous()
-        g = dropout_apply(dy, drop_out) if drop_out is not None else dy
         bf = x.dtype == torch.bfloat16
         wepi = EPI_ACCUM if bf else EPI_NONE
         flat = grad_buffer(F * D + F + Do * F + Do, x.device)
@@ -275,14 +292,17 @@ class FFNFn(torch.autograd.Function):
         db1 = flat[F * D:F * D + F]
         dw2 = flat[F * D + F:F * D + F + Do * F].view(Do, F)
         db2 = flat[F * D + F + Do * F:]
+        # dropout(dy) and its column sums (= db2) come out of one pass
+        g = dropout_colsum(dy, drop_out, db2) if drop_out is not None else dy
         # critical path (current stream): dpre -> dx;  auxiliary stream: dW2, db2, then (after dpre) dW1, db1
         side = aux_fork(x.device)
         with aux_on(side):
             gemm(g, LAYOUT_MN, h, LAYOUT_MN, Do, F, M, out=dw2, epi=wepi)
-            if pre_db2 is None:
-                _colsum_into(g, db2)
-            else:
-                db2 = pre_db2
+            if drop_out is None:
+                if pre_db2 is None:
+                    _colsum_into(g, db2)
+                else:
+                    db2 = pre_db2
         dpre = gemm(g, LAYOUT_K, w2_c, LAYOUT_MN, M, F, Do, epi=EPI_DACT, act=ctx.act, aux_in=pre, drop=drop_in)
         side = aux_fork(x.device)       # dW1 / db1 read dpre
         with aux_on(side):
