@@ -116,6 +116,16 @@ int b200_ggemm(const void* A, int lda, const void* B, int b_layout, void* out, i
 int b200_ggemm_wgrad(const void* A, int lda, const void* B, int ldb, float* out, int Mo, int No, int R,
                      int G, const int32_t* group_off, int dtype, void* stream);
 
+/* ---- gated linear unit ------------------------------------------------------------------------- */
+/* GatedLinearExpert (expert_types.py:448-515): pre = fc1(x) is [R, 2F] = [value | gate] (row pitch ld_pre);
+ * h[r,c] = dropout(value[r,c] * sigmoid(gate[r,c]))  (dropout element index = r*F + c).  Backward writes
+ * dpre = [dh*mask*sigmoid(gate) | dh*mask*value*sigmoid'(gate)].  tile_group (may be NULL) skips the rows of unused
+ * 128-row tiles of a grouped expert layout.  fp32 mode uses the same fast sigmoid (ex2/rcp.approx, rel. err ~1e-7). */
+int b200_glu_fwd(const void* pre, int ld_pre, void* h, int R, int F, int dtype, const int32_t* tile_group,
+                 const b200_dropout_t* drop, void* stream);
+int b200_glu_bwd(const void* dh, const void* pre, int ld_pre, void* dpre, int R, int F, int dtype,
+                 const int32_t* tile_group, const b200_dropout_t* drop, void* stream);
+
 /* ---- LayerNorm (+ residual) ------------------------------------------------------------------- */
 /* y = LN(x + res) * gamma[g] + beta[g]   (res may be NULL).  nn.LayerNorm after the residual adds at
  * vqa_model.py:301,305,309, expert_types.py:85-90, moe_layer.py:171, fusion_approaches.py:268-279.
@@ -202,7 +212,8 @@ int b200_moe_permute(const void* x, const int32_t* row_src, const int32_t* pad_o
 /* dx[n,:] = sum_k dxp[dest_row[n,k], :] (+ add[n,:] if add != NULL)   — backward of permute.        */
 int b200_moe_unpermute(const void* dxp, const int32_t* dest_row, const void* add, int N, int K, int D,
                        int dtype, void* dx, void* stream);
-/* out[n,:] = LN_out( sum_k w[n,k] * z[dest_row[n,k], :] )   (moe_layer.py:163-171).                  */
+/* out[n,:] = LN_out( sum_k w[n,k] * z[dest_row[n,k], :] )   (moe_layer.py:163-171).  gamma == NULL: the plain
+ * weighted sum without LayerNorm (HierarchicalMOE, moe_layer.py:489-543; mean / rstd / dgamma / dbeta unused).   */
 int b200_moe_combine_fwd(const void* z, const int32_t* dest_row, const float* w, const float* gamma,
                          const float* beta, float eps, int N, int K, int D, int dtype, void* out,
                          float* mean, float* rstd, void* stream);

@@ -182,7 +182,7 @@ def main():
          grads=grads_of(m))
 
 
-if __name__ == "__main__" and "--r2" not in sys.argv:
+if __name__ == "__main__" and "--r2" not in sys.argv and "--n4" not in sys.argv:
     main()
 
 
@@ -359,5 +359,97 @@ def main_r2():
          sd_keys=np.array(list(sd)), **fingerprint(tensors))
 
 
+def main_n4():
+    """GatedLinearExpert banks and HierarchicalMOE, from the reference's own modules."""
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    from src.modeling.moe.moe_layer import MOELayer, HierarchicalMOE
+    rng = np.random.default_rng(20261020)
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+
+    # ---- MOELayer over GatedLinearExperts ----------------------------------------------------------------------------
+    B, S, D, F, E, K = 3, 20, 64, 96, 4, 2
+    m = MOELayer(input_dim=D, hidden_dim=F, output_dim=D, num_experts=E, top_k=K, expert_type="glu", dropout=0.0)
+    sd = rnd_state_dict(m, 71)
+    m.load_state_dict(sd)
+    m.train()
+    x = f32(rng.standard_normal((B, S, D))).requires_grad_()
+    gout = f32(rng.standard_normal((B, S, D)))
+    out = m(x)
+    ((out * gout).sum() + 2.0 * m.get_aux_loss()).backward()
+    save("glu_moe_layer", cfg=np.array([B, S, D, F, E, K]), sd=sd, x=x, gout=gout, out=out, loss=m.get_aux_loss(),
+         d_x=x.grad, grads=grads_of(m))
+
+    # ---- HierarchicalMOE, homogeneous FFN groups -----------------------------------------------------------------------
+    B, S, D, F, G, Epg, Kg, Ke = 3, 16, 64, 96, 3, 2, 2, 2
+    m = HierarchicalMOE(input_dim=D, hidden_dim=F, output_dim=D, num_expert_groups=G, experts_per_group=Epg,
+                        top_k_groups=Kg, top_k_experts=Ke, dropout=0.0, expert_types=["feedforward"] * G)
+    sd = rnd_state_dict(m, 72)
+    m.load_state_dict(sd)
+    m.train()
+    x = f32(rng.standard_normal((B, S, D))).requires_grad_()
+    gout = f32(rng.standard_normal((B, S, D)))
+    out = m(x)
+    ((out * gout).sum() + 2.0 * m.get_aux_loss()).backward()
+    save("hierarchical_moe_ffn", cfg=np.array([B, S, D, F, G, Epg, Kg, Ke]), sd=sd, x=x, gout=gout, out=out,
+         loss=m.get_aux_loss(), d_x=x.grad, grads=grads_of(m))
+
+    # ---- HierarchicalMOE, default (heterogeneous) groups: expert bodies recorded as data -------------------------------
+    B, S, D, F, G, Epg, Kg, Ke = 2, 6, 64, 96, 4, 2, 2, 1
+    m = HierarchicalMOE(input_dim=D, hidden_dim=F, output_dim=D, num_expert_groups=G, experts_per_group=Epg,
+                        top_k_groups=Kg, top_k_experts=Ke, dropout=0.0)
+    torch.manual_seed(9)
+    for p in m.parameters():
+        if p.dim() >= 2:
+            torch.nn.init.normal_(p, std=1.0 / np.sqrt(p.shape[-1]))
+    kinds = [type(e).__name__ for grp in m.expert_groups for e in grp]
+    m.train()
+    x = f32(rng.standard_normal((B, S, D))).requires_grad_()
+    gout = f32(rng.standard_normal((B, S, D)))
+    ys, hooks = {}, []
+    flat = [e for grp in m.expert_groups for e in grp]
+    for i, ex in enumerate(flat):
+        def hook(mod, inp, outp, i=i):
+            if i not in ys:                       # the reference re-runs an expert per (slot, group): identical outputs
+                outp.retain_grad()
+                ys[i] = []
+            ys[i].append(outp)
+        hooks.append(ex.register_forward_hook(hook))
+    out = m(x)
+    ((out * gout).sum() + 2.0 * m.get_aux_loss()).backward()
+    N = B * S
+    ys_all, d_ys, used = torch.zeros(G * Epg, N, D), torch.zeros(G * Epg, N, D), np.zeros(G * Epg, dtype=np.int64)
+    for i, lst in ys.items():
+        ys_all[i] = lst[0].detach().reshape(N, D)
+        used[i] = 1
+    for h in hooks:
+        h.remove()
+    # router/combine-only gradients: second pass with the experts fed a detached input and every call's output gradient
+    # summed per expert
+    m.zero_grad()
+    x2 = x.detach().clone().requires_grad_()
+    leaves = {i: ys_all[i].view(B, S, D).clone().requires_grad_() for i in range(G * Epg)}
+    restore = []
+    for i, ex in enumerate(flat):
+        f = ex.forward
+        restore.append((ex, f))
+        ex.forward = (lambda i: (lambda t, **kw: leaves[i]))(i)
+    out2 = m(x2)
+    ((out2 * gout).sum() + 2.0 * m.get_aux_loss()).backward()
+    for ex, f in restore:
+        ex.forward = f
+    for i in range(G * Epg):
+        if leaves[i].grad is not None:
+            d_ys[i] = leaves[i].grad.reshape(N, D)
+    g = grads_of(m)
+    keep = {k: v for k, v in g.items() if not k.startswith("expert_groups.")}
+    rsd = {k: v for k, v in m.state_dict().items() if not k.startswith("expert_groups.")}
+    assert float((out2 - out).abs().max()) < 1e-6
+    save("hierarchical_moe_default", cfg=np.array([B, S, D, F, G, Epg, Kg, Ke]), expert_kinds=np.array(kinds), used=used,
+         sd=rsd, x=x, gout=gout, ys=ys_all, d_ys=d_ys, out=out, loss=m.get_aux_loss(), d_x_router=x2.grad, grads=keep)
+
+
 if __name__ == "__main__" and "--r2" in sys.argv:
     main_r2()
+if __name__ == "__main__" and "--n4" in sys.argv:
+    main_n4()

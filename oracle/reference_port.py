@@ -171,9 +171,55 @@ def feed_forward_expert(sd: SD, p: str, x: torch.Tensor, act: str = "gelu", pdro
     return layer_norm(h, sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"])
 
 
+# ---- N4: GatedLinearExpert (expert_types.py:448-515), dropout p = 0 ------------------------------------------------
+def gated_linear_expert(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
+    h = x @ sd[p + "fc1.weight"].t() + sd[p + "fc1.bias"]
+    value, gate = h.chunk(2, dim=-1)
+    h = value * torch.sigmoid(gate)
+    h = h @ sd[p + "fc2.weight"].t() + sd[p + "fc2.bias"]
+    if x.shape[-1] == h.shape[-1]:
+        h = h + x
+    return layer_norm(h, sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"])
+
+
+def token_expert(sd: SD, p: str, x: torch.Tensor, kind: str = "feedforward", act: str = "gelu", pdrop: float = 0.0):
+    return gated_linear_expert(sd, p, x) if kind == "glu" else feed_forward_expert(sd, p, x, act, pdrop)
+
+
+# ---- N4: HierarchicalMOE (moe_layer.py:361-548) -------------------------------------------------------------------
+def hierarchical_moe(sd: SD, x: torch.Tensor, G: int, Epg: int, Kg: int, Ke: int, kind: str = "feedforward",
+                     ys: Optional[torch.Tensor] = None, lb_weight: float = 0.01):
+    """The reference's loop structure: for every group slot k and group g that received a token, group g's expert
+    router is evaluated (and its aux loss added) and the selected experts' outputs are accumulated with weight
+    expert_weight * group_weight under the expert and group masks; then output_proj and output_norm.
+    `ys` [G*Epg, B, S, D] supplies the expert outputs for heterogeneous groups (expert bodies as data)."""
+    gw, gidx, gloss, gprobs, _ = topk_router(sd, "group_router.", x, Kg, lb_weight)
+    out = torch.zeros(x.shape[0], x.shape[1], sd["output_norm.weight"].shape[0], dtype=x.dtype)
+    total_aux = gloss
+    for k in range(Kg):
+        for g in range(G):
+            gmask = (gidx[:, :, k] == g)
+            if not bool(gmask.any()):
+                continue
+            ew, eidx, eloss, _, _ = topk_router(sd, f"expert_routers.{g}.", x, Ke, lb_weight)
+            total_aux = total_aux + eloss
+            gout = torch.zeros_like(out)
+            for ek in range(Ke):
+                for e in range(Epg):
+                    emask = (eidx[:, :, ek] == e)
+                    if not bool(emask.any()):
+                        continue
+                    y = ys[g * Epg + e] if ys is not None else token_expert(sd, f"expert_groups.{g}.{e}.", x, kind)
+                    w = ew[:, :, ek] * gw[:, :, k]
+                    gout = gout + y * w.unsqueeze(-1) * emask.unsqueeze(-1).to(x.dtype)
+            out = out + gout * gmask.unsqueeze(-1).to(x.dtype)
+    out = out @ sd["output_proj.weight"].t() + sd["output_proj.bias"]
+    return layer_norm(out, sd["output_norm.weight"], sd["output_norm.bias"]), total_aux, gprobs
+
+
 # ---- A6: MOELayer dense combine (moe_layer.py:146-171) -------------------------------------------------------------
 def moe_layer(sd: SD, x: torch.Tensor, num_experts: int, top_k: int, lb_weight: float = 0.01, act: str = "gelu",
-              noise=None, noise_std: float = 1.0, weights_indices=None, pdrop: float = 0.0):
+              noise=None, noise_std: float = 1.0, weights_indices=None, pdrop: float = 0.0, kind: str = "feedforward"):
     """The reference's algorithm verbatim in structure: every selected expert is evaluated on ALL tokens and masked
     by its routing weight; accumulation in ascending expert order from a zero tensor; output_norm."""
     if weights_indices is None:
@@ -187,7 +233,7 @@ def moe_layer(sd: SD, x: torch.Tensor, num_experts: int, top_k: int, lb_weight: 
         if not bool(hit.any()):
             continue
         we = (w * hit.to(w.dtype)).sum(dim=-1)
-        out = out + feed_forward_expert(sd, f"experts.{e}.", x, act, pdrop) * we.unsqueeze(-1)
+        out = out + token_expert(sd, f"experts.{e}.", x, kind, act, pdrop) * we.unsqueeze(-1)
     return layer_norm(out, sd["output_norm.weight"], sd["output_norm.bias"]), loss, probs, w, idx
 
 

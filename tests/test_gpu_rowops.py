@@ -47,11 +47,11 @@ def test_add_ln_fwd_bwd(R, D, dtype):
     assert rel_err(y2, torch.nn.functional.layer_norm(x.double(), (D,), gr, btr, 1e-5)) < t
 
 
-@pytest.mark.parametrize("R", [1, 63, 64, 4096, 4097, 20000])
+@pytest.mark.parametrize("R", [1, 63, 64, 4096, 4097, 20000, 116736])
 @pytest.mark.parametrize("N", [768, 100])
 def test_colsum_single_launch_and_two_stage_paths(R, N):
-    """R <= 4096 folds the partials in the last-arriving block (one launch); larger R uses the second-stage kernel;
-    N = 100 exercises the scalar (non-vectorised) variant for bf16."""
+    """Ungrouped column sums are ONE launch for any R (rows per block grow with R; the last-arriving block of a column
+    slab folds at most 64 partials in block order); N = 100 exercises the scalar (non-vectorised) variant for bf16."""
     g = torch.Generator(device=DEV).manual_seed(R + N)
     x = torch.randn(R, N, generator=g, device=DEV)
     for t in (x, x.to(torch.bfloat16)):
@@ -59,10 +59,29 @@ def test_colsum_single_launch_and_two_stage_paths(R, N):
         got = ops.colsum(t.contiguous())
         launches = _lib.launch_count()
         assert rel_err(got, t.double().sum(0)) < 2e-6
-        assert launches == (1 if R <= 4096 else 2), launches
+        assert launches == 1, launches
     # repeated calls reuse (and re-arm) the ticket counters
     for _ in range(3):
         assert rel_err(ops.colsum(x), x.double().sum(0)) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_dropout_colsum_matches_mask_then_sum(dtype):
+    """b200_dropout_colsum: out = x * keep-scales of the site, colsum = column sums of out, in one pass."""
+    from vqa_model_builder_b200 import runtime
+    R, N = 1000, 768
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(R, N, generator=g, device=DEV).to(dtype)
+    st = runtime.dropout_state(torch.device(DEV)).clone()
+    drop = (st, 0.1, 77)
+    mask = torch.empty(R * N, dtype=torch.float32, device=DEV)
+    _lib.call("b200_dropout_mask", _lib.dropout_arg(drop), R * N, mask, _lib.stream_ptr())
+    cs = torch.empty(N, dtype=torch.float32, device=DEV)
+    out = ops.dropout_colsum(x, drop, cs)
+    want = (x.double() * mask.view(R, N).double())
+    assert rel_err(out, want) < (1e-6 if dtype == torch.float32 else 4e-3)
+    assert rel_err(cs, out.double().sum(0)) < 2e-6
+    assert torch.equal(out, ops.dropout_apply(x, drop))
 
 
 def test_colsum_grouped_by_expert_tiles():

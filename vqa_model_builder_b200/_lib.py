@@ -40,6 +40,8 @@ SIGNATURES = {
     "b200_gemm": ("i", "piipiipiiiiiipiippipp"),
     "b200_ggemm": ("i", "pipipiiiiippiipiippipp"),
     "b200_ggemm_wgrad": ("i", "pipipiiiipip"),
+    "b200_glu_fwd": ("i", "pipiiippp"),
+    "b200_glu_bwd": ("i", "ppipiiippp"),
     "b200_add_ln_fwd": ("i", "pppppfpppiiipip"),
     "b200_add_ln_bwd_ws": ("z", "ii"),
     "b200_add_ln_bwd": ("i", "pppppppippppiiipippzp"),

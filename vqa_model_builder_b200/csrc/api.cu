@@ -107,19 +107,24 @@ __device__ __forceinline__ bool last_arrival(unsigned int* ticket, unsigned int 
 
 // fold part[b][c] over the row blocks b: out[g][c] for every group g (groups are contiguous tile ranges of the
 // padded expert layout; tile_group == nullptr: one group)
+// sum of part[b][c] over b = b0, b0 + step, ... < blocks (fixed order: deterministic)
+__device__ __forceinline__ float fold_strided(const float* __restrict__ part, int blocks, int N, int c, int b0, int step) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = b0;
+  for (; b + 3 * step < blocks; b += 4 * step) {
+    s0 += __ldcg(part + (long long)b * N + c);
+    s1 += __ldcg(part + (long long)(b + step) * N + c);
+    s2 += __ldcg(part + (long long)(b + 2 * step) * N + c);
+    s3 += __ldcg(part + (long long)(b + 3 * step) * N + c);
+  }
+  for (; b < blocks; b += step) s0 += __ldcg(part + (long long)b * N + c);
+  return (s0 + s1) + (s2 + s3);
+}
+
 __device__ __forceinline__ void fold_partials(const float* __restrict__ part, int blocks, int N, int c,
                                               const int* __restrict__ tile_group, int G, float* __restrict__ out) {
   if (tile_group == nullptr) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int b = 0;
-    for (; b + 4 <= blocks; b += 4) {
-      s0 += __ldcg(part + (long long)b * N + c);
-      s1 += __ldcg(part + (long long)(b + 1) * N + c);
-      s2 += __ldcg(part + (long long)(b + 2) * N + c);
-      s3 += __ldcg(part + (long long)(b + 3) * N + c);
-    }
-    for (; b < blocks; ++b) s0 += __ldcg(part + (long long)b * N + c);
-    out[c] = (s0 + s1) + (s2 + s3);
+    out[c] = fold_strided(part, blocks, N, c, 0, 1);
     return;
   }
   for (int g = 0; g < G; ++g) out[(long long)g * N + c] = 0.f;
@@ -142,15 +147,16 @@ __device__ __forceinline__ void fold_partials(const float* __restrict__ part, in
 // warp are in flight at a time.  With `drop` the kernel first applies the dropout keep-scales of the site (element
 // index = row * N + col), stores the scaled rows to `gout` and sums THOSE: the backward of "dropout(x W^T + b) +
 // residual" needs both dropout(dy) (operand of the dgrad / wgrad GEMMs) and its column sums (the bias gradient).
+constexpr int CS_WARPS = 16;
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(CS_WARPS * 32)
 colsum_stage1(const T* __restrict__ x, int R, int N, int rpb, float* __restrict__ part,
               const int* __restrict__ tile_group, int G, float* __restrict__ out, unsigned int* __restrict__ tickets,
               T* __restrict__ gout, const unsigned long long* drop_state, float drop_p, unsigned int drop_site) {
   pdl_trigger();
   pdl_wait();
   constexpr int VT = Vec16<T>::N;
-  __shared__ float red[8][32 * VT];
+  __shared__ float red[CS_WARPS][32 * VT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = (blockIdx.x * 32 + lane) * VT;
   const int r0 = blockIdx.y * rpb, r1 = min(R, r0 + rpb);
@@ -161,16 +167,16 @@ colsum_stage1(const T* __restrict__ x, int R, int N, int rpb, float* __restrict_
   // rows of unused 128-row tiles (expert-parallel buffers are sized for the worst case) are never read
   const bool live = tile_group == nullptr || tile_group[r0 / B200_GROUP_TILE] >= 0;
   if (col < N && live) {
-    for (int rb = r0 + warp; rb < r1; rb += 32) {
+    for (int rb = r0 + warp; rb < r1; rb += 4 * CS_WARPS) {
       Vec16<T> v[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = rb + 8 * q;
+      for (int q = 0; q < 4; ++q) {           // four row loads in flight per warp
+        const int r = rb + CS_WARPS * q;
         if (r < r1) v[q].load(x + (long long)r * N + col);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int r = rb + 8 * q;
+        const int r = rb + CS_WARPS * q;
         if (r < r1) {
           if (ds.on) {
             const unsigned long long base = (unsigned long long)r * N + col;
@@ -196,20 +202,37 @@ colsum_stage1(const T* __restrict__ x, int R, int N, int rpb, float* __restrict_
 #pragma unroll
   for (int u = 0; u < VT; ++u) red[warp][lane * VT + u] = acc[u];
   __syncthreads();
-  for (int c = threadIdx.x; c < 32 * VT; c += 256) {
+  for (int c = threadIdx.x; c < 32 * VT; c += blockDim.x) {
     const int gc = blockIdx.x * 32 * VT + c;
     if (gc < N) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w][c];
+      for (int w = 0; w < CS_WARPS; ++w) s += red[w][c];
       part[(long long)blockIdx.y * N + gc] = s;
     }
   }
   if (tickets == nullptr) return;                     // grouped: a second kernel folds per expert in parallel
   if (!last_arrival(tickets + blockIdx.x, gridDim.y)) return;
-  for (int c = threadIdx.x; c < 32 * VT; c += 256) {
-    const int gc = blockIdx.x * 32 * VT + c;
-    if (gc < N) fold_partials(part, gridDim.y, N, gc, tile_group, G, out);
+  // fold the (at most 64) partials of this column slab: every thread sums a strided subset of the row blocks of one
+  // column, the subsets are combined through shared memory in a fixed order
+  constexpr int COLS = 32 * VT;
+  constexpr int SUB = (CS_WARPS * 32) / COLS >= 1 ? (CS_WARPS * 32) / COLS : 1;     // threads per column
+  float* fold = &red[0][0];
+  __syncthreads();
+  for (int i = threadIdx.x; i < COLS * SUB; i += blockDim.x) {
+    const int c = i % COLS, sub = i / COLS;
+    const int gc = blockIdx.x * COLS + c;
+    fold[sub * COLS + c] = gc < N ? fold_strided(part, gridDim.y, N, gc, sub, SUB) : 0.f;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < COLS; c += blockDim.x) {
+    const int gc = blockIdx.x * COLS + c;
+    if (gc < N) {
+      float s = 0.f;
+#pragma unroll
+      for (int sub = 0; sub < SUB; ++sub) s += fold[sub * COLS + c];
+      out[gc] = s;
+    }
   }
 }
 // scalar fallback for widths that are not a multiple of the vector length
@@ -361,8 +384,8 @@ static int launch_colsum(const void* x, void* gout, const b200_dropout_t* drop, 
   const float dp = don ? drop->p : 0.f;
   const unsigned int dsite = don ? drop->site : 0u;
   if (vec) {
-    if (dtype == B200_F32) launch_kernel(colsum_stage1<float>, dim3(g1), dim3(256), 0, stream, (const float*)x, R, N, rpb, part, tile_group, G, out, tk, (float*)gout, dst, dp, dsite);
-    else launch_kernel(colsum_stage1<bf16>, dim3(g1), dim3(256), 0, stream, (const bf16*)x, R, N, rpb, part, tile_group, G, out, tk, (bf16*)gout, dst, dp, dsite);
+    if (dtype == B200_F32) launch_kernel(colsum_stage1<float>, dim3(g1), dim3(CS_WARPS * 32), 0, stream, (const float*)x, R, N, rpb, part, tile_group, G, out, tk, (float*)gout, dst, dp, dsite);
+    else launch_kernel(colsum_stage1<bf16>, dim3(g1), dim3(CS_WARPS * 32), 0, stream, (const bf16*)x, R, N, rpb, part, tile_group, G, out, tk, (bf16*)gout, dst, dp, dsite);
   } else {
     if (dtype == B200_F32) launch_kernel(colsum_stage1_scalar<float>, dim3(g1), dim3(128), 0, stream, (const float*)x, R, N, rpb, part, tile_group, G, out, tk);
     else launch_kernel(colsum_stage1_scalar<bf16>, dim3(g1), dim3(128), 0, stream, (const bf16*)x, R, N, rpb, part, tile_group, G, out, tk);

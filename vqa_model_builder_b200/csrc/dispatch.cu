@@ -212,6 +212,10 @@ combine_fwd_kernel(const T* __restrict__ z, const int* __restrict__ dest_row, co
       const float wk = w[n * K + k];
       if (d >= 0 && wk != 0.f) acc.axpy(z + (long long)d * D, wk, D, lane);
     }
+    if (gamma == nullptr) {      // plain weighted sum (HierarchicalMOE applies output_proj before its LayerNorm)
+      acc.store(out + (long long)n * D, D, lane);
+      continue;
+    }
     const float mean = acc.sum(D, lane) / D;
     const float var = acc.sumsq_centered(mean, D, lane) / D;
     const float rstd = rsqrtf(var + eps);
@@ -266,12 +270,13 @@ combine_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ z, const in
       if (d >= 0 && wk != 0.f) s.axpy(z + (long long)d * D, wk, D, lane);
     }
     g.load(dout + (long long)n * D, D, lane);
-    const float mean = mean_in[n], rstd = rstd_in[n];
+    const bool norm = gamma != nullptr;
+    const float mean = norm ? mean_in[n] : 0.f, rstd = norm ? rstd_in[n] : 1.f;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int vi = lane + 32 * j;
-      if (vi < nv) {
+      if (vi < nv && norm) {
         float gv[VT];
         load_param<VT>(gamma, vi, gv);
         float* ag = acc_g + vi * VT;
@@ -298,12 +303,14 @@ combine_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ z, const in
         }
       }
     }
-    s1 = warp_sum(s1) / D;
-    s2 = warp_sum(s2) / D;
+    if (norm) {
+      s1 = warp_sum(s1) / D;
+      s2 = warp_sum(s2) / D;
 #pragma unroll
-    for (int j = 0; j < NV; ++j)
+      for (int j = 0; j < NV; ++j)
 #pragma unroll
-      for (int u = 0; u < VT; ++u) g.v[j][u] = rstd * (g.v[j][u] - s1 - s.v[j][u] * s2);  // ds
+        for (int u = 0; u < VT; ++u) g.v[j][u] = rstd * (g.v[j][u] - s1 - s.v[j][u] * s2);  // ds
+    }                                                                                      // else ds = dout
     for (int k = 0; k < K; ++k) {
       const int d = dest_row[n * K + k];
       const float wk = w[n * K + k];
@@ -516,6 +523,7 @@ int b200_moe_combine_bwd(const void* dout, const void* z, const int32_t* dest_ro
   }
   B200_LAUNCH_CHECK("combine_bwd_kernel");
   count_launch(2);
+  if (gamma == nullptr) return 0;       // plain weighted sum: no LayerNorm parameters
   return launch_ln_param_reduce(part, blocks, tokens_per_block, D, nullptr, 1, dgamma, dbeta, stream);
 }
 

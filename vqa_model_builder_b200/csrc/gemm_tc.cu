@@ -31,15 +31,23 @@ constexpr int CHUNK_BYTES = 64 * BK * 2;  // one 64(MN) x 64(K) MN-major TMA box
 constexpr int NUM_EPI_WARPS = B200_EPI_WARPS;      // multiple of 4: one warp per TMEM lane quadrant and column part
 constexpr int EPI_PARTS = NUM_EPI_WARPS / 4;
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
-constexpr int STG_PITCH = 144;                     // bytes per staged row: 128 B payload + 16 B pad (bank spread)
-constexpr int STG_BYTES = 32 * STG_PITCH;          // per epilogue warp
-constexpr int BIAS_FLOATS = 128;                   // per epilogue warp: the columns of its (at most 4) chunks
+// Epilogue staging (per warp, 4 KB): a 32 x 32 tile goes thread-row -> shared -> row-contiguous global accesses.
+//   bf16 tiles: 64-byte rows at a pitch of 80 bytes (the 16-byte pad spreads the banks);
+//   fp32 tiles: 128-byte rows at a pitch of 128 bytes, the 16-byte units of row r XOR-swizzled by (r & 7).
+// Keeping the buffer at 4 KB (no padded fp32 rows, no bias copy: a lane holds one bias value and broadcasts it with
+// shuffles) is what leaves room for a FOURTH 48 KB pipeline stage of the 128 x 256 tile: with three stages only two
+// k-blocks are in flight behind the one being multiplied (0.55 us of cover for ~1 us of TMA latency) and the tensor
+// pipe idled half of the time (ncu: sm__pipe_tensor_cycles_active 44-53 % on the large GEMMs, profiles/r02e).
+constexpr int STG_PITCH_BF16 = 80;
+constexpr int STG_BYTES = 32 * 128;                // per epilogue warp
 
-template <int BN> constexpr int num_stages() { return BN == 256 ? 3 : (BN == 128 ? 5 : 6); }
+template <int BN> constexpr int num_stages() { return BN == 256 ? 4 : (BN == 128 ? 6 : 8); }
 template <int BN> constexpr int stage_bytes() { return A_BYTES + BN * BK * 2; }
 template <int BN> constexpr int smem_bytes() {
-  return num_stages<BN>() * stage_bytes<BN>() + NUM_EPI_WARPS * (STG_BYTES + BIAS_FLOATS * 4) + 1024 + 256;
+  return num_stages<BN>() * stage_bytes<BN>() + NUM_EPI_WARPS * STG_BYTES + 1024 + 256;
 }
+static_assert(smem_bytes<256>() <= 227 * 1024 && smem_bytes<128>() <= 227 * 1024 && smem_bytes<64>() <= 227 * 1024,
+              "pipeline stages + epilogue staging must fit the 227 KB a CTA can own");
 
 struct TileInfo {
   int valid, group, m_tile, n_tile;
@@ -164,50 +172,54 @@ __device__ __forceinline__ void tile_act_bwd(float (&v)[32], const float (&aux)[
 
 // ---- epilogue helpers: a warp moves a 32-row x 32-column tile between registers (thread = row) and global
 // memory (row-contiguous 16-byte accesses) through its padded staging buffer -----------------------------------
+// byte offset of 16-byte unit `u` of staged row `r`
+template <int ELEM_BYTES>
+__device__ __forceinline__ int stg_off(int r, int u) {
+  return ELEM_BYTES == 2 ? r * STG_PITCH_BF16 + 16 * u : r * 128 + 16 * (u ^ (r & 7));
+}
+
 template <int ELEM_BYTES>  // 2 (bf16) or 4 (fp32)
 __device__ __forceinline__ void stage_store_tile(uint8_t* stg, int lane, const float (&v)[32], void* gbase, long long ld,
                                                  long long row0, int rows_ok, int col0) {
   constexpr int ROW_BYTES = 32 * ELEM_BYTES;       // 64 or 128
   constexpr int LPR = ROW_BYTES / 16;              // lanes per row: 4 or 8
   constexpr int RPI = 32 / LPR;                    // rows per instruction: 8 or 4
-  uint8_t* mine = stg + lane * STG_PITCH;
   if (ELEM_BYTES == 2) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint4 t;
       t.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); t.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
       t.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); t.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-      *reinterpret_cast<uint4*>(mine + 16 * j) = t;
+      *reinterpret_cast<uint4*>(stg + stg_off<2>(lane, j)) = t;
     }
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<float4*>(mine + 16 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      *reinterpret_cast<float4*>(stg + stg_off<4>(lane, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
   __syncwarp();
   const int sub = lane % LPR, rsel = lane / LPR;
-  // running pointers (one 64-bit add per row instead of a 64-bit multiply-add chain)
+  // running pointer (one 64-bit add per row instead of a 64-bit multiply-add chain)
   uint8_t* dst = reinterpret_cast<uint8_t*>(gbase) + ((row0 + rsel) * ld + col0) * ELEM_BYTES + 16 * sub;
   const long long dstep = (long long)RPI * ld * ELEM_BYTES;
-  const uint8_t* src = stg + rsel * STG_PITCH + 16 * sub;
 #pragma unroll
   for (int i = 0; i < 32 / RPI; ++i) {
-    if (i * RPI + rsel < rows_ok) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+    const int r = i * RPI + rsel;
+    if (r < rows_ok) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(stg + stg_off<ELEM_BYTES>(r, sub));
     dst += dstep;
-    src += RPI * STG_PITCH;
   }
   __syncwarp();
 }
 
 __device__ __forceinline__ void stage_accum_tile(uint8_t* stg, int lane, const float (&v)[32], float* gbase, long long ld,
                                                  long long row0, int rows_ok, int col0) {
-  uint8_t* mine = stg + lane * STG_PITCH;
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(mine + 16 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    *reinterpret_cast<float4*>(stg + stg_off<4>(lane, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   __syncwarp();
   for (int r = 0; r < rows_ok; ++r)   // one row (32 consecutive floats) per warp instruction
-    atomicAdd(gbase + (row0 + r) * ld + col0 + lane, *reinterpret_cast<const float*>(stg + r * STG_PITCH + 4 * lane));
+    atomicAdd(gbase + (row0 + r) * ld + col0 + lane,
+              *reinterpret_cast<const float*>(stg + stg_off<4>(r, lane >> 2) + 4 * (lane & 3)));
   __syncwarp();
 }
 
@@ -224,12 +236,11 @@ __device__ __forceinline__ void stage_load_tile_bf16(uint8_t* stg, int lane, flo
     src += sstep;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + (i * 8 + rsel) * STG_PITCH + 16 * sub) = t[i];
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + stg_off<2>(i * 8 + rsel, sub)) = t[i];
   __syncwarp();
-  const uint8_t* mine = stg + lane * STG_PITCH;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const uint4 t = *reinterpret_cast<const uint4*>(mine + 16 * j);
+    const uint4 t = *reinterpret_cast<const uint4*>(stg + stg_off<2>(lane, j));
     const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
     v[8 * j + 0] = a.x; v[8 * j + 1] = a.y; v[8 * j + 2] = b.x; v[8 * j + 3] = b.y;
     v[8 * j + 4] = c.x; v[8 * j + 5] = c.y; v[8 * j + 6] = d.x; v[8 * j + 7] = d.y;
@@ -248,8 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   uint8_t* stg_all = smem + STAGES * STAGE;
-  float* bias_all = reinterpret_cast<float*>(stg_all + NUM_EPI_WARPS * STG_BYTES);
-  const uint32_t bar0 = base + STAGES * STAGE + NUM_EPI_WARPS * (STG_BYTES + BIAS_FLOATS * 4);
+  const uint32_t bar0 = base + STAGES * STAGE + NUM_EPI_WARPS * STG_BYTES;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
@@ -360,7 +370,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int part = ew >> 2;                // this warp handles chunks part, part + EPI_PARTS, ...
     constexpr int NCHUNK = BN / 32;
     uint8_t* stg = stg_all + ew * STG_BYTES;
-    float* bias_s = bias_all + ew * BIAS_FLOATS;
     const bool out_bf16 = !p.out_f32;
     // fast path: every 16-byte group of a row is either fully inside or fully outside the matrix
     const bool vec_ok = (p.N % 8 == 0) && (p.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
@@ -376,16 +385,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int acc = acc_it & 1;
       const uint32_t acc_ph = (acc_it >> 1) & 1;
       const int ncol0 = t.n_tile * BN;                          // first column of the tile
-      // bias slice of this warp -> shared memory (broadcast reads later)
       const float* bias = p.bias;
-      if (bias != nullptr) {
-        if (p.mode == GEMM_GROUP_ROWS) bias += (long long)t.group * p.N;
-        for (int c = part, k = 0; c < NCHUNK; c += EPI_PARTS, ++k) {
-          const int col = ncol0 + c * 32 + lane;
-          bias_s[k * 32 + lane] = (col < p.N) ? __ldg(bias + col) : 0.f;
-        }
-        __syncwarp();
-      }
+      if (bias != nullptr && p.mode == GEMM_GROUP_ROWS) bias += (long long)t.group * p.N;
       if (have_acc) {
         ptx::mbar_wait(tmem_full_bar(acc), acc_ph);
         ptx::tc_fence_after();
@@ -411,9 +412,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         if (col0 >= p.N) continue;               // warp-uniform
         if (vec_ok && col0 + 32 <= p.N) {
-          if (bias != nullptr) {
+          if (bias != nullptr) {      // lane j holds the bias of column col0 + j: one coalesced load, 32 broadcasts
+            const float bl = __ldg(bias + col0 + lane);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += bias_s[k * 32 + j];
+            for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
           }
           if (p.epi == B200_EPI_ACT) {
             if (p.aux_out != nullptr) stage_store_tile<2>(stg, lane, v, p.aux_out, p.ld_aux, row0, rows_ok, col0);
@@ -551,7 +553,9 @@ int launch_gemm_tc(const void* A, int lda, int a_layout, long long a_mn_extent, 
   const int kblocks = args.mode == GEMM_GROUP_WGRAD ? (int)((a_k_extent / (groups > 0 ? groups : 1) + BK - 1) / BK)
                                                     : (args.K + BK - 1) / BK;
   const bool can_split = args.mode == GEMM_DENSE && args.epi == B200_EPI_ACCUM;
-  const float epi256 = (args.epi == B200_EPI_ACT || args.epi == B200_EPI_DACT) ? 40.f
+  // epilogue of a 128 x 256 tile in k-block units (8 warps, 32 x 32 chunks): GELU / GELU' ~ 1 000 warp instructions per
+  // chunk (profiles/r01o_ncu_source_gemm_act_after.txt) = about 9 k-blocks; it overlaps the next tile's main loop
+  const float epi256 = (args.epi == B200_EPI_ACT || args.epi == B200_EPI_DACT) ? 9.f
                        : (args.epi == B200_EPI_ACCUM ? 8.f : (args.epi == B200_EPI_ADD ? 5.f : 3.f));
   int bn = 64, splits = 1;
   float best = 1e30f;

@@ -226,15 +226,15 @@ inline int ln_bwd_rpw(int R) {
 // 32 columns x 8 partial-lanes per block: loads are independent across threads instead of one serial chain.
 // Expert segments are contiguous tile ranges, so the block first finds [first,last] tile of its group (parallel scan
 // of the tile map) and then walks only that block range — no per-iteration indirection through tile_group.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 partial_reduce_kernel(const float* __restrict__ part, int blocks, int rows_per_block, int width, int nz,
                       const int* __restrict__ tile_group, int tiles, float* __restrict__ out0,
                       float* __restrict__ out1, float* __restrict__ out2) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
   __shared__ int s_lo, s_hi;
-  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;     // 32 columns x 32 partial lanes
   const int c = blockIdx.x * 32 + x;
   const int g = blockIdx.y, z = blockIdx.z;
   int b_lo = 0, b_hi = blocks;
@@ -248,16 +248,26 @@ partial_reduce_kernel(const float* __restrict__ part, int blocks, int rows_per_b
     b_lo = s_lo * bpt;
     b_hi = min(blocks, (s_hi + 1) * bpt);
   }
-  float s = 0.f;
+  // four independent loads in flight per thread; the order of the additions is fixed (deterministic result)
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (c < width) {
-    for (int b = b_lo + y; b < b_hi; b += 8) s += part[((long long)b * nz + z) * width + c];
+    const float* p = part + (long long)z * width + c;
+    const long long step = (long long)nz * width;
+    int b = b_lo + y;
+    for (; b + 96 < b_hi; b += 128) {
+      s0 += p[(long long)b * step];
+      s1 += p[(long long)(b + 32) * step];
+      s2 += p[(long long)(b + 64) * step];
+      s3 += p[(long long)(b + 96) * step];
+    }
+    for (; b < b_hi; b += 32) s0 += p[(long long)b * step];
   }
-  red[y][x] = s;
+  red[y][x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (y == 0 && c < width) {
     float t = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) t += red[j][x];
+    for (int j = 0; j < 32; ++j) t += red[j][x];
     (z == 0 ? out0 : (z == 1 ? out1 : out2))[(long long)g * width + c] = t;
   }
 }
@@ -270,7 +280,7 @@ int launch_ln_param_reduce(const float* part, int blocks, int rows_per_block, in
   const int nz = dcol != nullptr ? 3 : 2;
   dim3 grid((D + 31) / 32, G, nz);
   const int tiles = (int)(((long long)blocks * rows_per_block + B200_GROUP_TILE - 1) / B200_GROUP_TILE);
-  launch_kernel(partial_reduce_kernel, dim3(grid), dim3(256), 0, stream, part, blocks, rows_per_block, D, nz, tile_group, tiles, dgamma, dbeta, dcol);
+  launch_kernel(partial_reduce_kernel, dim3(grid), dim3(1024), 0, stream, part, blocks, rows_per_block, D, nz, tile_group, tiles, dgamma, dbeta, dcol);
   B200_LAUNCH_CHECK("partial_reduce_kernel");
   count_launch();
   return 0;
@@ -281,7 +291,7 @@ int launch_partial_reduce(const float* part, int blocks, int rows_per_block, int
                           float* out, cudaStream_t stream) {
   dim3 grid((width + 31) / 32, G, 1);
   const int tiles = (int)(((long long)blocks * rows_per_block + B200_GROUP_TILE - 1) / B200_GROUP_TILE);
-  launch_kernel(partial_reduce_kernel, dim3(grid), dim3(256), 0, stream, part, blocks, rows_per_block, width, 1, tile_group, tiles, out, out, out);
+  launch_kernel(partial_reduce_kernel, dim3(grid), dim3(1024), 0, stream, part, blocks, rows_per_block, width, 1, tile_group, tiles, out, out, out);
   B200_LAUNCH_CHECK("partial_reduce_kernel");
   count_launch();
   return 0;

@@ -45,7 +45,7 @@ def install(verbose: bool = False) -> Dict[str, str]:
                         ref_special.SceneUnderstandingExpert],
     }
     for kind, cls in (("vision", ref_experts.VisionExpert), ("text", ref_experts.TextExpert),
-                      ("multimodal", ref_experts.MultimodalExpert), ("glu", ref_experts.GatedLinearExpert)):
+                      ("multimodal", ref_experts.MultimodalExpert)):      # 'feedforward' and 'glu' are native
         _moe.register_expert_type(kind, cls)
 
     done: Dict[str, str] = {}
@@ -59,11 +59,12 @@ def install(verbose: bool = False) -> Dict[str, str]:
     moe_syms = {"MOELayer": _moe.MOELayer, "SparseMOELayer": _moe.SparseMOELayer, "VQAMOELayer": _moe.VQAMOELayer,
                 "TopKRouter": _moe.TopKRouter, "NoisyTopKRouter": _moe.NoisyTopKRouter,
                 "create_router": _moe.create_router, "FeedForwardExpert": _moe.FeedForwardExpert,
+                "GatedLinearExpert": _moe.GatedLinearExpert, "HierarchicalMOE": _moe.HierarchicalMOE,
                 "create_expert": _moe.create_expert}
     bind_all(ref_moe, moe_syms)              # `from src.modeling.moe import VQAMOELayer` (vqa_model.py:529)
     bind_all(ref_layer, moe_syms)
     bind_all(ref_router, {k: moe_syms[k] for k in ("TopKRouter", "NoisyTopKRouter", "create_router")})
-    bind_all(ref_experts, {k: moe_syms[k] for k in ("FeedForwardExpert", "create_expert")})
+    bind_all(ref_experts, {k: moe_syms[k] for k in ("FeedForwardExpert", "GatedLinearExpert", "create_expert")})
     bind_all(ref_vqa, {"MultimodalFusion": _fusion.MultimodalFusion,           # vqa_model.py:503
                        "CrossModalAttention": _fusion.CrossModalAttention,     # vqa_model.py:331
                        "AnswerHead": _heads.AnswerHead})                       # vqa_model.py:436

@@ -103,7 +103,47 @@ class FeedForwardExpert(BaseExpert):
         return ops.to_compute(y, x.dtype).view(*lead, self.output_dim)
 
 
-_EXPERTS = {"feedforward": FeedForwardExpert}
+class GatedLinearExpert(BaseExpert):
+    """expert_types.py:448-515: [value | gate] = fc1(x) (2 * hidden wide); h = drop(value * sigmoid(gate));
+    out = LN( drop(fc2 h) + x ) (residual only when input_dim == output_dim).  Token-wise, so MOELayer evaluates a bank
+    of these through the same grouped GEMMs as FeedForwardExpert (ops.ExpertFFNFn with ACT_GLU)."""
+
+    activation_name = "glu"
+
+    def __init__(self, input_dim: int = 768, hidden_dim: int = 3072, output_dim: int = 768,
+                 expert_id: Optional[int] = None, dropout: float = 0.1):
+        super().__init__(input_dim, hidden_dim, output_dim, expert_id, dropout)
+        self.fc1 = nn.Linear(input_dim, hidden_dim * 2)
+        self.fc2 = nn.Linear(hidden_dim, output_dim)
+        self.dropout = nn.Dropout(dropout)
+        self.layer_norm = nn.LayerNorm(output_dim)
+        self._sites = alloc_sites(2)
+
+    @property
+    def act_code(self) -> int:
+        return ops.ACT_GLU
+
+    def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
+        lead = x.shape[:-1]
+        cdt = resolve_compute_dtype(x)
+        x2 = ops.to_compute(x.reshape(-1, x.shape[-1]), cdt)
+        w1, w2 = self.fc1.weight, self.fc2.weight
+        w1c = w1.detach() if cdt == torch.float32 else ops.cast(w1.detach(), cdt)
+        w2c = w2.detach() if cdt == torch.float32 else ops.cast(w2.detach(), cdt)
+        dc = DropCtx(self.training, float(self.dropout_rate), x.device, self._sites)
+        pre = ops.LinearFn.apply(x2, w1, self.fc1.bias, w1c, None)
+        h = ops.GLUFn.apply(pre, dc.site(0))
+        h = ops.LinearFn.apply(h, w2, self.fc2.bias, w2c, None)
+        if x.shape[-1] == self.output_dim:   # LN(dropout(h) + x)
+            y = ops.AddLNFn.apply(x2, h, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps, dc.site(1))
+        else:
+            if dc.on:
+                h = ops.DropoutFn.apply(h, dc.site(1))
+            y = ops.AddLNFn.apply(h, None, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps, None)
+        return ops.to_compute(y, x.dtype).view(*lead, self.output_dim)
+
+
+_EXPERTS = {"feedforward": FeedForwardExpert, "glu": GatedLinearExpert}
 
 
 def register_expert_type(name: str, cls) -> None:

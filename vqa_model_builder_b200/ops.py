@@ -318,6 +318,44 @@ class FFNFn(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2, None, None, None, (dy if ctx.has_res else None), None, None, None
 
 
+# ---- gated linear unit ---------------------------------------------------------------------------------------------
+ACT_GLU = -1     # Python-side marker: the hidden activation of an expert bank is a gated linear unit
+
+
+def glu_fwd(pre: torch.Tensor, F: int, drop=None, tile_group=None) -> torch.Tensor:
+    R = pre.shape[0]
+    h = torch.empty((R, F), dtype=pre.dtype, device=pre.device)
+    call("b200_glu_fwd", pre, pre.stride(0), h, R, F, dtype_code(pre.dtype), tile_group, dropout_arg(drop), stream_ptr())
+    return h
+
+
+def glu_bwd(dh: torch.Tensor, pre: torch.Tensor, F: int, drop=None, tile_group=None) -> torch.Tensor:
+    R = pre.shape[0]
+    dpre = torch.empty_like(pre)
+    call("b200_glu_bwd", dh.contiguous(), pre, pre.stride(0), dpre, R, F, dtype_code(pre.dtype), tile_group,
+         dropout_arg(drop), stream_ptr())
+    return dpre
+
+
+class GLUFn(torch.autograd.Function):
+    """h = dropout(value * sigmoid(gate)) with [value | gate] = pre [R, 2F]  (GatedLinearExpert, expert_types.py:497-501)."""
+
+    @staticmethod
+    def forward(ctx, pre, drop=None):
+        _lib.ensure_device(pre)
+        pre = pre.contiguous()
+        F = pre.shape[1] // 2
+        ctx.save_for_backward(pre)
+        ctx.cfg = (F, drop)
+        return glu_fwd(pre, F, drop)
+
+    @staticmethod
+    def backward(ctx, dh):
+        (pre,) = ctx.saved_tensors
+        F, drop = ctx.cfg
+        return glu_bwd(dh, pre, F, drop), None
+
+
 # ---- residual add + LayerNorm ------------------------------------------------------------------------------
 class AddLNFn(torch.autograd.Function):
     """y = LayerNorm(x + dropout(branch))   (post-LN residual blocks, vqa_model.py:301,305,309); branch may be None."""
@@ -589,18 +627,24 @@ class ExpertFFNFn(torch.autograd.Function):
         _lib.ensure_device(xp)
         drop_in, drop_out = drops if drops is not None else (None, None)
         R, D = xp.shape
-        w1s, b1s, w2s, b2s, lng, lnb = stacks  # [E,F,D] c, [E,F] f32, [E,Do,F] c, [E,Do] f32, [E,Do] f32 x2
-        E, F = w1s.shape[0], w1s.shape[1]
-        Do = w2s.shape[1]
+        w1s, b1s, w2s, b2s, lng, lnb = stacks  # [E,F1,D] c, [E,F1] f32, [E,Do,F] c, [E,Do] f32, [E,Do] f32 x2
+        E, F1 = w1s.shape[0], w1s.shape[1]     # F1 = F, or 2F for gated (GLU) experts: fc1 emits [value | gate]
+        Do, F = w2s.shape[1], w2s.shape[2]
+        gated = act == ACT_GLU
         dt = dtype_code(xp.dtype)
         st = stream_ptr()
         dev = xp.device
         rows_used = pad_off[E:E + 1]          # rows in use (device): tiles beyond are never visited
         ctx.local = _LOCAL[0]
-        pre = torch.empty((R, F), dtype=xp.dtype, device=dev)
-        h = torch.empty((R, F), dtype=xp.dtype, device=dev)
-        call("b200_ggemm", xp, D, w1s, LAYOUT_K, h, F, R, F, D, E, tile_group, rows_used, dt, dt, b1s, EPI_ACT, act, None, pre, F,
-             dropout_arg(drop_in), st)
+        pre = torch.empty((R, F1), dtype=xp.dtype, device=dev)
+        if gated:
+            call("b200_ggemm", xp, D, w1s, LAYOUT_K, pre, F1, R, F1, D, E, tile_group, rows_used, dt, dt, b1s, EPI_NONE,
+                 ACT_NONE, None, None, 0, None, st)
+            h = glu_fwd(pre, F, drop_in, tile_group)
+        else:
+            h = torch.empty((R, F), dtype=xp.dtype, device=dev)
+            call("b200_ggemm", xp, D, w1s, LAYOUT_K, h, F, R, F, D, E, tile_group, rows_used, dt, dt, b1s, EPI_ACT, act,
+                 None, pre, F, dropout_arg(drop_in), st)
         y2 = torch.empty((R, Do), dtype=xp.dtype, device=dev)
         call("b200_ggemm", h, F, w2s, LAYOUT_K, y2, Do, R, Do, F, E, tile_group, rows_used, dt, dt, b2s, EPI_NONE, ACT_NONE, None,
              None, 0, None, st)
@@ -610,21 +654,22 @@ class ExpertFFNFn(torch.autograd.Function):
         call("b200_add_ln_fwd", y2, xp if residual else None, lng, lnb, tile_group, float(eps), z, mean_e, rstd_e, R,
              Do, dt, dropout_arg(drop_out), 1 if drop_out is not None else 0, st)
         ctx.save_for_backward(xp, pre, h, y2, mean_e, rstd_e, w1s, w2s, lng, tile_group, pad_off)
-        ctx.cfg = (R, D, E, F, Do, act, residual)
+        ctx.cfg = (R, D, E, F, Do, act, residual, F1)
         ctx.drops = (drop_in, drop_out)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         xp, pre, h, y2, mean_e, rstd_e, w1s, w2s, lng, tile_group, pad_off = ctx.saved_tensors
-        R, D, E, F, Do, act, residual = ctx.cfg
+        R, D, E, F, Do, act, residual, F1 = ctx.cfg
+        gated = act == ACT_GLU
         dz = dz.contiguous()
         dev = dz.device
         dt = dtype_code(dz.dtype)
         st = stream_ptr()
         rows_used = pad_off[E:E + 1]
         # one flat fp32 buffer for every parameter gradient of the expert bank (one DP all-reduce bucket)
-        sizes = [E * F * D, E * F, E * Do * F, E * Do, E * Do, E * Do]
+        sizes = [E * F1 * D, E * F1, E * Do * F, E * Do, E * Do, E * Do]
         flat = grad_buffer(sum(sizes), dev, local=ctx.local)
         offs = [0]
         for sz in sizes:
@@ -638,34 +683,40 @@ class ExpertFFNFn(torch.autograd.Function):
         call("b200_add_ln_bwd", dz, y2, xp if residual else None, mean_e, rstd_e, lng, tile_group, E, dsum, dlng, dlnb,
              db2, R, Do, dt, dropout_arg(drop_out), 1 if drop_out is not None else 0,
              dr if drop_out is not None else None, ws, nb, st)      # db2 = per-expert column sums of dr, fused
-        nb = query("b200_colsum_ws", R, max(F, Do))
+        nb = query("b200_colsum_ws", R, max(F1, Do))
         ws = _ws(nb, dev)
         # critical path (current stream): dpre -> dxp;  auxiliary stream: db2, dW2, then (after dpre) db1, dW1
         side = aux_fork(dev)
         with aux_on(side):
             sa = stream_ptr()
             call("b200_ggemm_wgrad", dr, Do, h, F, dw2, Do, F, R, E, pad_off, dt, sa)
-        dpre = torch.empty((R, F), dtype=dz.dtype, device=dev)
-        call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, tile_group, rows_used, dt, dt, None, EPI_DACT, act, pre,
-             None, F, dropout_arg(drop_in), st)
+        if gated:
+            dh = torch.empty((R, F), dtype=dz.dtype, device=dev)
+            call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dh, F, R, F, Do, E, tile_group, rows_used, dt, dt, None, EPI_NONE,
+                 ACT_NONE, None, None, 0, None, st)
+            dpre = glu_bwd(dh, pre, F, drop_in, tile_group)
+        else:
+            dpre = torch.empty((R, F), dtype=dz.dtype, device=dev)
+            call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, tile_group, rows_used, dt, dt, None, EPI_DACT,
+                 act, pre, None, F, dropout_arg(drop_in), st)
         side = aux_fork(dev)
         with aux_on(side):
             sa = stream_ptr()
-            call("b200_colsum", dpre, dt, R, F, tile_group, E, db1, ws, nb, sa)
-            call("b200_ggemm_wgrad", dpre, F, xp, D, dw1, F, D, R, E, pad_off, dt, sa)
+            call("b200_colsum", dpre, dt, R, F1, tile_group, E, db1, ws, nb, sa)
+            call("b200_ggemm_wgrad", dpre, F1, xp, D, dw1, F1, D, R, E, pad_off, dt, sa)
         dxp = None
         if ctx.needs_input_grad[0]:
             dxp = torch.empty((R, D), dtype=dz.dtype, device=dev)
             if residual:
-                call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, tile_group, rows_used, dt, dt, None, EPI_ADD,
+                call("b200_ggemm", dpre, F1, w1s, LAYOUT_MN, dxp, D, R, D, F1, E, tile_group, rows_used, dt, dt, None, EPI_ADD,
                      ACT_NONE, dsum, None, Do, None, st)
             else:
-                call("b200_ggemm", dpre, F, w1s, LAYOUT_MN, dxp, D, R, D, F, E, tile_group, rows_used, dt, dt, None, EPI_NONE,
-                     ACT_NONE, None, None, 0, None, st)
+                call("b200_ggemm", dpre, F1, w1s, LAYOUT_MN, dxp, D, R, D, F1, E, tile_group, rows_used, dt, dt, None,
+                     EPI_NONE, ACT_NONE, None, None, 0, None, st)
         aux_join(side)
         # hand every per-expert Parameter its slice of the flat buffer
         grads: List[torch.Tensor] = []
-        for buf, shape in ((dw1, (F, D)), (db1, (F,)), (dw2, (Do, F)), (db2, (Do,)), (dlng, (Do,)), (dlnb, (Do,))):
+        for buf, shape in ((dw1, (F1, D)), (db1, (F1,)), (dw2, (Do, F)), (db2, (Do,)), (dlng, (Do,)), (dlnb, (Do,))):
             per = buf.view(E, *shape)
             grads.extend(per[e] for e in range(E))
         return (dxp, None, None, None, None, None, None, None, *grads)
@@ -683,8 +734,9 @@ class CombineFn(torch.autograd.Function):
         Do = z.shape[1]
         dev = z.device
         out = torch.empty((N, Do), dtype=z.dtype, device=dev)
-        mean_o = torch.empty(N, dtype=torch.float32, device=dev)
-        rstd_o = torch.empty(N, dtype=torch.float32, device=dev)
+        norm = out_gamma is not None        # None: plain weighted sum (HierarchicalMOE normalises after output_proj)
+        mean_o = torch.empty(N, dtype=torch.float32, device=dev) if norm else None
+        rstd_o = torch.empty(N, dtype=torch.float32, device=dev) if norm else None
         call("b200_moe_combine_fwd", z, dest, w, out_gamma, out_beta, float(eps), N, K, Do, dtype_code(z.dtype), out,
              mean_o, rstd_o, stream_ptr())
         ctx.save_for_backward(z, w, dest, row_src, mean_o, rstd_o, out_gamma)
@@ -699,12 +751,14 @@ class CombineFn(torch.autograd.Function):
         dev = dout.device
         dz = torch.empty((R, Do), dtype=dout.dtype, device=dev)
         d_w = torch.empty((N, K), dtype=torch.float32, device=dev)
-        flat = grad_buffer(2 * Do, dev)
+        norm = out_gamma is not None
+        flat = grad_buffer(2 * Do, dev) if norm else None
         nb = query("b200_moe_combine_bwd_ws", N, Do)
         ws = _ws(nb, dev)
         call("b200_moe_combine_bwd", dout, z, dest, w, mean_o, rstd_o, out_gamma, row_src, N, K, Do, R,
-             dtype_code(dout.dtype), dz, d_w, flat[:Do], flat[Do:], ws, nb, stream_ptr())
-        return dz, d_w, None, None, flat[:Do], flat[Do:], None
+             dtype_code(dout.dtype), dz, d_w, flat[:Do] if norm else None, flat[Do:] if norm else None, ws, nb,
+             stream_ptr())
+        return dz, d_w, None, None, (flat[:Do] if norm else None), (flat[Do:] if norm else None), None
 
 
 class DenseCombineFn(torch.autograd.Function):
@@ -723,8 +777,9 @@ class DenseCombineFn(torch.autograd.Function):
         valid = (idx >= 0) & (idx < E)
         dest = torch.where(valid, idx * N + n_ar, torch.full_like(idx, -1)).to(torch.int32).contiguous()
         out = torch.empty((N, D), dtype=ys.dtype, device=ys.device)
-        mean = torch.empty(N, dtype=torch.float32, device=ys.device)
-        rstd = torch.empty(N, dtype=torch.float32, device=ys.device)
+        norm = out_gamma is not None
+        mean = torch.empty(N, dtype=torch.float32, device=ys.device) if norm else None
+        rstd = torch.empty(N, dtype=torch.float32, device=ys.device) if norm else None
         call("b200_moe_combine_fwd", ys, dest, w, out_gamma, out_beta, float(eps), N, K, D, dtype_code(ys.dtype), out,
              mean, rstd, stream_ptr())
         ctx.save_for_backward(ys, dest, w, mean, rstd, out_gamma)
@@ -744,12 +799,14 @@ class DenseCombineFn(torch.autograd.Function):
         row_src[flat_dest[ok]] = torch.arange(N * K, device=dev, dtype=torch.int32)[ok]
         dys = torch.empty_like(ys)
         d_w = torch.empty((N, K), dtype=torch.float32, device=dev)
-        flat = grad_buffer(2 * D, dev)
+        norm = out_gamma is not None
+        flat = grad_buffer(2 * D, dev) if norm else None
         nb = query("b200_moe_combine_bwd_ws", N, D)
         ws = _ws(nb, dev)
         call("b200_moe_combine_bwd", dout, ys, dest, w, mean, rstd, out_gamma, row_src, N, K, D, E * N,
-             dtype_code(ys.dtype), dys, d_w, flat[:D], flat[D:], ws, nb, stream_ptr())
-        return dys, d_w, None, flat[:D], flat[D:], None
+             dtype_code(ys.dtype), dys, d_w, flat[:D] if norm else None, flat[D:] if norm else None, ws, nb,
+             stream_ptr())
+        return dys, d_w, None, (flat[:D] if norm else None), (flat[D:] if norm else None), None
 
 
 # ---- cross-attention projections from one packed in_proj ------------------------------------------------------
