@@ -319,4 +319,4 @@ def test_hierarchical_moe_default_groups_router_and_combine():
     assert rel_err(x.grad, g["d_x_router"]) < TOL
     used = g["used"].bool()
     assert rel_err(ys.grad.view(G * Epg, B * S, D)[used], g["d_ys"][used]) < TOL
-    _check_grads(sd, g["grads"])
+    _check_grads(sd, g["grads"], tol=1e-4)     # aux-only gradients of the top-1 expert routers are ~1e-3 in norm
