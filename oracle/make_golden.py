@@ -182,7 +182,7 @@ def main():
          grads=grads_of(m))
 
 
-if __name__ == "__main__" and "--r2" not in sys.argv and "--n4" not in sys.argv:
+if __name__ == "__main__" and not ({"--r2", "--n4", "--n3"} & set(sys.argv)):
     main()
 
 
@@ -449,6 +449,37 @@ def main_n4():
          sd=rsd, x=x, gout=gout, ys=ys_all, d_ys=d_ys, out=out, loss=m.get_aux_loss(), d_x_router=x2.grad, grads=keep)
 
 
+def main_n3():
+    """QFormerFusion and SingleStreamFusion from the reference's fusion registry."""
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    from src.modeling.fusion.fusion_approaches import create_fusion_model
+    rng = np.random.default_rng(20261021)
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+    B, V, T, D, H, L, I = 2, 36, 20, 64, 4, 2, 128            # token counts of examples/fusion_examples.py:24-29
+    vis = f32(rng.standard_normal((B, V, D)))
+    txt = f32(rng.standard_normal((B, T, D)))
+    tvalid = torch.ones(B, T, dtype=torch.bool)
+    tvalid[:, -5:] = False
+    vvalid = torch.ones(B, V, dtype=torch.bool)
+    vvalid[1, -7:] = False
+    gout = f32(rng.standard_normal((B, D)))
+    for name, kw, seed in (("qformer", dict(num_query_tokens=8, num_attention_heads=H, num_layers=L, intermediate_dim=I), 81),
+                           ("single_stream", dict(num_attention_heads=H, num_layers=L, intermediate_dim=I,
+                                                  max_vision_tokens=40, max_text_tokens=24), 82)):
+        m = create_fusion_model(name, vision_dim=D, text_dim=D, output_dim=D, dropout=0.0, **kw)
+        sd = rnd_state_dict(m, seed)
+        m.load_state_dict(sd)
+        m.train()
+        v, t = vis.clone().requires_grad_(), txt.clone().requires_grad_()
+        out = m(v, t, vision_mask=vvalid, text_mask=tvalid)
+        (out * gout).sum().backward()
+        save(f"{name}_fusion", cfg=np.array([B, V, T, D, H, L, I]), sd=sd, vision=v, text=t, vision_valid=vvalid,
+             text_valid=tvalid, gout=gout, out=out, d_vision=v.grad, d_text=t.grad, grads=grads_of(m))
+
+
+if __name__ == "__main__" and "--n3" in sys.argv:
+    main_n3()
 if __name__ == "__main__" and "--r2" in sys.argv:
     main_r2()
 if __name__ == "__main__" and "--n4" in sys.argv:

@@ -141,6 +141,50 @@ def cross_attention_fusion(sd: SD, num_heads: int, num_layers: int, fusion_metho
     return layer_norm(h, sd["fusion_layer.5.weight"], sd["fusion_layer.5.bias"])
 
 
+# ---- N3: QFormerFusion / QFormerLayer (fusion_approaches.py:284-513) ------------------------------------------------
+def qformer_fusion(sd: SD, num_heads: int, num_layers: int, vision, text, vision_mask=None, text_mask=None):
+    v = vision @ sd["vision_projection.weight"].t() + sd["vision_projection.bias"]
+    t = text @ sd["text_projection.weight"].t() + sd["text_projection.bias"]
+    q = sd["query_tokens"].expand(vision.shape[0], -1, -1)
+    vpad = None if vision_mask is None else ~vision_mask.bool()
+    tpad = None if text_mask is None else ~text_mask.bool()
+    for l in range(num_layers):
+        p = f"qformer_layers.{l}."
+        q = layer_norm(q + mha(sd, p + "self_attention.", q, q, num_heads, None), sd[p + "self_norm1.weight"],
+                       sd[p + "self_norm1.bias"])
+        q = layer_norm(q + ffn(sd, p + "self_ffn.0.", p + "self_ffn.3.", q), sd[p + "self_norm2.weight"],
+                       sd[p + "self_norm2.bias"])
+        q = layer_norm(q + mha(sd, p + "vision_cross_attention.", q, v, num_heads, vpad), sd[p + "vision_norm1.weight"],
+                       sd[p + "vision_norm1.bias"])
+        q = layer_norm(q + ffn(sd, p + "vision_ffn.0.", p + "vision_ffn.3.", q), sd[p + "vision_norm2.weight"],
+                       sd[p + "vision_norm2.bias"])
+        q = layer_norm(q + mha(sd, p + "text_cross_attention.", q, t, num_heads, tpad), sd[p + "text_norm1.weight"],
+                       sd[p + "text_norm1.bias"])
+        q = layer_norm(q + ffn(sd, p + "text_ffn.0.", p + "text_ffn.3.", q), sd[p + "text_norm2.weight"],
+                       sd[p + "text_norm2.bias"])
+    q = layer_norm(q, sd["output_projection.0.weight"], sd["output_projection.0.bias"])
+    q = q @ sd["output_projection.1.weight"].t() + sd["output_projection.1.bias"]
+    return q.mean(dim=1)
+
+
+# ---- N3: SingleStreamFusion (fusion_approaches.py:516-677) ----------------------------------------------------------
+def single_stream_fusion(sd: SD, num_heads: int, num_layers: int, vision, text, vision_mask=None, text_mask=None):
+    B, V, _ = vision.shape
+    T = text.shape[1]
+    v = vision @ sd["vision_projection.weight"].t() + sd["vision_projection.bias"] + sd["modality_embeddings.weight"][0]
+    t = text @ sd["text_projection.weight"].t() + sd["text_projection.bias"] + sd["modality_embeddings.weight"][1]
+    x = torch.cat([sd["cls_token"].expand(B, -1, -1), v, t], dim=1)
+    x = x + sd["position_embeddings"][:, :x.shape[1], :]
+    pad = None
+    if vision_mask is not None or text_mask is not None:
+        vm = vision_mask.bool() if vision_mask is not None else torch.ones(B, V, dtype=torch.bool)
+        tm = text_mask.bool() if text_mask is not None else torch.ones(B, T, dtype=torch.bool)
+        pad = ~torch.cat([torch.ones(B, 1, dtype=torch.bool), vm, tm], dim=1)
+    for l in range(num_layers):
+        x = transformer_encoder_layer_prenorm(sd, f"transformer.layers.{l}.", x, num_heads, pad)
+    return layer_norm(x, sd["norm.weight"], sd["norm.bias"])[:, 0, :]
+
+
 # ---- A5: routers (router.py:105-178, 287-366) -------------------------------------------------------------------
 def topk_router(sd: SD, p: str, x: torch.Tensor, top_k: int, lb_weight: float = 0.01,
                 noise: Optional[torch.Tensor] = None, noise_std: float = 1.0):

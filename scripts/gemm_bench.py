@@ -29,6 +29,10 @@ def main():
                   (f"fwd_ffn1_M{M}", "KK", M, 3072, 768, EPI_ACT), (f"fwd_ffn2_M{M}", "KK", M, 768, 3072, EPI_NONE),
                   (f"dgrad_ffn2_M{M}", "KMN", M, 3072, 768, EPI_DACT), (f"dgrad_ffn1_M{M}", "KMN", M, 768, 3072, EPI_NONE),
                   (f"wgrad_ffn1_M{M}", "MNMN", 3072, 768, M, EPI_ACCUM), (f"wgrad_proj_M{M}", "MNMN", 768, 768, M, EPI_ACCUM)]
+    M = 14592          # config 5: 128 samples x 114 tokens, encoder FFN 768 <-> 2048
+    cases += [(f"fwd_qkv_M{M}", "KK", M, 2304, 768, EPI_NONE), (f"fwd_ffn1_M{M}", "KK", M, 2048, 768, EPI_ACT),
+              (f"fwd_ffn2_M{M}", "KK", M, 768, 2048, EPI_NONE), (f"dgrad_ffn2_M{M}", "KMN", M, 2048, 768, EPI_DACT),
+              (f"dgrad_ffn1_M{M}", "KMN", M, 768, 2048, EPI_NONE), (f"wgrad_ffn1_M{M}", "MNMN", 2048, 768, M, EPI_ACCUM)]
     res = {}
     for name, lay, M, N, K, epi in cases:
         if args.only and args.only not in name:

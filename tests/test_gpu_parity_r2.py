@@ -526,3 +526,36 @@ def test_hierarchical_moe_default_groups_matches_reference(mode, tol):
     assert rel_err(d_ys[used], ref["d_ys"][used]) < tol
     errs = _grad_errs(m, ref["grads"])
     assert worst(errs)[0] < tol, worst(errs)
+
+
+# ---- QFormerFusion and SingleStreamFusion against the reference ---------------------------------------
+@pytest.mark.parametrize("mode,tol", MODES)
+@pytest.mark.parametrize("name", ["qformer", "single_stream"])
+def test_qformer_and_single_stream_fusion_match_reference(mode, tol, name):
+    g = load_golden(f"{name}_fusion")
+    B, V, T, D, H, L, I = [int(v) for v in g["cfg"]]
+    oracle = rp.qformer_fusion if name == "qformer" else rp.single_stream_fusion
+    sd, vis0, txt0 = g["sd"], g["vision"], g["text"]
+    ref = dict(out=g["out"], d_v=g["d_vision"], d_t=g["d_text"], grads=g["grads"])
+    if mode == "bf16":
+        sd, vis0, txt0 = round_sd_for_bf16(sd), bf16_representable(vis0), bf16_representable(txt0)
+        sdr, vr, tr = leafs(sd), vis0.clone().requires_grad_(), txt0.clone().requires_grad_()
+        o = oracle(sdr, H, L, vr, tr, g["vision_valid"], g["text_valid"])
+        (o * g["gout"]).sum().backward()
+        ref = dict(out=o.detach(), d_v=vr.grad, d_t=tr.grad, grads={k: v.grad for k, v in sdr.items() if v.grad is not None})
+    kw = dict(num_query_tokens=8, num_attention_heads=H, num_layers=L, intermediate_dim=I) if name == "qformer" else \
+        dict(num_attention_heads=H, num_layers=L, intermediate_dim=I, max_vision_tokens=40, max_text_tokens=24)
+    with computing(mode):
+        m = fusion.create_fusion_model(name, vision_dim=D, text_dim=D, output_dim=D, dropout=0.0, **kw).to(DEV)
+        assert set(m.state_dict()) == set(sd)
+        m.load_state_dict(sd)
+        m.train()
+        vis, txt = vis0.to(DEV).requires_grad_(), txt0.to(DEV).requires_grad_()
+        out = m(vis, txt, vision_mask=g["vision_valid"].to(DEV), text_mask=g["text_valid"].to(DEV))
+        (out * g["gout"].to(DEV)).sum().backward()
+    assert out.shape == (B, D)
+    assert rel_err(out, ref["out"]) < tol, rel_err(out, ref["out"])
+    assert rel_err(vis.grad, ref["d_v"]) < tol, rel_err(vis.grad, ref["d_v"])
+    assert rel_err(txt.grad, ref["d_t"]) < tol, rel_err(txt.grad, ref["d_t"])
+    errs = _grad_errs(m, ref["grads"])
+    assert worst(errs)[0] < tol, worst(errs)

@@ -320,3 +320,28 @@ def test_hierarchical_moe_default_groups_router_and_combine():
     used = g["used"].bool()
     assert rel_err(ys.grad.view(G * Epg, B * S, D)[used], g["d_ys"][used]) < TOL
     _check_grads(sd, g["grads"], tol=1e-4)     # aux-only gradients of the top-1 expert routers are ~1e-3 in norm
+
+
+# ---- QFormerFusion, SingleStreamFusion ---------------------------------------------------------------
+def test_qformer_fusion():
+    g = load_golden("qformer_fusion")
+    B, V, T, D, H, L, I = [int(v) for v in g["cfg"]]
+    sd = _leafs(g["sd"])
+    vis, txt = g["vision"].clone().requires_grad_(), g["text"].clone().requires_grad_()
+    out = rp.qformer_fusion(sd, H, L, vis, txt, g["vision_valid"], g["text_valid"])
+    assert rel_err(out, g["out"]) < TOL
+    (out * g["gout"]).sum().backward()
+    assert rel_err(vis.grad, g["d_vision"]) < TOL and rel_err(txt.grad, g["d_text"]) < TOL
+    _check_grads(sd, g["grads"], tol=5e-5)
+
+
+def test_single_stream_fusion():
+    g = load_golden("single_stream_fusion")
+    B, V, T, D, H, L, I = [int(v) for v in g["cfg"]]
+    sd = _leafs(g["sd"])
+    vis, txt = g["vision"].clone().requires_grad_(), g["text"].clone().requires_grad_()
+    out = rp.single_stream_fusion(sd, H, L, vis, txt, g["vision_valid"], g["text_valid"])
+    assert rel_err(out, g["out"]) < TOL
+    (out * g["gout"]).sum().backward()
+    assert rel_err(vis.grad, g["d_vision"]) < TOL and rel_err(txt.grad, g["d_text"]) < TOL
+    _check_grads(sd, g["grads"], tol=5e-5)

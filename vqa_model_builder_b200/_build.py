@@ -71,18 +71,33 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return _build_locked(verbose)
 
 
+def _source_digest(src: Path) -> str:
+    """digest of one translation unit: its own text, every header of csrc/ and the public header, the flags"""
+    h = hashlib.sha256()
+    for p in [src] + sorted(CSRC.glob("*.cuh")) + [INCLUDE / "b200vqa.h"]:
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(f for f in NVCC_FLAGS if f != str(INCLUDE)).encode())
+    return h.hexdigest()
+
+
 def _build_locked(verbose: bool) -> Path:
     nvcc = _nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
 
     def compile_one(src: Path) -> Path:
         obj = OBJ_DIR / (src.stem + ".o")
+        stamp = OBJ_DIR / (src.stem + ".digest")
+        dig = _source_digest(src)
+        if not verbose and obj.exists() and stamp.exists() and stamp.read_text().strip() == dig:
+            return obj                 # unchanged translation unit (router.cu alone takes minutes to compile)
         cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             sys.stderr.write(r.stderr)
+        stamp.write_text(dig)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:

@@ -79,7 +79,7 @@ __global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, long
 // counter, __threadfence reduction) folds the slab's partials in block order, so the result does not depend on
 // scheduling.  Tickets live in a device-global ring (zero at load, reset by the folding block): launches in flight
 // at the same time on different streams get different slots.
-constexpr int CS_ROWS = 64;  // rows per partial block; divides B200_GROUP_TILE
+constexpr int CS_ROWS = 128;  // rows per partial block of the grouped path; divides B200_GROUP_TILE
 constexpr int TICKETS = 8192;
 __device__ unsigned int g_tickets[TICKETS];
 
@@ -167,15 +167,16 @@ colsum_stage1(const T* __restrict__ x, int R, int N, int rpb, float* __restrict_
   // rows of unused 128-row tiles (expert-parallel buffers are sized for the worst case) are never read
   const bool live = tile_group == nullptr || tile_group[r0 / B200_GROUP_TILE] >= 0;
   if (col < N && live) {
-    for (int rb = r0 + warp; rb < r1; rb += 4 * CS_WARPS) {
-      Vec16<T> v[4];
+    constexpr int INF = 8;                    // row loads in flight per warp (16 warps x 32 lanes x 8 x 16 B = 64 KB / CTA)
+    for (int rb = r0 + warp; rb < r1; rb += INF * CS_WARPS) {
+      Vec16<T> v[INF];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {           // four row loads in flight per warp
+      for (int q = 0; q < INF; ++q) {
         const int r = rb + CS_WARPS * q;
         if (r < r1) v[q].load(x + (long long)r * N + col);
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < INF; ++q) {
         const int r = rb + CS_WARPS * q;
         if (r < r1) {
           if (ds.on) {
@@ -370,11 +371,19 @@ static int launch_colsum(const void* x, void* gout, const b200_dropout_t* drop, 
   // straddle a 128-row expert tile, and a second kernel folds per expert in parallel.
   int rpb = CS_ROWS;
   const bool single = tile_group == nullptr;
-  if (single)
-    while ((R + rpb - 1) / rpb > 64) rpb *= 2;
+  const int slabs = vec ? (N + 32 * vt - 1) / (32 * vt) : (N + 127) / 128;
+  if (single) {
+    // row blocks: at most 64 (the serial part of the fold), and slabs x row-blocks close to ONE full wave of equally
+    // loaded CTAs (a 171-CTA grid on 148 SMs took two rounds: profiles/r02f)
+    int rb = num_sms() / slabs;
+    if (rb > 64) rb = 64;
+    if (rb < 1) rb = 1;
+    rpb = ((R + rb - 1) / rb + CS_WARPS - 1) / CS_WARPS * CS_WARPS;
+    if (rpb < CS_ROWS) rpb = CS_ROWS;
+  }
   const int blocks = (R + rpb - 1) / rpb;
   float* part = (float*)workspace;
-  dim3 g1(vec ? (N + 32 * vt - 1) / (32 * vt) : (N + 127) / 128, blocks);
+  dim3 g1(slabs, blocks);
   unsigned int* tk = nullptr;
   if (single) {
     B200_CUDA(cudaGetSymbolAddress((void**)&tk, g_tickets));

@@ -375,7 +375,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const bool vec_ok = (p.N % 8 == 0) && (p.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
                         (p.ld_aux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0) &&
-                        (p.mode != GEMM_GROUP_WGRAD || p.out_group_elems % 4 == 0);
+                        (p.mode != GEMM_GROUP_WGRAD || p.out_group_elems % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     const DropState drop = drop_load(p.drop_state, p.drop_p, p.drop_site);
     int acc_it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -412,10 +413,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         if (col0 >= p.N) continue;               // warp-uniform
         if (vec_ok && col0 + 32 <= p.N) {
-          if (bias != nullptr) {      // lane j holds the bias of column col0 + j: one coalesced load, 32 broadcasts
-            const float bl = __ldg(bias + col0 + lane);
+          if (bias != nullptr) {      // every lane needs the same 32 values: 8 uniform 16-byte loads (L1 broadcast)
+            const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
+            for (int j = 0; j < 8; ++j) {
+              const float4 t4 = __ldg(b4 + j);
+              v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+            }
           }
           if (p.epi == B200_EPI_ACT) {
             if (p.aux_out != nullptr) stage_store_tile<2>(stg, lane, v, p.aux_out, p.ld_aux, row0, rows_ok, col0);

@@ -70,19 +70,11 @@ def install(verbose: bool = False) -> Dict[str, str]:
                        "AnswerHead": _heads.AnswerHead})                       # vqa_model.py:436
     bind_all(ref_gen, {"MOELayer": _moe.MOELayer, "VQAMOELayer": _moe.VQAMOELayer,   # generative_vqa_model.py:23
                        "SparseMOELayer": _moe.SparseMOELayer, "CrossModalFusion": _fusion.CrossModalFusion})
-    fus_syms = {"CrossAttentionFusion": _fusion.CrossAttentionFusion, "CrossAttentionBlock": _fusion.CrossAttentionBlock}
-    bind_all(ref_fusion, fus_syms)
+    fus_syms = {"CrossAttentionFusion": _fusion.CrossAttentionFusion, "CrossAttentionBlock": _fusion.CrossAttentionBlock,
+                "QFormerFusion": _fusion.QFormerFusion, "QFormerLayer": _fusion.QFormerLayer,
+                "SingleStreamFusion": _fusion.SingleStreamFusion, "create_fusion_model": _fusion.create_fusion_model}
+    bind_all(ref_fusion, fus_syms)          # the whole registry (fusion_approaches.py:719-725) is native
     bind_all(ref_fusion_impl, fus_syms)
-    # keep the reference's registry (qformer / single_stream stay theirs), route 'cross_attention' to ours
-    ref_create = ref_fusion_impl.create_fusion_model
-
-    def create_fusion_model(fusion_type: str, **kwargs):
-        if fusion_type == "cross_attention":
-            return _fusion.CrossAttentionFusion(**kwargs)
-        return ref_create(fusion_type, **kwargs)
-
-    bind_all(ref_fusion, {"create_fusion_model": create_fusion_model})
-    bind_all(ref_fusion_impl, {"create_fusion_model": create_fusion_model})
     if verbose:
         for k, v in done.items():
             print(f"[b200] {k} -> {v}")
