@@ -247,7 +247,7 @@ router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
   const bool v0 = lane < E, v1 = lane + 32 < E;
   float cnt0 = 0.f, cnt1 = 0.f, ps0 = 0.f, ps1 = 0.f, ns0 = 0.f, ns1 = 0.f;
 
-  constexpr bool FAST = (EB == 8) && (sizeof(T) == 2);
+  constexpr bool FAST = (EB == 8) && (sizeof(T) == 2) && (NV <= 4);   // D <= 1024: the fully unrolled blocked path
   constexpr int TBC = FAST ? RT_TB : 1;
   const bool fast = FAST && !noisy;
   const int tb = fast ? TBC : 1;
@@ -423,7 +423,7 @@ router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w_gate, con
   extern __shared__ float smem[];
   float* wg = smem;
   float* wn = smem + (size_t)E * DP;
-  constexpr bool FAST = (EB == 8) && (sizeof(T) == 2);
+  constexpr bool FAST = (EB == 8) && (sizeof(T) == 2) && (NV <= 4);   // D <= 1024: the fully unrolled blocked path
   constexpr int TBC = FAST ? RT_TB : 1;
   __shared__ float s_dl[RT_WARPS][TBC][RT_MAX_E], s_du[RT_WARPS][RT_MAX_E];
   const bool noisy = (eps != nullptr);
@@ -647,7 +647,7 @@ int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* 
   const size_t smem = (size_t)E * nvb * 32 * (dtype == B200_BF16 ? 8 : 4) * sizeof(float) * (eps != nullptr ? 2 : 1);
   B200_CHECK_ARG(smem <= 200 * 1024, "router_fwd: gate weights (%zu B) do not fit in shared memory", smem);
   int blocks = router_grid(N);
-  if (dtype == B200_BF16 && E <= 8 && eps == nullptr) blocks = router_grid_blocked(N);   // <= router_grid(N)
+  if (dtype == B200_BF16 && E <= 8 && eps == nullptr && nvb <= 4) blocks = router_grid_blocked(N);   // <= router_grid(N)
   float* part = (float*)workspace;
   if (dtype == B200_BF16) {
     B200_NV_SWITCH(nvb, {
@@ -705,7 +705,7 @@ int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* 
   float* du = dl + (size_t)N * E;
   float* part = du + (size_t)N * E;
   int blocks = router_grid(N);
-  if (dtype == B200_BF16 && E <= 8 && !noisy) blocks = router_grid_blocked(N);
+  if (dtype == B200_BF16 && E <= 8 && !noisy && nvb <= 4) blocks = router_grid_blocked(N);
   const int chunks = (N + RW_CHUNK - 1) / RW_CHUNK;
   dim3 wg_grid((D + 127) / 128, chunks);
   const int ED = E * D;
