@@ -70,7 +70,9 @@ def test_create_router_filters_kwargs_and_rejects_unknown():
     with pytest.raises(ValueError):
         moe.create_expert("nope", 8, 8, 8)
     with pytest.raises(ValueError):
-        fusion.create_fusion_model("qformer")
+        fusion.create_fusion_model("mcan")
+    assert type(fusion.create_fusion_model("qformer", vision_dim=32, text_dim=32, output_dim=32, num_query_tokens=4,
+                                           num_attention_heads=2, num_layers=1, intermediate_dim=64)).__name__ == "QFormerFusion"
 
 
 def test_vqa_moe_layer_accepts_explicit_heterogeneous_experts():
