@@ -66,7 +66,8 @@ def test_size_queries_work_without_gpu():
     assert _lib.query("b200_moe_max_rows", 64, 8) == 1152          # 64 + 8*127 rounded up to 128
     assert _lib.query("b200_moe_max_rows", 29184, 8) % 128 == 0
     assert _lib.query("b200_router_ws", 1024, 8) > 0
-    assert _lib.query("b200_add_ln_bwd_ws", 2048, 768) == (2048 // 8) * 3 * 768 * 4
+    assert _lib.query("b200_add_ln_bwd_ws", 2048, 768) >= (2048 // 8) * 3 * 768 * 4
+    assert _lib.query("b200_add_ln_bwd_ws", 32, 768) > 4 * 3 * 768 * 4     # the staged kernel also keeps a group map
 
 
 def test_product_path_fails_loudly_without_cuda():

@@ -94,3 +94,58 @@ def test_colsum_grouped_by_expert_tiles():
                          [x[:0]])
         assert rel_err(got[e], rows.double().sum(0)) < 2e-6 or float(rows.abs().sum()) == 0.0
     assert float(got[1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("D", [256, 768, 1024])
+@pytest.mark.parametrize("drop_target", [0, 1, 2])
+def test_grouped_add_ln_staged_path_against_torch(D, drop_target):
+    """Per-expert add+LayerNorm over a padded expert layout (the persistent shared-memory-staged bf16 kernels:
+    D == 256 * k): dead 128-row tiles in the middle and at the end, a group change inside a block's row range,
+    dropout on either operand (mask materialised by b200_dropout_mask), dgamma / dbeta / bias-gradient sums per group."""
+    G = 3
+    tiles = torch.tensor([0, 0, -1, 1, 2, 2, 2, -1, -1], dtype=torch.int32, device=DEV)
+    R = tiles.numel() * 128
+    g = torch.Generator(device=DEV).manual_seed(D + drop_target)
+    x = torch.randn(R, D, generator=g, device=DEV).bfloat16()
+    res = torch.randn(R, D, generator=g, device=DEV).bfloat16()
+    dy = torch.randn(R, D, generator=g, device=DEV).bfloat16()
+    gamma = 1 + 0.1 * torch.randn(G, D, generator=g, device=DEV)
+    beta = 0.1 * torch.randn(G, D, generator=g, device=DEV)
+    st = torch.tensor([77, 5], dtype=torch.int64, device=DEV)
+    drop = (st, 0.2, 9) if drop_target else None
+    y = torch.zeros_like(x)
+    mean = torch.zeros(R, device=DEV)
+    rstd = torch.zeros(R, device=DEV)
+    _lib.call("b200_add_ln_fwd", x, res, gamma, beta, tiles, 1e-5, y, mean, rstd, R, D, _lib.BF16,
+              _lib.dropout_arg(drop), drop_target, _lib.stream_ptr())
+    dsum = torch.zeros_like(x)
+    ddrop = torch.zeros_like(x)
+    dgam, dbet, dcol = (torch.zeros(G, D, device=DEV) for _ in range(3))
+    nb = _lib.query("b200_add_ln_bwd_ws", R, D)
+    ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    _lib.call("b200_add_ln_bwd", dy, x, res, mean, rstd, gamma, tiles, G, dsum, dgam, dbet, dcol, R, D, _lib.BF16,
+              _lib.dropout_arg(drop), drop_target, ddrop if drop_target else None, ws, nb, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    mask = torch.ones(R, D, dtype=torch.float64, device=DEV)
+    if drop_target:
+        m = torch.empty(R * D, dtype=torch.float32, device=DEV)
+        _lib.call("b200_dropout_mask", _lib.dropout_arg(drop), R * D, m, _lib.stream_ptr())
+        mask = m.view(R, D).double()
+    live = (tiles >= 0).repeat_interleave(128)
+    grp = tiles.clamp(min=0).long().repeat_interleave(128)
+    xr, rr = x.double().requires_grad_(), res.double().requires_grad_()
+    gr, br = gamma.double().requires_grad_(), beta.double().requires_grad_()
+    xs = (xr * mask if drop_target == 1 else xr) + (rr * mask if drop_target == 2 else rr)
+    ref = torch.nn.functional.layer_norm(xs, (D,)) * gr[grp] + br[grp]
+    (ref * dy.double())[live].sum().backward()
+    assert rel_err(y[live], ref[live]) < 6e-3
+    dxs = rr.grad if drop_target == 1 else xr.grad      # gradient of the sum = gradient of the operand NOT dropped
+    assert rel_err(dsum[live], dxs[live]) < 6e-3
+    if drop_target:
+        dropped = xr.grad if drop_target == 1 else rr.grad
+        assert rel_err(ddrop[live], dropped[live]) < 6e-3
+        assert (ddrop[live][mask[live] == 0] == 0).all()
+    assert rel_err(dgam, gr.grad) < 3e-3 and rel_err(dbet, br.grad) < 1e-5
+    want_col = (xr.grad if drop_target == 1 else rr.grad if drop_target == 2 else dxs)
+    col_ref = torch.zeros(G, D, dtype=torch.float64, device=DEV).index_add_(0, grp[live], want_col[live])
+    assert rel_err(dcol, col_ref) < 3e-3

@@ -4,6 +4,19 @@
 
 namespace b200 {
 
+// layernorm_staged.cu: persistent shared-memory-staged bf16 kernels (return -1 when a shape is not covered)
+bool ln_staged_enabled();
+size_t ln_bwd_staged_ws(int R, int D);
+int launch_add_ln_fwd_staged(const bf16* x, const bf16* res, const float* gamma, const float* beta,
+                             const int* tile_group, float eps, bf16* y, float* mean, float* rstd, int R, int D,
+                             const unsigned long long* dst, float dp, unsigned int dsite, int drop_target,
+                             cudaStream_t stream);
+int launch_add_ln_bwd_staged(const bf16* dy, const bf16* x, const bf16* res, const float* mean, const float* rstd,
+                             const float* gamma, const int* tile_group, int G, bf16* dsum, float* dgamma, float* dbeta,
+                             float* d_colsum, int R, int D, const unsigned long long* dst, float dp, unsigned int dsite,
+                             int drop_target, bf16* d_dropped, void* workspace, size_t workspace_bytes,
+                             cudaStream_t stream);
+
 namespace {
 
 constexpr int LN_WARPS = 8;
@@ -313,6 +326,11 @@ int b200_add_ln_fwd(const void* x, const void* res, const float* gamma, const fl
   const float dp = don ? drop->p : 0.f;
   const unsigned int dsite = don ? drop->site : 0u;
   const int blocks = (R + LN_WARPS - 1) / LN_WARPS;
+  if (dtype == B200_BF16 && ln_staged_enabled()) {
+    const int rc = launch_add_ln_fwd_staged((const bf16*)x, (const bf16*)res, gamma, beta, tile_group, eps, (bf16*)y, mean,
+                                            rstd, R, D, dst, dp, dsite, drop_target, stream);
+    if (rc >= 0) return rc;
+  }
   if (dtype == B200_BF16) {
     B200_CHECK_ARG(RowRegs<bf16>::supported(D), "add_ln_fwd: D=%d unsupported for bf16 (need D%%8==0, D<=2048)", D);
     B200_NV_SWITCH(row_nv<bf16>(D), launch_kernel(add_ln_fwd_kernel<bf16, NV>, dim3(blocks), dim3(LN_WARPS * 32), 0, stream, 
@@ -329,7 +347,8 @@ int b200_add_ln_fwd(const void* x, const void* res, const float* gamma, const fl
 
 size_t b200_add_ln_bwd_ws(int R, int D) {
   const size_t blocks = (size_t)(R + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK;
-  return blocks * 3 * (size_t)D * sizeof(float);
+  const size_t a = blocks * 3 * (size_t)D * sizeof(float), b = ln_bwd_staged_ws(R, D);
+  return a > b ? a : b;
 }
 
 int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float* mean, const float* rstd,
@@ -343,6 +362,12 @@ int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float*
   const float dp = don ? drop->p : 0.f;
   const unsigned int dsite = don ? drop->site : 0u;
   B200_CHECK_ARG(workspace_bytes >= b200_add_ln_bwd_ws(R, D), "add_ln_bwd: workspace too small");
+  if (dtype == B200_BF16 && ln_staged_enabled()) {
+    const int rc = launch_add_ln_bwd_staged((const bf16*)dy, (const bf16*)x, (const bf16*)res, mean, rstd, gamma, tile_group,
+                                            G, (bf16*)dsum, dgamma, dbeta, d_colsum, R, D, dst, dp, dsite, drop_target,
+                                            (bf16*)d_dropped, workspace, workspace_bytes, stream);
+    if (rc >= 0) return rc;
+  }
   const int rpw = ln_bwd_rpw(R);
   const int rows_per_block = LN_WARPS * rpw;
   const int blocks = (R + rows_per_block - 1) / rows_per_block;
