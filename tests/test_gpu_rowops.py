@@ -149,3 +149,41 @@ def test_grouped_add_ln_staged_path_against_torch(D, drop_target):
     want_col = (xr.grad if drop_target == 1 else rr.grad if drop_target == 2 else dxs)
     col_ref = torch.zeros(G, D, dtype=torch.float64, device=DEV).index_add_(0, grp[live], want_col[live])
     assert rel_err(dcol, col_ref) < 3e-3
+
+
+@pytest.mark.parametrize("D,K", [(768, 2), (256, 1), (1024, 2), (768, 3), (64, 2)])
+def test_combine_fwd_bwd_against_torch(D, K):
+    """Weighted combine + output LayerNorm over scattered expert rows (bf16): the staged kernels (D == 256 k, K <= 2)
+    and the register kernels (everything else) against torch fp64; dropped pairs (dest < 0), zero weights (capacity),
+    a token count that is not a multiple of the 8-token chunk."""
+    N = 1003
+    R = N * K + 300
+    g = torch.Generator(device=DEV).manual_seed(D * K)
+    z = torch.randn(R, D, generator=g, device=DEV).bfloat16()
+    w = torch.rand(N, K, generator=g, device=DEV)
+    perm = torch.randperm(R, generator=g, device=DEV)[:N * K].view(N, K).to(torch.int32)
+    dest = perm.clone()
+    dest[5, 0] = -1
+    dest[77, K - 1] = -1
+    w[9, 0] = 0.0
+    gamma = (1 + 0.1 * torch.randn(D, generator=g, device=DEV)).requires_grad_()
+    beta = (0.1 * torch.randn(D, generator=g, device=DEV)).requires_grad_()
+    dout = torch.randn(N, D, generator=g, device=DEV).bfloat16()
+    row_src = torch.full((R,), -1, dtype=torch.int32, device=DEV)
+    flat = torch.arange(N * K, device=DEV, dtype=torch.int32).view(N, K)
+    ok = dest >= 0
+    row_src[dest[ok].long()] = flat[ok]
+    zz = z.clone().requires_grad_()
+    ww = w.clone().requires_grad_()
+    out = ops.CombineFn.apply(zz, ww, dest.contiguous(), row_src, gamma, beta, 1e-5)
+    (out.float() * dout.float()).sum().backward()
+    zr, wr = z.double().requires_grad_(), w.double().requires_grad_()
+    gr, br = gamma.detach().double().requires_grad_(), beta.detach().double().requires_grad_()
+    rows = zr[dest.clamp(min=0).long()] * ok.unsqueeze(-1)
+    ref = torch.nn.functional.layer_norm((wr.unsqueeze(-1) * rows).sum(1), (D,), gr, br, 1e-5)
+    (ref * dout.double()).sum().backward()
+    assert rel_err(out, ref) < 6e-3
+    assert rel_err(zz.grad, zr.grad) < 8e-3
+    assert (zz.grad[row_src < 0] == 0).all()
+    assert rel_err(ww.grad, wr.grad * ok) < 6e-3
+    assert rel_err(gamma.grad, gr.grad) < 3e-3 and rel_err(beta.grad, br.grad) < 1e-5

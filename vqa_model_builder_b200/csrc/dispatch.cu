@@ -5,6 +5,16 @@
 
 namespace b200 {
 
+// combine_staged.cu: persistent shared-memory-staged bf16 kernels for top-k <= 2 (return -1 when not covered)
+size_t combine_bwd_staged_ws(int D);
+int launch_combine_fwd_staged(const bf16* z, const int* dest_row, const float* w, const float* gamma,
+                              const float* beta, float eps, int N, int K, int D, bf16* out, float* mean, float* rstd,
+                              cudaStream_t stream);
+int launch_combine_bwd_staged(const bf16* dout, const bf16* z, const int* dest_row, const float* w, const float* mean,
+                              const float* rstd, const float* gamma, int N, int K, int D, bf16* dz, float* d_w,
+                              float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                              cudaStream_t stream);
+
 int launch_ln_param_reduce(const float* part, int blocks, int rows_per_block, int D, const int* tile_group, int G,
                            float* dgamma, float* dbeta, cudaStream_t stream, float* dcol = nullptr);
 
@@ -471,6 +481,11 @@ int b200_moe_combine_fwd(const void* z, const int32_t* dest_row, const float* w,
                          void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_ROW_DISPATCH(dtype, D, "moe_combine_fwd");
+  if (dtype == B200_BF16) {
+    const int rc = launch_combine_fwd_staged((const bf16*)z, dest_row, w, gamma, beta, eps, N, K, D, (bf16*)out, mean, rstd,
+                                             stream);
+    if (rc >= 0) return rc;
+  }
   const int blocks = row_grid(N);
   if (dtype == B200_BF16) {
     B200_NV_SWITCH(row_nv<bf16>(D), launch_kernel(combine_fwd_kernel<bf16, NV>, dim3(blocks), dim3(256), 0, stream, 
@@ -486,7 +501,8 @@ int b200_moe_combine_fwd(const void* z, const int32_t* dest_row, const float* w,
 
 size_t b200_moe_combine_bwd_ws(int N, int D) {
   const size_t blocks = (size_t)(N + CMB_TOKENS_PER_BLOCK - 1) / CMB_TOKENS_PER_BLOCK;
-  return blocks * 2 * (size_t)D * sizeof(float);
+  const size_t a = blocks * 2 * (size_t)D * sizeof(float), b = combine_bwd_staged_ws(D);
+  return a > b ? a : b;
 }
 
 int b200_moe_combine_bwd(const void* dout, const void* z, const int32_t* dest_row, const float* w, const float* mean,
@@ -506,6 +522,12 @@ int b200_moe_combine_bwd(const void* dout, const void* z, const int32_t* dest_ro
   const int zb = row_grid(Rmax);
   if (dtype == B200_BF16) {
     launch_kernel(zero_unwritten_rows_kernel<bf16>, dim3(zb), dim3(256), 0, stream, row_src, w, Rmax, D, (bf16*)dz);
+    const int rc = launch_combine_bwd_staged((const bf16*)dout, (const bf16*)z, dest_row, w, mean, rstd, gamma, N, K, D,
+                                             (bf16*)dz, d_w, dgamma, dbeta, workspace, workspace_bytes, stream);
+    if (rc >= 0) {
+      if (rc == 0) count_launch();     // the zeroing kernel above
+      return rc;
+    }
     B200_NV_SWITCH(row_nv<bf16>(D), {
       if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(combine_bwd_kernel<bf16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
