@@ -266,10 +266,11 @@ def test_cross_modal_fusion_d768_bf16_matches_oracle(mode, tol):
     assert rel_err(q.grad, qr.grad) < 3e-2, rel_err(q.grad, qr.grad)
 
 
-# ---- router: the token-blocked bf16 path against the oracle ---------------------------------------------------------
-@pytest.mark.parametrize("N,E,K", [(32, 8, 2), (1000, 8, 2), (14592, 8, 2), (333, 5, 3)])
-def test_router_bf16_fast_path_matches_oracle_at_d768(N, E, K):
-    D = 768
+# ---- router: the bf16 tensor-core path (E <= 8, D % 128 == 0: 3-term bf16 split of the fp32 gate weights) and the
+# token-blocked FMA path (other D) against the oracle --------------------------------------------------------------
+@pytest.mark.parametrize("N,E,K,D", [(32, 8, 2, 768), (1000, 8, 2, 768), (14592, 8, 2, 768), (333, 5, 3, 768),
+                                     (17, 3, 1, 128), (4097, 7, 4, 1024), (2050, 8, 8, 256), (555, 8, 2, 320)])
+def test_router_bf16_fast_path_matches_oracle_at_d768(N, E, K, D):
     rng = np.random.default_rng(N + E)
     x0 = bf16_representable(torch.tensor(rng.standard_normal((1, N, D)), dtype=torch.float32))
     wg = torch.tensor(rng.standard_normal((E, D)) / np.sqrt(D), dtype=torch.float32)

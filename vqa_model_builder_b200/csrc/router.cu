@@ -8,6 +8,13 @@ namespace b200 {
 
 int launch_partial_reduce(const float* part, int blocks, int rows_per_block, int width, const int* tile_group, int G,
                           float* out, cudaStream_t stream);
+// router_mma.cu: tensor-core kernels for the common case (bf16 rows, E <= 8, no noise, D % 128 == 0)
+int launch_router_fwd_mma(const bf16* x, const float* w_gate, int N, int D, int E, int K, int* idx, float* w,
+                          float* topk_sum, float* probs, float* part, cudaStream_t stream);
+int launch_router_bwd_mma(const float* w_gate, float lb_weight, int N, int D, int E, int K, const int* idx,
+                          const float* w, const float* topk_sum, const float* probs, const float* counts,
+                          const float* d_w, const float* d_loss, const float* d_probs, bf16* dx, float* dl_out,
+                          cudaStream_t stream);
 
 namespace {
 
@@ -649,6 +656,17 @@ int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* 
   int blocks = router_grid(N);
   if (dtype == B200_BF16 && E <= 8 && eps == nullptr && nvb <= 4) blocks = router_grid_blocked(N);   // <= router_grid(N)
   float* part = (float*)workspace;
+  if (dtype == B200_BF16 && eps == nullptr) {
+    const int mb = launch_router_fwd_mma((const bf16*)x, w_gate, N, D, E, K, idx, w, topk_sum, probs, part, stream);
+    if (mb == -2) return cuda_fail(cudaGetLastError(), "launch router_fwd_mma_kernel");
+    if (mb > 0) {
+      launch_kernel(router_finalize_kernel, dim3(1), dim3(1024), 0, stream, part, mb, N, E, lb_weight, counts, psum, loss,
+                    (float*)nullptr);
+      B200_LAUNCH_CHECK("router_finalize_kernel");
+      count_launch(2);
+      return 0;
+    }
+  }
   if (dtype == B200_BF16) {
     B200_NV_SWITCH(nvb, {
       if (E <= 8) {
@@ -709,7 +727,15 @@ int b200_router_bwd(const void* x, int dtype, const float* w_gate, const float* 
   const int chunks = (N + RW_CHUNK - 1) / RW_CHUNK;
   dim3 wg_grid((D + 127) / 128, chunks);
   const int ED = E * D;
-  if (dtype == B200_BF16) {
+  int mma_rc = -1;
+  if (dtype == B200_BF16 && !noisy) {
+    mma_rc = launch_router_bwd_mma(w_gate, lb_weight, N, D, E, K, idx, w, topk_sum, probs, counts, d_w, d_loss, d_probs,
+                                   (bf16*)dx, dl, stream);
+    if (mma_rc == -2) return cuda_fail(cudaGetLastError(), "launch router_bwd_mma_kernel");
+  }
+  if (mma_rc == 0) {
+    // dl and dx are done: only the weight gradient below remains
+  } else if (dtype == B200_BF16) {
     B200_NV_SWITCH(nvb, {
       if (E <= 8) {
         if (int rc = set_smem(router_bwd_kernel<bf16, NV, 8>, smem)) return rc;
