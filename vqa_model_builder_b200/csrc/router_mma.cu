@@ -26,6 +26,7 @@ namespace {
 
 constexpr int RM_WARPS = 8;
 constexpr int RM_MAX_E = 64;   // partial layout shared with router_finalize_kernel: [grid][3][64]
+constexpr int RM_BATCH = 8;    // 32-column chunks per load batch: 2 x 8 x 16 B per thread in flight, double-buffered
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                           uint32_t b0, uint32_t b1) {
@@ -114,7 +115,7 @@ __device__ __forceinline__ void route_row(float l0, float l1, int n, bool ok, in
   }
 }
 
-__global__ void __launch_bounds__(RM_WARPS * 32, 2)
+__global__ void __launch_bounds__(RM_WARPS * 32, 1)
 router_fwd_mma_kernel(const bf16* __restrict__ x, const float* __restrict__ w_gate, int N, int D, int E, int K,
                       int* __restrict__ idx, float* __restrict__ w, float* __restrict__ topk_sum,
                       float* __restrict__ probs, float* __restrict__ part /* [grid][3][64] */) {
@@ -125,30 +126,37 @@ router_fwd_mma_kernel(const bf16* __restrict__ x, const float* __restrict__ w_ga
   pdl_wait();
   const int chunks = D >> 5;
   // stage the split gate weights in fragment order: unit (c, lane): expert g = lane >> 2, columns 32c + 8t .. +7
-  for (int u = threadIdx.x; u < chunks * 32; u += blockDim.x) {
-    const int c = u >> 5, ln = u & 31, g = ln >> 2, t = ln & 3;
-    float v[8];
-    if (g < E) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(w_gate + (long long)g * D + c * 32 + t * 8));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(w_gate + (long long)g * D + c * 32 + t * 8 + 4));
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
+  auto stage_weights = [&]() {
+#pragma unroll 2
+    for (int u = threadIdx.x; u < chunks * 32; u += blockDim.x) {
+      const int c = u >> 5, ln = u & 31, eg = ln >> 2, et = ln & 3;
+      float v[8];
+      if (eg < E) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w_gate + (long long)eg * D + c * 32 + et * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(w_gate + (long long)eg * D + c * 32 + et * 8 + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      bf16 h[8], m[8], l[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) split3(v[i], h[i], m[i], l[i]);
+      ws[(0 * chunks + c) * 32 + ln] = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+      ws[(1 * chunks + c) * 32 + ln] = make_uint4(pack2(m[0], m[1]), pack2(m[2], m[3]), pack2(m[4], m[5]), pack2(m[6], m[7]));
+      ws[(2 * chunks + c) * 32 + ln] = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
     }
-    bf16 h[8], m[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) split3(v[i], h[i], m[i], l[i]);
-    ws[(0 * chunks + c) * 32 + ln] = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-    ws[(1 * chunks + c) * 32 + ln] = make_uint4(pack2(m[0], m[1]), pack2(m[2], m[3]), pack2(m[4], m[5]), pack2(m[6], m[7]));
-    ws[(2 * chunks + c) * 32 + ln] = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
-  }
-  __syncthreads();
+    __syncthreads();
+  };
+  bool staged = false;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int ntiles = (N + 15) >> 4;
   float cnt[2] = {0.f, 0.f}, ps[2] = {0.f, 0.f};
-  for (int tile = blockIdx.x * RM_WARPS + warp; tile < ntiles; tile += gridDim.x * RM_WARPS) {
+  // every warp of the block runs the same number of iterations (staging has a block-wide barrier in the first one)
+  const int iters = (ntiles - blockIdx.x * RM_WARPS + gridDim.x * RM_WARPS - 1) / (gridDim.x * RM_WARPS);
+  for (int it = 0; it < iters; ++it) {
+    const int tile = blockIdx.x * RM_WARPS + warp + it * gridDim.x * RM_WARPS;
     const int n0 = tile * 16 + g, n1 = n0 + 8;
     const bool ok0 = n0 < N, ok1 = n1 < N;
     const uint4* r0 = reinterpret_cast<const uint4*>(x + (long long)(ok0 ? n0 : 0) * D) + t;
@@ -158,32 +166,38 @@ router_fwd_mma_kernel(const bf16* __restrict__ x, const float* __restrict__ w_ga
     for (int s = 0; s < 3; ++s)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[s][i] = 0.f;
-    // batches of 4 chunks (128 columns): the loads of batch b+1 are in flight while batch b multiplies
-    uint4 a0[4], a1[4];
+    // batches of RM_BATCH chunks: the loads of batch b+1 are in flight while batch b multiplies
+    uint4 a0[RM_BATCH], a1[RM_BATCH];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      a0[i] = ok0 ? __ldg(r0 + 4 * i) : make_uint4(0, 0, 0, 0);
-      a1[i] = ok1 ? __ldg(r1 + 4 * i) : make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < RM_BATCH; ++i) {
+      a0[i] = (ok0 && i < chunks) ? __ldg(r0 + 4 * i) : make_uint4(0, 0, 0, 0);
+      a1[i] = (ok1 && i < chunks) ? __ldg(r1 + 4 * i) : make_uint4(0, 0, 0, 0);
     }
-    for (int cb = 0; cb < chunks; cb += 4) {
-      uint4 b0[4], b1[4];
-      const bool more = cb + 4 < chunks;
+    if (!staged) {          // first tile: the weight staging below overlaps the first batch of row loads
+      stage_weights();
+      staged = true;
+    }
+    for (int cb = 0; cb < chunks; cb += RM_BATCH) {
+      uint4 b0[RM_BATCH], b1[RM_BATCH];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        b0[i] = (more && ok0) ? __ldg(r0 + 4 * (cb + 4 + i)) : make_uint4(0, 0, 0, 0);
-        b1[i] = (more && ok1) ? __ldg(r1 + 4 * (cb + 4 + i)) : make_uint4(0, 0, 0, 0);
+      for (int i = 0; i < RM_BATCH; ++i) {
+        const bool in = cb + RM_BATCH + i < chunks;
+        b0[i] = (in && ok0) ? __ldg(r0 + 4 * (cb + RM_BATCH + i)) : make_uint4(0, 0, 0, 0);
+        b1[i] = (in && ok1) ? __ldg(r1 + 4 * (cb + RM_BATCH + i)) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < RM_BATCH; ++i) {
+        if (cb + i < chunks) {
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const uint4 wv = ws[(s * chunks + cb + i) * 32 + lane];
-          mma_16816(acc[s], a0[i].x, a1[i].x, a0[i].y, a1[i].y, wv.x, wv.y);
-          mma_16816(acc[s], a0[i].z, a1[i].z, a0[i].w, a1[i].w, wv.z, wv.w);
+          for (int s = 0; s < 3; ++s) {
+            const uint4 wv = ws[(s * chunks + cb + i) * 32 + lane];
+            mma_16816(acc[s], a0[i].x, a1[i].x, a0[i].y, a1[i].y, wv.x, wv.y);
+            mma_16816(acc[s], a0[i].z, a1[i].z, a0[i].w, a1[i].w, wv.z, wv.w);
+          }
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a0[i] = b0[i]; a1[i] = b1[i]; }
+      for (int i = 0; i < RM_BATCH; ++i) { a0[i] = b0[i]; a1[i] = b1[i]; }
     }
     float lg[4];
 #pragma unroll
@@ -326,9 +340,9 @@ router_bwd_mma_kernel(const float* __restrict__ w_gate, float lb_weight, int N, 
   }
 }
 
-inline int mma_grid(int N) {
+inline int mma_grid(int N, int per_sm) {
   const int need = (((N + 15) >> 4) + RM_WARPS - 1) / RM_WARPS;
-  const int cap = num_sms() * 2;
+  const int cap = num_sms() * per_sm;
   return need < cap ? (need < 1 ? 1 : need) : cap;
 }
 
@@ -356,7 +370,7 @@ int launch_router_fwd_mma(const bf16* x, const float* w_gate, int N, int D, int 
       return -2;
     attr_set = true;
   }
-  const int grid = mma_grid(N);
+  const int grid = mma_grid(N, 1);
   launch_kernel(router_fwd_mma_kernel, dim3(grid), dim3(RM_WARPS * 32), smem, stream, x, w_gate, N, D, E, K, idx, w,
                 topk_sum, probs, part);
   if (cudaGetLastError() != cudaSuccess) return -2;
@@ -375,7 +389,7 @@ int launch_router_bwd_mma(const float* w_gate, float lb_weight, int N, int D, in
       return -2;
     attr_set = true;
   }
-  const int grid = mma_grid(N);
+  const int grid = mma_grid(N, 2);
   launch_kernel(router_bwd_mma_kernel, dim3(grid), dim3(RM_WARPS * 32), smem, stream, w_gate, lb_weight, N, D, E, K, idx,
                 w, topk_sum, probs, counts, d_w, d_loss, d_probs, dx, dl_out);
   if (cudaGetLastError() != cudaSuccess) return -2;
