@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200VQA_ABI_VERSION 1
+#define B200VQA_ABI_VERSION 2
 
 enum { B200_OK = 0, B200_ERR_INVALID = 1, B200_ERR_CUDA = 2, B200_ERR_UNSUPPORTED = 3 };
 enum { B200_F32 = 0, B200_BF16 = 1 };
@@ -149,15 +149,37 @@ int b200_add_ln_bwd(const void* dy, const void* x, const void* res, const float*
  * (vqa_model.py:300,304; fusion_approaches.py:262-277; TransformerEncoderLayer self-attn in
  * generative_vqa_model.py:203-214).  q/k/v are [B, T|S, H, dh] views with row pitches ldq/ldk/ldv
  * (elements; lets q,k,v alias one packed in-proj output).  key_pad [B,S] uint8, 1 = ignore, or NULL.
+ * causal != 0 (needs T == S): key s is visible to query t only if s <= t — the tgt_mask of the generative decoder's
+ * self-attention (generative_vqa_model.py:404-406,448-451; nn.TransformerDecoderLayer).
  * lse [B,H,T] fp32 is saved for backward.  The [B,H,T,S] score tensor never touches HBM.  `drop` applies
  * attention-probability dropout (element index = ((b*H+h)*T+t)*S+s).                                 */
 int b200_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
-                  const uint8_t* key_pad, void* o, int ldo, float* lse, int B, int H, int T, int S, int dh,
+                  const uint8_t* key_pad, int causal, void* o, int ldo, float* lse, int B, int H, int T, int S, int dh,
                   float scale, int dtype, const b200_dropout_t* drop, void* stream);
 int b200_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
-                  const uint8_t* key_pad, const void* o, int ldo, const void* d_o, int lddo,
+                  const uint8_t* key_pad, int causal, const void* o, int ldo, const void* d_o, int lddo,
                   const float* lse, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int B,
                   int H, int T, int S, int dh, float scale, int dtype, const b200_dropout_t* drop, void* stream);
+
+/* ---- generative decoder glue ---------------------------------------------------------------- */
+/* out[n,:] = dropout(table[ids[n],:] + pos[n % T,:]): nn.Embedding + PositionalEncoding (+ its dropout) of the answer
+ * decoder (generative_vqa_model.py:400-402, 453-476).  ids int32 [N] (N = B*T, clamped to [0,V)), table [V,D] in the
+ * compute dtype, pos fp32 [>= T, D] (the registered `pe` buffer).  Dropout element index = n*D + d.              */
+int b200_embed_fwd(const int32_t* ids, const void* table, const float* pos, void* out, int N, int T, int D, int V,
+                   int dtype, const b200_dropout_t* drop, void* stream);
+/* dtable[ids[n],:] += mask * dout[n,:]  (fp32 atomics into a caller-zeroed or accumulating [V,D] buffer).       */
+int b200_embed_bwd(const int32_t* ids, const void* dout, float* dtable, int N, int D, int V, int dtype,
+                   const b200_dropout_t* drop, void* stream);
+/* nn.CrossEntropyLoss(ignore_index, label_smoothing) with mean reduction over the non-ignored rows
+ * (generative_vqa_model.py:508-511,585-587; classification loss of vqa_model.py:705-713 with smoothing 0).
+ * logits [R, C] with row pitch ld (elements), labels int32 [R].  One streaming pass: loss_rows[R], lse[R] (saved for
+ * backward), loss[1] = sum(loss_rows) / n_valid, n_valid[1].  Backward: one pass, dlogits = dloss/n_valid *
+ * (softmax - (1-eps) onehot - eps/C), zeros for ignored rows; dlogits may alias logits.                          */
+int b200_ce_fwd(const void* logits, long long ld, const int32_t* labels, int R, int C, int ignore_index, float smoothing,
+                int dtype, float* loss_rows, float* lse, float* loss, float* n_valid, void* stream);
+int b200_ce_bwd(const void* logits, long long ld, const int32_t* labels, const float* lse, int R, int C,
+                int ignore_index, float smoothing, int dtype, const float* dloss, const float* n_valid, void* dlogits,
+                long long ldd, void* stream);
 
 /* ---- MOE router ------------------------------------------------------------------------------ */
 /* TopKRouter / NoisyTopKRouter forward (router.py:105-178, 287-366): logits = x Wg^T in fp32,

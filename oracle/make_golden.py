@@ -182,7 +182,7 @@ def main():
          grads=grads_of(m))
 
 
-if __name__ == "__main__" and not ({"--r2", "--n4", "--n3"} & set(sys.argv)):
+if __name__ == "__main__" and not ({"--r2", "--n4", "--n3", "--n2"} & set(sys.argv)):
     main()
 
 
@@ -478,6 +478,44 @@ def main_n3():
              text_valid=tvalid, gout=gout, out=out, d_vision=v.grad, d_text=t.grad, grads=grads_of(m))
 
 
+def main_n2():
+    """the reference's TransformerDecoder (tied 97-way vocabulary, 2 layers) and its label-smoothed
+    cross-entropy with ignored positions, forward + backward."""
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    from src.modeling.meta_arch.generative_vqa_model import GenerativeVQAConfig, TransformerDecoder
+    rng = np.random.default_rng(20261022)
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+    B, T, S, D, H, L, F, V = 3, 9, 11, 64, 4, 2, 128, 97
+    cfg = GenerativeVQAConfig(hidden_size=D, num_decoder_layers=L, num_attention_heads=H, decoder_ff_dim=F,
+                              decoder_dropout=0.0, max_answer_length=16, vocab_size=V, tie_word_embeddings=True,
+                              label_smoothing=0.1)
+    emb = torch.nn.Embedding(V, D)
+    m = TransformerDecoder(cfg, embedding=emb)
+    sd = rnd_state_dict(m, 91)
+    sd["output_projection.weight"] = sd["embedding.weight"]          # tied
+    sd["pos_encoding.pe"] = m.state_dict()["pos_encoding.pe"]        # the sinusoid buffer is not random
+    m.load_state_dict(sd)
+    m.train()
+    memory = f32(rng.standard_normal((B, S, D))).requires_grad_()
+    ids = torch.tensor(rng.integers(0, V, size=(B, T)), dtype=torch.long)
+    mem_mask = torch.ones(B, S)
+    mem_mask[1, -3:] = 0
+    tgt_mask = torch.ones(B, T)
+    tgt_mask[0, -2:] = 0
+    tgt_mask[2, -4:] = 0
+    labels = torch.tensor(rng.integers(0, V, size=(B, T)), dtype=torch.long)
+    labels[tgt_mask == 0] = -100
+    logits = m(memory, ids, encoder_attention_mask=mem_mask, decoder_attention_mask=tgt_mask)
+    loss = torch.nn.CrossEntropyLoss(ignore_index=-100, label_smoothing=0.1)(logits.view(-1, V), labels.view(-1))
+    loss.backward()
+    save("generative_decoder", cfg=np.array([B, T, S, D, H, L, F, V]), sd=sd, memory=memory.detach(), ids=ids,
+         mem_mask=mem_mask, tgt_mask=tgt_mask, labels=labels, logits=logits, loss=loss, d_memory=memory.grad,
+         grads=grads_of(m))
+
+
+if __name__ == "__main__" and "--n2" in sys.argv:
+    main_n2()
 if __name__ == "__main__" and "--n3" in sys.argv:
     main_n3()
 if __name__ == "__main__" and "--r2" in sys.argv:

@@ -349,3 +349,75 @@ def cross_modal_fusion(sd: SD, num_heads: int, num_layers: int, visual, question
         fused, aux, _, _, _ = moe_layer(sub, fused, moe["num_experts"], moe["top_k"], moe.get("lb_weight", 0.01),
                                         pdrop=pdrop)
     return layer_norm(fused, sd["layer_norm.weight"], sd["layer_norm.bias"]), aux
+
+
+# ---- N2: TransformerDecoder + label-smoothed cross-entropy (generative_vqa_model.py:342-451, 453-476, 508-511,
+# 585-587) ------------------------------------------------------------------------------------------------------------
+def mha_masked(sd: SD, p: str, q_in, kv_in, num_heads: int, key_padding_mask, causal: bool, pdrop: float = 0.0):
+    """mha() plus the additive causal mask of the decoder's self-attention (tgt_mask = triu(-inf, diagonal=1),
+    generative_vqa_model.py:404-406,448-451).  The reference passes the padding masks as float 0 / -inf tensors
+    (:411-430): added to the scores, which is the same as masked_fill(-inf)."""
+    B, T, D = q_in.shape
+    S = kv_in.shape[1]
+    W, bias = sd[p + "in_proj_weight"], sd[p + "in_proj_bias"]
+    q = q_in @ W[:D].t() + bias[:D]
+    k = kv_in @ W[D:2 * D].t() + bias[D:2 * D]
+    v = kv_in @ W[2 * D:].t() + bias[2 * D:]
+    dh = D // num_heads
+    q = q.view(B, T, num_heads, dh).transpose(1, 2) * (1.0 / math.sqrt(dh))
+    k = k.view(B, S, num_heads, dh).transpose(1, 2)
+    v = v.view(B, S, num_heads, dh).transpose(1, 2)
+    scores = q @ k.transpose(-1, -2)
+    if causal:
+        scores = scores + torch.triu(torch.full((T, S), float("-inf"), dtype=scores.dtype), diagonal=1)
+    if key_padding_mask is not None:
+        scores = scores.masked_fill(key_padding_mask.bool()[:, None, None, :], float("-inf"))
+    ctx = drop(torch.softmax(scores, dim=-1), pdrop) @ v
+    ctx = ctx.transpose(1, 2).reshape(B, T, D)
+    return ctx @ sd[p + "out_proj.weight"].t() + sd[p + "out_proj.bias"]
+
+
+def sinusoidal_positions(max_len: int, d_model: int) -> torch.Tensor:
+    """PositionalEncoding.pe (generative_vqa_model.py:458-467)."""
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(max_len, d_model)
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def transformer_decoder(sd: SD, num_heads: int, num_layers: int, memory, ids, memory_mask=None, tgt_mask=None,
+                        pdrop: float = 0.0):
+    """TransformerDecoder.forward: embedding + positions (+dropout), L x nn.TransformerDecoderLayer(norm_first=True,
+    gelu): x += drop(SA(LN1 x, causal, tgt padding)); x += drop(CA(LN2 x, memory, memory padding));
+    x += drop(FF(LN3 x)); final LayerNorm; tied / untied output projection without bias.  Masks: 1 = attend."""
+    E = sd["embedding.weight"]
+    T = ids.shape[1]
+    pe = sd["pos_encoding.pe"][0] if "pos_encoding.pe" in sd else sinusoidal_positions(T, E.shape[1])
+    x = drop(E[ids] + pe[:T].to(E.dtype), pdrop)
+    mem_pad = (memory_mask == 0) if memory_mask is not None else None
+    tgt_pad = (tgt_mask == 0) if tgt_mask is not None else None
+    for l in range(num_layers):
+        p = f"decoder.layers.{l}."
+        h = layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+        x = x + drop(mha_masked(sd, p + "self_attn.", h, h, num_heads, tgt_pad, True, pdrop), pdrop)
+        h = layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+        x = x + drop(mha_masked(sd, p + "multihead_attn.", h, memory, num_heads, mem_pad, False, pdrop), pdrop)
+        h = layer_norm(x, sd[p + "norm3.weight"], sd[p + "norm3.bias"])
+        x = x + ffn(sd, p + "linear1.", p + "linear2.", h, pdrop=pdrop)
+    x = layer_norm(x, sd["layer_norm.weight"], sd["layer_norm.bias"])
+    return x @ sd["output_projection.weight"].t()
+
+
+def smoothed_cross_entropy(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100,
+                           smoothing: float = 0.0) -> torch.Tensor:
+    """nn.CrossEntropyLoss(ignore_index, label_smoothing), mean over the non-ignored rows:
+    loss_n = (1 - eps) * (lse - z_y) + eps * (lse - mean_c z_c)."""
+    z = logits.reshape(-1, logits.shape[-1])
+    y = labels.reshape(-1)
+    valid = y != ignore_index
+    lse = torch.logsumexp(z, dim=-1)
+    zy = z.gather(1, y.clamp(min=0).unsqueeze(1)).squeeze(1)
+    per = (1.0 - smoothing) * (lse - zy) + smoothing * (lse - z.mean(dim=-1))
+    return (per * valid).sum() / valid.sum()

@@ -50,7 +50,7 @@ def test_library_builds_loads_and_exports_every_symbol():
     for name in parse_header():
         assert hasattr(lib, name), f"{name} declared in b200vqa.h but not exported"
     lib.b200_abi_version.restype = ctypes.c_int
-    assert lib.b200_abi_version() == 1
+    assert lib.b200_abi_version() == 2
 
 
 def test_ctypes_signatures_match_header():

@@ -14,7 +14,7 @@ from vqa_model_builder_b200 import ops  # noqa: E402
 DEV = "cuda"
 
 
-def ref_attn(q, k, v, pad, H):
+def ref_attn(q, k, v, pad, H, causal=False):
     B, T, D = q.shape
     S = k.shape[1]
     dh = D // H
@@ -24,6 +24,8 @@ def ref_attn(q, k, v, pad, H):
     s = qh @ kh.transpose(-1, -2)
     if pad is not None:
         s = s.masked_fill(pad.bool()[:, None, None, :], float("-inf"))
+    if causal:
+        s = s.masked_fill(torch.triu(torch.ones(T, S, dtype=torch.bool, device=s.device), diagonal=1), float("-inf"))
     return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, T, D)
 
 
@@ -68,6 +70,28 @@ def test_self_attention_packed(dtype):
     (o.float() * gout.float()).sum().backward()
     r = qkv.detach().double().requires_grad_()
     ref = ref_attn(r[:, :D].reshape(B, T, D), r[:, D:2 * D].reshape(B, T, D), r[:, 2 * D:].reshape(B, T, D), pad, H)
+    (ref.reshape(B * T, D) * gout.double()).sum().backward()
+    t = 2e-5 if dtype == torch.float32 else 8e-3
+    assert rel_err(o, ref.reshape(B * T, D)) < t
+    assert rel_err(qkv.grad, r.grad) < t
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,T,D", [(3, 8, 64, 768), (2, 4, 9, 64), (2, 8, 114, 768), (2, 8, 33, 768), (1, 2, 200, 64)])
+def test_causal_self_attention(B, H, T, D, dtype):
+    """Decoder self-attention (generative_vqa_model.py:404-406): causal mask combined with a key-padding mask, on the
+    64-row and 128-row tensor-core flavours (bf16), the SIMT kernels (fp32, T > 128) — forward and backward."""
+    g = torch.Generator(device=DEV).manual_seed(B * 100 + T)
+    qkv = torch.randn(B * T, 3 * D, generator=g, device=DEV).to(dtype).requires_grad_()
+    pad = torch.zeros(B, T, dtype=torch.uint8, device=DEV)
+    for b in range(B):
+        pad[b, T - b:] = 1 if b else 0           # trailing padding; position 0 always valid
+    gout = torch.randn(B * T, D, generator=g, device=DEV).to(dtype)
+    o = ops.AttentionFn.apply(qkv, None, pad, B, T, T, H, True, None, True)
+    (o.float() * gout.float()).sum().backward()
+    r = qkv.detach().double().requires_grad_()
+    ref = ref_attn(r[:, :D].reshape(B, T, D), r[:, D:2 * D].reshape(B, T, D), r[:, 2 * D:].reshape(B, T, D), pad, H,
+                   causal=True)
     (ref.reshape(B * T, D) * gout.double()).sum().backward()
     t = 2e-5 if dtype == torch.float32 else 8e-3
     assert rel_err(o, ref.reshape(B * T, D)) < t

@@ -345,3 +345,21 @@ def test_single_stream_fusion():
     (out * g["gout"]).sum().backward()
     assert rel_err(vis.grad, g["d_vision"]) < TOL and rel_err(txt.grad, g["d_text"]) < TOL
     _check_grads(sd, g["grads"], tol=5e-5)
+
+
+def test_generative_decoder_and_smoothed_cross_entropy():
+    """the restated TransformerDecoder (causal + padding masks, cross-attention to the fused memory,
+    tied output projection) and label-smoothed CE with ignored positions against the reference's own run."""
+    g = load_golden("generative_decoder")
+    B, T, S, D, H, L, F, V = [int(v) for v in g["cfg"]]
+    sd = _leafs(g["sd"])
+    mem = g["memory"].clone().requires_grad_()
+    logits = rp.transformer_decoder(sd, H, L, mem, g["ids"].long(), g["mem_mask"], g["tgt_mask"])
+    assert rel_err(logits, g["logits"]) < TOL
+    loss = rp.smoothed_cross_entropy(logits, g["labels"].long(), -100, 0.1)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    loss.backward()
+    assert rel_err(mem.grad, g["d_memory"]) < TOL
+    tied = sd["embedding.weight"].grad + sd["output_projection.weight"].grad
+    assert rel_err(tied, g["grads"]["embedding.weight"]) < TOL
+    _check_grads(sd, {k: v for k, v in g["grads"].items() if k != "embedding.weight"})

@@ -45,8 +45,12 @@ SIGNATURES = {
     "b200_add_ln_fwd": ("i", "pppppfpppiiipip"),
     "b200_add_ln_bwd_ws": ("z", "ii"),
     "b200_add_ln_bwd": ("i", "pppppppippppiiipippzp"),
-    "b200_attn_fwd": ("i", "pipipippipiiiiifipp"),
-    "b200_attn_bwd": ("i", "pipipippipippipipiiiiiifipp"),
+    "b200_attn_fwd": ("i", "pipipipipipiiiiifipp"),
+    "b200_attn_bwd": ("i", "pipipipipipippipipiiiiiifipp"),
+    "b200_embed_fwd": ("i", "ppppiiiiipp"),
+    "b200_embed_bwd": ("i", "pppiiiipp"),
+    "b200_ce_fwd": ("i", "plpiiifippppp"),
+    "b200_ce_bwd": ("i", "plppiiifippplp"),
     "b200_router_ws": ("z", "ii"),
     "b200_router_fwd": ("i", "pipppffiiiippppppppppzp"),
     "b200_router_bwd_ws": ("z", "iii"),
@@ -111,7 +115,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = {"s": ctypes.c_char_p, "v": None}.get(res, _C.get(res))
         fn.argtypes = [_C[c] for c in args]
-    if lib.b200_abi_version() != 1:
+    if lib.b200_abi_version() != 2:
         raise RuntimeError("libb200vqa.so ABI version mismatch")
     _lib = lib
     return lib

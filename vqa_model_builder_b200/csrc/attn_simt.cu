@@ -21,7 +21,7 @@ template <typename T>
 __global__ void __launch_bounds__(FA_WARPS * 32)
 attn_fwd_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int ldk, const T* __restrict__ v, int ldv,
                 const uint8_t* __restrict__ key_pad, T* __restrict__ o, int ldo, float* __restrict__ lse, int H, int Tq,
-                int S, int dh, float scale, const unsigned long long* drop_state, float drop_p, unsigned int drop_site) {
+                int S, int dh, float scale, const unsigned long long* drop_state, float drop_p, unsigned int drop_site, int causal) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
@@ -73,7 +73,7 @@ attn_fwd_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int l
       for (int jj = 0; jj < FA_SC / 32; ++jj) {
         const int j = lane + 32 * jj;
         float s = -INFINITY;
-        if (j < sc && !(key_pad != nullptr && key_pad[(long long)b * S + s0 + j])) {
+        if (j < sc && !(key_pad != nullptr && key_pad[(long long)b * S + s0 + j]) && !(causal && s0 + j > t)) {
           s = 0.f;
           const float* kr = Ks + j * LD;
           for (int d = 0; d < dh; ++d) s = fmaf(qs[d], kr[d], s);
@@ -166,7 +166,7 @@ attn_bwd_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int l
                 const uint8_t* __restrict__ key_pad, const T* __restrict__ o, int ldo, const T* __restrict__ d_o,
                 int lddo, const float* __restrict__ lse, T* __restrict__ dq, int lddq, T* __restrict__ dk, int lddk,
                 T* __restrict__ dv, int lddv, int H, int Tq, int S, int dh, float scale,
-                const unsigned long long* drop_state, float drop_p, unsigned int drop_site) {
+                const unsigned long long* drop_state, float drop_p, unsigned int drop_site, int causal) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
@@ -252,7 +252,7 @@ attn_bwd_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int l
       const int r = i / BT, c = i % BT;
       const int t = t0 + r, s = s0 + c;
       float p = 0.f;
-      if (t < Tq && s < S && !(key_pad != nullptr && key_pad[(long long)b * S + s]))
+      if (t < Tq && s < S && !(key_pad != nullptr && key_pad[(long long)b * S + s]) && !(causal && s > t))
         p = __expf(Ps[r * LS + c] - lses[r]);
       float keep = 1.f;
       if (ds.on && p != 0.f)
@@ -301,10 +301,10 @@ int set_smem(K kern, size_t bytes) {
 // tensor-core path (attn_tc.cu)
 bool attn_tc_supported(int T, int S, int dh, int ldq, int ldk, int ldv, const void* q, const void* k, const void* v);
 int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
-                       void* o, int ldo, float* lse, int B, int H, int T, int S, int dh, float scale,
+                       int causal, void* o, int ldo, float* lse, int B, int H, int T, int S, int dh, float scale,
                        const unsigned long long* drop_state, float drop_p, unsigned int drop_site, cudaStream_t stream);
 int launch_attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
-                       const void* o, int ldo, const void* d_o, int lddo, const float* lse, void* dq, int lddq, void* dk,
+                       int causal, const void* o, int ldo, const void* d_o, int lddo, const float* lse, void* dq, int lddq, void* dk,
                        int lddk, void* dv, int lddv, int B, int H, int T, int S, int dh, float scale,
                        const unsigned long long* drop_state, float drop_p, unsigned int drop_site, cudaStream_t stream);
 
@@ -323,7 +323,7 @@ using namespace b200;
 extern "C" {
 
 int b200_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
-                  void* o, int ldo, float* lse, int B, int H, int T, int S, int dh, float scale, int dtype,
+                  int causal, void* o, int ldo, float* lse, int B, int H, int T, int S, int dh, float scale, int dtype,
                   const b200_dropout_t* drop, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool don = drop != nullptr && drop->p > 0.f;
@@ -332,9 +332,10 @@ int b200_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v,
   const unsigned int dsite = don ? drop->site : 0u;
   B200_CHECK_ARG(B > 0 && H > 0 && T > 0 && S > 0 && dh > 0 && dh <= 128 && dh % 4 == 0,
                  "attn_fwd: bad shape B=%d H=%d T=%d S=%d dh=%d (dh<=128, dh%%4==0)", B, H, T, S, dh);
+  B200_CHECK_ARG(!causal || T == S, "attn_fwd: the causal mask needs T == S (got %d, %d)", T, S);
   if (dtype == B200_BF16 && use_tc_attention() && attn_tc_supported(T, S, dh, ldq, ldk, ldv, q, k, v) &&
       ldo % 8 == 0 && ((uintptr_t)o & 15) == 0)
-    return launch_attn_fwd_tc(q, ldq, k, ldk, v, ldv, key_pad, o, ldo, lse, B, H, T, S, dh, scale, dst, dpp, dsite,
+    return launch_attn_fwd_tc(q, ldq, k, ldk, v, ldv, key_pad, causal, o, ldo, lse, B, H, T, S, dh, scale, dst, dpp, dsite,
                               stream);
   dim3 grid(B * H, (T + FA_TQ - 1) / FA_TQ);
   const size_t smem = fwd_smem(dh);
@@ -342,12 +343,12 @@ int b200_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v,
     if (int rc = set_smem(attn_fwd_kernel<bf16>, smem)) return rc;
     launch_kernel(attn_fwd_kernel<bf16>, dim3(grid), dim3(FA_WARPS * 32), smem, stream, (const bf16*)q, ldq, (const bf16*)k, ldk,
                                                                  (const bf16*)v, ldv, key_pad, (bf16*)o, ldo, lse, H, T,
-                                                                 S, dh, scale, dst, dpp, dsite);
+                                                                 S, dh, scale, dst, dpp, dsite, causal);
   } else {
     if (int rc = set_smem(attn_fwd_kernel<float>, smem)) return rc;
     launch_kernel(attn_fwd_kernel<float>, dim3(grid), dim3(FA_WARPS * 32), smem, stream, (const float*)q, ldq, (const float*)k, ldk,
                                                                   (const float*)v, ldv, key_pad, (float*)o, ldo, lse, H,
-                                                                  T, S, dh, scale, dst, dpp, dsite);
+                                                                  T, S, dh, scale, dst, dpp, dsite, causal);
   }
   B200_LAUNCH_CHECK("attn_fwd_kernel");
   count_launch();
@@ -355,7 +356,7 @@ int b200_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v,
 }
 
 int b200_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
-                  const void* o, int ldo, const void* d_o, int lddo, const float* lse, void* dq, int lddq, void* dk,
+                  int causal, const void* o, int ldo, const void* d_o, int lddo, const float* lse, void* dq, int lddq, void* dk,
                   int lddk, void* dv, int lddv, int B, int H, int T, int S, int dh, float scale, int dtype,
                   const b200_dropout_t* drop, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -365,10 +366,11 @@ int b200_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v,
   const unsigned int dsite = don ? drop->site : 0u;
   B200_CHECK_ARG(B > 0 && H > 0 && T > 0 && S > 0 && dh > 0 && dh <= 128 && dh % 4 == 0,
                  "attn_bwd: bad shape B=%d H=%d T=%d S=%d dh=%d (dh<=128, dh%%4==0)", B, H, T, S, dh);
+  B200_CHECK_ARG(!causal || T == S, "attn_bwd: the causal mask needs T == S (got %d, %d)", T, S);
   if (dtype == B200_BF16 && use_tc_attention() && attn_tc_supported(T, S, dh, ldq, ldk, ldv, q, k, v) &&
       ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 &&
       (((uintptr_t)o | (uintptr_t)d_o | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0)
-    return launch_attn_bwd_tc(q, ldq, k, ldk, v, ldv, key_pad, o, ldo, d_o, lddo, lse, dq, lddq, dk, lddk, dv, lddv, B,
+    return launch_attn_bwd_tc(q, ldq, k, ldk, v, ldv, key_pad, causal, o, ldo, d_o, lddo, lse, dq, lddq, dk, lddk, dv, lddv, B,
                               H, T, S, dh, scale, dst, dpp, dsite, stream);
   const int bt = bwd_smem(dh, 64) <= 200 * 1024 ? 64 : 32;
   const size_t smem = bwd_smem(dh, bt);
@@ -379,11 +381,11 @@ int b200_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v,
     if (int rc = set_smem(attn_bwd_kernel<TT, 1, BTV>, smem)) return rc;                                         \
     launch_kernel(attn_bwd_kernel<TT, 0, BTV>, dim3(g0), dim3(256), smem, stream,                                                       \
         (const TT*)q, ldq, (const TT*)k, ldk, (const TT*)v, ldv, key_pad, (const TT*)o, ldo, (const TT*)d_o,     \
-        lddo, lse, (TT*)dq, lddq, (TT*)dk, lddk, (TT*)dv, lddv, H, T, S, dh, scale, dst, dpp, dsite);          \
+        lddo, lse, (TT*)dq, lddq, (TT*)dk, lddk, (TT*)dv, lddv, H, T, S, dh, scale, dst, dpp, dsite, causal);  \
     B200_LAUNCH_CHECK("attn_bwd_kernel<0>");                                                                     \
     launch_kernel(attn_bwd_kernel<TT, 1, BTV>, dim3(g1), dim3(256), smem, stream,                                                       \
         (const TT*)q, ldq, (const TT*)k, ldk, (const TT*)v, ldv, key_pad, (const TT*)o, ldo, (const TT*)d_o,     \
-        lddo, lse, (TT*)dq, lddq, (TT*)dk, lddk, (TT*)dv, lddv, H, T, S, dh, scale, dst, dpp, dsite);          \
+        lddo, lse, (TT*)dq, lddq, (TT*)dk, lddk, (TT*)dv, lddv, H, T, S, dh, scale, dst, dpp, dsite, causal);  \
     B200_LAUNCH_CHECK("attn_bwd_kernel<1>");                                                                     \
   } while (0)
   if (dtype == B200_BF16) {

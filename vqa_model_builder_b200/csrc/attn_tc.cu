@@ -25,6 +25,7 @@ struct AttnTcArgs {
   int B, H, T, S, dh;
   float scale;
   const uint8_t* key_pad;   // [B,S] 1 = ignore, or null
+  int causal;               // 1: key s is visible to query t only if s <= t (decoder self-attention)
   bf16* o; int ldo;         // fwd out
   float* lse;               // [B,H,T]
   // backward
@@ -194,7 +195,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int col = c * 32 + i;
-        const bool ok = col < n_valid && !(kp && kp[j * R + col]);
+        const bool ok = col < n_valid && !(kp && kp[j * R + col]) && !(a.causal && j * R + col > r);
         if (ok) m = fmaxf(m, v[i]);
       }
     }
@@ -214,7 +215,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int col = c * 32 + i;
-        const bool ok = col < n_valid && !(kp && kp[j * R + col]);
+        const bool ok = col < n_valid && !(kp && kp[j * R + col]) && !(a.causal && j * R + col > r);
         const float p = ok ? ex2(fmaf(v[i], sl2, -m_s)) : 0.f;
         // round to bf16 first so the normaliser matches the probabilities the tensor core actually sees
         const float pr = __bfloat162float(__float2bfloat16_rn(p));
@@ -399,7 +400,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int col = c * 32 + i;
-        const bool ok = row_ok && col < n_valid && !(kp && kp[j * R + col]);
+        const bool ok = row_ok && col < n_valid && !(kp && kp[j * R + col]) && !(a.causal && j * R + col > r);
         const float p = ok ? ex2(fmaf(s[i], sl2, -lse_l2)) : 0.f;
         s[i] = p * keep[i];                                               // dropped P feeds dV = P^T dO
         dp[i] = ok ? p * (dp[i] * keep[i] - delta) * a.scale : 0.f;       // dS = P (dP*mask/(1-p) - delta)
@@ -508,7 +509,7 @@ bool attn_tc_supported(int T, int S, int dh, int ldq, int ldk, int ldv, const vo
 }
 
 int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
-                       void* o, int ldo, float* lse, int B, int H, int T, int S, int dh, float scale,
+                       int causal, void* o, int ldo, float* lse, int B, int H, int T, int S, int dh, float scale,
                        const unsigned long long* drop_state, float drop_p, unsigned int drop_site, cudaStream_t stream) {
   CUtensorMap qm, km, vm;
   const long long cols = (long long)H * dh;
@@ -518,7 +519,7 @@ int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
   if (int rc = make_tma_map_bf16(&km, k, cols, (long long)B * S, ldk, box)) return rc;
   if (int rc = make_tma_map_bf16(&vm, v, cols, (long long)B * S, ldv, box)) return rc;
   AttnTcArgs a{};
-  a.B = B; a.H = H; a.T = T; a.S = S; a.dh = dh; a.scale = scale; a.key_pad = key_pad;
+  a.B = B; a.H = H; a.T = T; a.S = S; a.dh = dh; a.scale = scale; a.key_pad = key_pad; a.causal = causal;
   a.o = (bf16*)o; a.ldo = ldo; a.lse = lse;
   a.drop_state = drop_state; a.drop_p = drop_p; a.drop_site = drop_site;
   const int nt = (S + ROWS - 1) / ROWS;
@@ -540,7 +541,7 @@ int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
 }
 
 int launch_attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* key_pad,
-                       const void* o, int ldo, const void* d_o, int lddo, const float* lse, void* dq, int lddq, void* dk,
+                       int causal, const void* o, int ldo, const void* d_o, int lddo, const float* lse, void* dq, int lddq, void* dk,
                        int lddk, void* dv, int lddv, int B, int H, int T, int S, int dh, float scale,
                        const unsigned long long* drop_state, float drop_p, unsigned int drop_site, cudaStream_t stream) {
   CUtensorMap qm, km, vm, dom;
@@ -552,7 +553,7 @@ int launch_attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
   if (int rc = make_tma_map_bf16(&vm, v, cols, (long long)B * S, ldv, box)) return rc;
   if (int rc = make_tma_map_bf16(&dom, d_o, cols, (long long)B * T, lddo, box)) return rc;
   AttnTcArgs a{};
-  a.B = B; a.H = H; a.T = T; a.S = S; a.dh = dh; a.scale = scale; a.key_pad = key_pad;
+  a.B = B; a.H = H; a.T = T; a.S = S; a.dh = dh; a.scale = scale; a.key_pad = key_pad; a.causal = causal;
   a.lse = const_cast<float*>(lse);
   a.o_in = (const bf16*)o; a.ldo_in = ldo; a.d_o = (const bf16*)d_o; a.lddo = lddo;
   a.dq = (bf16*)dq; a.lddq = lddq; a.dk = (bf16*)dk; a.lddk = lddk; a.dv = (bf16*)dv; a.lddv = lddv;

@@ -22,7 +22,7 @@ def pad_mask_u8(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 def self_attention(x2, B, T, mha: nn.MultiheadAttention, slab: ParamSlab, key_pad_u8, residual=None, drop_attn=None,
-                   drop_out=None, passthrough=False):
+                   drop_out=None, passthrough=False, causal=False):
     """out_proj(softmax(q k^T / sqrt(dh) + mask) v) over x2 [B*T, D]; optional (dropout +) residual fused into
     out_proj.  passthrough=True returns (out, alias of x2): use the alias for the residual connection around this
     branch so the two gradients of x2 are summed in the in-projection's dgrad epilogue."""
@@ -34,14 +34,14 @@ def self_attention(x2, B, T, mha: nn.MultiheadAttention, slab: ParamSlab, key_pa
     else:
         qkv = ops.LinearFn.apply(x2, mha.in_proj_weight, mha.in_proj_bias,
                                  slab.compute_view(mha.in_proj_weight, cdt), None)
-    ctx = ops.AttentionFn.apply(qkv, None, key_pad_u8, B, T, T, mha.num_heads, True, drop_attn)
+    ctx = ops.AttentionFn.apply(qkv, None, key_pad_u8, B, T, T, mha.num_heads, True, drop_attn, causal)
     out = ops.LinearFn.apply(ctx, mha.out_proj.weight, mha.out_proj.bias,
                              slab.compute_view(mha.out_proj.weight, cdt), residual, drop_out)
     return (out, xr if xr is not None else x2) if passthrough else out
 
 
 def cross_attention(x2, kv2, B, T, S, mha: nn.MultiheadAttention, slab: ParamSlab, key_pad_u8, residual=None,
-                    drop_attn=None, passthrough=False):
+                    drop_attn=None, passthrough=False, drop_out=None):
     """Queries from x2 [B*T, D], keys/values from kv2 [B*S, D] (question -> image patches).  passthrough: see
     self_attention."""
     cdt = x2.dtype
@@ -54,7 +54,7 @@ def cross_attention(x2, kv2, B, T, S, mha: nn.MultiheadAttention, slab: ParamSla
                                        slab.compute_view(mha.in_proj_weight, cdt))
     ctx = ops.AttentionFn.apply(q, kvp, key_pad_u8, B, T, S, mha.num_heads, False, drop_attn)
     out = ops.LinearFn.apply(ctx, mha.out_proj.weight, mha.out_proj.bias,
-                             slab.compute_view(mha.out_proj.weight, cdt), residual)
+                             slab.compute_view(mha.out_proj.weight, cdt), residual, drop_out)
     return (out, xr if xr is not None else x2) if passthrough else out
 
 

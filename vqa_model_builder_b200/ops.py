@@ -186,7 +186,10 @@ class LinearFn(torch.autograd.Function):
         epi = EPI_ADD if residual is not None else EPI_NONE
         if residual is None:
             drop = None
-        y = gemm(x, LAYOUT_K, w_c, LAYOUT_K, M, N, K, bias=bias, epi=epi, aux_in=residual, drop=drop)
+        out = None
+        if residual is None and N % 8 != 0:     # e.g. a vocabulary that is not a multiple of 8: pad the row pitch
+            out = torch.empty((M, (N + 7) // 8 * 8), dtype=x.dtype, device=x.device)[:, :N]
+        y = gemm(x, LAYOUT_K, w_c, LAYOUT_K, M, N, K, out=out, bias=bias, epi=epi, aux_in=residual, drop=drop)
         ctx.save_for_backward(x, w_c)
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
@@ -200,7 +203,7 @@ class LinearFn(torch.autograd.Function):
         M, K = x.shape
         N = w_c.shape[0]
         pre_db = _take_colsum(dy, N) if ctx.drop is None else None
-        dy = dy.contiguous()
+        dy = _rows_aligned(dy)
         dx = dw = db = None
         side = None
         g = None
@@ -234,6 +237,17 @@ class LinearFn(torch.autograd.Function):
                 dx = gemm(g, LAYOUT_K, w_c, LAYOUT_MN, M, K, N)
         aux_join(side)
         return dx, dw, db, None, (dy if ctx.has_res else None), None, None
+
+
+def _rows_aligned(t: torch.Tensor) -> torch.Tensor:
+    """A 2-D operand whose rows start on 16-byte boundaries (row pitch padded to 8 elements when needed)."""
+    if t.stride(1) == 1 and (t.stride(0) * t.element_size()) % 16 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    if (t.shape[1] * t.element_size()) % 16 == 0:
+        return t.contiguous()
+    buf = torch.zeros((t.shape[0], (t.shape[1] + 7) // 8 * 8), dtype=t.dtype, device=t.device)
+    buf[:, :t.shape[1]] = t
+    return buf[:, :t.shape[1]]
 
 
 def _as_rows(g: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
@@ -400,6 +414,83 @@ class AddLNFn(torch.autograd.Function):
         return dsum, dbr, flat[:D], flat[D:2 * D], None, None
 
 
+# ---- generative decoder glue ------------------------------------------------------------------
+class EmbedFn(torch.autograd.Function):
+    """x[n] = dropout(E[ids[n]] + pe[n % T])  (nn.Embedding + PositionalEncoding, generative_vqa_model.py:400-402,
+    453-476).  `table_c` is the compute-dtype copy of the embedding matrix; the gradient goes to the fp32 master."""
+
+    @staticmethod
+    def forward(ctx, ids, table, table_c, pos, T, drop=None):
+        _lib.ensure_device(table_c)
+        ids = ids.reshape(-1).to(torch.int32).contiguous()
+        N = ids.numel()
+        V, D = table_c.shape
+        out = torch.empty((N, D), dtype=table_c.dtype, device=table_c.device)
+        call("b200_embed_fwd", ids, table_c, pos.contiguous(), out, N, int(T), D, V, dtype_code(table_c.dtype),
+             dropout_arg(drop), stream_ptr())
+        ctx.save_for_backward(ids)
+        ctx.cfg = (N, D, V, drop)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        N, D, V, drop = ctx.cfg
+        dout = dout.contiguous()
+        dtable = grad_buffer(V * D, dout.device).view(V, D)
+        dtable.zero_()
+        call("b200_embed_bwd", ids, dout, dtable, N, D, V, dtype_code(dout.dtype), dropout_arg(drop), stream_ptr())
+        return None, dtable, None, None, None, None
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """nn.CrossEntropyLoss(ignore_index, label_smoothing), mean over the non-ignored rows
+    (generative_vqa_model.py:508-511,585-587; vqa_model.py:705-713): one streaming pass over the logits for the loss,
+    one for the gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index, smoothing):
+        _lib.ensure_device(logits)
+        assert logits.dim() == 2 and logits.stride(1) == 1
+        R, C = logits.shape
+        labels = labels.reshape(-1).to(torch.int32).contiguous()
+        dev = logits.device
+        loss_rows = torch.empty(R, dtype=torch.float32, device=dev)
+        lse = torch.empty(R, dtype=torch.float32, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)      # loss, n_valid
+        call("b200_ce_fwd", logits, logits.stride(0), labels, R, C, int(ignore_index), float(smoothing),
+             dtype_code(logits.dtype), loss_rows, lse, out[:1], out[1:], stream_ptr())
+        ctx.save_for_backward(logits, labels, lse, out)
+        ctx.cfg = (int(ignore_index), float(smoothing))
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, labels, lse, out = ctx.saved_tensors
+        ignore_index, smoothing = ctx.cfg
+        R, C = logits.shape
+        dl = dloss.reshape(1).to(torch.float32).contiguous()
+        dlogits = torch.empty((R, logits.stride(0)), dtype=logits.dtype, device=logits.device)[:, :C]
+        call("b200_ce_bwd", logits, logits.stride(0), labels, lse, R, C, ignore_index, smoothing,
+             dtype_code(logits.dtype), dl, out[1:], dlogits, dlogits.stride(0), stream_ptr())
+        return dlogits, None, None, None
+
+
+def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100,
+                  label_smoothing: float = 0.0) -> torch.Tensor:
+    """Fused replacement of F.cross_entropy(logits.view(-1, C), labels.view(-1), ignore_index, label_smoothing)."""
+    C = logits.shape[-1]
+    l2 = logits.reshape(-1, C)
+    if l2.dtype == torch.float16:
+        l2 = l2.float()
+    if l2.stride(1) != 1 or (l2.stride(0) * l2.element_size()) % 16 != 0 or l2.data_ptr() % 16 != 0:
+        pitch = (C + 7) // 8 * 8
+        buf = torch.zeros((l2.shape[0], pitch), dtype=l2.dtype, device=l2.device)
+        buf[:, :C] = l2
+        l2 = buf[:, :C]
+    return CrossEntropyFn.apply(l2, labels, ignore_index, label_smoothing)
+
+
 # ---- attention -----------------------------------------------------------------------------------------------
 class AttentionFn(torch.autograd.Function):
     """Multi-head attention core on packed projections.
@@ -407,7 +498,7 @@ class AttentionFn(torch.autograd.Function):
     cross-attention: q_src = q [B*T, D], kv_src = kv [B*S, 2D] (k | v column blocks)."""
 
     @staticmethod
-    def forward(ctx, q_src, kv_src, key_pad, B, T, S, H, self_attn, drop=None):
+    def forward(ctx, q_src, kv_src, key_pad, B, T, S, H, self_attn, drop=None, causal=False):
         _lib.ensure_device(q_src)
         es = q_src.element_size()
         if self_attn:
@@ -423,11 +514,12 @@ class AttentionFn(torch.autograd.Function):
         scale = 1.0 / float(dh) ** 0.5
         o = torch.empty((B * T, D), dtype=q_src.dtype, device=q_src.device)
         lse = torch.empty((B, H, T), dtype=torch.float32, device=q_src.device)
-        call("b200_attn_fwd", qp, ldq, kp, ldk, vp, ldv, key_pad, o, D, lse, B, H, T, S, dh, scale,
+        call("b200_attn_fwd", qp, ldq, kp, ldk, vp, ldv, key_pad, 1 if causal else 0, o, D, lse, B, H, T, S, dh, scale,
              dtype_code(q_src.dtype), dropout_arg(drop), stream_ptr())
         ctx.save_for_backward(q_src, kv_src if not self_attn else None, key_pad, o, lse)
         ctx.dims = (B, T, S, H, D, dh, scale, self_attn)
         ctx.drop = drop
+        ctx.causal = 1 if causal else 0
         return o
 
     @staticmethod
@@ -442,16 +534,16 @@ class AttentionFn(torch.autograd.Function):
             ldq = ldk = ldv = q_src.stride(0)
             dqp, dkp, dvp = dqkv.data_ptr(), dqkv.data_ptr() + D * es, dqkv.data_ptr() + 2 * D * es
             ldd = 3 * D
-            call("b200_attn_bwd", qp, ldq, kp, ldk, vp, ldv, key_pad, o, D, do, D, lse, dqp, ldd, dkp, ldd, dvp, ldd,
-                 B, H, T, S, dh, scale, dtype_code(q_src.dtype), dropout_arg(ctx.drop), stream_ptr())
-            return dqkv, None, None, None, None, None, None, None, None
+            call("b200_attn_bwd", qp, ldq, kp, ldk, vp, ldv, key_pad, ctx.causal, o, D, do, D, lse, dqp, ldd, dkp, ldd,
+                 dvp, ldd, B, H, T, S, dh, scale, dtype_code(q_src.dtype), dropout_arg(ctx.drop), stream_ptr())
+            return dqkv, None, None, None, None, None, None, None, None, None
         dq = torch.empty((B * T, D), dtype=q_src.dtype, device=q_src.device)
         dkv = torch.empty((B * S, 2 * D), dtype=q_src.dtype, device=q_src.device)
         qp, kp, vp = q_src.data_ptr(), kv_src.data_ptr(), kv_src.data_ptr() + D * es
-        call("b200_attn_bwd", qp, q_src.stride(0), kp, kv_src.stride(0), vp, kv_src.stride(0), key_pad, o, D, do, D,
-             lse, dq, D, dkv.data_ptr(), 2 * D, dkv.data_ptr() + D * es, 2 * D, B, H, T, S, dh, scale,
+        call("b200_attn_bwd", qp, q_src.stride(0), kp, kv_src.stride(0), vp, kv_src.stride(0), key_pad, ctx.causal, o, D,
+             do, D, lse, dq, D, dkv.data_ptr(), 2 * D, dkv.data_ptr() + D * es, 2 * D, B, H, T, S, dh, scale,
              dtype_code(q_src.dtype), dropout_arg(ctx.drop), stream_ptr())
-        return dq, dkv, None, None, None, None, None, None, None
+        return dq, dkv, None, None, None, None, None, None, None, None
 
 
 # ---- MOE router ----------------------------------------------------------------------------------------------
