@@ -52,6 +52,13 @@ CONFIGS = {
     5: dict(COMMON, kind="generative", tag="configs[4]", B=128, V=50, E=8,
             desc="CrossModalFusion (2 pre-LN encoder layers over [visual;question] = 114 tokens, ff 2048) + MOELayer(E8 "
                  "top2 F2048) on all B*114 tokens; decoder excluded (out of scope, SURVEY 8(d))"),
+    # configs[4] followed by the answer decoder and the label-smoothed cross-entropy (the generative
+    # pipeline's whole trainable path behind the encoders); not a BASELINE.json configuration, selected explicitly
+    6: dict(COMMON, kind="generative", tag="configs[4] + decoder (SURVEY 8(f) N2)", B=128, V=50, E=8,
+            dec=dict(L=6, Ta=64, vocab=64000, smoothing=0.1, moe_loss_weight=0.01),
+            desc="CrossModalFusion + MOELayer(E8 top2 F2048) on B*114 tokens -> TransformerDecoder (6 pre-LN layers, "
+                 "causal self-attention + cross-attention to the 114 fused tokens, 64 answer tokens, tied 64000-way "
+                 "projection) -> label-smoothed cross-entropy"),
 }
 
 
@@ -87,6 +94,13 @@ def algorithmic_flops(c) -> dict:
         moe_g = S * K * 2 * D * F
         gemm = (L * layer_gemm + moe_g) * 6
         total = (L * (layer_gemm + layer_attn) + moe_g + S * D * E) * 6
+        if c.get("dec"):
+            d = c["dec"]
+            Ta, Ld, Vv = d["Ta"], d["L"], d["vocab"]
+            dec_gemm = Ld * (6 * Ta * D * D + 2 * S * D * D + 2 * Ta * D * F) + Ta * D * Vv
+            dec_attn = Ld * (2 * Ta * Ta * D + 2 * Ta * S * D)
+            gemm += dec_gemm * 6
+            total += (dec_gemm + dec_attn) * 6
         return dict(total=total, gemm=gemm, total_full=total, gemm_full=gemm)
     layer_gemm = 14 * T * D * D + 2 * V * D * D            # in/out projections + FFN(4D)
     layer_attn = 2 * T * D * (T + V)                       # QK^T and PV, self + cross
@@ -117,6 +131,19 @@ def synth_inputs(c, rank: int):
     lens = torch.randint(8, c["T"] + 1, (c["B"],), generator=torch.Generator().manual_seed(4321 + rank))
     pad = ~(torch.arange(c["T"])[None, :] < lens[:, None])       # True = PAD; position 0 always valid
     return vis, txt, pad
+
+
+def synth_answers(c, rank: int):
+    """Teacher-forcing inputs of the decoder: answer token ids, their attention mask (1 = token) and the labels
+    (-100 on padding), generative_vqa_model.py:540-587."""
+    d = c["dec"]
+    g = torch.Generator().manual_seed(777 + rank)
+    ids = torch.randint(0, d["vocab"], (c["B"], d["Ta"]), generator=g)
+    labels = torch.randint(0, d["vocab"], (c["B"], d["Ta"]), generator=g)
+    lens = torch.randint(4, d["Ta"] + 1, (c["B"],), generator=g)
+    mask = (torch.arange(d["Ta"])[None, :] < lens[:, None]).long()
+    labels[mask == 0] = -100
+    return ids, mask, labels
 
 
 class ClockSampler:
@@ -200,6 +227,23 @@ def cpu_reference_step_factory(c, threads: int, batch: int):
         sd_f = {k: v.requires_grad_() for k, v in init_weights.cross_modal_fusion_sd(D, H, L, F).items()}
         sd_f.update({"moe_layer." + k: v for k, v in sd_m.items()})
         leaves = list(sd_f.values()) + [vis, txt]
+        if c.get("dec"):
+            d = c["dec"]
+            sd_d = {k: (v.requires_grad_() if v.dtype.is_floating_point and k != "pos_encoding.pe" else v)
+                    for k, v in init_weights.decoder_sd(D, H, d["L"], F, d["vocab"], d["Ta"]).items()}
+            ids, amask, labels = synth_answers(cb, 0)
+            enc_mask = torch.cat([torch.ones(batch, c["V"]), (~pad).float()], dim=1)
+            leaves += [v for v in sd_d.values() if v.requires_grad]
+
+            def step_dec():
+                for t in leaves:
+                    t.grad = None
+                out, aux = rp.cross_modal_fusion(sd_f, H, L, vis, txt, ~pad, moe=dict(num_experts=E, top_k=K),
+                                                 pdrop=c["dropout"])
+                logits = rp.transformer_decoder(sd_d, H, d["L"], out, ids, enc_mask, amask, pdrop=c["dropout"])
+                loss = rp.smoothed_cross_entropy(logits, labels, -100, d["smoothing"]) + d["moe_loss_weight"] * aux
+                loss.backward()
+            return step_dec
 
         def step():
             for t in leaves:
@@ -293,6 +337,16 @@ class Workload:
             self.fus = fusion.CrossModalFusion(cfg).to(dev).train()
             self.fus.return_aux_tensor = True      # the reference's .item() on the aux loss is a host sync per step
             layer = self.fus.moe_layer
+            self.dec = None
+            if c.get("dec"):
+                from vqa_model_builder_b200.decoder import DecoderConfig, TransformerDecoder
+                d = c["dec"]
+                self.dec = TransformerDecoder(DecoderConfig(
+                    vocab_size=d["vocab"], decoder_hidden_dim=D, decoder_num_layers=d["L"], decoder_num_heads=H,
+                    decoder_ff_dim=F, decoder_dropout=c["dropout"], max_answer_length=d["Ta"],
+                    label_smoothing=d["smoothing"])).to(dev).train()
+                ids, amask, labels = synth_answers(c, rank)
+                self.ans = (ids.to(dev), amask.to(dev), labels.to(dev))
         else:
             self.fus = fusion.MultimodalFusion(fusion.FusionConfig("cross_attention", D, D, H, L, c["dropout"],
                                                                    True)).to(dev).train()
@@ -317,6 +371,8 @@ class Workload:
             self.sharded = list(layer.expert_parameters()) if self.moe_parallel == "ep" else []
             if self.moe_parallel != "ep":
                 self.replicated = list(self.fus.parameters())
+            if self.dec is not None:
+                self.replicated = self.replicated + list(self.dec.parameters())
         else:
             rep_moe = list(layer.replicated_parameters()) if self.moe_parallel == "ep" else list(layer.parameters())
             self.replicated = list(self.fus.parameters()) + rep_moe
@@ -331,7 +387,13 @@ class Workload:
         c, fus, layer = self.c, self.fus, self.layer
         moe_rep = [p for p in self.replicated if any(p is q for q in layer.parameters())]
         if c["kind"] == "generative":
-            out = [list(fus.layer_norm.parameters()) + moe_rep]
+            out = []
+            if self.dec is not None:       # backward reaches the decoder first: tied projection, then layers 5..0
+                dec = self.dec
+                out.append(list(dec.layer_norm.parameters()) + [dec.embedding.weight])
+                for blk in reversed(list(dec.decoder.layers)):
+                    out.append(list(blk.parameters()))
+            out.append(list(fus.layer_norm.parameters()) + moe_rep)
             for blk in reversed(list(fus.layers)):
                 out.append(list(blk.parameters()))
             return out
@@ -363,6 +425,15 @@ class Workload:
         c = self.c
         if c["kind"] == "generative":
             out, aux = self.fus(self.vis, self.txt, (~self.pad).long())
+            if self.dec is not None:
+                from vqa_model_builder_b200 import ops
+                d = c["dec"]
+                ids, amask, labels = self.ans
+                enc_mask = torch.cat([torch.ones(c["B"], c["V"], dtype=torch.long, device=self.dev),
+                                      (~self.pad).long()], dim=1)
+                logits = self.dec(out, ids, encoder_attention_mask=enc_mask, decoder_attention_mask=amask)
+                ce = ops.cross_entropy(logits.view(-1, logits.shape[-1]), labels.view(-1), -100, d["smoothing"])
+                return ce + d["moe_loss_weight"] * aux
             return out.float().square().mean() + aux
         fused = self.fus(self.vis, self.txt, text_mask=self.pad)
         out = self.layer(fused.unsqueeze(1))

@@ -83,3 +83,25 @@ def seeded_state_dict(template: dict, seed: int, keys=None) -> dict:
             a = 0.1 * rng.standard_normal(tuple(v.shape))
         sd[k] = torch.tensor(a, dtype=torch.float32)
     return sd
+
+
+def decoder_sd(D: int, H: int, L: int, F: int, vocab: int, max_len: int) -> dict:
+    """TransformerDecoder (generative_vqa_model.py:345-381): embedding tied to the output projection, sinusoidal
+    positions, L pre-LN nn.TransformerDecoderLayer key sets, the final LayerNorm."""
+    from .reference_port import sinusoidal_positions
+    emb = nn.Embedding(vocab, D).weight.detach().clone()
+    sd = {"embedding.weight": emb, "output_projection.weight": emb,
+          "pos_encoding.pe": sinusoidal_positions(max_len, D).unsqueeze(0)}
+    for l in range(L):
+        p = f"decoder.layers.{l}."
+        for name in ("self_attn", "multihead_attn"):
+            m = nn.MultiheadAttention(D, H, batch_first=True)
+            for k, v in m.state_dict().items():
+                sd[p + name + "." + k] = v.detach().clone()
+        l1, l2 = nn.Linear(D, F), nn.Linear(F, D)
+        sd[p + "linear1.weight"], sd[p + "linear1.bias"] = l1.weight.detach().clone(), l1.bias.detach().clone()
+        sd[p + "linear2.weight"], sd[p + "linear2.bias"] = l2.weight.detach().clone(), l2.bias.detach().clone()
+        for n in ("norm1", "norm2", "norm3"):
+            sd[p + n + ".weight"], sd[p + n + ".bias"] = torch.ones(D), torch.zeros(D)
+    sd["layer_norm.weight"], sd["layer_norm.bias"] = torch.ones(D), torch.zeros(D)
+    return sd

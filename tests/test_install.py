@@ -51,6 +51,16 @@ def test_install_rebinds_and_reference_code_builds_our_modules(installed):
     assert vqa.AnswerHead is heads.AnswerHead
     head = vqa.AnswerHead(AnswerHeadConfig(num_answers=37), 64)
     assert isinstance(head, heads.AnswerHead) and head.classifier[-1].out_features == 37
+    # the reference's GenerativeVQAModel constructs our decoder (generative_vqa_model.py:503) with its
+    # own config object and the shared answer embedding; state_dict keys equal the reference class's
+    from vqa_model_builder_b200 import decoder as b200_decoder
+    assert gen.TransformerDecoder is b200_decoder.TransformerDecoder
+    dcfg = gen.GenerativeVQAConfig(hidden_size=64, num_decoder_layers=1, num_attention_heads=4, decoder_ff_dim=128,
+                                   vocab_size=50, max_answer_length=12)
+    import torch
+    emb = torch.nn.Embedding(50, 64)
+    dec = gen.TransformerDecoder(dcfg, embedding=emb)
+    assert isinstance(dec, b200_decoder.TransformerDecoder) and dec.output_projection.weight is emb.weight
     # registry: cross_attention -> ours, others stay the reference's
     import src.modeling.fusion as ref_fusion
     assert isinstance(ref_fusion.create_fusion_model("cross_attention", vision_dim=64, text_dim=64, output_dim=64,

@@ -12,6 +12,7 @@ from __future__ import annotations
 import importlib
 from typing import Dict, List, Tuple
 
+from . import decoder as _decoder
 from . import fusion as _fusion
 from . import heads as _heads
 from . import moe as _moe
@@ -69,7 +70,9 @@ def install(verbose: bool = False) -> Dict[str, str]:
                        "CrossModalAttention": _fusion.CrossModalAttention,     # vqa_model.py:331
                        "AnswerHead": _heads.AnswerHead})                       # vqa_model.py:436
     bind_all(ref_gen, {"MOELayer": _moe.MOELayer, "VQAMOELayer": _moe.VQAMOELayer,   # generative_vqa_model.py:23
-                       "SparseMOELayer": _moe.SparseMOELayer, "CrossModalFusion": _fusion.CrossModalFusion})
+                       "SparseMOELayer": _moe.SparseMOELayer, "CrossModalFusion": _fusion.CrossModalFusion,
+                       "TransformerDecoder": _decoder.TransformerDecoder,            # :342
+                       "PositionalEncoding": _decoder.PositionalEncoding})           # :453
     fus_syms = {"CrossAttentionFusion": _fusion.CrossAttentionFusion, "CrossAttentionBlock": _fusion.CrossAttentionBlock,
                 "QFormerFusion": _fusion.QFormerFusion, "QFormerLayer": _fusion.QFormerLayer,
                 "SingleStreamFusion": _fusion.SingleStreamFusion, "create_fusion_model": _fusion.create_fusion_model}
