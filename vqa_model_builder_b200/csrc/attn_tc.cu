@@ -82,11 +82,34 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t tile, int kk, int ch = CHB)
   return ptx::umma_smem_desc(tile + kk * 2048, ch, 1024);
 }
 
+// Key visibility as bit masks: the per-element "col < n_valid && !key_pad[col] && !(causal && col > row)" test was a
+// byte load, two compares and a branch per score element (ncu, profiles/r02l: 40 % of the forward kernel's
+// instructions were ISETP / BRA / BSSY / BSYNC / LDG).  The CTA builds one 32-bit word per 32 key columns once
+// (valid and not padded); the causal part is a per-row word computed from the row index.
+__device__ __forceinline__ void build_key_mask(uint32_t* words, const uint8_t* kp, int S, int cols, int tid, int nthr) {
+  for (int col = tid; col < cols; col += nthr) {     // cols and nthr are multiples of 32: whole warps iterate together
+    const bool ok = col < S && !(kp != nullptr && kp[col] != 0);
+    const uint32_t w = __ballot_sync(0xffffffffu, ok);
+    if ((tid & 31) == 0) words[col >> 5] = w;
+  }
+}
+__device__ __forceinline__ uint32_t causal_word(int causal, int row, int col0) {
+  if (!causal) return 0xffffffffu;
+  const int d = row - col0;                          // columns col0 .. col0+31 are visible while col <= row
+  return d >= 31 ? 0xffffffffu : (d < 0 ? 0u : ((2u << d) - 1u));
+}
+
 // Geometry of the two kernel flavours.  R = 128: the general kernel (T <= 128, kv tiles of 128 rows, 128 threads).
 // R = 64: T <= 64 and S <= 64 (the question / image-patch shapes of the fusion block): TMA boxes of 64 rows, 64
 // threads, half the shared memory and a quarter of the TMEM, so 3 (forward) / 2 (backward) CTAs share an SM and
 // hide each other's TMA -> MMA -> softmax -> MMA latency chain.  The UMMAs keep M = 128: accumulator rows 64..127
 // are computed from whatever follows the 64-row operand in shared memory and are never read back.
+// P may take Q's shared-memory buffer when there is a single kv tile and Q is at least as large as a P tile
+template <int NT, int R>
+__host__ __device__ constexpr bool fwd_alias_possible() { return NT == 1 && R == 128; }
+template <int NT, int R>
+__host__ __device__ inline bool fwd_alias(int dh) { return fwd_alias_possible<NT, R>() && dh > 64; }
+
 template <int R> struct Geo {
   static constexpr int CH = R * 128;                 // bytes of one TMA-loaded [R rows x 64 bf16] chunk
   static constexpr int PT = (R == 64) ? 8192 : 2 * CHB;   // bytes of a P / dS tile ([R x 64] or [128 x 128])
@@ -118,14 +141,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   constexpr int CH = Geo<R>::CH;
   constexpr bool SMALL = (R == 64);
   static_assert(!SMALL || NT == 1, "the 64-row flavour handles a single kv tile");
-  const uint32_t sQ = sm.base, sK = sQ + nch * CH, sV = sK, sP = sK + nch * CH;
-  uint8_t* pP = sm.ptr + 2 * nch * CH;
-  const uint32_t bars = sP + Geo<R>::PT + Geo<R>::SLACK;
+  // Single-kv-tile 128-row flavour: Q is dead once S = Q K^T has completed and S is dead once P sits in shared
+  // memory, so P takes Q's buffer and O takes S's TMEM columns: 64 KB of shared memory and 128 TMEM columns per CTA,
+  // three CTAs per SM hide each other's TMA -> MMA -> softmax -> MMA chain (two before).
+  const bool alias = fwd_alias<NT, R>(a.dh);
+  const uint32_t sQ = sm.base, sK = sQ + nch * CH, sV = sK, sP = alias ? sQ : sK + nch * CH;
+  uint8_t* pP = alias ? sm.ptr : sm.ptr + 2 * nch * CH;
+  const int tail = 2 * nch * CH + (alias ? 0 : Geo<R>::PT + Geo<R>::SLACK);
+  const uint32_t bars = sm.base + tail;
   const uint32_t bar_q = bars, bar_k = bars + 8, bar_v = bars + 16, bar_mma = bars + 24;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.ptr + 2 * nch * CH + Geo<R>::PT + Geo<R>::SLACK + 32);
-  // 64-row flavour: O overwrites S (S is dead once P sits in shared memory) -> 128 columns, 4 CTAs' worth per SM
-  constexpr uint32_t TCOLS = SMALL ? 128 : (NT == 1 ? 256 : 512);
-  constexpr uint32_t O_COL = SMALL ? 0 : NT * 128;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.ptr + tail + 32);
+  uint32_t* s_ok = reinterpret_cast<uint32_t*>(sm.ptr + tail + 64);   // [NT*R/32]
+  // 64-row flavour and the aliased 128-row one: O overwrites S -> 128 columns
+  constexpr uint32_t TCOLS = (SMALL || NT == 1) ? 128 : 512;
+  constexpr uint32_t O_COL = (SMALL || NT == 1) ? 0 : NT * 128;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
@@ -185,6 +214,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   const int r = tid;
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
   const uint8_t* kp = a.key_pad ? a.key_pad + (long long)b * a.S : nullptr;
+  build_key_mask(s_ok, kp, a.S, NT * R, tid, R);
+  __syncthreads();
   float m = -INFINITY;
   for (int j = 0; j < NT; ++j) {
     const int n_valid = min(R, a.S - j * R);
@@ -192,12 +223,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
     for (int c = 0; c * 32 < n_valid; ++c) {
       float v[32];
       ld32(lane_base + j * 128 + c * 32, v);
+      const uint32_t okb = s_ok[j * (R / 32) + c] & causal_word(a.causal, r, j * R + c * 32);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int col = c * 32 + i;
-        const bool ok = col < n_valid && !(kp && kp[j * R + col]) && !(a.causal && j * R + col > r);
-        if (ok) m = fmaxf(m, v[i]);
-      }
+      for (int i = 0; i < 32; ++i) m = fmaxf(m, (okb >> i) & 1u ? v[i] : -INFINITY);
     }
   }
   const float sl2 = a.scale * LOG2E;
@@ -212,11 +240,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
     for (int c = 0; c * 32 < n16; ++c) {
       float v[32];
       ld32(lane_base + j * 128 + c * 32, v);
+      const uint32_t okb = s_ok[j * (R / 32) + c] & causal_word(a.causal, r, j * R + c * 32);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int col = c * 32 + i;
-        const bool ok = col < n_valid && !(kp && kp[j * R + col]) && !(a.causal && j * R + col > r);
-        const float p = ok ? ex2(fmaf(v[i], sl2, -m_s)) : 0.f;
+        const float p = (okb >> i) & 1u ? ex2(fmaf(v[i], sl2, -m_s)) : 0.f;
         // round to bf16 first so the normaliser matches the probabilities the tensor core actually sees
         const float pr = __bfloat162float(__float2bfloat16_rn(p));
         l += pr;
@@ -301,6 +328,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   const uint32_t bars = sdS + PT + Geo<R>::SLACK;
   const uint32_t bar_q = bars, bar_kv = bars + 8, bar_mma = bars + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.ptr + 4 * nch * CH + 2 * PT + Geo<R>::SLACK + 32);
+  uint32_t* s_ok = reinterpret_cast<uint32_t*>(sm.ptr + 4 * nch * CH + 2 * PT + Geo<R>::SLACK + 64);   // [ntiles*R/32]
   constexpr uint32_t TCOLS = SMALL ? 256 : 512, C_S = 0, C_DP = SMALL ? 64 : 128, C_DV = 0, C_DK = 128,
                      C_DQ = SMALL ? 0 : 256;
 
@@ -355,6 +383,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   }
   const float sl2 = a.scale * LOG2E;
   const uint8_t* kp = a.key_pad ? a.key_pad + (long long)b * a.S : nullptr;
+  build_key_mask(s_ok, kp, a.S, ntiles * R, tid, R);
+  __syncthreads();
   const DropState ds = drop_load(a.drop_state, a.drop_p, a.drop_site);
   const unsigned long long drow = ((unsigned long long)blockIdx.x * a.T + r) * (unsigned long long)(((a.S + ROWS - 1) / ROWS) * ROWS);
 
@@ -397,10 +427,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 #pragma unroll
         for (int q = 0; q < 8; ++q) keep[i8 + q] = sc[q];
       }
+      const uint32_t okb = row_ok ? (s_ok[j * (R / 32) + c] & causal_word(a.causal, r, j * R + c * 32)) : 0u;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int col = c * 32 + i;
-        const bool ok = row_ok && col < n_valid && !(kp && kp[j * R + col]) && !(a.causal && j * R + col > r);
+        const bool ok = (okb >> i) & 1u;
         const float p = ok ? ex2(fmaf(s[i], sl2, -lse_l2)) : 0.f;
         s[i] = p * keep[i];                                               // dropped P feeds dV = P^T dO
         dp[i] = ok ? p * (dp[i] * keep[i] - delta) * a.scale : 0.f;       // dS = P (dP*mask/(1-p) - delta)
@@ -492,6 +522,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   if (warp == 0) ptx::tmem_dealloc(tmem, TCOLS);
 }
 
+template <int R> size_t fwd_smem_aliased(int dh) {     // P in Q's buffer (single kv tile, see fwd_alias)
+  return (size_t)2 * ((dh + 63) / 64) * Geo<R>::CH + 1024 + 128;
+}
 template <int R> size_t fwd_smem(int dh) {
   return (size_t)2 * ((dh + 63) / 64) * Geo<R>::CH + Geo<R>::PT + Geo<R>::SLACK + 1024 + 128;
 }
@@ -533,7 +566,9 @@ int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
     configured = true;
   }
   if (small) launch_kernel(attn_fwd_tc_kernel<1, 64>, dim3(B * H), dim3(64), fwd_smem<64>(dh), stream, qm, km, vm, a);
-  else if (nt == 1) launch_kernel(attn_fwd_tc_kernel<1, 128>, dim3(B * H), dim3(128), fwd_smem<128>(dh), stream, qm, km, vm, a);
+  else if (nt == 1)
+    launch_kernel(attn_fwd_tc_kernel<1, 128>, dim3(B * H), dim3(128),
+                  fwd_alias<1, 128>(dh) ? fwd_smem_aliased<128>(dh) : fwd_smem<128>(dh), stream, qm, km, vm, a);
   else launch_kernel(attn_fwd_tc_kernel<3, 128>, dim3(B * H), dim3(128), fwd_smem<128>(dh), stream, qm, km, vm, a);
   B200_LAUNCH_CHECK("attn_fwd_tc_kernel");
   count_launch();
