@@ -40,13 +40,17 @@ enum {
   B200_EPI_ACT = 1,      /* pre = acc+bias; aux_out = pre (if given); out = act(pre)        */
   B200_EPI_ADD = 2,      /* out = acc (+bias) + aux_in          (residual add)              */
   B200_EPI_DACT = 3,     /* out = acc * act'(aux_in)            (backward through act)      */
-  B200_EPI_ACCUM = 4     /* out(fp32) = acc, K may be split (zeroed + atomic partial sums)   */
+  B200_EPI_ACCUM = 4,    /* out(fp32) = acc, K may be split (zeroed + atomic partial sums)   */
+  B200_EPI_ACT_D = 5,    /* pre = acc+bias; out = dropout(act(pre)); aux_out = act'(pre) * keep-scale: the factor
+                            the backward pass multiplies by (derivative and dropout mask, evaluated once, while the
+                            exponential of the activation is at hand)                                            */
+  B200_EPI_MUL = 6       /* out = acc * aux_in               (backward through EPI_ACT_D: no erf, no RNG)        */
 };
 
 #define B200_GROUP_TILE 128 /* expert row segments are padded to this many rows */
 
 /* Dropout (nn.Dropout / MHA attention dropout in train mode: vqa_model.py:258-277, expert_types.py:56,81-83).
- * Masks are never stored: every kernel regenerates keep/drop decisions from a counter-based Philox4x32-10 stream
+ * Masks are never stored: every kernel regenerates keep/drop decisions from a counter-based Philox4x32-7 stream
  * keyed by (rng_state[0] = seed, rng_state[1] = step offset, site, element index), so forward and backward of the same
  * site see the same mask (one Philox call covers 8 consecutive elements, 16 random bits each: p is resolved to
  * 2^-16).  rng_state is a DEVICE pointer to two uint64 (read at execution time: CUDA-graph replays

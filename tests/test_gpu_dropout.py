@@ -10,7 +10,7 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 
 from vqa_model_builder_b200 import _lib, fusion, moe, ops, runtime  # noqa: E402
-from vqa_model_builder_b200._lib import ACT_GELU, EPI_ACT, EPI_ADD, EPI_DACT, LAYOUT_K  # noqa: E402
+from vqa_model_builder_b200._lib import ACT_GELU, EPI_ACT, EPI_ACT_D, EPI_ADD, EPI_DACT, EPI_MUL, LAYOUT_K  # noqa: E402
 import vqa_model_builder_b200 as pkg  # noqa: E402
 
 DEV = "cuda"
@@ -58,6 +58,16 @@ def test_gemm_epilogue_dropout_exact(dtype):
     assert rel_err(d, acc * x.grad * mask) < t
     r = ops.gemm(a, LAYOUT_K, b, LAYOUT_K, M, N, K, epi=EPI_ADD, aux_in=aux, drop=drop)
     assert rel_err(r, acc * mask + aux.double()) < t
+    # activation + saved backward factor (derivative x keep-scale), and the plain-multiply backward epilogue
+    xa = acc.clone().requires_grad_()
+    torch.nn.functional.gelu(xa).sum().backward()
+    fac = torch.empty(M, N, dtype=dtype, device=DEV)
+    h2 = ops.gemm(a, LAYOUT_K, b, LAYOUT_K, M, N, K, epi=EPI_ACT_D, act=ACT_GELU, aux_out=fac, drop=drop)
+    assert rel_err(h2, torch.nn.functional.gelu(acc) * mask) < t
+    assert rel_err(fac, xa.grad * mask) < t
+    assert (fac[mask == 0] == 0).all()
+    mlt = ops.gemm(a, LAYOUT_K, b, LAYOUT_K, M, N, K, epi=EPI_MUL, aux_in=aux)
+    assert rel_err(mlt, acc * aux.double()) < t
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])

@@ -17,7 +17,7 @@ from . import _build
 F32, BF16 = 0, 1
 LAYOUT_K, LAYOUT_MN = 0, 1
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_SILU, ACT_TANH = 0, 1, 2, 3, 4
-EPI_NONE, EPI_ACT, EPI_ADD, EPI_DACT, EPI_ACCUM = 0, 1, 2, 3, 4
+EPI_NONE, EPI_ACT, EPI_ADD, EPI_DACT, EPI_ACCUM, EPI_ACT_D, EPI_MUL = 0, 1, 2, 3, 4, 5, 6
 GROUP_TILE = 128
 
 ACT_CODES = {"none": ACT_NONE, "gelu": ACT_GELU, "relu": ACT_RELU, "silu": ACT_SILU, "tanh": ACT_TANH}

@@ -418,9 +418,10 @@ int b200_dropout_colsum(const void* x, void* out, int dtype, int R, int N, const
 }
 
 static int check_epi(int epi, int act, const void* aux_in, int out_dtype) {
-  B200_CHECK_ARG(epi >= B200_EPI_NONE && epi <= B200_EPI_ACCUM, "gemm: bad epilogue %d", epi);
+  B200_CHECK_ARG(epi >= B200_EPI_NONE && epi <= B200_EPI_MUL, "gemm: bad epilogue %d", epi);
   B200_CHECK_ARG(act >= B200_ACT_NONE && act <= B200_ACT_TANH, "gemm: bad activation %d", act);
-  B200_CHECK_ARG(!(epi == B200_EPI_ADD || epi == B200_EPI_DACT) || aux_in != nullptr, "gemm: epilogue needs aux_in");
+  B200_CHECK_ARG(!(epi == B200_EPI_ADD || epi == B200_EPI_DACT || epi == B200_EPI_MUL) || aux_in != nullptr,
+                 "gemm: epilogue needs aux_in");
   B200_CHECK_ARG(epi != B200_EPI_ACCUM || out_dtype == B200_F32, "gemm: ACCUM epilogue needs fp32 output");
   return 0;
 }

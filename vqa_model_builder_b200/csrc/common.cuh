@@ -164,14 +164,18 @@ __device__ __forceinline__ float act_bwd(float x, int act) {  // d act(x) / dx
 }
 
 // ---------------------------------------------------------------------------------------------
-// Counter-based RNG for dropout: Philox4x32-10 keyed by (seed, stream), counter = element index/8.
+// Counter-based RNG for dropout: Philox4x32-7 keyed by (seed, stream), counter = element index/8.  Seven rounds are
+// the fewest with which Philox4x32 passes BigCrush (Salmon et al., SC'11, table 2; curand's default of 10 is a safety
+// margin): the generator sits in the epilogues of the GEMMs and in the attention softmax, where its ~9 instructions
+// per round and 8 elements are a visible share of the per-element budget (ncu, profiles/r02l).
 // The same (seed, stream, index) reproduces the same keep-mask in backward without storing it.
 // ---------------------------------------------------------------------------------------------
+constexpr int PHILOX_ROUNDS = 7;
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr, uint32_t stream) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = stream, c3 = 0x9E3779B9u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < PHILOX_ROUNDS; ++r) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
@@ -197,7 +201,7 @@ __device__ __forceinline__ DropState drop_load(const unsigned long long* rng_sta
   d.key = d.on ? (rng_state[0] ^ (rng_state[1] * 0x9E3779B97F4A7C15ull)) : 0ull;
   return d;
 }
-// One Philox4x32-10 call serves 8 consecutive elements (16 random bits each: p is resolved to 2^-16):
+// One Philox4x32-7 call serves 8 consecutive elements (16 random bits each: p is resolved to 2^-16):
 // keep-scales of the elements 8*idx8 .. 8*idx8+7.
 __device__ __forceinline__ void drop_scales8(const DropState& d, unsigned long long idx8, float (&s)[8]) {
   const uint4 r = philox4x32(d.key, idx8, d.site);

@@ -76,7 +76,25 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& p, int group, lon
   }
 
   constexpr int VT = Vec16<T>::N;
-  if (p.epi == B200_EPI_ACT) {
+  if (p.epi == B200_EPI_ACT_D) {      // out = dropout(act(pre)), aux_out = act'(pre) * keep-scale
+    float dv[CNT];
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) {
+      dv[j] = act_bwd(acc[j], p.act);
+      acc[j] = act_fwd(acc[j], p.act);
+    }
+    if (p.drop_state != nullptr && p.drop_p > 0.f) {
+      const DropState ds = drop_load(p.drop_state, p.drop_p, p.drop_site);
+      apply_dropout_row<CNT>(ds, row, p.ldo, col0, acc);
+      apply_dropout_row<CNT>(ds, row, p.ldo, col0, dv);
+    }
+    if (p.aux_out != nullptr) {
+      T* ao = reinterpret_cast<T*>(p.aux_out) + abase;
+#pragma unroll
+      for (int j = 0; j < CNT; ++j)
+        if (col0 + j < p.N) ao[j] = from_f32<T>(dv[j]);
+    }
+  } else if (p.epi == B200_EPI_ACT) {
     if (p.aux_out != nullptr) {
       T* ao = reinterpret_cast<T*>(p.aux_out) + abase;
       if (full && (CNT % VT == 0) && (p.ld_aux % VT == 0) && (col0 % VT == 0)) {
@@ -99,7 +117,7 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& p, int group, lon
       const DropState ds = drop_load(p.drop_state, p.drop_p, p.drop_site);
       apply_dropout_row<CNT>(ds, row, p.ldo, col0, acc);
     }
-  } else if (p.epi == B200_EPI_ADD || p.epi == B200_EPI_DACT) {
+  } else if (p.epi == B200_EPI_ADD || p.epi == B200_EPI_DACT || p.epi == B200_EPI_MUL) {
     const T* ai = reinterpret_cast<const T*>(p.aux_in) + abase;
     float aux[CNT];
     if (full && (CNT % VT == 0) && (p.ld_aux % VT == 0) && (col0 % VT == 0)) {
@@ -121,6 +139,9 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& p, int group, lon
       }
 #pragma unroll
       for (int j = 0; j < CNT; ++j) acc[j] += aux[j];
+    } else if (p.epi == B200_EPI_MUL) {
+#pragma unroll
+      for (int j = 0; j < CNT; ++j) acc[j] *= aux[j];
     } else {
 #pragma unroll
       for (int j = 0; j < CNT; ++j) acc[j] *= act_bwd(aux[j], p.act);

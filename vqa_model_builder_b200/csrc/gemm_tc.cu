@@ -141,6 +141,64 @@ __device__ __forceinline__ float act1_bwd(float x) {
   }
   return 1.f;
 }
+// activation and its derivative from one evaluation (GELU: Phi and the exponential are shared)
+template <int ACT>
+__device__ __forceinline__ void act1_fwd_d(float x, float& y, float& d) {
+  if (ACT == B200_ACT_GELU) {
+    float e;
+    const float cdf = gelu_cdf(x, e);
+    y = x * cdf;
+    d = fmaf(x * 0.39894228040143267794f, e, cdf);
+  } else if (ACT == B200_ACT_SILU) {
+    const float sg = rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
+    y = x * sg;
+    d = sg * (1.0f + x * (1.0f - sg));
+  } else {
+    y = act1_fwd<ACT>(x);
+    d = act1_bwd<ACT>(x);
+  }
+}
+// 32 pre-activations -> packed bf16 activation and packed bf16 backward factor (derivative x dropout keep-scale),
+// eight elements at a time so that the fp32 inputs die as the packed outputs appear (no extra live registers: a
+// separate 32-float derivative tile made the whole kernel spill).
+template <int ACT>
+__device__ __forceinline__ void tile_act_fwd_d_packed(const float (&v)[32], uint32_t (&ypk)[16], uint32_t (&dpk)[16],
+                                                      const DropState& dsr, long long row, int ldo, int col0) {
+  const unsigned long long base = (unsigned long long)row * (unsigned long long)ldo + (unsigned long long)col0;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    float sc[8];
+    if (dsr.on) {
+      if ((base & 7ull) == 0) {
+        drop_scales8(dsr, (base + j) >> 3, sc);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sc[q] = drop_scale1(dsr, base + j + q);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sc[q] = 1.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      float y0, d0, y1, d1;
+      act1_fwd_d<ACT>(v[j + q], y0, d0);
+      act1_fwd_d<ACT>(v[j + q + 1], y1, d1);
+      ypk[(j + q) >> 1] = pack_bf16x2(y0 * sc[q], y1 * sc[q + 1]);
+      dpk[(j + q) >> 1] = pack_bf16x2(d0 * sc[q], d1 * sc[q + 1]);
+    }
+  }
+}
+__device__ __forceinline__ void tile_act_fwd_d_packed(const float (&v)[32], uint32_t (&ypk)[16], uint32_t (&dpk)[16],
+                                                      int act, const DropState& dsr, long long row, int ldo, int col0) {
+  switch (act) {
+    case B200_ACT_GELU: tile_act_fwd_d_packed<B200_ACT_GELU>(v, ypk, dpk, dsr, row, ldo, col0); break;
+    case B200_ACT_RELU: tile_act_fwd_d_packed<B200_ACT_RELU>(v, ypk, dpk, dsr, row, ldo, col0); break;
+    case B200_ACT_SILU: tile_act_fwd_d_packed<B200_ACT_SILU>(v, ypk, dpk, dsr, row, ldo, col0); break;
+    case B200_ACT_TANH: tile_act_fwd_d_packed<B200_ACT_TANH>(v, ypk, dpk, dsr, row, ldo, col0); break;
+    default: tile_act_fwd_d_packed<B200_ACT_NONE>(v, ypk, dpk, dsr, row, ldo, col0); break;
+  }
+}
 template <int ACT>
 __device__ __forceinline__ void tile_act_fwd(float (&v)[32]) {
 #pragma unroll
@@ -206,6 +264,25 @@ __device__ __forceinline__ void stage_store_tile(uint8_t* stg, int lane, const f
   for (int i = 0; i < 32 / RPI; ++i) {
     const int r = i * RPI + rsel;
     if (r < rows_ok) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(stg + stg_off<ELEM_BYTES>(r, sub));
+    dst += dstep;
+  }
+  __syncwarp();
+}
+
+// the same for a tile whose 32 bf16 values per row are already packed (16 words per thread)
+__device__ __forceinline__ void stage_store_packed_bf16(uint8_t* stg, int lane, const uint32_t (&pk)[16], void* gbase,
+                                                        long long ld, long long row0, int rows_ok, int col0) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(stg + stg_off<2>(lane, j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  __syncwarp();
+  const int sub = lane % 4, rsel = lane / 4;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(gbase) + ((row0 + rsel) * ld + col0) * 2 + 16 * sub;
+  const long long dstep = 8ll * ld * 2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + rsel;
+    if (r < rows_ok) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(stg + stg_off<2>(r, sub));
     dst += dstep;
   }
   __syncwarp();
@@ -421,10 +498,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
             }
           }
-          if (p.epi == B200_EPI_ACT) {
+          if (p.epi == B200_EPI_ACT_D && out_bf16) {
+            uint32_t ypk[16], dpk[16];
+            tile_act_fwd_d_packed(v, ypk, dpk, p.act, drop, my_row, p.ldo, col0);
+            if (p.aux_out != nullptr) stage_store_packed_bf16(stg, lane, dpk, p.aux_out, p.ld_aux, row0, rows_ok, col0);
+            stage_store_packed_bf16(stg, lane, ypk, reinterpret_cast<bf16*>(p.out) + obase, p.ldo, row0, rows_ok, col0);
+            continue;
+          } else if (p.epi == B200_EPI_ACT_D) {      // fp32 output (not used by the drop-in modules): generic path
+            epilogue_store<bf16, 32>(p, t.group, my_row, col0, v, my_row < p.M);
+            continue;
+          } else if (p.epi == B200_EPI_ACT) {
             if (p.aux_out != nullptr) stage_store_tile<2>(stg, lane, v, p.aux_out, p.ld_aux, row0, rows_ok, col0);
             tile_act_fwd(v, p.act);
             if (drop.on) apply_dropout_row<32>(drop, my_row, p.ldo, col0, v);
+          } else if (p.epi == B200_EPI_MUL) {
+            float aux[32];
+            stage_load_tile_bf16(stg, lane, aux, p.aux_in, p.ld_aux, row0, rows_ok, col0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= aux[j];
           } else if (p.epi == B200_EPI_ADD || p.epi == B200_EPI_DACT) {
             float aux[32];
             stage_load_tile_bf16(stg, lane, aux, p.aux_in, p.ld_aux, row0, rows_ok, col0);
@@ -559,8 +650,9 @@ int launch_gemm_tc(const void* A, int lda, int a_layout, long long a_mn_extent, 
   const bool can_split = args.mode == GEMM_DENSE && args.epi == B200_EPI_ACCUM;
   // epilogue of a 128 x 256 tile in k-block units (8 warps, 32 x 32 chunks): GELU / GELU' ~ 1 000 warp instructions per
   // chunk (profiles/r01o_ncu_source_gemm_act_after.txt) = about 9 k-blocks; it overlaps the next tile's main loop
-  const float epi256 = (args.epi == B200_EPI_ACT || args.epi == B200_EPI_DACT) ? 9.f
-                       : (args.epi == B200_EPI_ACCUM ? 8.f : (args.epi == B200_EPI_ADD ? 5.f : 3.f));
+  const float epi256 = (args.epi == B200_EPI_ACT || args.epi == B200_EPI_DACT || args.epi == B200_EPI_ACT_D) ? 9.f
+                       : (args.epi == B200_EPI_ACCUM ? 8.f
+                          : ((args.epi == B200_EPI_ADD || args.epi == B200_EPI_MUL) ? 5.f : 3.f));
   int bn = 64, splits = 1;
   float best = 1e30f;
   static const int forced_bn = []() { const char* e = getenv("B200VQA_GEMM_BN"); return e ? atoi(e) : 0; }();

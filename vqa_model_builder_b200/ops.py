@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from .runtime import aux_fork, aux_join, aux_on
-from ._lib import (ACT_CODES, ACT_NONE, EPI_ACCUM, EPI_ACT, EPI_ADD, EPI_DACT, EPI_NONE, GROUP_TILE, LAYOUT_K,
+from ._lib import (ACT_CODES, ACT_NONE, EPI_ACCUM, EPI_ACT, EPI_ACT_D, EPI_ADD, EPI_DACT, EPI_MUL, EPI_NONE, GROUP_TILE, LAYOUT_K,
                    LAYOUT_MN, call, dropout_arg, dtype_code, query, stream_ptr)
 
 
@@ -269,8 +269,10 @@ def _colsum_into(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
 # ---- two-layer FFN with fused activation ----------------------------------------------------------------
 class FFNFn(torch.autograd.Function):
     """y = drop_in(act(x W1^T + b1)) W2^T + b2, optionally y = drop_out(...) + residual
-    (ffn of vqa_model.py:265-271; TransformerEncoderLayer FF).  The activation (+dropout) runs in GEMM-1's epilogue;
-    its derivative (x the same mask) in the epilogue of GEMM-2's dgrad."""
+    (ffn of vqa_model.py:265-271; TransformerEncoderLayer FF).  GEMM-1's epilogue evaluates the activation AND its
+    derivative (x the dropout keep-scale) while the exponential is at hand and stores the latter (`dact`) instead of
+    the pre-activation; GEMM-2's dgrad epilogue is then a plain multiply (no erf, no RNG: it is no longer
+    epilogue-bound)."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, w1_c, w2_c, act, residual, drop_in=None, drop_out=None, passthrough=False):
@@ -278,8 +280,8 @@ class FFNFn(torch.autograd.Function):
         M, D = x.shape
         F = w1_c.shape[0]
         Do = w2_c.shape[0]
-        pre = torch.empty((M, F), dtype=x.dtype, device=x.device)
-        h = gemm(x, LAYOUT_K, w1_c, LAYOUT_K, M, F, D, bias=b1, epi=EPI_ACT, act=act, aux_out=pre, drop=drop_in)
+        pre = torch.empty((M, F), dtype=x.dtype, device=x.device)       # holds act'(pre) * keep-scale
+        h = gemm(x, LAYOUT_K, w1_c, LAYOUT_K, M, F, D, bias=b1, epi=EPI_ACT_D, act=act, aux_out=pre, drop=drop_in)
         epi = EPI_ADD if residual is not None else EPI_NONE
         if residual is None:
             drop_out = None
@@ -317,7 +319,7 @@ class FFNFn(torch.autograd.Function):
                     _colsum_into(g, db2)
                 else:
                     db2 = pre_db2
-        dpre = gemm(g, LAYOUT_K, w2_c, LAYOUT_MN, M, F, Do, epi=EPI_DACT, act=ctx.act, aux_in=pre, drop=drop_in)
+        dpre = gemm(g, LAYOUT_K, w2_c, LAYOUT_MN, M, F, Do, epi=EPI_MUL, aux_in=pre)
         side = aux_fork(x.device)       # dW1 / db1 read dpre
         with aux_on(side):
             gemm(dpre, LAYOUT_MN, x, LAYOUT_MN, F, D, M, out=dw1, epi=wepi)
@@ -735,8 +737,8 @@ class ExpertFFNFn(torch.autograd.Function):
             h = glu_fwd(pre, F, drop_in, tile_group)
         else:
             h = torch.empty((R, F), dtype=xp.dtype, device=dev)
-            call("b200_ggemm", xp, D, w1s, LAYOUT_K, h, F, R, F, D, E, tile_group, rows_used, dt, dt, b1s, EPI_ACT, act,
-                 None, pre, F, dropout_arg(drop_in), st)
+            call("b200_ggemm", xp, D, w1s, LAYOUT_K, h, F, R, F, D, E, tile_group, rows_used, dt, dt, b1s, EPI_ACT_D, act,
+                 None, pre, F, dropout_arg(drop_in), st)      # `pre` receives act'(pre) * keep-scale (see FFNFn)
         y2 = torch.empty((R, Do), dtype=xp.dtype, device=dev)
         call("b200_ggemm", h, F, w2s, LAYOUT_K, y2, Do, R, Do, F, E, tile_group, rows_used, dt, dt, b2s, EPI_NONE, ACT_NONE, None,
              None, 0, None, st)
@@ -789,8 +791,8 @@ class ExpertFFNFn(torch.autograd.Function):
             dpre = glu_bwd(dh, pre, F, drop_in, tile_group)
         else:
             dpre = torch.empty((R, F), dtype=dz.dtype, device=dev)
-            call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, tile_group, rows_used, dt, dt, None, EPI_DACT,
-                 act, pre, None, F, dropout_arg(drop_in), st)
+            call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, tile_group, rows_used, dt, dt, None, EPI_MUL,
+                 ACT_NONE, pre, None, F, None, st)
         side = aux_fork(dev)
         with aux_on(side):
             sa = stream_ptr()
