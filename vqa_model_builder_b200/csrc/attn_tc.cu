@@ -110,6 +110,9 @@ __host__ __device__ constexpr bool fwd_alias_possible() { return NT == 1 && R ==
 template <int NT, int R>
 __host__ __device__ inline bool fwd_alias(int dh) { return fwd_alias_possible<NT, R>() && dh > 64; }
 
+template <int R> struct BwdGeo {
+  static constexpr int NTHR = (R == 128) ? 256 : 64;     // threads of the backward kernel: two per row for R = 128
+};
 template <int R> struct Geo {
   static constexpr int CH = R * 128;                 // bytes of one TMA-loaded [R rows x 64 bf16] chunk
   static constexpr int PT = (R == 64) ? 8192 : 2 * CHB;   // bytes of a P / dS tile ([R x 64] or [128 x 128])
@@ -311,7 +314,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 // R = 64: S at 0, dP at 64; dV at 0 and dK at 128 are drained first, then dQ reuses column 0 (256 columns in all,
 // two CTAs per SM).
 template <int R>
-__global__ void __launch_bounds__(R)
+__global__ void __launch_bounds__(BwdGeo<R>::NTHR)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                    const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap domap,
                    const AttnTcArgs a) {
@@ -332,7 +335,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   constexpr uint32_t TCOLS = SMALL ? 256 : 512, C_S = 0, C_DP = SMALL ? 64 : 128, C_DV = 0, C_DK = 128,
                      C_DQ = SMALL ? 0 : 256;
 
+  // 128-row flavour: TWO threads per row (256 threads).  One CTA per SM is all the 192 KB of operand tiles allow, and
+  // with one warp per scheduler the softmax / dS arithmetic and the TMEM drains were a serial chain per row; the
+  // second half-CTA takes every other 32-column chunk of S / dP, the other one of the dV / dK drains and part of dQ.
+  constexpr int NTHR = BwdGeo<R>::NTHR, HALVES = NTHR / R;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int half = tid / R;                 // warp-uniform
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int ksteps_d = a.dh / 16;
   const int ksteps_t = (min(a.T, R) + 15) / 16;
@@ -355,7 +363,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   const uint32_t tmem = *tmem_slot;
   pdl_trigger();
   pdl_wait();
-  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // a warp reads TMEM lanes 32 (w % 4) ..
   uint32_t ph_kv = 0, ph_mma = 0;
 
   if (tid == 0) {
@@ -366,13 +374,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
     }
   }
   // per-row statistics: delta = sum_d dO*O, lse
-  const int r = tid;
+  const int r = tid % R;
   float delta = 0.f, lse_l2 = 0.f;
   const bool row_ok = r < a.T;
   if (row_ok) {
     const bf16* orow = a.o_in + ((long long)b * a.T + r) * a.ldo_in + h * a.dh;
     const bf16* grow = a.d_o + ((long long)b * a.T + r) * a.lddo + h * a.dh;
-    for (int d = 0; d < a.dh; d += 8) {
+    const int dsplit = (a.dh / 8 + HALVES - 1) / HALVES * 8;          // each half-CTA sums its share of the head dim
+    for (int d = half * dsplit; d < min(a.dh, (half + 1) * dsplit); d += 8) {
       Vec16<bf16> ov, gv;
       ov.load(orow + d);
       gv.load(grow + d);
@@ -383,8 +392,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   }
   const float sl2 = a.scale * LOG2E;
   const uint8_t* kp = a.key_pad ? a.key_pad + (long long)b * a.S : nullptr;
-  build_key_mask(s_ok, kp, a.S, ntiles * R, tid, R);
+  build_key_mask(s_ok, kp, a.S, ntiles * R, tid, NTHR);
+  if (HALVES == 2) reinterpret_cast<float*>(pP)[half * R + r] = delta;    // the P buffer is free until the first tile
   __syncthreads();
+  if (HALVES == 2) {
+    delta = reinterpret_cast<float*>(pP)[r] + reinterpret_cast<float*>(pP)[R + r];
+    __syncthreads();                                                      // before P is written
+  }
   const DropState ds = drop_load(a.drop_state, a.drop_p, a.drop_site);
   const unsigned long long drow = ((unsigned long long)blockIdx.x * a.T + r) * (unsigned long long)(((a.S + ROWS - 1) / ROWS) * ROWS);
 
@@ -413,7 +427,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
     ptx::tc_fence_after();
 
     // P = exp(S*scale - lse), dS = P * (dP - delta) * scale  -> swizzled smem tiles (bf16)
-    for (int c = 0; c < R / 32; ++c) {
+    for (int c = half; c < R / 32; c += HALVES) {
       float s[32], dp[32];
       if (c * 32 < n16) {
         ld32(lane_base + C_S + c * 32, s);
@@ -466,19 +480,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
       bf16* dvrow = a.dv + ((long long)b * a.S + srow) * a.lddv + h * a.dh;
       bf16* dkrow = a.dk + ((long long)b * a.S + srow) * a.lddk + h * a.dh;
       for (int c = 0; c < a.dh / 32; ++c) {
-        float v[32], k[32];
-        ld32(lane_base + C_DV + c * 32, v);
-        ld32(lane_base + C_DK + c * 32, k);
-        if (ok) {
 #pragma unroll
-          for (int jv = 0; jv < 4; ++jv) {
-            uint4 t;
-            t.x = pack_bf16x2(v[8 * jv + 0], v[8 * jv + 1]); t.y = pack_bf16x2(v[8 * jv + 2], v[8 * jv + 3]);
-            t.z = pack_bf16x2(v[8 * jv + 4], v[8 * jv + 5]); t.w = pack_bf16x2(v[8 * jv + 6], v[8 * jv + 7]);
-            *reinterpret_cast<uint4*>(dvrow + c * 32 + jv * 8) = t;
-            t.x = pack_bf16x2(k[8 * jv + 0], k[8 * jv + 1]); t.y = pack_bf16x2(k[8 * jv + 2], k[8 * jv + 3]);
-            t.z = pack_bf16x2(k[8 * jv + 4], k[8 * jv + 5]); t.w = pack_bf16x2(k[8 * jv + 6], k[8 * jv + 7]);
-            *reinterpret_cast<uint4*>(dkrow + c * 32 + jv * 8) = t;
+        for (int which = 0; which < 2; ++which) {         // 0: dV, 1: dK; with two half-CTAs each drains one of them
+          if (HALVES == 2 && which != half) continue;
+          float v[32];
+          ld32(lane_base + (which == 0 ? C_DV : C_DK) + c * 32, v);
+          bf16* orow = which == 0 ? dvrow : dkrow;
+          if (ok) {
+#pragma unroll
+            for (int jv = 0; jv < 4; ++jv) {
+              uint4 t;
+              t.x = pack_bf16x2(v[8 * jv + 0], v[8 * jv + 1]); t.y = pack_bf16x2(v[8 * jv + 2], v[8 * jv + 3]);
+              t.z = pack_bf16x2(v[8 * jv + 4], v[8 * jv + 5]); t.w = pack_bf16x2(v[8 * jv + 6], v[8 * jv + 7]);
+              *reinterpret_cast<uint4*>(orow + c * 32 + jv * 8) = t;
+            }
           }
         }
       }
@@ -503,7 +518,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   ptx::tc_fence_after();
   {
     bf16* dqrow = a.dq + ((long long)b * a.T + r) * a.lddq + h * a.dh;
-    for (int c = 0; c < a.dh / 32; ++c) {
+    for (int c = half; c < a.dh / 32; c += HALVES) {
       float v[32];
       ld32(lane_base + C_DQ + c * 32, v);
       if (row_ok) {
@@ -600,8 +615,8 @@ int launch_attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
     B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = true;
   }
-  if (small) launch_kernel(attn_bwd_tc_kernel<64>, dim3(B * H), dim3(64), bwd_smem<64>(dh), stream, qm, km, vm, dom, a);
-  else launch_kernel(attn_bwd_tc_kernel<128>, dim3(B * H), dim3(128), bwd_smem<128>(dh), stream, qm, km, vm, dom, a);
+  if (small) launch_kernel(attn_bwd_tc_kernel<64>, dim3(B * H), dim3(BwdGeo<64>::NTHR), bwd_smem<64>(dh), stream, qm, km, vm, dom, a);
+  else launch_kernel(attn_bwd_tc_kernel<128>, dim3(B * H), dim3(BwdGeo<128>::NTHR), bwd_smem<128>(dh), stream, qm, km, vm, dom, a);
   B200_LAUNCH_CHECK("attn_bwd_tc_kernel");
   count_launch();
   return 0;
