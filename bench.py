@@ -378,6 +378,10 @@ class Workload:
             self.replicated = list(self.fus.parameters()) + rep_moe
             self.sharded = list(layer.expert_parameters()) if self.moe_parallel == "ep" else []
         self.params = self.replicated + self.sharded
+        import vqa_model_builder_b200 as pkg
+        self.pkg = pkg
+        self.prefetch = not getattr(args, "no_prefetch", False)
+        self.later_modules = [self.layer] + ([self.dec] if getattr(self, "dec", None) is not None else [])
         self.reducer = None
         self.arena = None
 
@@ -446,6 +450,10 @@ class Workload:
         self.txt.grad = None
         if self.arena is not None:
             self.arena.reset()
+        if self.prefetch:
+            # modules that run later in the step get their bf16 weight copies refreshed on a side stream while the
+            # fusion's first kernels run (the public API a trainer calls after optimizer.step())
+            self.pkg.prefetch_compute_weights(*self.later_modules)
         loss = self.forward_loss()
         if self.world > 1:
             # mean-over-ranks loss with SUM gradient exchange: replicated gradients are summed by the all-reduce,
@@ -810,6 +818,8 @@ def main():
                     help="comma list of further configurations measured briefly and reported under 'other_configs' "
                          "('none' to skip)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true",
+                    help="do not refresh the later modules' bf16 weight copies on a side stream (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dp-transport", default="arena", choices=["arena", "nccl"],
                     help="data-parallel gradient all-reduce: gradient arena in symmetric memory reduced through the "

@@ -33,7 +33,12 @@ CASES = [(2, 4, 12, 7, 64), (32, 8, 64, 50, 768), (4, 8, 64, 257, 768), (3, 8, 1
          (2, 4, 70, 130, 128),
          # 64-row flavour (T, S <= 64): odd sizes, d_h = 64 / 96 / 128, a single query, many co-resident CTAs
          (5, 8, 33, 17, 768), (3, 4, 64, 64, 256), (2, 8, 1, 50, 768), (3, 8, 64, 3, 1024), (200, 8, 64, 50, 768),
-         (2, 8, 65, 64, 768), (2, 8, 64, 65, 768)]
+         (2, 8, 65, 64, 768), (2, 8, 64, 65, 768),
+         # more than 128 query rows on the tensor cores (bf16): one CTA per 128-row query tile forward; backward splits
+         # into dQ-tile and dK/dV-tile CTAs.  ViT-B/16 (197) and DINOv2 (257) patch tokens as queries, the single-stream
+         # fusion's 328 tokens, a ragged last tile, three key tiles
+         (2, 8, 197, 64, 768), (2, 8, 257, 40, 768), (3, 8, 129, 50, 768), (1, 8, 328, 328, 768), (2, 4, 300, 130, 128),
+         (2, 2, 384, 384, 256)]
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -77,10 +82,12 @@ def test_self_attention_packed(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,H,T,D", [(3, 8, 64, 768), (2, 4, 9, 64), (2, 8, 114, 768), (2, 8, 33, 768), (1, 2, 200, 64)])
+@pytest.mark.parametrize("B,H,T,D", [(3, 8, 64, 768), (2, 4, 9, 64), (2, 8, 114, 768), (2, 8, 33, 768), (1, 2, 200, 64),
+                                     (2, 8, 328, 768), (3, 4, 257, 128)])
 def test_causal_self_attention(B, H, T, D, dtype):
     """Decoder self-attention (generative_vqa_model.py:404-406): causal mask combined with a key-padding mask, on the
-    64-row and 128-row tensor-core flavours (bf16), the SIMT kernels (fp32, T > 128) — forward and backward."""
+    64-row and 128-row tensor-core flavours (bf16; T > 128 runs one CTA per query tile), the SIMT kernels (fp32) —
+    forward and backward."""
     g = torch.Generator(device=DEV).manual_seed(B * 100 + T)
     qkv = torch.randn(B * T, 3 * D, generator=g, device=DEV).to(dtype).requires_grad_()
     pad = torch.zeros(B, T, dtype=torch.uint8, device=DEV)

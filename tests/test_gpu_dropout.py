@@ -95,6 +95,7 @@ def test_add_ln_branch_dropout_exact(dtype):
 
 
 @pytest.mark.parametrize("dtype,B,H,T,S,D", [(torch.bfloat16, 4, 8, 64, 50, 768), (torch.bfloat16, 2, 8, 40, 257, 768),
+                                              (torch.bfloat16, 2, 8, 197, 200, 768),   # query tiles x key tiles
                                               (torch.float32, 2, 4, 12, 7, 64), (torch.float32, 2, 8, 64, 150, 768)])
 def test_attention_probability_dropout_exact(dtype, B, H, T, S, D):
     g = torch.Generator(device=DEV).manual_seed(2)

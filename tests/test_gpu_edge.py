@@ -99,7 +99,7 @@ def test_fusion_without_masks_and_query_length_one(mode):
 
 
 def test_cross_attention_fusion_vision_queries_longer_than_tile():
-    """Vision stream as queries with V = 257 > 128 rows: falls back to the CUDA-core attention, same numbers."""
+    """Vision stream as queries with V = 257 > 128 rows: three query tiles on the tensor-core attention."""
     torch.manual_seed(0)
     D, H = 128, 4
     pkg.set_compute_dtype("bf16")

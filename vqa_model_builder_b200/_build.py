@@ -26,6 +26,10 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-I", str(INCLUDE),
 ]
+if os.environ.get("B200VQA_GEMM_TRACE") == "1":   # instrumented GEMM (scripts/gemm_trace.py): separate library + objects
+    NVCC_FLAGS.append("-DB200_GEMM_TRACE")
+    LIB_PATH = PKG_DIR / "libb200vqa_trace.so"
+    OBJ_DIR = PKG_DIR / "build_trace"
 if os.environ.get("B200VQA_EPI_WARPS"):     # experiment knob: epilogue warps of the tcgen05 GEMM (8 | 12 | 16)
     NVCC_FLAGS.append("-DB200_EPI_WARPS=" + os.environ["B200VQA_EPI_WARPS"])
 

@@ -1,6 +1,6 @@
 // Fused attention core on the 5th-gen tensor cores (bf16 in, fp32 softmax/accumulate), forward and backward.
-// One CTA per (batch, head): all T <= 128 query rows form the M=128 dimension of every UMMA; keys/values are
-// walked in tiles of 128.  Q/K/V/dO tiles arrive by TMA into 128B-swizzled shared memory; S = Q K^T, dP = dO V^T,
+// One CTA per (batch, head, 128-row query tile): the query rows form the M=128 dimension of every UMMA; keys/values
+// are walked in tiles of 128 (S <= 384 forward; any T).  Q/K/V/dO tiles arrive by TMA into 128B-swizzled shared memory; S = Q K^T, dP = dO V^T,
 // O/dQ/dK/dV accumulate in TMEM; the 128 threads (thread = TMEM lane = matrix row) do the softmax math in
 // registers and hand P / dS back to the tensor core through shared memory written in the same swizzled layout.
 // The [B,H,T,S] score tensor never exists in HBM.
@@ -99,7 +99,7 @@ __device__ __forceinline__ uint32_t causal_word(int causal, int row, int col0) {
   return d >= 31 ? 0xffffffffu : (d < 0 ? 0u : ((2u << d) - 1u));
 }
 
-// Geometry of the two kernel flavours.  R = 128: the general kernel (T <= 128, kv tiles of 128 rows, 128 threads).
+// Geometry of the two kernel flavours.  R = 128: the general kernel (query tiles and kv tiles of 128 rows, 128 threads).
 // R = 64: T <= 64 and S <= 64 (the question / image-patch shapes of the fusion block): TMA boxes of 64 rows, 64
 // threads, half the shared memory and a quarter of the TMEM, so 3 (forward) / 2 (backward) CTAs share an SM and
 // hide each other's TMA -> MMA -> softmax -> MMA latency chain.  The UMMAs keep M = 128: accumulator rows 64..127
@@ -161,6 +161,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int q0 = blockIdx.y * R;         // first query row of this CTA's tile (blockIdx.y > 0 only when T > 128)
   const int ksteps_d = a.dh / 16;
 
   if (tid == 0) {
@@ -185,7 +186,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   // ---- S_j = Q K_j^T for every kv tile (K buffer reused serially; the tensor-core work here is tiny) ----
   if (tid == 0) {
     ptx::mbar_arrive_expect_tx(bar_q, nch * CH);
-    for (int c = 0; c < nch; ++c) ptx::tma_load_2d(sQ + c * CH, &qmap, bar_q, h * a.dh + 64 * c, b * a.T);
+    for (int c = 0; c < nch; ++c) ptx::tma_load_2d(sQ + c * CH, &qmap, bar_q, h * a.dh + 64 * c, b * a.T + q0);
   }
   for (int j = 0; j < NT; ++j) {
     const int n_valid = min(R, a.S - j * R);
@@ -215,6 +216,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 
   // ---- softmax: thread = query row -------------------------------------------------------------------
   const int r = tid;
+  const int rg = q0 + r;                 // query row inside the (batch, head) problem
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
   const uint8_t* kp = a.key_pad ? a.key_pad + (long long)b * a.S : nullptr;
   build_key_mask(s_ok, kp, a.S, NT * R, tid, R);
@@ -226,7 +228,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
     for (int c = 0; c * 32 < n_valid; ++c) {
       float v[32];
       ld32(lane_base + j * 128 + c * 32, v);
-      const uint32_t okb = s_ok[j * (R / 32) + c] & causal_word(a.causal, r, j * R + c * 32);
+      const uint32_t okb = s_ok[j * (R / 32) + c] & causal_word(a.causal, rg, j * R + c * 32);
 #pragma unroll
       for (int i = 0; i < 32; ++i) m = fmaxf(m, (okb >> i) & 1u ? v[i] : -INFINITY);
     }
@@ -234,7 +236,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   const float sl2 = a.scale * LOG2E;
   const float m_s = (m == -INFINITY) ? 0.f : m * sl2;
   const DropState ds = drop_load(a.drop_state, a.drop_p, a.drop_site);
-  const unsigned long long drow = ((unsigned long long)blockIdx.x * a.T + r) * (unsigned long long)(((a.S + ROWS - 1) / ROWS) * ROWS);
+  const unsigned long long drow = ((unsigned long long)blockIdx.x * a.T + rg) * (unsigned long long)(((a.S + ROWS - 1) / ROWS) * ROWS);
   float l = 0.f;
   for (int j = 0; j < NT; ++j) {
     const int n_valid = min(R, a.S - j * R);
@@ -243,7 +245,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
     for (int c = 0; c * 32 < n16; ++c) {
       float v[32];
       ld32(lane_base + j * 128 + c * 32, v);
-      const uint32_t okb = s_ok[j * (R / 32) + c] & causal_word(a.causal, r, j * R + c * 32);
+      const uint32_t okb = s_ok[j * (R / 32) + c] & causal_word(a.causal, rg, j * R + c * 32);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float p = (okb >> i) & 1u ? ex2(fmaf(v[i], sl2, -m_s)) : 0.f;
@@ -288,11 +290,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   // ---- epilogue: O / l -> bf16 -> global; log-sum-exp for backward -----------------------------------------
   const float inv = l > 0.f ? 1.f / l : 0.f;
   {
-    bf16* orow = a.o + ((long long)b * a.T + r) * a.ldo + h * a.dh;
+    bf16* orow = a.o + ((long long)b * a.T + rg) * a.ldo + h * a.dh;
     for (int c = 0; c < a.dh / 32; ++c) {
       float v[32];
       ld32(lane_base + O_COL + c * 32, v);   // .aligned: executed by the whole warp, stores are predicated
-      if (r < a.T) {
+      if (rg < a.T) {
 #pragma unroll
         for (int jv = 0; jv < 4; ++jv) {
           uint4 t;
@@ -302,7 +304,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
         }
       }
     }
-    if (r < a.T) a.lse[((long long)b * a.H + h) * a.T + r] = (l > 0.f) ? m * a.scale + __logf(l) : -INFINITY;
+    if (rg < a.T) a.lse[((long long)b * a.H + h) * a.T + rg] = (l > 0.f) ? m * a.scale + __logf(l) : -INFINITY;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -310,11 +312,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 }
 
 // ============================================ backward =============================================
-// smem: Q[nch] | dO[nch] | K[nch] | V[nch] | P | dS.  TMEM (R = 128): S/dV at 0, dP/dK at 128, dQ at 256.
-// R = 64: S at 0, dP at 64; dV at 0 and dK at 128 are drained first, then dQ reuses column 0 (256 columns in all,
-// two CTAs per SM).
+// smem: Q[nch] | dO[nch] | K[nch] | V[nch] | P | dS.  TMEM (R = 128): S at 0, dP at 128, dQ at 256; dV / dK take the
+// S / dP columns once P / dS sit in shared memory.  R = 64: S at 0, dP at 64; dV at 0 and dK at 128 are drained first,
+// then dQ reuses column 0 (256 columns in all, two CTAs per SM).
+//
+// More than 128 query rows (vision-token queries of ViT-B/16 / DINOv2, the single-stream fusion's 300+ tokens): the
+// grid grows a second dimension and every CTA owns ONE output tile completely, so nothing is accumulated across CTAs
+// (no atomics, deterministic):
+//   role Q  (blockIdx.y <  q_tiles): query tile i fixed, key tiles streamed  -> dQ_i   (S, dP, dS_ij, dQ_i += dS_ij K_j)
+//   role KV (blockIdx.y >= q_tiles): key tile j fixed, query tiles streamed  -> dV_j, dK_j accumulate in TMEM columns
+//                                    256 / 384 over the query tiles (S / dP columns are rewritten every step)
+// S and dP are computed by both roles; with T <= 128 there is one CTA per (batch, head) doing everything (role ALL).
+enum { ROLE_ALL = 0, ROLE_Q = 1, ROLE_KV = 2 };
+
 template <int R>
-__global__ void __launch_bounds__(BwdGeo<R>::NTHR)
+__global__ void __launch_bounds__(BwdGeo<R>::NTHR, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                    const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap domap,
                    const AttnTcArgs a) {
@@ -332,8 +344,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   const uint32_t bar_q = bars, bar_kv = bars + 8, bar_mma = bars + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.ptr + 4 * nch * CH + 2 * PT + Geo<R>::SLACK + 32);
   uint32_t* s_ok = reinterpret_cast<uint32_t*>(sm.ptr + 4 * nch * CH + 2 * PT + Geo<R>::SLACK + 64);   // [ntiles*R/32]
-  constexpr uint32_t TCOLS = SMALL ? 256 : 512, C_S = 0, C_DP = SMALL ? 64 : 128, C_DV = 0, C_DK = 128,
-                     C_DQ = SMALL ? 0 : 256;
+  constexpr uint32_t TCOLS = SMALL ? 256 : 512, C_S = 0, C_DP = SMALL ? 64 : 128, C_DQ = SMALL ? 0 : 256;
 
   // 128-row flavour: TWO threads per row (256 threads).  One CTA per SM is all the 192 KB of operand tiles allow, and
   // with one warp per scheduler the softmax / dS arithmetic and the TMEM drains were a serial chain per row; the
@@ -343,8 +354,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   const int half = tid / R;                 // warp-uniform
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int ksteps_d = a.dh / 16;
-  const int ksteps_t = (min(a.T, R) + 15) / 16;
   const int ntiles = (a.S + R - 1) / R;
+  const int q_tiles = (a.T + R - 1) / R;
+  const int role = q_tiles == 1 ? ROLE_ALL : ((int)blockIdx.y < q_tiles ? ROLE_Q : ROLE_KV);
+  const int i_fixed = role == ROLE_Q ? (int)blockIdx.y : 0;
+  const int j_fixed = role == ROLE_KV ? (int)blockIdx.y - q_tiles : 0;
+  const int nsteps = role == ROLE_KV ? q_tiles : ntiles;
+  const uint32_t C_DV = role == ROLE_KV ? 256u : 0u, C_DK = role == ROLE_KV ? 384u : 128u;
 
   if (tid == 0) {
     ptx::prefetch_tensormap(&qmap);
@@ -364,55 +380,76 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   pdl_trigger();
   pdl_wait();
   const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // a warp reads TMEM lanes 32 (w % 4) ..
-  uint32_t ph_kv = 0, ph_mma = 0;
+  uint32_t ph_q = 0, ph_kv = 0, ph_mma = 0;
 
-  if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(bar_q, 2 * nch * CH);
-    for (int c = 0; c < nch; ++c) {
-      ptx::tma_load_2d(sQ + c * CH, &qmap, bar_q, h * a.dh + 64 * c, b * a.T);
-      ptx::tma_load_2d(sdO + c * CH, &domap, bar_q, h * a.dh + 64 * c, b * a.T);
-    }
-  }
-  // per-row statistics: delta = sum_d dO*O, lse
   const int r = tid % R;
-  float delta = 0.f, lse_l2 = 0.f;
-  const bool row_ok = r < a.T;
-  if (row_ok) {
-    const bf16* orow = a.o_in + ((long long)b * a.T + r) * a.ldo_in + h * a.dh;
-    const bf16* grow = a.d_o + ((long long)b * a.T + r) * a.lddo + h * a.dh;
-    const int dsplit = (a.dh / 8 + HALVES - 1) / HALVES * 8;          // each half-CTA sums its share of the head dim
-    for (int d = half * dsplit; d < min(a.dh, (half + 1) * dsplit); d += 8) {
-      Vec16<bf16> ov, gv;
-      ov.load(orow + d);
-      gv.load(grow + d);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) delta = fmaf(ov.v[u], gv.v[u], delta);
-    }
-    lse_l2 = a.lse[((long long)b * a.H + h) * a.T + r] * LOG2E;
-  }
   const float sl2 = a.scale * LOG2E;
   const uint8_t* kp = a.key_pad ? a.key_pad + (long long)b * a.S : nullptr;
   build_key_mask(s_ok, kp, a.S, ntiles * R, tid, NTHR);
-  if (HALVES == 2) reinterpret_cast<float*>(pP)[half * R + r] = delta;    // the P buffer is free until the first tile
   __syncthreads();
-  if (HALVES == 2) {
-    delta = reinterpret_cast<float*>(pP)[r] + reinterpret_cast<float*>(pP)[R + r];
-    __syncthreads();                                                      // before P is written
-  }
   const DropState ds = drop_load(a.drop_state, a.drop_p, a.drop_site);
-  const unsigned long long drow = ((unsigned long long)blockIdx.x * a.T + r) * (unsigned long long)(((a.S + ROWS - 1) / ROWS) * ROWS);
+  const unsigned long long spad = (unsigned long long)(((a.S + ROWS - 1) / ROWS) * ROWS);
+  // per-row state of the current query tile
+  float delta = 0.f, lse_l2 = 0.f;
+  bool row_ok = false;
+  int rg = r;
+  unsigned long long drow = 0;
 
-  for (int j = 0; j < ntiles; ++j) {
+  for (int st = 0; st < nsteps; ++st) {
+    const int i = role == ROLE_KV ? st : i_fixed;        // query tile
+    const int j = role == ROLE_KV ? j_fixed : st;        // key tile
+    const bool load_q = st == 0 || role == ROLE_KV;
+    const bool load_kv = st == 0 || role != ROLE_KV;
+    const int q0 = i * R;
+    const int ksteps_t = (min(a.T - q0, R) + 15) / 16;
     const int n_valid = min(R, a.S - j * R);
     const int n16 = (n_valid + 15) & ~15;
     if (tid == 0) {
-      ptx::mbar_arrive_expect_tx(bar_kv, 2 * nch * CH);
-      for (int c = 0; c < nch; ++c) {
-        ptx::tma_load_2d(sK + c * CH, &kmap, bar_kv, h * a.dh + 64 * c, b * a.S + j * R);
-        ptx::tma_load_2d(sV + c * CH, &vmap, bar_kv, h * a.dh + 64 * c, b * a.S + j * R);
+      if (load_q) {
+        ptx::mbar_arrive_expect_tx(bar_q, 2 * nch * CH);
+        for (int c = 0; c < nch; ++c) {
+          ptx::tma_load_2d(sQ + c * CH, &qmap, bar_q, h * a.dh + 64 * c, b * a.T + q0);
+          ptx::tma_load_2d(sdO + c * CH, &domap, bar_q, h * a.dh + 64 * c, b * a.T + q0);
+        }
       }
-      if (j == 0) ptx::mbar_wait(bar_q, 0);
-      ptx::mbar_wait(bar_kv, ph_kv);
+      if (load_kv) {
+        ptx::mbar_arrive_expect_tx(bar_kv, 2 * nch * CH);
+        for (int c = 0; c < nch; ++c) {
+          ptx::tma_load_2d(sK + c * CH, &kmap, bar_kv, h * a.dh + 64 * c, b * a.S + j * R);
+          ptx::tma_load_2d(sV + c * CH, &vmap, bar_kv, h * a.dh + 64 * c, b * a.S + j * R);
+        }
+      }
+    }
+    if (load_q) {
+      // per-row statistics of this query tile: delta = sum_d dO*O, lse
+      rg = q0 + r;
+      row_ok = rg < a.T;
+      delta = 0.f;
+      lse_l2 = 0.f;
+      if (row_ok) {
+        const bf16* orow = a.o_in + ((long long)b * a.T + rg) * a.ldo_in + h * a.dh;
+        const bf16* grow = a.d_o + ((long long)b * a.T + rg) * a.lddo + h * a.dh;
+        const int dsplit = (a.dh / 8 + HALVES - 1) / HALVES * 8;          // each half-CTA sums its share of the head dim
+        for (int d = half * dsplit; d < min(a.dh, (half + 1) * dsplit); d += 8) {
+          Vec16<bf16> ov, gv;
+          ov.load(orow + d);
+          gv.load(grow + d);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) delta = fmaf(ov.v[u], gv.v[u], delta);
+        }
+        lse_l2 = a.lse[((long long)b * a.H + h) * a.T + rg] * LOG2E;
+      }
+      drow = ((unsigned long long)blockIdx.x * a.T + rg) * spad;
+      if (HALVES == 2) {                                                  // the P buffer is free between steps
+        reinterpret_cast<float*>(pP)[half * R + r] = delta;
+        __syncthreads();
+        delta = reinterpret_cast<float*>(pP)[r] + reinterpret_cast<float*>(pP)[R + r];
+        __syncthreads();                                                  // before P is written
+      }
+    }
+    if (tid == 0) {
+      if (load_q) ptx::mbar_wait(bar_q, ph_q);
+      if (load_kv) ptx::mbar_wait(bar_kv, ph_kv);
       ptx::tc_fence_after();
       const uint32_t id = idesc(128, n16, false, false);
       for (int kk = 0; kk < ksteps_d; ++kk)   // S = Q K^T
@@ -421,7 +458,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
         ptx::umma_bf16(tmem + C_DP, desc_k(sdO, kk, CH), desc_k(sV, kk, CH), id, kk > 0 ? 1u : 0u);
       ptx::umma_commit(bar_mma);
     }
-    ph_kv ^= 1;
+    if (load_q) ph_q ^= 1;
+    if (load_kv) ph_kv ^= 1;
     ptx::mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
     ptx::tc_fence_after();
@@ -441,13 +479,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 #pragma unroll
         for (int q = 0; q < 8; ++q) keep[i8 + q] = sc[q];
       }
-      const uint32_t okb = row_ok ? (s_ok[j * (R / 32) + c] & causal_word(a.causal, r, j * R + c * 32)) : 0u;
+      const uint32_t okb = row_ok ? (s_ok[j * (R / 32) + c] & causal_word(a.causal, rg, j * R + c * 32)) : 0u;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const bool ok = (okb >> i) & 1u;
-        const float p = ok ? ex2(fmaf(s[i], sl2, -lse_l2)) : 0.f;
-        s[i] = p * keep[i];                                               // dropped P feeds dV = P^T dO
-        dp[i] = ok ? p * (dp[i] * keep[i] - delta) * a.scale : 0.f;       // dS = P (dP*mask/(1-p) - delta)
+      for (int e = 0; e < 32; ++e) {
+        const bool ok = (okb >> e) & 1u;
+        const float p = ok ? ex2(fmaf(s[e], sl2, -lse_l2)) : 0.f;
+        s[e] = p * keep[e];                                               // dropped P feeds dV = P^T dO
+        dp[e] = ok ? p * (dp[e] * keep[e] - delta) * a.scale : 0.f;       // dS = P (dP*mask/(1-p) - delta)
       }
       // columns >= n16 are written as zeros too: the dV/dK products read all 128 columns of these tiles (M dim)
       store_row32(pP, r, c, s);
@@ -458,23 +496,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
     __syncthreads();
     if (tid == 0) {
       ptx::tc_fence_after();
-      const uint32_t id_t = idesc(128, a.dh, true, true);    // A^T B with A = P / dS (MN-major), B = dO / Q (MN-major)
-      for (int kk = 0; kk < ksteps_t; ++kk)   // dV = P^T dO
-        ptx::umma_bf16(tmem + C_DV, desc_mn(sP, kk, PCH), desc_mn(sdO, kk, CH), id_t, kk > 0 ? 1u : 0u);
-      for (int kk = 0; kk < ksteps_t; ++kk)   // dK = dS^T Q
-        ptx::umma_bf16(tmem + C_DK, desc_mn(sdS, kk, PCH), desc_mn(sQ, kk, CH), id_t, kk > 0 ? 1u : 0u);
-      if (!SMALL) {
+      if (role != ROLE_Q) {
+        const uint32_t acc0 = (role == ROLE_KV && st > 0) ? 1u : 0u;   // role KV: sums over the query tiles
+        const uint32_t id_t = idesc(128, a.dh, true, true);    // A^T B with A = P / dS (MN-major), B = dO / Q (MN-major)
+        for (int kk = 0; kk < ksteps_t; ++kk)   // dV = P^T dO
+          ptx::umma_bf16(tmem + C_DV, desc_mn(sP, kk, PCH), desc_mn(sdO, kk, CH), id_t, kk > 0 ? 1u : acc0);
+        for (int kk = 0; kk < ksteps_t; ++kk)   // dK = dS^T Q
+          ptx::umma_bf16(tmem + C_DK, desc_mn(sdS, kk, PCH), desc_mn(sQ, kk, CH), id_t, kk > 0 ? 1u : acc0);
+      }
+      if (!SMALL && role != ROLE_KV) {
         const uint32_t id_q = idesc(128, a.dh, false, true);   // dQ += dS K  (A = dS K-major, B = K MN-major)
         for (int kk = 0; kk < n16 / 16; ++kk)
-          ptx::umma_bf16(tmem + C_DQ, desc_k(sdS, kk, PCH), desc_mn(sK, kk, CH), id_q, (j > 0 || kk > 0) ? 1u : 0u);
+          ptx::umma_bf16(tmem + C_DQ, desc_k(sdS, kk, PCH), desc_mn(sK, kk, CH), id_q, (st > 0 || kk > 0) ? 1u : 0u);
       }
       ptx::umma_commit(bar_mma);
     }
     ptx::mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
     ptx::tc_fence_after();
-    // dV, dK rows of this tile: thread = kv row
-    {
+    // dV, dK rows of this key tile: thread = kv row (role ALL: every step; role KV: once, after the last query tile)
+    if (role == ROLE_ALL || (role == ROLE_KV && st == nsteps - 1)) {
       const int srow = j * R + r;
       const bool ok = r < n_valid;
       bf16* dvrow = a.dv + ((long long)b * a.S + srow) * a.lddv + h * a.dh;
@@ -499,7 +540,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
       }
     }
     ptx::tc_fence_before();
-    __syncthreads();   // TMEM S/dP regions and the K/V/P/dS buffers may be overwritten by the next tile
+    __syncthreads();   // TMEM S/dP regions and the Q/dO/K/V/P/dS buffers may be overwritten by the next step
   }
 
   if (SMALL) {   // dV / dK are drained: dQ = dS K takes their columns (single kv tile in this flavour)
@@ -514,10 +555,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
     ptx::mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
   }
-  // dQ rows
+  // dQ rows (rg / row_ok still describe the fixed query tile in roles ALL and Q)
   ptx::tc_fence_after();
-  {
-    bf16* dqrow = a.dq + ((long long)b * a.T + r) * a.lddq + h * a.dh;
+  if (role != ROLE_KV) {
+    bf16* dqrow = a.dq + ((long long)b * a.T + rg) * a.lddq + h * a.dh;
     for (int c = half; c < a.dh / 32; c += HALVES) {
       float v[32];
       ld32(lane_base + C_DQ + c * 32, v);
@@ -552,7 +593,7 @@ bool small_shape(int T, int S) { return T <= 64 && S <= 64; }
 
 bool attn_tc_supported(int T, int S, int dh, int ldq, int ldk, int ldv, const void* q, const void* k, const void* v) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  return T <= ROWS && S <= 3 * ROWS && dh % 32 == 0 && dh <= 128 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 &&
+  return S <= 3 * ROWS && dh % 32 == 0 && dh <= 128 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 &&
          al(q) && al(k) && al(v);
 }
 
@@ -580,11 +621,12 @@ int launch_attn_fwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
     B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<1, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = true;
   }
+  const int q_tiles = (T + ROWS - 1) / ROWS;     // one CTA per (batch, head, 128-row query tile)
   if (small) launch_kernel(attn_fwd_tc_kernel<1, 64>, dim3(B * H), dim3(64), fwd_smem<64>(dh), stream, qm, km, vm, a);
   else if (nt == 1)
-    launch_kernel(attn_fwd_tc_kernel<1, 128>, dim3(B * H), dim3(128),
+    launch_kernel(attn_fwd_tc_kernel<1, 128>, dim3(B * H, q_tiles), dim3(128),
                   fwd_alias<1, 128>(dh) ? fwd_smem_aliased<128>(dh) : fwd_smem<128>(dh), stream, qm, km, vm, a);
-  else launch_kernel(attn_fwd_tc_kernel<3, 128>, dim3(B * H), dim3(128), fwd_smem<128>(dh), stream, qm, km, vm, a);
+  else launch_kernel(attn_fwd_tc_kernel<3, 128>, dim3(B * H, q_tiles), dim3(128), fwd_smem<128>(dh), stream, qm, km, vm, a);
   B200_LAUNCH_CHECK("attn_fwd_tc_kernel");
   count_launch();
   return 0;
@@ -616,7 +658,12 @@ int launch_attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const voi
     configured = true;
   }
   if (small) launch_kernel(attn_bwd_tc_kernel<64>, dim3(B * H), dim3(BwdGeo<64>::NTHR), bwd_smem<64>(dh), stream, qm, km, vm, dom, a);
-  else launch_kernel(attn_bwd_tc_kernel<128>, dim3(B * H), dim3(BwdGeo<128>::NTHR), bwd_smem<128>(dh), stream, qm, km, vm, dom, a);
+  else {
+    // T > 128: q_tiles CTAs own a dQ tile each, k_tiles CTAs a dK / dV tile each (see the kernel's header comment)
+    const int q_tiles = (T + ROWS - 1) / ROWS, k_tiles = (S + ROWS - 1) / ROWS;
+    const dim3 grid(B * H, q_tiles == 1 ? 1 : q_tiles + k_tiles);
+    launch_kernel(attn_bwd_tc_kernel<128>, grid, dim3(BwdGeo<128>::NTHR), bwd_smem<128>(dh), stream, qm, km, vm, dom, a);
+  }
   B200_LAUNCH_CHECK("attn_bwd_tc_kernel");
   count_launch();
   return 0;

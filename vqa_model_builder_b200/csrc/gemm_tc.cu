@@ -49,6 +49,27 @@ template <int BN> constexpr int smem_bytes() {
 static_assert(smem_bytes<256>() <= 227 * 1024 && smem_bytes<128>() <= 227 * 1024 && smem_bytes<64>() <= 227 * 1024,
               "pipeline stages + epilogue staging must fit the 227 KB a CTA can own");
 
+// Optional in-kernel timeline (build with -DB200_GEMM_TRACE, scripts/gemm_trace.py): CTA 0 of every launch records
+// %globaltimer / clock64 at the phase boundaries of its first tile.  Not part of the shipped library.
+#ifdef B200_GEMM_TRACE
+__device__ unsigned long long g_trace[256 * 16];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define B200_TRACE(idx_)                                                                      \
+  do {                                                                                         \
+    if (blockIdx.x == 0 && tr_slot < 256u) {                                                   \
+      g_trace[tr_slot * 16 + (idx_)] = trace_now();                                            \
+      g_trace[tr_slot * 16 + 8 + (idx_)] = (unsigned long long)clock64();                      \
+    }                                                                                          \
+  } while (0)
+#else
+#define B200_TRACE(idx_) do { } while (0)
+#endif
+
 struct TileInfo {
   int valid, group, m_tile, n_tile;
   int a_mn0, a_k0, b_mn0, b_k0, k_begin, k_blocks;
@@ -344,6 +365,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar0 - base) + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef B200_GEMM_TRACE
+  __shared__ unsigned int tr_slot_s;
+  unsigned int tr_slot = 0xffffffffu;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    tr_slot_s = atomicAdd(&g_trace_n, 1u);
+    tr_slot = tr_slot_s;
+    B200_TRACE(0);
+  }
+#endif
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tma_a);
@@ -363,9 +393,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef B200_GEMM_TRACE
+  if (blockIdx.x == 0) tr_slot = tr_slot_s;
+  if (threadIdx.x == 0) B200_TRACE(1);
+#endif
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
   pdl_trigger();
   pdl_wait();
+  if (threadIdx.x == 0) B200_TRACE(2);
   // Expert-parallel receive buffers are sized for the worst case; the rows actually in use are only known on the
   // device (tiles are numbered m-major, so bounding m_tiles bounds the tile walk).
   int m_tiles = m_tiles_arg, total_tiles = total_tiles_arg;
@@ -423,6 +458,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint32_t ph = (it / STAGES) & 1;
           ptx::mbar_wait(full_bar(s), ph);
           ptx::tc_fence_after();
+          if (it == 0) B200_TRACE(3);
           const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -437,6 +473,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           ptx::umma_commit(empty_bar(s));       // frees the smem slot once these MMAs retire
         }
         ptx::umma_commit(tmem_full_bar(acc));   // accumulator complete -> epilogue
+        if (acc_it == 0) B200_TRACE(4);
         ++acc_it;
       }
     }
@@ -469,6 +506,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         ptx::mbar_wait(tmem_full_bar(acc), acc_ph);
         ptx::tc_fence_after();
       }
+      if (acc_it == 0 && ew == 0 && lane == 0) B200_TRACE(5);
       const long long row0 = (long long)t.m_tile * BM + quad * 32;
       const long long my_row = row0 + lane;
       long long rows_left = (long long)p.M - row0;
@@ -539,6 +577,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           epilogue_store<bf16, 32>(p, t.group, my_row, col0, v, my_row < p.M);
         }
       }
+      if (acc_it == 0 && ew == 0 && lane == 0) B200_TRACE(6);
       if (have_acc) {
         ptx::tc_fence_before();
         __syncwarp();
@@ -550,6 +589,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) B200_TRACE(7);
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 2 * BN);
 }
 
@@ -697,3 +737,14 @@ int launch_gemm_tc(const void* A, int lda, int a_layout, long long a_mn_extent, 
 }
 
 }  // namespace b200
+
+#ifdef B200_GEMM_TRACE
+// copies the timeline out and resets the launch counter: out[launch * 16 + {0..7: globaltimer ns, 8..15: clock64}]
+extern "C" int b200_debug_gemm_trace(unsigned long long* host_out, unsigned int* n_out) {
+  unsigned int zero = 0;
+  if (cudaMemcpyFromSymbol(host_out, b200::g_trace, sizeof(unsigned long long) * 256 * 16) != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(n_out, b200::g_trace_n, sizeof(unsigned int)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(b200::g_trace_n, &zero, sizeof(unsigned int)) != cudaSuccess) return 1;
+  return 0;
+}
+#endif

@@ -48,6 +48,7 @@ def resolve_compute_dtype(x: torch.Tensor) -> torch.dtype:
 # ---------------------------------------------------------------------------------------------------------
 _AUX = [os.environ.get("B200VQA_AUX_STREAM", "1") != "0"]
 _aux_streams = {}
+_prefetch_streams = {}
 
 
 def set_aux_stream(enabled: bool) -> None:
@@ -120,6 +121,37 @@ class SlabOwner:
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         return new
+
+
+def prefetch_compute_weights(*modules: nn.Module) -> int:
+    """Start refreshing the bf16 compute copies of the given drop-in modules (and their drop-in children) on a
+    side stream; returns how many slabs were queued.  Call it at the top of a training step (after
+    `optimizer.step()` changed the fp32 masters) for modules that run LATER in the step — e.g. the MOE layer and the
+    answer decoder while the fusion runs first — so that their cast (one pass over 6 bytes per parameter) overlaps the
+    first module's kernels instead of sitting in front of their own first GEMM.  Each module's forward waits for its own
+    copy only.  Every prefetched module must run its forward in the same step (inside a CUDA-graph capture an unused
+    prefetch would leave the auxiliary stream un-joined).  With the auxiliary stream disabled this is a no-op: the
+    forward casts as usual."""
+    n = 0
+    for root in modules:
+        for m in root.modules():
+            if not isinstance(m, SlabOwner):
+                continue
+            slab: Optional[ParamSlab] = m.__dict__.get("_slab")
+            if slab is None or slab.master is None or slab._ready is not None:
+                continue                       # never ran (nothing to refresh yet) or already queued
+            if not _AUX[0]:
+                return n
+            dev = slab.master.device
+            key = dev.index if dev.index is not None else torch.cuda.current_device()
+            s = _prefetch_streams.get(key)      # its own stream: the fork / join pairs of the auxiliary stream inside
+            if s is None:                       # the autograd Functions must not end up waiting for a weight cast
+                s = torch.cuda.Stream(device=dev)
+                _prefetch_streams[key] = s
+            s.wait_stream(torch.cuda.current_stream(dev))
+            slab.prefetch(dev, s)
+            n += 1
+    return n
 
 
 def invalidate_all(model: nn.Module) -> None:

@@ -53,6 +53,8 @@ class ParamSlab:
         #: set by SlabOwner.invalidate(): forces the next refresh to re-cast (writes through `p.data`, e.g. an EMA
         #: weight swap or Lookahead's slow-weight copy, do not bump the version counters checked below)
         self.dirty = False
+        #: set by prefetch(): the event the consuming stream waits for instead of casting again
+        self._ready = None
 
     # -- packing --------------------------------------------------------------------------------------
     def _packed(self) -> bool:
@@ -116,6 +118,10 @@ class ParamSlab:
         self.ensure(device)
         if dtype != torch.bfloat16:
             return
+        if self._ready is not None:          # the copy is being made on the auxiliary stream (prefetch): wait, not cast
+            torch.cuda.current_stream(device).wait_event(self._ready)
+            self._ready = None
+            return
         versions = [p._version for p in self.params]
         capturing = torch.cuda.is_current_stream_capturing()
         if self.shadow is None:
@@ -125,3 +131,18 @@ class ParamSlab:
             _lib.call("b200_cast", self.master, _lib.F32, self.shadow, _lib.BF16, self.total, _lib.stream_ptr())
             self._versions = versions
             self.dirty = False
+
+    def prefetch(self, device: torch.device, stream) -> None:
+        """Re-cast the bf16 compute copy on `stream` (ordered after the work already enqueued on the current stream)
+        and remember the completion event: the next refresh() on the consuming stream waits for it and skips its own
+        cast.  See runtime.prefetch_compute_weights."""
+        self.ensure(device)
+        if self.shadow is None:
+            self.shadow = torch.empty(self.total, dtype=torch.bfloat16, device=device)
+        with torch.cuda.stream(stream):
+            _lib.call("b200_cast", self.master, _lib.F32, self.shadow, _lib.BF16, self.total, _lib.stream_ptr())
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        self._versions = [p._version for p in self.params]
+        self.dirty = False
+        self._ready = ev
