@@ -534,7 +534,7 @@ def measure(wl: Workload, args, steps: int, warm_iters: int, want_e2e: bool, wan
     if not args.no_graph:
         try:
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=torch.cuda.current_stream()):
                 wl.step()
         except Exception as e:  # capture unsupported for this configuration: time eagerly
             if rank == 0:
@@ -720,7 +720,10 @@ def run_ours(args, c):
     # Nothing below runs on the legacy default stream: autograd's AccumulateGrad nodes remember the stream they were
     # created on (the gradient hooks and aux_outputs keep them alive across steps), and a node created on the default
     # stream would synchronise with it inside the CUDA-graph capture, which invalidates the capture.
-    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    # The step runs (and is captured) on a HIGH-priority stream: the library's auxiliary streams (weight / bias
+    # gradients) have the default, lower priority, so when a critical-path dgrad GEMM and a wgrad GEMM become ready
+    # together the block scheduler hands the free SMs to the dgrad first (kernel nodes keep the priority in a graph).
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1 if args.main_priority == "high" else 0))
 
     wl = Workload(c, dev, rank, world, args)
     ep_res = wl.check_expert_parallel() if world > 1 else None
@@ -818,6 +821,8 @@ def main():
                     help="comma list of further configurations measured briefly and reported under 'other_configs' "
                          "('none' to skip)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--main-priority", default="high", choices=["high", "normal"],
+                    help="CUDA priority of the stream the step runs on (auxiliary streams are always 'normal')")
     ap.add_argument("--no-prefetch", action="store_true",
                     help="do not refresh the later modules' bf16 weight copies on a side stream (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

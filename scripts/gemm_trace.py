@@ -4,7 +4,7 @@
 A chain of identical GEMMs is captured in a CUDA graph (programmatic dependent launch edges, like a bench step) and
 replayed; CTA 0 of every launch records %globaltimer at: 0 kernel entry, 1 setup done (barriers, TMEM), 2 after
 griddepcontrol.wait, 3 first k-block landed, 4 last MMA committed, 5 epilogue sees the accumulator, 6 first tile stored,
-7 CTA done.  Printed: per-launch chain time (events) and the median phase durations in microseconds."""
+7 CTA done, 8 / 9 / 10 first chunk of the first tile: accumulator in registers / bias added / stores issued.  Printed: per-launch chain time (events) and the median phase durations in microseconds."""
 import ctypes
 import os
 import statistics
@@ -24,7 +24,7 @@ def main():
     lib = _lib.load()
     lib.b200_debug_gemm_trace.restype = ctypes.c_int
     lib.b200_debug_gemm_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-    buf = (ctypes.c_ulonglong * (256 * 16))()
+    buf = (ctypes.c_ulonglong * (256 * 32))()
     n = ctypes.c_uint(0)
     g = torch.Generator(device=dev).manual_seed(0)
     cases = [("fwd_proj_M2048", "KK", 2048, 768, 768, EPI_NONE), ("fwd_proj_M32", "KK", 32, 768, 768, EPI_NONE),
@@ -62,18 +62,19 @@ def main():
             st.synchronize()
         chain_us = e0.elapsed_time(e1) * 1e3 / CH
         lib.b200_debug_gemm_trace(buf, ctypes.byref(n))
-        rows = [[buf[i * 16 + k] for k in range(16)] for i in range(min(n.value, 256))]
+        rows = [[buf[i * 32 + k] for k in range(32)] for i in range(min(n.value, 256))]
         rows.sort(key=lambda r: r[0])
         mid = rows[4:-2]
         ph = lambda i, j: statistics.median((r[j] - r[i]) / 1e3 for r in mid)   # noqa: E731
         gap = statistics.median((rows[k + 1][2] - rows[k][7]) / 1e3 for k in range(4, len(rows) - 3))
         period = statistics.median((rows[k + 1][7] - rows[k][7]) / 1e3 for k in range(4, len(rows) - 3))
-        clk = lambda i, j: statistics.median((r[8 + j] - r[8 + i]) for r in mid)   # noqa: E731
+        clk = lambda i, j: statistics.median((r[16 + j] - r[16 + i]) for r in mid)   # noqa: E731
         print(f"{name:18s} M={M} N={N} K={K} epi={epi}: chain {chain_us:6.2f} us/launch (graph of {CH}), "
               f"exit-to-exit {period:5.2f} | entry->setup {ph(0, 1):5.2f} setup->dep-wait-done {ph(1, 2):5.2f} "
               f"wait->first-kblock {ph(2, 3):5.2f} mainloop {ph(3, 4):5.2f} commit->epilogue-sees {ph(4, 5):5.2f} "
               f"epilogue(first tile) {ph(5, 6):5.2f} ->cta-done {ph(6, 7):5.2f} | prev-exit -> this wait-done {gap:5.2f} "
-              f"| clocks: mainloop {clk(3, 4):.0f} epilogue {clk(5, 6):.0f}", flush=True)
+              f"| clocks: mainloop {clk(3, 4):.0f} epilogue {clk(5, 6):.0f} [first chunk: tmem-ld {clk(5, 8):.0f} bias {clk(8, 9):.0f} "
+              f"stage+store {clk(9, 10):.0f}]", flush=True)
 
 
 if __name__ == "__main__":

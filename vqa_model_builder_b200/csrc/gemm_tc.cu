@@ -52,7 +52,7 @@ static_assert(smem_bytes<256>() <= 227 * 1024 && smem_bytes<128>() <= 227 * 1024
 // Optional in-kernel timeline (build with -DB200_GEMM_TRACE, scripts/gemm_trace.py): CTA 0 of every launch records
 // %globaltimer / clock64 at the phase boundaries of its first tile.  Not part of the shipped library.
 #ifdef B200_GEMM_TRACE
-__device__ unsigned long long g_trace[256 * 16];
+__device__ unsigned long long g_trace[256 * 32];
 __device__ unsigned int g_trace_n;
 __device__ __forceinline__ unsigned long long trace_now() {
   unsigned long long t;
@@ -62,8 +62,8 @@ __device__ __forceinline__ unsigned long long trace_now() {
 #define B200_TRACE(idx_)                                                                      \
   do {                                                                                         \
     if (blockIdx.x == 0 && tr_slot < 256u) {                                                   \
-      g_trace[tr_slot * 16 + (idx_)] = trace_now();                                            \
-      g_trace[tr_slot * 16 + 8 + (idx_)] = (unsigned long long)clock64();                      \
+      g_trace[tr_slot * 32 + (idx_)] = trace_now();                                            \
+      g_trace[tr_slot * 32 + 16 + (idx_)] = (unsigned long long)clock64();                     \
     }                                                                                          \
   } while (0)
 #else
@@ -520,6 +520,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           uint32_t r[32];
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
           ptx::tmem_ld_wait();
+          if (acc_it == 0 && ew == 0 && lane == 0 && k == 0) B200_TRACE(8);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         } else {
@@ -536,6 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
             }
           }
+          if (acc_it == 0 && ew == 0 && lane == 0 && k == 0) B200_TRACE(9);
           if (p.epi == B200_EPI_ACT_D && out_bf16) {
             uint32_t ypk[16], dpk[16];
             tile_act_fwd_d_packed(v, ypk, dpk, p.act, drop, my_row, p.ldo, col0);
@@ -572,6 +574,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             stage_store_tile<2>(stg, lane, v, reinterpret_cast<bf16*>(p.out) + obase, p.ldo, row0, rows_ok, col0);
           else
             stage_store_tile<4>(stg, lane, v, reinterpret_cast<float*>(p.out) + obase, p.ldo, row0, rows_ok, col0);
+          if (acc_it == 0 && ew == 0 && lane == 0 && k == 0) B200_TRACE(10);
         } else {
           // ragged / unaligned tile: per-thread row path (bias handled inside)
           epilogue_store<bf16, 32>(p, t.group, my_row, col0, v, my_row < p.M);
@@ -739,10 +742,10 @@ int launch_gemm_tc(const void* A, int lda, int a_layout, long long a_mn_extent, 
 }  // namespace b200
 
 #ifdef B200_GEMM_TRACE
-// copies the timeline out and resets the launch counter: out[launch * 16 + {0..7: globaltimer ns, 8..15: clock64}]
+// copies the timeline out and resets the launch counter: out[launch * 32 + {0..15: globaltimer ns, 16..31: clock64}]
 extern "C" int b200_debug_gemm_trace(unsigned long long* host_out, unsigned int* n_out) {
   unsigned int zero = 0;
-  if (cudaMemcpyFromSymbol(host_out, b200::g_trace, sizeof(unsigned long long) * 256 * 16) != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(host_out, b200::g_trace, sizeof(unsigned long long) * 256 * 32) != cudaSuccess) return 1;
   if (cudaMemcpyFromSymbol(n_out, b200::g_trace_n, sizeof(unsigned int)) != cudaSuccess) return 1;
   if (cudaMemcpyToSymbol(b200::g_trace_n, &zero, sizeof(unsigned int)) != cudaSuccess) return 1;
   return 0;

@@ -205,8 +205,10 @@ class LinearFn(torch.autograd.Function):
         pre_db = _take_colsum(dy, N) if ctx.drop is None else None
         dy = _rows_aligned(dy)
         dx = dw = db = None
-        side = None
+        side = side2 = None
         g = None
+        need_db = False
+        epi = EPI_NONE
         if ctx.needs_input_grad[1]:
             need_db = ctx.has_bias and pre_db is None
             flat = grad_buffer(N * K + (N if need_db else 0), x.device)
@@ -219,23 +221,29 @@ class LinearFn(torch.autograd.Function):
                 g = dy
             # split-K accumulates atomically when the [N,K] tile grid cannot fill the machine
             epi = EPI_ACCUM if x.dtype == torch.bfloat16 else EPI_NONE
-            side = aux_fork(x.device) if ctx.needs_input_grad[0] else None
-            with aux_on(side):          # parameter gradients run beside the dgrad GEMM
-                gemm(g, LAYOUT_MN, x, LAYOUT_MN, N, K, M, out=dw, epi=epi)
-                if need_db and ctx.drop is None:
-                    _colsum_into(g, db)
+            if ctx.needs_input_grad[0]:     # fork here (g is ready); the side work is ENQUEUED after the dgrad GEMM
+                side = aux_fork(x.device)
+                side2 = aux_fork(x.device, 1) if need_db and ctx.drop is None else None
             if ctx.has_bias and pre_db is not None:
                 db = pre_db
         if g is None:
             g = dropout_apply(dy, ctx.drop) if ctx.drop is not None else dy
         if dw is None and ctx.has_bias and ctx.needs_input_grad[2]:
             db = pre_db if pre_db is not None else colsum(g)
+        # critical path first: when both GEMMs are ready at the same time the one launched first gets the SMs
         if ctx.needs_input_grad[0]:
             if dx_alias is not None:
                 dx = gemm(g, LAYOUT_K, w_c, LAYOUT_MN, M, K, N, epi=EPI_ADD, aux_in=_as_rows(dx_alias, x))
             else:
                 dx = gemm(g, LAYOUT_K, w_c, LAYOUT_MN, M, K, N)
+        if dw is not None:
+            with aux_on(side):          # parameter gradients run beside the dgrad GEMM
+                gemm(g, LAYOUT_MN, x, LAYOUT_MN, N, K, M, out=dw, epi=epi)
+            if need_db and ctx.drop is None:
+                with aux_on(side2):
+                    _colsum_into(g, db)
         aux_join(side)
+        aux_join(side2)
         return dx, dw, db, None, (dy if ctx.has_res else None), None, None
 
 
@@ -310,27 +318,35 @@ class FFNFn(torch.autograd.Function):
         db2 = flat[F * D + F + Do * F:]
         # dropout(dy) and its column sums (= db2) come out of one pass
         g = dropout_colsum(dy, drop_out, db2) if drop_out is not None else dy
-        # critical path (current stream): dpre -> dx;  auxiliary stream: dW2, db2, then (after dpre) dW1, db1
+        # critical path (current stream): dpre -> dx;  auxiliary streams: dW2 | db2, then (after dpre) dW1 | db1.
+        # Forks are taken when the operand is ready, the side work is enqueued AFTER the critical GEMM it runs beside.
         side = aux_fork(x.device)
+        side2 = None
+        if drop_out is None:
+            if pre_db2 is None:
+                side2 = aux_fork(x.device, 1)
+            else:
+                db2 = pre_db2
+        dpre = gemm(g, LAYOUT_K, w2_c, LAYOUT_MN, M, F, Do, epi=EPI_MUL, aux_in=pre)
         with aux_on(side):
             gemm(g, LAYOUT_MN, h, LAYOUT_MN, Do, F, M, out=dw2, epi=wepi)
-            if drop_out is None:
-                if pre_db2 is None:
-                    _colsum_into(g, db2)
-                else:
-                    db2 = pre_db2
-        dpre = gemm(g, LAYOUT_K, w2_c, LAYOUT_MN, M, F, Do, epi=EPI_MUL, aux_in=pre)
+        if drop_out is None and pre_db2 is None:
+            with aux_on(side2):
+                _colsum_into(g, db2)
         side = aux_fork(x.device)       # dW1 / db1 read dpre
-        with aux_on(side):
-            gemm(dpre, LAYOUT_MN, x, LAYOUT_MN, F, D, M, out=dw1, epi=wepi)
-            _colsum_into(dpre, db1)
+        side2 = aux_fork(x.device, 1)
         dx = None
         if ctx.needs_input_grad[0]:
             if dx_alias is not None:
                 dx = gemm(dpre, LAYOUT_K, w1_c, LAYOUT_MN, M, D, F, epi=EPI_ADD, aux_in=_as_rows(dx_alias, x))
             else:
                 dx = gemm(dpre, LAYOUT_K, w1_c, LAYOUT_MN, M, D, F)
+        with aux_on(side):
+            gemm(dpre, LAYOUT_MN, x, LAYOUT_MN, F, D, M, out=dw1, epi=wepi)
+        with aux_on(side2):
+            _colsum_into(dpre, db1)
         aux_join(side)
+        aux_join(side2)
         return dx, dw1, db1, dw2, db2, None, None, None, (dy if ctx.has_res else None), None, None, None
 
 
@@ -779,11 +795,9 @@ class ExpertFFNFn(torch.autograd.Function):
              dr if drop_out is not None else None, ws, nb, st)      # db2 = per-expert column sums of dr, fused
         nb = query("b200_colsum_ws", R, max(F1, Do))
         ws = _ws(nb, dev)
-        # critical path (current stream): dpre -> dxp;  auxiliary stream: db2, dW2, then (after dpre) db1, dW1
+        # critical path (current stream): dpre -> dxp;  auxiliary streams: dW2, then (after dpre) dW1 | db1.  Forks are
+        # taken when the operand is ready; the side work is enqueued AFTER the critical GEMM it runs beside.
         side = aux_fork(dev)
-        with aux_on(side):
-            sa = stream_ptr()
-            call("b200_ggemm_wgrad", dr, Do, h, F, dw2, Do, F, R, E, pad_off, dt, sa)
         if gated:
             dh = torch.empty((R, F), dtype=dz.dtype, device=dev)
             call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dh, F, R, F, Do, E, tile_group, rows_used, dt, dt, None, EPI_NONE,
@@ -793,11 +807,10 @@ class ExpertFFNFn(torch.autograd.Function):
             dpre = torch.empty((R, F), dtype=dz.dtype, device=dev)
             call("b200_ggemm", dr, Do, w2s, LAYOUT_MN, dpre, F, R, F, Do, E, tile_group, rows_used, dt, dt, None, EPI_MUL,
                  ACT_NONE, pre, None, F, None, st)
-        side = aux_fork(dev)
         with aux_on(side):
-            sa = stream_ptr()
-            call("b200_colsum", dpre, dt, R, F1, tile_group, E, db1, ws, nb, sa)
-            call("b200_ggemm_wgrad", dpre, F1, xp, D, dw1, F1, D, R, E, pad_off, dt, sa)
+            call("b200_ggemm_wgrad", dr, Do, h, F, dw2, Do, F, R, E, pad_off, dt, stream_ptr())
+        side = aux_fork(dev)
+        side2 = aux_fork(dev, 1)
         dxp = None
         if ctx.needs_input_grad[0]:
             dxp = torch.empty((R, D), dtype=dz.dtype, device=dev)
@@ -807,7 +820,12 @@ class ExpertFFNFn(torch.autograd.Function):
             else:
                 call("b200_ggemm", dpre, F1, w1s, LAYOUT_MN, dxp, D, R, D, F1, E, tile_group, rows_used, dt, dt, None,
                      EPI_NONE, ACT_NONE, None, None, 0, None, st)
+        with aux_on(side):
+            call("b200_ggemm_wgrad", dpre, F1, xp, D, dw1, F1, D, R, E, pad_off, dt, stream_ptr())
+        with aux_on(side2):
+            call("b200_colsum", dpre, dt, R, F1, tile_group, E, db1, ws, nb, stream_ptr())
         aux_join(side)
+        aux_join(side2)
         # hand every per-expert Parameter its slice of the flat buffer
         grads: List[torch.Tensor] = []
         for buf, shape in ((dw1, (F1, D)), (db1, (F1,)), (dw2, (Do, F)), (db2, (Do,)), (dlng, (Do,)), (dlnb, (Do,))):
@@ -938,12 +956,8 @@ class CrossProjFn(torch.autograd.Function):
         flat = grad_buffer(3 * D * D + 3 * D, x.device)
         dw = flat[:3 * D * D].view(3 * D, D)
         db = flat[3 * D * D:]
-        side = aux_fork(x.device)       # parameter gradients beside the two dgrad GEMMs
-        with aux_on(side):
-            gemm(dq, LAYOUT_MN, x, LAYOUT_MN, D, D, M, out=dw[:D], epi=wepi)
-            gemm(dkvp, LAYOUT_MN, kv, LAYOUT_MN, 2 * D, D, Mk, out=dw[D:], epi=wepi)
-            _colsum_into(dq, db[:D])
-            _colsum_into(dkvp, db[D:])
+        side = aux_fork(x.device)       # parameter gradients beside the two dgrad GEMMs (enqueued after them)
+        side2 = aux_fork(x.device, 1)
         dx = None
         if ctx.needs_input_grad[0]:
             if dx_alias is not None:
@@ -951,7 +965,14 @@ class CrossProjFn(torch.autograd.Function):
             else:
                 dx = gemm(dq, LAYOUT_K, in_w_c[:D], LAYOUT_MN, M, D, D)
         dkv = gemm(dkvp, LAYOUT_K, in_w_c[D:], LAYOUT_MN, Mk, D, 2 * D) if ctx.needs_input_grad[1] else None
+        with aux_on(side):
+            gemm(dq, LAYOUT_MN, x, LAYOUT_MN, D, D, M, out=dw[:D], epi=wepi)
+            gemm(dkvp, LAYOUT_MN, kv, LAYOUT_MN, 2 * D, D, Mk, out=dw[D:], epi=wepi)
+        with aux_on(side2):
+            _colsum_into(dq, db[:D])
+            _colsum_into(dkvp, db[D:])
         aux_join(side)
+        aux_join(side2)
         return dx, dkv, dw, (db if ctx.has_bias else None), None, None
 
 
@@ -1015,12 +1036,9 @@ class MLPFn(torch.autograd.Function):
             N, K = wc.shape
             flat = grad_buffer(N * K + (N if has_bias[i] else 0), dev)
             dw = flat[:N * K].view(N, K)
-            side = aux_fork(dev)
-            with aux_on(side):                    # parameter gradients beside the dgrad GEMM
-                gemm(g, LAYOUT_MN, h, LAYOUT_MN, N, K, M, out=dw, epi=wepi)
-                if has_bias[i]:
-                    _colsum_into(g_dense, flat[N * K:])
-                    grads[3 * i + 1] = flat[N * K:]
+            side = aux_fork(dev)                  # parameter gradients beside the dgrad GEMM (enqueued after it)
+            side2 = aux_fork(dev, 1) if has_bias[i] else None
+            g_w, g_b = g, g_dense
             grads[3 * i] = dw
             if i > 0:      # gradient wrt the previous layer's pre-activation: act' and the dropout mask in the epilogue
                 g = gemm(g, LAYOUT_K, wc, LAYOUT_MN, M, K, N, epi=EPI_DACT, act=acts[i - 1], aux_in=pres[i - 1],
@@ -1028,5 +1046,12 @@ class MLPFn(torch.autograd.Function):
                 g_dense = g
             elif ctx.needs_input_grad[0]:
                 dx = gemm(g, LAYOUT_K, wc, LAYOUT_MN, M, K, N)
+            with aux_on(side):
+                gemm(g_w, LAYOUT_MN, h, LAYOUT_MN, N, K, M, out=dw, epi=wepi)
+            if has_bias[i]:
+                with aux_on(side2):
+                    _colsum_into(g_b, flat[N * K:])
+                grads[3 * i + 1] = flat[N * K:]
             aux_join(side)
+            aux_join(side2)
         return (dx, None, None, *grads)

@@ -55,11 +55,13 @@ def set_aux_stream(enabled: bool) -> None:
     _AUX[0] = bool(enabled)
 
 
-def aux_fork(device: torch.device) -> Optional["torch.cuda.Stream"]:
-    """Order the device's auxiliary stream after the current stream and return it (None when disabled)."""
+def aux_fork(device: torch.device, lane: int = 0) -> Optional["torch.cuda.Stream"]:
+    """Order the device's auxiliary stream `lane` after the current stream and return it (None when disabled).
+    Lane 0 carries the weight-gradient GEMMs, lane 1 the bias-gradient column sums: a column sum is a handful of
+    blocks that fits beside two GEMMs, queued behind the wgrad GEMM it only made the join wait longer."""
     if not _AUX[0]:
         return None
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    key = (device.index if device.index is not None else torch.cuda.current_device(), lane)
     s = _aux_streams.get(key)
     if s is None:
         s = torch.cuda.Stream(device=device)
