@@ -24,7 +24,7 @@ def main():
     lib = _lib.load()
     lib.b200_debug_gemm_trace.restype = ctypes.c_int
     lib.b200_debug_gemm_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-    buf = (ctypes.c_ulonglong * (256 * 32))()
+    buf = (ctypes.c_ulonglong * (256 * 64))()
     n = ctypes.c_uint(0)
     g = torch.Generator(device=dev).manual_seed(0)
     cases = [("fwd_proj_M2048", "KK", 2048, 768, 768, EPI_NONE), ("fwd_proj_M32", "KK", 32, 768, 768, EPI_NONE),
@@ -62,7 +62,7 @@ def main():
             st.synchronize()
         chain_us = e0.elapsed_time(e1) * 1e3 / CH
         lib.b200_debug_gemm_trace(buf, ctypes.byref(n))
-        rows = [[buf[i * 32 + k] for k in range(32)] for i in range(min(n.value, 256))]
+        rows = [[buf[i * 64 + k] for k in range(64)] for i in range(min(n.value, 256))]
         rows.sort(key=lambda r: r[0])
         mid = rows[4:-2]
         ph = lambda i, j: statistics.median((r[j] - r[i]) / 1e3 for r in mid)   # noqa: E731
@@ -75,6 +75,10 @@ def main():
               f"epilogue(first tile) {ph(5, 6):5.2f} ->cta-done {ph(6, 7):5.2f} | prev-exit -> this wait-done {gap:5.2f} "
               f"| clocks: mainloop {clk(3, 4):.0f} epilogue {clk(5, 6):.0f} [first chunk: tmem-ld {clk(5, 8):.0f} bias {clk(8, 9):.0f} "
               f"stage+store {clk(9, 10):.0f}]", flush=True)
+        nkb = min(32, (K + 63) // 64)
+        r = mid[len(mid) // 2]
+        print("    k-block arrivals (clocks after the first, one launch): " +
+              " ".join(str(int(r[32 + k] - r[32])) for k in range(nkb) if r[32 + k] >= r[32]), flush=True)
 
 
 if __name__ == "__main__":

@@ -122,6 +122,76 @@ plan_scatter_kernel(const int* __restrict__ idx, int NK, int E, const int* __res
   }
 }
 
+// ---- the whole plan in one block when every (token, slot) pair fits one chunk (NK <= 1024: the classification
+// pipelines route B pooled vectors) -- histogram, offsets, tile map, stable scatter and the row_src fill that the
+// three-kernel path does with a memset: one launch instead of three kernels and a memset node on the forward chain.
+__global__ void __launch_bounds__(PLAN_CHUNK)
+plan_small_kernel(const int* __restrict__ idx, int NK, int E, int Rmax, int* __restrict__ counts,
+                  int* __restrict__ cmp_off, int* __restrict__ pad_off, int* __restrict__ tile_group,
+                  int* __restrict__ dest_row, int* __restrict__ cmp_pos, int* __restrict__ row_src,
+                  int* __restrict__ cmp_src) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ int warp_hist[PLAN_CHUNK / 32][MAX_E];
+  __shared__ int s_cmp[MAX_E + 1], s_pad[MAX_E + 1];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int j = t; j < (PLAN_CHUNK / 32) * MAX_E; j += blockDim.x) (&warp_hist[0][0])[j] = 0;
+  for (int r = t; r < Rmax; r += blockDim.x) row_src[r] = -1;
+  if (cmp_src != nullptr && t < NK) cmp_src[t] = -1;
+  __syncthreads();
+  int e = -1;
+  if (t < NK) {
+    e = idx[t];
+    if (e < 0 || e >= E) e = -1;
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, e >= 0 ? e : (MAX_E + lane));
+  const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+  if (e >= 0 && rank_in_warp == 0) warp_hist[warp][e] = __popc(peers);
+  __syncthreads();
+  if (t == 0) {
+    int c = 0, p = 0;
+    for (int x = 0; x < E; ++x) {
+      int n = 0;
+      for (int w = 0; w < PLAN_CHUNK / 32; ++w) n += warp_hist[w][x];
+      counts[x] = n;
+      cmp_off[x] = c;
+      pad_off[x] = p;
+      s_cmp[x] = c;
+      s_pad[x] = p;
+      c += n;
+      p += (n + B200_GROUP_TILE - 1) / B200_GROUP_TILE * B200_GROUP_TILE;
+    }
+    cmp_off[E] = c;
+    pad_off[E] = p;
+    s_cmp[E] = c;
+    s_pad[E] = p;
+  }
+  __syncthreads();
+  const int tiles = Rmax / B200_GROUP_TILE;
+  for (int tile = t; tile < tiles; tile += blockDim.x) {
+    const int r = tile * B200_GROUP_TILE;
+    int g = -1;
+    for (int x = 0; x < E; ++x)
+      if (r >= s_pad[x] && r < s_pad[x + 1]) g = x;
+    tile_group[tile] = g;
+  }
+  if (t < NK) {
+    if (e >= 0) {
+      int before = 0;
+      for (int w = 0; w < warp; ++w) before += warp_hist[w][e];
+      const int k = before + rank_in_warp;
+      const int d = s_pad[e] + k;
+      dest_row[t] = d;
+      cmp_pos[t] = s_cmp[e] + k;
+      row_src[d] = t;
+      if (cmp_src != nullptr) cmp_src[s_cmp[e] + k] = t;
+    } else {
+      dest_row[t] = -1;
+      cmp_pos[t] = -1;
+    }
+  }
+}
+
 // ---- capacity masking (SparseMOELayer) -----------------------------------------------------------------
 __global__ void capacity_init_kernel(const float* __restrict__ w, int NK, float* __restrict__ w_eff,
                                      uint8_t* __restrict__ keep) {
@@ -415,6 +485,13 @@ int b200_moe_plan(const int32_t* idx, int NK, int E, int Rmax, int32_t* counts, 
   B200_CHECK_ARG(workspace_bytes >= b200_moe_plan_ws(NK, E), "moe_plan: workspace too small");
   const int chunks = (NK + PLAN_CHUNK - 1) / PLAN_CHUNK;
   int* block_counts = (int*)workspace;
+  if (chunks == 1) {
+    launch_kernel(plan_small_kernel, dim3(1), dim3(PLAN_CHUNK), 0, stream, idx, NK, E, Rmax, counts, cmp_off, pad_off,
+                  tile_group, dest_row, cmp_pos, row_src, cmp_src);
+    B200_LAUNCH_CHECK("plan_small_kernel");
+    count_launch(1);
+    return 0;
+  }
   B200_CUDA(cudaMemsetAsync(row_src, 0xFF, (size_t)Rmax * sizeof(int), stream));
   if (cmp_src != nullptr) B200_CUDA(cudaMemsetAsync(cmp_src, 0xFF, (size_t)NK * sizeof(int), stream));
   launch_kernel(plan_count_kernel, dim3(chunks), dim3(PLAN_CHUNK), 0, stream, idx, NK, E, block_counts);

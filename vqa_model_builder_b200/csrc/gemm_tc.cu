@@ -52,7 +52,7 @@ static_assert(smem_bytes<256>() <= 227 * 1024 && smem_bytes<128>() <= 227 * 1024
 // Optional in-kernel timeline (build with -DB200_GEMM_TRACE, scripts/gemm_trace.py): CTA 0 of every launch records
 // %globaltimer / clock64 at the phase boundaries of its first tile.  Not part of the shipped library.
 #ifdef B200_GEMM_TRACE
-__device__ unsigned long long g_trace[256 * 32];
+__device__ unsigned long long g_trace[256 * 64];
 __device__ unsigned int g_trace_n;
 __device__ __forceinline__ unsigned long long trace_now() {
   unsigned long long t;
@@ -62,12 +62,19 @@ __device__ __forceinline__ unsigned long long trace_now() {
 #define B200_TRACE(idx_)                                                                      \
   do {                                                                                         \
     if (blockIdx.x == 0 && tr_slot < 256u) {                                                   \
-      g_trace[tr_slot * 32 + (idx_)] = trace_now();                                            \
-      g_trace[tr_slot * 32 + 16 + (idx_)] = (unsigned long long)clock64();                     \
+      g_trace[tr_slot * 64 + (idx_)] = trace_now();                                            \
+      g_trace[tr_slot * 64 + 16 + (idx_)] = (unsigned long long)clock64();                     \
     }                                                                                          \
+  } while (0)
+// arrival of k-block kb_ (< 32) of the first tile, seen by the MMA issuer
+#define B200_TRACE_KB(kb_)                                                                     \
+  do {                                                                                         \
+    if (blockIdx.x == 0 && tr_slot < 256u && (kb_) < 32)                                       \
+      g_trace[tr_slot * 64 + 32 + (kb_)] = (unsigned long long)clock64();                      \
   } while (0)
 #else
 #define B200_TRACE(idx_) do { } while (0)
+#define B200_TRACE_KB(kb_) do { } while (0)
 #endif
 
 struct TileInfo {
@@ -349,7 +356,8 @@ __device__ __forceinline__ void stage_load_tile_bf16(uint8_t* stg, int lane, flo
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const GemmArgs p, const int m_tiles_arg, const int n_tiles, const int total_tiles_arg) {
+               const GemmArgs p, const int m_tiles_arg, const int n_tiles, const int total_tiles_arg,
+               const int a_tx_bytes /* bytes one k-block of A brings in: A_BYTES, less for a short-row box */) {
   constexpr int STAGES = num_stages<BN>();
   constexpr int STAGE = stage_bytes<BN>();
   extern __shared__ uint8_t smem_raw[];
@@ -420,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-          ptx::mbar_arrive_expect_tx(full_bar(s), STAGE);
+          ptx::mbar_arrive_expect_tx(full_bar(s), (uint32_t)(a_tx_bytes + BN * BK * 2));
           const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
           const int kc = (t.k_begin + kb) * BK;
           if (!A_MN) {
@@ -459,6 +467,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           ptx::mbar_wait(full_bar(s), ph);
           ptx::tc_fence_after();
           if (it == 0) B200_TRACE(3);
+          if (acc_it == 0) B200_TRACE_KB(kb);
           const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -645,7 +654,7 @@ namespace {
 
 template <int BN, bool A_MN, bool B_MN>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int m_tiles, int n_tiles,
-                   int total_tiles, cudaStream_t stream) {
+                   int total_tiles, int a_tx_bytes, cudaStream_t stream) {
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
   if (!configured) {
@@ -653,7 +662,8 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
     configured = true;
   }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  launch_kernel(kern, dim3(grid), dim3(NUM_THREADS), smem_bytes<BN>(), stream, ta, tb, args, m_tiles, n_tiles, total_tiles);
+  launch_kernel(kern, dim3(grid), dim3(NUM_THREADS), smem_bytes<BN>(), stream, ta, tb, args, m_tiles, n_tiles, total_tiles,
+                a_tx_bytes);
   B200_LAUNCH_CHECK("gemm_tc_kernel");
   count_launch();
   return 0;
@@ -661,11 +671,11 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
 
 template <int BN>
 int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int m_tiles,
-              int n_tiles, int total_tiles, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_variant<BN, false, false>(ta, tb, args, m_tiles, n_tiles, total_tiles, stream);
-  if (!a_mn && b_mn) return launch_variant<BN, false, true>(ta, tb, args, m_tiles, n_tiles, total_tiles, stream);
-  if (a_mn && b_mn) return launch_variant<BN, true, true>(ta, tb, args, m_tiles, n_tiles, total_tiles, stream);
-  return launch_variant<BN, true, false>(ta, tb, args, m_tiles, n_tiles, total_tiles, stream);
+              int n_tiles, int total_tiles, int a_tx, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_variant<BN, false, false>(ta, tb, args, m_tiles, n_tiles, total_tiles, a_tx, stream);
+  if (!a_mn && b_mn) return launch_variant<BN, false, true>(ta, tb, args, m_tiles, n_tiles, total_tiles, a_tx, stream);
+  if (a_mn && b_mn) return launch_variant<BN, true, true>(ta, tb, args, m_tiles, n_tiles, total_tiles, a_tx, stream);
+  return launch_variant<BN, true, false>(ta, tb, args, m_tiles, n_tiles, total_tiles, a_tx, stream);
 }
 
 }  // namespace
@@ -725,7 +735,15 @@ int launch_gemm_tc(const void* A, int lda, int a_layout, long long a_mn_extent, 
 
   CUtensorMap ta, tb;
   int rc;
-  if (!a_mn) rc = make_tma_map_bf16(&ta, A, a_k_extent, a_mn_extent, lda, BM);
+  // A single row tile with few rows (the CLS-row GEMMs of the last fusion layer, the pooled vectors of the
+  // classification pipeline: M = batch): the TMA box covers only 32 or 64 rows.  A k-block of a 128-row box costs the
+  // producer the same whether its rows are in bounds or zero-filled (timeline: 525 clocks per k-block at M = 32 and at
+  // M = 2048); the UMMA still multiplies 128 rows, rows beyond the box hold whatever the stage held before and only
+  // reach accumulator rows that are never stored.
+  int a_box = BM;
+  if (!a_mn && m_tiles == 1 && args.mode == GEMM_DENSE) a_box = a_mn_extent <= 32 ? 32 : (a_mn_extent <= 64 ? 64 : BM);
+  const int a_tx = a_mn ? A_BYTES : a_box * BK * 2;
+  if (!a_mn) rc = make_tma_map_bf16(&ta, A, a_k_extent, a_mn_extent, lda, a_box);
   else rc = make_tma_map_bf16(&ta, A, a_mn_extent, a_k_extent, lda, BK);
   if (rc) return rc;
   if (!b_mn) rc = make_tma_map_bf16(&tb, B, b_k_extent, b_mn_extent, ldb, bn);
@@ -734,18 +752,18 @@ int launch_gemm_tc(const void* A, int lda, int a_layout, long long a_mn_extent, 
 
   const int n_tiles = (args.N + bn - 1) / bn;
   const int total = (int)(m_tiles * n_tiles * (args.mode == GEMM_GROUP_WGRAD ? groups : splits));
-  if (bn == 256) return launch_bn<256>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, stream);
-  if (bn == 128) return launch_bn<128>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, stream);
-  return launch_bn<64>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, stream);
+  if (bn == 256) return launch_bn<256>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, a_tx, stream);
+  if (bn == 128) return launch_bn<128>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, a_tx, stream);
+  return launch_bn<64>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, a_tx, stream);
 }
 
 }  // namespace b200
 
 #ifdef B200_GEMM_TRACE
-// copies the timeline out and resets the launch counter: out[launch * 32 + {0..15: globaltimer ns, 16..31: clock64}]
+// copies the timeline out and resets the launch counter: out[launch * 64 + {0..15: globaltimer ns, 16..31: clock64, 32..63: clock64 at the arrival of k-block 0..31}]
 extern "C" int b200_debug_gemm_trace(unsigned long long* host_out, unsigned int* n_out) {
   unsigned int zero = 0;
-  if (cudaMemcpyFromSymbol(host_out, b200::g_trace, sizeof(unsigned long long) * 256 * 32) != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(host_out, b200::g_trace, sizeof(unsigned long long) * 256 * 64) != cudaSuccess) return 1;
   if (cudaMemcpyFromSymbol(n_out, b200::g_trace_n, sizeof(unsigned int)) != cudaSuccess) return 1;
   if (cudaMemcpyToSymbol(b200::g_trace_n, &zero, sizeof(unsigned int)) != cudaSuccess) return 1;
   return 0;
