@@ -134,3 +134,27 @@ def test_deepcopy_to_device_and_state_dict_roundtrip():
     layer(x).square().mean().backward()
     opt.step()
     assert not torch.equal(layer(x), y0)
+
+
+def test_prefetch_compute_weights_matches_in_line_cast():
+    """runtime.prefetch_compute_weights: the bf16 weight copy refreshed on the side stream is the one the next forward
+    uses (after an optimizer-style in-place update of the fp32 masters), eagerly and across repeated steps."""
+    torch.manual_seed(0)
+    pkg.set_compute_dtype("bf16")
+    try:
+        layer = moe.MOELayer(input_dim=256, hidden_dim=512, output_dim=256, num_experts=4, top_k=2, dropout=0.0).to(DEV).eval()
+        x = torch.randn(4, 9, 256, device=DEV)
+        y0 = layer(x).float()
+        for step in range(3):
+            with torch.no_grad():
+                for p in layer.parameters():
+                    p.mul_(1.01)                      # what an optimizer step does: in-place update of the masters
+            assert pkg.prefetch_compute_weights(layer) == 1
+            assert pkg.prefetch_compute_weights(layer) == 0          # already queued
+            y1 = layer(x).float()                                    # waits for the side-stream copy
+            layer.invalidate()
+            y2 = layer(x).float()                                    # in-line cast of the same masters
+            assert torch.equal(y1, y2), step
+            assert not torch.equal(y1, y0)
+    finally:
+        pkg.set_compute_dtype("auto")

@@ -79,6 +79,40 @@ def test_gemm_split_k_accumulate():
     assert rel_err(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("M", [1, 7, 32, 33, 64])
+@pytest.mark.parametrize("N,K", [(768, 768), (768, 3072), (3072, 768), (104, 256), (768, 320), (64, 1024)])
+def test_gemm_small_m_cluster_split_k(M, N, K):
+    """Single-row-tile GEMMs with M <= 64 split K over a thread-block cluster (partial tiles reduced through
+    distributed shared memory into the CTA that runs the epilogue): every epilogue, both weight layouts, K with and
+    without a power-of-two number of k-blocks (K = 320: five k-blocks, no split), ragged N."""
+    from vqa_model_builder_b200._lib import EPI_ACT_D, EPI_MUL
+    dtype = torch.bfloat16
+    g = torch.Generator(device=DEV).manual_seed(M * 131 + N + K)
+    a, b = mk((M, K), dtype, g), mk((N, K), dtype, g, 0.05)
+    bias = torch.randn(N, generator=g, device=DEV)
+    aux = mk((M, N), dtype, g)
+    acc = a.double() @ b.double().t()
+    out = ops.gemm(a, LAYOUT_K, b, LAYOUT_K, M, N, K, bias=bias)
+    assert rel_err(out, acc + bias.double()) < tol(dtype), rel_err(out, acc + bias.double())
+    out = ops.gemm(a, LAYOUT_K, b.t().contiguous(), LAYOUT_MN, M, N, K)            # dgrad layout
+    assert rel_err(out, acc) < tol(dtype), rel_err(out, acc)
+    out = ops.gemm(a, LAYOUT_K, b, LAYOUT_K, M, N, K, bias=bias, epi=EPI_ADD, aux_in=aux)
+    assert rel_err(out, acc + bias.double() + aux.double()) < tol(dtype)
+    out = ops.gemm(a, LAYOUT_K, b, LAYOUT_K, M, N, K, epi=EPI_MUL, aux_in=aux)
+    assert rel_err(out, acc * aux.double()) < tol(dtype)
+    if N % 8 == 0:
+        dact = torch.empty((M, N), dtype=dtype, device=DEV)
+        out = ops.gemm(a, LAYOUT_K, b, LAYOUT_K, M, N, K, bias=bias, epi=EPI_ACT_D, act=ACT_GELU, aux_out=dact)
+        x = (acc + bias.double()).requires_grad_()
+        y = torch.nn.functional.gelu(x)
+        y.sum().backward()
+        assert rel_err(out, y) < tol(dtype)
+        assert rel_err(dact, x.grad) < tol(dtype)
+    # fp32 output of the same products (classifier logits)
+    out = ops.gemm(a, LAYOUT_K, b, LAYOUT_K, M, N, K, bias=bias, out_dtype=torch.float32)
+    assert rel_err(out, acc + bias.double()) < 1e-5
+
+
 def test_gemm_strided_rows():
     """A = CLS rows of a [B, T, D] activation (pitch T*D) — the pooled Linear of MultimodalFusion."""
     B, T, D, N = 32, 64, 768, 768

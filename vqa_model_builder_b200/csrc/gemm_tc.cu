@@ -77,6 +77,32 @@ __device__ __forceinline__ unsigned long long trace_now() {
 #define B200_TRACE_KB(kb_) do { } while (0)
 #endif
 
+// ---- thread-block clusters / distributed shared memory (split-K of small GEMMs, see launch_gemm_tc) -------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// every thread of every CTA of the cluster (warp-converged): orders prior (distributed) shared-memory accesses
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+// byte offset of the 16-byte unit j4 (4 columns) of (partial kr >= 1, 32-column chunk c, row) in the leader's reduction
+// buffer: rows are the fastest index, so the 32 lanes of a warp (= 32 consecutive rows) touch 512 contiguous bytes
+__device__ __forceinline__ uint32_t red_off(int kr, int c, int j4, int row, int nchunk, int red_rows) {
+  return (uint32_t)(((((kr - 1) * nchunk + c) * 8 + j4) * red_rows + row) * 16);
+}
+
 struct TileInfo {
   int valid, group, m_tile, n_tile;
   int a_mn0, a_k0, b_mn0, b_k0, k_begin, k_blocks;
@@ -357,7 +383,9 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmArgs p, const int m_tiles_arg, const int n_tiles, const int total_tiles_arg,
-               const int a_tx_bytes /* bytes one k-block of A brings in: A_BYTES, less for a short-row box */) {
+               const int a_tx_bytes /* bytes one k-block of A brings in: A_BYTES, less for a short-row box */,
+               const int kc /* > 1: cluster of kc CTAs splits K of ONE tile; rank 0 reduces + runs the epilogue */,
+               const int red_rows /* kc > 1: rows of the tile that exist (32 or 64) */) {
   constexpr int STAGES = num_stages<BN>();
   constexpr int STAGE = stage_bytes<BN>();
   extern __shared__ uint8_t smem_raw[];
@@ -417,11 +445,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (used_tiles < m_tiles) { m_tiles = used_tiles; total_tiles = used_tiles * n_tiles; }
   }
 
+  // Cluster split-K: grid = tiles * kc, the kc CTAs of a cluster share a tile and take consecutive K ranges (get_tile's
+  // split logic with z = rank).  Each CTA walks exactly one work item.
+  const int kc_rank = kc > 1 ? (int)cluster_ctarank() : 0;
+  const int tile0 = kc > 1 ? (int)(blockIdx.x / kc) + kc_rank * (m_tiles * n_tiles) : (int)blockIdx.x;
+  const int tile_step = kc > 1 ? total_tiles : (int)gridDim.x;
+
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const TileInfo t = get_tile<BN, B_MN>(p, tile, m_tiles, n_tiles);
         if (!t.valid) continue;
         for (int kb = 0; kb < t.k_blocks; ++kb, ++it) {
@@ -448,12 +482,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       }
     }
+    if (kc > 1) {          // every thread of the cluster takes part in the two reduction barriers (epilogue branch)
+      __syncwarp();
+      cluster_sync_all();
+      cluster_sync_all();
+    }
   } else if (warp == 1) {
     // ================= UMMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN, B_MN);
       int it = 0, acc_it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const TileInfo t = get_tile<BN, B_MN>(p, tile, m_tiles, n_tiles);
         if (!t.valid || t.k_blocks == 0) continue;
         const int acc = acc_it & 1;
@@ -486,6 +525,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         ++acc_it;
       }
     }
+    if (kc > 1) {
+      __syncwarp();
+      cluster_sync_all();
+      cluster_sync_all();
+    }
   } else {
     // ================= epilogue warps =================
     const int ew = warp - 2;                 // 0..7
@@ -502,9 +546,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     const DropState drop = drop_load(p.drop_state, p.drop_p, p.drop_site);
     int acc_it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const TileInfo t = get_tile<BN, B_MN>(p, tile, m_tiles, n_tiles);
-      if (!t.valid) continue;
+      if (!t.valid) {
+        if (kc > 1) {        // never leave the cluster's barriers short of a CTA (the host keeps every rank busy)
+          __syncwarp();
+          cluster_sync_all();
+          cluster_sync_all();
+        }
+        continue;
+      }
       const bool have_acc = t.k_blocks > 0;
       const int acc = acc_it & 1;
       const uint32_t acc_ph = (acc_it >> 1) & 1;
@@ -521,6 +572,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       long long rows_left = (long long)p.M - row0;
       const int rows_ok = rows_left >= 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);
       const long long obase = (p.mode == GEMM_GROUP_WGRAD) ? (long long)t.group * p.out_group_elems : 0ll;
+      const bool red_warp = kc > 1 && quad * 32 < red_rows;      // this warp's TMEM lanes hold rows that exist
+      if (kc > 1) {
+        // #1: every CTA's MMAs have completed (its epilogue warps waited for the accumulator), so the leader's pipeline
+        // stages are free to receive the partial tiles
+        __syncwarp();
+        cluster_sync_all();
+        if (kc_rank != 0) {
+          if (red_warp && have_acc) {
+            const uint32_t rbase = mapa_shared(base, 0);
+#pragma unroll 1
+            for (int c = part; c < NCHUNK; c += EPI_PARTS) {
+              uint32_t r[32];
+              ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                st_cluster_v4(rbase + red_off(kc_rank, c, j4, quad * 32 + lane, NCHUNK, red_rows),
+                              __uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
+                              __uint_as_float(r[4 * j4 + 3]));
+            }
+          }
+          __syncwarp();
+          cluster_sync_all();        // #2: partial tiles have landed in the leader
+          ++acc_it;
+          continue;                  // only the leader runs the epilogue
+        }
+        __syncwarp();
+        cluster_sync_all();          // #2
+      }
 #pragma unroll 1
       for (int c = part, k = 0; c < NCHUNK; c += EPI_PARTS, ++k) {
         const int col0 = ncol0 + c * 32;
@@ -535,6 +615,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (red_warp) {                          // leader of a split-K cluster: add the other CTAs' partial tiles
+          for (int kr = 1; kr < kc; ++kr) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 q4 = *reinterpret_cast<const float4*>(smem + red_off(kr, c, j4, quad * 32 + lane, NCHUNK, red_rows));
+              v[4 * j4] += q4.x; v[4 * j4 + 1] += q4.y; v[4 * j4 + 2] += q4.z; v[4 * j4 + 3] += q4.w;
+            }
+          }
         }
         if (col0 >= p.N) continue;               // warp-uniform
         if (vec_ok && col0 + 32 <= p.N) {
@@ -652,18 +741,49 @@ int make_tma_map_bf16(void* map_out, const void* ptr, long long inner, long long
 
 namespace {
 
+// launch_kernel (common.cuh) plus a thread-block cluster of `cluster_x` CTAs along x
+template <typename... KP, typename... A>
+cudaError_t launch_kernel_cluster(void (*kern)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  int cluster_x, A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster_x;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KP>(args)...);
+}
+
 template <int BN, bool A_MN, bool B_MN>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int m_tiles, int n_tiles,
-                   int total_tiles, int a_tx_bytes, cudaStream_t stream) {
+                   int total_tiles, int a_tx_bytes, int kc, int red_rows, cudaStream_t stream) {
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN>()));
     configured = true;
   }
+  if (kc > 1) {     // one CTA per (tile, K range): total_tiles = tiles * kc, clusters of kc consecutive CTAs
+    B200_CHECK_ARG((size_t)(kc - 1) * BN * red_rows * 4 <= (size_t)num_stages<BN>() * stage_bytes<BN>(),
+                   "gemm: split-K reduction buffer does not fit the pipeline stages (kc=%d BN=%d rows=%d)", kc, BN, red_rows);
+    launch_kernel_cluster(kern, dim3(total_tiles), dim3(NUM_THREADS), smem_bytes<BN>(), stream, kc, ta, tb, args, m_tiles,
+                          n_tiles, total_tiles, a_tx_bytes, kc, red_rows);
+    B200_LAUNCH_CHECK("gemm_tc_kernel (cluster split-K)");
+    count_launch();
+    return 0;
+  }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   launch_kernel(kern, dim3(grid), dim3(NUM_THREADS), smem_bytes<BN>(), stream, ta, tb, args, m_tiles, n_tiles, total_tiles,
-                a_tx_bytes);
+                a_tx_bytes, 1, 0);
   B200_LAUNCH_CHECK("gemm_tc_kernel");
   count_launch();
   return 0;
@@ -671,11 +791,14 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
 
 template <int BN>
 int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int m_tiles,
-              int n_tiles, int total_tiles, int a_tx, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_variant<BN, false, false>(ta, tb, args, m_tiles, n_tiles, total_tiles, a_tx, stream);
-  if (!a_mn && b_mn) return launch_variant<BN, false, true>(ta, tb, args, m_tiles, n_tiles, total_tiles, a_tx, stream);
-  if (a_mn && b_mn) return launch_variant<BN, true, true>(ta, tb, args, m_tiles, n_tiles, total_tiles, a_tx, stream);
-  return launch_variant<BN, true, false>(ta, tb, args, m_tiles, n_tiles, total_tiles, a_tx, stream);
+              int n_tiles, int total_tiles, int a_tx, int kc, int red_rows, cudaStream_t stream) {
+  if (!a_mn && !b_mn)
+    return launch_variant<BN, false, false>(ta, tb, args, m_tiles, n_tiles, total_tiles, a_tx, kc, red_rows, stream);
+  if (!a_mn && b_mn)
+    return launch_variant<BN, false, true>(ta, tb, args, m_tiles, n_tiles, total_tiles, a_tx, kc, red_rows, stream);
+  if (a_mn && b_mn)
+    return launch_variant<BN, true, true>(ta, tb, args, m_tiles, n_tiles, total_tiles, a_tx, kc, red_rows, stream);
+  return launch_variant<BN, true, false>(ta, tb, args, m_tiles, n_tiles, total_tiles, a_tx, kc, red_rows, stream);
 }
 
 }  // namespace
@@ -725,6 +848,36 @@ int launch_gemm_tc(const void* A, int lda, int a_layout, long long a_mn_extent, 
       if (t < best * 0.999f) { best = t; bn = cand; splits = s_; }
     }
   }
+  // Cluster split-K for single-row-tile GEMMs with few rows (M = batch: the CLS-row GEMMs of the last fusion layer,
+  // the pooled vectors, the classifier head).  Their main loop is bound by 140 clocks per 128-row UMMA x k-steps on a
+  // handful of SMs (timeline in DESIGN.md, section 4) while 130+ SMs idle: kc CTAs of a thread-block cluster take K / kc
+  // each, push their partial tiles (only the rows that exist) into the leader's free pipeline stages through distributed
+  // shared memory, and the leader runs the unchanged epilogue.  No atomics, no workspace, deterministic.
+  int kc = 1;
+  static const bool cluster_on = []() { const char* e = getenv("B200VQA_GEMM_CLUSTER"); return !(e && e[0] == '0'); }();
+  if (cluster_on && !forced_bn && !a_mn && m_tiles == 1 && a_mn_extent <= 64 && args.mode == GEMM_DENSE &&
+      args.epi != B200_EPI_ACCUM && kblocks >= 4) {
+    const int rows = a_mn_extent <= 32 ? 32 : 64;
+    float best_t = 1e30f;
+    int best_bn = bn, best_kc = 1;
+    for (int cand : {64, 128}) {
+      const int tiles = (args.N + cand - 1) / cand;
+      const size_t stage_cap = cand == 64 ? (size_t)num_stages<64>() * stage_bytes<64>() : (size_t)num_stages<128>() * stage_bytes<128>();
+      for (int c : {8, 4, 2}) {
+        if (kblocks % c != 0 || tiles * c > sms) continue;
+        if ((size_t)(c - 1) * cand * rows * 4 > stage_cap) continue;
+        // k-blocks per CTA at the UMMA instruction floor + the reduction (barriers, partial tiles) + epilogue chunks
+        const float t = (float)(kblocks / c) * (cand == 64 ? 561.f : 585.f) + 900.f + 300.f * c + 2000.f * (cand / 64);
+        if (t < best_t) { best_t = t; best_bn = cand; best_kc = c; }
+      }
+    }
+    const float t_plain = (float)kblocks * (bn == 64 ? 561.f : (bn == 128 ? 585.f : 800.f)) + 2000.f * (bn / 64);
+    if (best_kc > 1 && best_t < t_plain) {
+      bn = best_bn;
+      kc = best_kc;
+      splits = kc;
+    }
+  }
   args.k_splits = splits;
   if (args.epi == B200_EPI_ACCUM && args.mode == GEMM_DENSE) {
     if (splits > 1)   // partial sums are added atomically into a zeroed buffer
@@ -752,9 +905,10 @@ int launch_gemm_tc(const void* A, int lda, int a_layout, long long a_mn_extent, 
 
   const int n_tiles = (args.N + bn - 1) / bn;
   const int total = (int)(m_tiles * n_tiles * (args.mode == GEMM_GROUP_WGRAD ? groups : splits));
-  if (bn == 256) return launch_bn<256>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, a_tx, stream);
-  if (bn == 128) return launch_bn<128>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, a_tx, stream);
-  return launch_bn<64>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, a_tx, stream);
+  const int red_rows = kc > 1 ? a_box : 0;
+  if (bn == 256) return launch_bn<256>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, a_tx, 1, 0, stream);
+  if (bn == 128) return launch_bn<128>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, a_tx, kc, red_rows, stream);
+  return launch_bn<64>(a_mn, b_mn, ta, tb, args, (int)m_tiles, n_tiles, total, a_tx, kc, red_rows, stream);
 }
 
 }  // namespace b200
