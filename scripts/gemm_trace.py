@@ -28,6 +28,7 @@ def main():
     n = ctypes.c_uint(0)
     g = torch.Generator(device=dev).manual_seed(0)
     cases = [("fwd_proj_M2048", "KK", 2048, 768, 768, EPI_NONE), ("fwd_proj_M32", "KK", 32, 768, 768, EPI_NONE),
+             ("fwd_ffn2_M32", "KK", 32, 768, 3072, EPI_NONE), ("fwd_ffn1_M32", "KK", 32, 3072, 768, EPI_ACT_D),
              ("fwd_qkv_M2048", "KK", 2048, 2304, 768, EPI_NONE), ("fwd_ffn1_M2048", "KK", 2048, 3072, 768, EPI_ACT_D),
              ("fwd_ffn2_M2048", "KK", 2048, 768, 3072, EPI_NONE), ("dgrad_proj_M2048", "KMN", 2048, 768, 768, EPI_NONE),
              ("wgrad_proj_M2048", "MNMN", 768, 768, 2048, EPI_ACCUM)]
