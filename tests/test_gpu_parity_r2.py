@@ -563,3 +563,41 @@ def test_qformer_and_single_stream_fusion_match_reference(mode, tol, name):
     assert rel_err(txt.grad, ref["d_t"]) < gtol, rel_err(txt.grad, ref["d_t"])
     errs = _grad_errs(m, ref["grads"])
     assert worst(errs)[0] < gtol, worst(errs)
+
+
+@pytest.mark.parametrize("name,V,T", [("single_stream", 257, 40), ("single_stream", 197, 64), ("cross_attention", 257, 30)])
+def test_fusion_with_more_than_128_query_rows_on_the_tensor_cores(name, V, T):
+    """ViT-B/16 (197) / DINOv2 (257) patch tokens: the single-stream sequence (V + T > 128 rows of self-attention) and the
+    vision-query direction of CrossAttentionFusion run on the query-tiled tcgen05 attention (bf16); forward and backward
+    against the oracle on bf16-representable copies of the same random-init weights, with padded text positions."""
+    torch.manual_seed(V + T)
+    B, D, H, L, I = 3, 256, 4, 2, 512
+    kw = dict(num_attention_heads=H, num_layers=L, intermediate_dim=I)
+    if name == "single_stream":
+        kw.update(max_vision_tokens=V + 1, max_text_tokens=T)      # the table also holds the [CLS] position
+    else:
+        kw.update(fusion_method="add")
+    with computing("bf16"):
+        m = fusion.create_fusion_model(name, vision_dim=D, text_dim=D, output_dim=D, dropout=0.0, **kw).to(DEV).train()
+        sd = round_sd_for_bf16({k: v.detach().cpu().clone() for k, v in m.state_dict().items()})
+        m.load_state_dict(sd)
+        vis0 = bf16_representable(torch.randn(B, V, D))
+        txt0 = bf16_representable(torch.randn(B, T, D))
+        valid = torch.ones(B, T, dtype=torch.bool)
+        valid[1, T - 5:] = False
+        valid[2, T // 2:] = False
+        gout = torch.randn(B, D)
+        vis, txt = vis0.to(DEV).requires_grad_(), txt0.to(DEV).requires_grad_()
+        out = m(vis, txt, text_mask=valid.to(DEV))
+        (out * gout.to(DEV)).sum().backward()
+    sdr, vr, tr = leafs(sd), vis0.clone().requires_grad_(), txt0.clone().requires_grad_()
+    if name == "single_stream":
+        o = rp.single_stream_fusion(sdr, H, L, vr, tr, None, valid)
+    else:
+        o = rp.cross_attention_fusion(sdr, H, L, "add", vr, tr, None, valid)
+    (o * gout).sum().backward()
+    assert rel_err(out, o.detach()) < 1e-2, rel_err(out, o.detach())
+    assert rel_err(vis.grad, vr.grad) < 2e-2, rel_err(vis.grad, vr.grad)
+    assert rel_err(txt.grad, tr.grad) < 2e-2, rel_err(txt.grad, tr.grad)
+    errs = _grad_errs(m, {k: v.grad for k, v in sdr.items() if v.grad is not None})
+    assert worst(errs)[0] < 2e-2, worst(errs)
