@@ -87,6 +87,13 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// split-phase form: arrive early (kernel prologue), wait where the guarantee is needed
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -385,7 +392,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                const GemmArgs p, const int m_tiles_arg, const int n_tiles, const int total_tiles_arg,
                const int a_tx_bytes /* bytes one k-block of A brings in: A_BYTES, less for a short-row box */,
                const int kc /* > 1: cluster of kc CTAs splits K of ONE tile; rank 0 reduces + runs the epilogue */,
-               const int red_rows /* kc > 1: rows of the tile that exist (32 or 64) */) {
+               const int red_rows /* kc > 1: rows of the tile that exist (32 or 64) */,
+               const int red_base /* kc > 1: byte offset of the reduction buffer inside the pipeline-stage area; >= 0 and
+                                     beyond the stages this launch's short pipelines touch: partial tiles may be
+                                     pushed without waiting for the leader (one cluster barrier); < 0: offset 0, two */) {
   constexpr int STAGES = num_stages<BN>();
   constexpr int STAGE = stage_bytes<BN>();
   extern __shared__ uint8_t smem_raw[];
@@ -429,6 +439,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Split-K cluster whose reduction buffer lies behind the stages in use: the only thing the first cluster barrier has
+  // to guarantee is that the leader CTA is running before anyone stores into its shared memory.  Arrive here, wait
+  // (long since satisfied) right before the remote stores: a barrier phase without latency.
+  if (kc > 1 && red_base >= 0) cluster_arrive_relaxed();
 #ifdef B200_GEMM_TRACE
   if (blockIdx.x == 0) tr_slot = tr_slot_s;
   if (threadIdx.x == 0) B200_TRACE(1);
@@ -482,9 +496,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       }
     }
-    if (kc > 1) {          // every thread of the cluster takes part in the two reduction barriers (epilogue branch)
+    if (kc > 1) {          // every thread of the cluster takes part in the reduction barriers (epilogue branch)
       __syncwarp();
-      cluster_sync_all();
+      if (red_base < 0) cluster_sync_all(); else cluster_wait();
       cluster_sync_all();
     }
   } else if (warp == 1) {
@@ -527,7 +541,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     if (kc > 1) {
       __syncwarp();
-      cluster_sync_all();
+      if (red_base < 0) cluster_sync_all(); else cluster_wait();
       cluster_sync_all();
     }
   } else {
@@ -551,7 +565,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (!t.valid) {
         if (kc > 1) {        // never leave the cluster's barriers short of a CTA (the host keeps every rank busy)
           __syncwarp();
-          cluster_sync_all();
+          if (red_base < 0) cluster_sync_all(); else cluster_wait();
           cluster_sync_all();
         }
         continue;
@@ -573,14 +587,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int rows_ok = rows_left >= 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);
       const long long obase = (p.mode == GEMM_GROUP_WGRAD) ? (long long)t.group * p.out_group_elems : 0ll;
       const bool red_warp = kc > 1 && quad * 32 < red_rows;      // this warp's TMEM lanes hold rows that exist
+      const uint32_t red_at = red_base > 0 ? (uint32_t)red_base : 0u;
       if (kc > 1) {
-        // #1: every CTA's MMAs have completed (its epilogue warps waited for the accumulator), so the leader's pipeline
-        // stages are free to receive the partial tiles
+        // #1 (only when the buffer overlaps stages the leader's pipeline uses): every CTA's MMAs have completed (its
+        // epilogue warps waited for the accumulator), so the leader's pipeline stages are free to receive the partials
         __syncwarp();
-        cluster_sync_all();
+        if (red_base < 0) cluster_sync_all(); else cluster_wait();
         if (kc_rank != 0) {
           if (red_warp && have_acc) {
-            const uint32_t rbase = mapa_shared(base, 0);
+            const uint32_t rbase = mapa_shared(base + red_at, 0);
 #pragma unroll 1
             for (int c = part; c < NCHUNK; c += EPI_PARTS) {
               uint32_t r[32];
@@ -620,7 +635,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int kr = 1; kr < kc; ++kr) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 q4 = *reinterpret_cast<const float4*>(smem + red_off(kr, c, j4, quad * 32 + lane, NCHUNK, red_rows));
+              const float4 q4 = *reinterpret_cast<const float4*>(smem + red_at + red_off(kr, c, j4, quad * 32 + lane, NCHUNK, red_rows));
               v[4 * j4] += q4.x; v[4 * j4 + 1] += q4.y; v[4 * j4 + 2] += q4.z; v[4 * j4 + 3] += q4.w;
             }
           }
@@ -775,15 +790,22 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
   if (kc > 1) {     // one CTA per (tile, K range): total_tiles = tiles * kc, clusters of kc consecutive CTAs
     B200_CHECK_ARG((size_t)(kc - 1) * BN * red_rows * 4 <= (size_t)num_stages<BN>() * stage_bytes<BN>(),
                    "gemm: split-K reduction buffer does not fit the pipeline stages (kc=%d BN=%d rows=%d)", kc, BN, red_rows);
+    // Each CTA runs K / kc k-blocks through stages 0 .. kb-1 once; a reduction buffer behind them can be written while
+    // the leader is still multiplying (no barrier before the partial tiles are pushed).
+    const int kb_per_cta = ((args.K + BK - 1) / BK + kc - 1) / kc;
+    const size_t red_bytes = (size_t)(kc - 1) * BN * red_rows * 4;
+    const size_t area = (size_t)num_stages<BN>() * stage_bytes<BN>();
+    const size_t used = (size_t)(kb_per_cta < num_stages<BN>() ? kb_per_cta : num_stages<BN>()) * stage_bytes<BN>();
+    const int red_base = (used + red_bytes <= area && used > 0) ? (int)(area - red_bytes) / 1024 * 1024 : -1;
     launch_kernel_cluster(kern, dim3(total_tiles), dim3(NUM_THREADS), smem_bytes<BN>(), stream, kc, ta, tb, args, m_tiles,
-                          n_tiles, total_tiles, a_tx_bytes, kc, red_rows);
+                          n_tiles, total_tiles, a_tx_bytes, kc, red_rows, red_base >= (int)used ? red_base : -1);
     B200_LAUNCH_CHECK("gemm_tc_kernel (cluster split-K)");
     count_launch();
     return 0;
   }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   launch_kernel(kern, dim3(grid), dim3(NUM_THREADS), smem_bytes<BN>(), stream, ta, tb, args, m_tiles, n_tiles, total_tiles,
-                a_tx_bytes, 1, 0);
+                a_tx_bytes, 1, 0, -1);
   B200_LAUNCH_CHECK("gemm_tc_kernel");
   count_launch();
   return 0;
