@@ -296,6 +296,31 @@ def test_router_bf16_fast_path_matches_oracle_at_d768(N, E, K, D):
     assert rel_err(r.gate.weight.grad, sd["gate.weight"].grad) < 1e-4
 
 
+def test_router_forward_is_one_launch_and_rearms_its_ticket():
+    """bf16, E <= 8: the statistics / load-balance loss are folded by the last block of the forward kernel (no finalize
+    launch); the ticket is re-armed, so repeated forwards (and other token counts in between) give identical results."""
+    from vqa_model_builder_b200 import _lib
+    torch.manual_seed(0)
+    D, E, K = 768, 8, 2
+    r = moe.TopKRouter(D, E, top_k=K).to(DEV)
+    xs = {n: torch.randn(1, n, D, device=DEV).to(torch.bfloat16) for n in (32, 14592, 3000)}
+    first = {}
+    for rep in range(3):
+        for n, x in xs.items():
+            _lib.reset_launch_count()
+            w, idx, aux = r(x)
+            assert _lib.launch_count() == 1, _lib.launch_count()
+            cur = (float(aux["load_balance_loss"]), aux["expert_counts"].clone() if "expert_counts" in aux else None)
+            if n in first:
+                assert cur[0] == first[n][0]
+                if cur[1] is not None:
+                    assert torch.equal(cur[1], first[n][1])
+            else:
+                first[n] = cur
+                if cur[1] is not None:
+                    assert int(cur[1].sum()) == n * K
+
+
 # ---- cfg3 / cfg4 shapes, forward + backward -------------------------------------------------------------------------
 @pytest.mark.parametrize("mode,tol", MODES)
 @pytest.mark.parametrize("V,E", [(257, 16), (49, 32)])

@@ -18,6 +18,8 @@
 // dx = dl . W runs as m16n8k8 MMAs with dl and W each split into two bf16 terms (three products, error ~2^-17,
 // below the bf16 rounding of dx), column-permuted so that every thread owns 8 consecutive output columns (16-byte
 // stores).
+#include <atomic>
+
 #include "rowops.cuh"
 
 namespace b200 {
@@ -26,7 +28,12 @@ namespace {
 
 constexpr int RM_WARPS = 8;
 constexpr int RM_MAX_E = 64;   // partial layout shared with router_finalize_kernel: [grid][3][64]
-constexpr int RM_BATCH = 8;    // 32-column chunks per load batch: 2 x 8 x 16 B per thread in flight, double-buffered
+constexpr int RM_BATCH = 8;
+// Tickets of the fused finalize: the block of a forward launch that finishes LAST folds the per-block statistics
+// (counts, sum of probabilities, load-balance loss) -- what a second single-block kernel used to do.  Device-global ring
+// (zero at load, reset by the folding block); launches in flight at the same time on different streams get different slots.
+constexpr int RM_TICKETS = 256;
+__device__ unsigned int g_rm_tickets[RM_TICKETS];    // 32-column chunks per load batch: 2 x 8 x 16 B per thread in flight, double-buffered
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                           uint32_t b0, uint32_t b1) {
@@ -118,7 +125,9 @@ __device__ __forceinline__ void route_row(float l0, float l1, int n, bool ok, in
 __global__ void __launch_bounds__(RM_WARPS * 32, 1)
 router_fwd_mma_kernel(const bf16* __restrict__ x, const float* __restrict__ w_gate, int N, int D, int E, int K,
                       int* __restrict__ idx, float* __restrict__ w, float* __restrict__ topk_sum,
-                      float* __restrict__ probs, float* __restrict__ part /* [grid][3][64] */) {
+                      float* __restrict__ probs, float* __restrict__ part /* [grid][3][64] */, float lb_weight,
+                      float* __restrict__ counts, float* __restrict__ psum, float* __restrict__ loss,
+                      unsigned int* __restrict__ ticket) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint4* ws = reinterpret_cast<uint4*>(smem_raw);     // [3 splits][D/32 chunks][32 lanes]
   __shared__ float red[RM_WARPS][2][8];
@@ -227,6 +236,39 @@ router_fwd_mma_kernel(const bf16* __restrict__ x, const float* __restrict__ w_ga
       for (int wp = 0; wp < RM_WARPS; ++wp) s += red[wp][which][e];
     }
     part[((long long)blockIdx.x * 3 + which) * RM_MAX_E + e] = s;
+  }
+  // ---- finalize in the last block to arrive: counts[e], psum[e], loss = lb_weight * E * sum_e (counts/N) (psum/N) ----
+  __shared__ bool s_last;
+  __shared__ float s_tot[2][8];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int arrived = atomicAdd(ticket, 1u);
+    s_last = (arrived == gridDim.x - 1);
+    if (s_last) *ticket = 0u;          // ready for the next launch that is handed this slot
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {
+    // 16 (statistic, expert) pairs x 16 threads each: fixed strided partial sums, then a shuffle tree (deterministic)
+    const int pair = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+    const int which = pair >> 3, e = pair & 7;
+    float s = 0.f;
+    for (int b = l16; b < (int)gridDim.x; b += 16) s += __ldcg(part + ((long long)b * 3 + which) * RM_MAX_E + e);
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (l16 == 0) s_tot[which][e] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < E) {
+    counts[threadIdx.x] = s_tot[0][threadIdx.x];
+    if (psum != nullptr) psum[threadIdx.x] = s_tot[1][threadIdx.x];
+  }
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int i = 0; i < E; ++i) acc += (s_tot[0][i] / (float)N) * (s_tot[1][i] / (float)N);
+    loss[0] = lb_weight * (float)E * acc;
   }
 }
 
@@ -361,7 +403,8 @@ static bool router_mma_covers(int D, int E, int K) { return router_mma_enabled()
 
 // returns the number of blocks launched (> 0), or -1 when the shape is not covered, or -2 on a launch error
 int launch_router_fwd_mma(const bf16* x, const float* w_gate, int N, int D, int E, int K, int* idx, float* w,
-                          float* topk_sum, float* probs, float* part, cudaStream_t stream) {
+                          float* topk_sum, float* probs, float* part, float lb_weight, float* counts, float* psum,
+                          float* loss, cudaStream_t stream) {
   if (!router_mma_covers(D, E, K)) return -1;
   const size_t smem = (size_t)3 * D * 16;       // 3 splits x D/32 chunks x 32 lanes x 16 B
   static bool attr_set = false;
@@ -371,8 +414,12 @@ int launch_router_fwd_mma(const bf16* x, const float* w_gate, int N, int D, int 
     attr_set = true;
   }
   const int grid = mma_grid(N, 1);
+  static std::atomic<unsigned int> next_ticket{0};
+  unsigned int* tk = nullptr;
+  if (cudaGetSymbolAddress((void**)&tk, g_rm_tickets) != cudaSuccess) return -2;
+  tk += next_ticket.fetch_add(1u) % RM_TICKETS;
   launch_kernel(router_fwd_mma_kernel, dim3(grid), dim3(RM_WARPS * 32), smem, stream, x, w_gate, N, D, E, K, idx, w,
-                topk_sum, probs, part);
+                topk_sum, probs, part, lb_weight, counts, psum, loss, tk);
   if (cudaGetLastError() != cudaSuccess) return -2;
   return grid;
 }
