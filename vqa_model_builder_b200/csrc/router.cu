@@ -12,6 +12,7 @@ int launch_partial_reduce(const float* part, int blocks, int rows_per_block, int
 int launch_router_fwd_mma(const bf16* x, const float* w_gate, int N, int D, int E, int K, int* idx, float* w,
                           float* topk_sum, float* probs, float* part, float lb_weight, float* counts, float* psum,
                           float* loss, cudaStream_t stream);
+bool router_fold_enabled();
 int launch_router_bwd_mma(const float* w_gate, float lb_weight, int N, int D, int E, int K, const int* idx,
                           const float* w, const float* topk_sum, const float* probs, const float* counts,
                           const float* d_w, const float* d_loss, const float* d_probs, bf16* dx, float* dl_out,
@@ -663,6 +664,12 @@ int b200_router_fwd(const void* x, int dtype, const float* w_gate, const float* 
                                          counts, psum, loss, stream);
     if (mb == -2) return cuda_fail(cudaGetLastError(), "launch router_fwd_mma_kernel");
     if (mb > 0) {
+      if (!router_fold_enabled()) {
+        launch_kernel(router_finalize_kernel, dim3(1), dim3(1024), 0, stream, part, mb, N, E, lb_weight, counts, psum, loss,
+                      (float*)nullptr);
+        B200_LAUNCH_CHECK("router_finalize_kernel");
+        count_launch(1);
+      }
       count_launch(1);
       return 0;
     }

@@ -238,6 +238,7 @@ router_fwd_mma_kernel(const bf16* __restrict__ x, const float* __restrict__ w_ga
     part[((long long)blockIdx.x * 3 + which) * RM_MAX_E + e] = s;
   }
   // ---- finalize in the last block to arrive: counts[e], psum[e], loss = lb_weight * E * sum_e (counts/N) (psum/N) ----
+  if (ticket == nullptr) return;       // statistics are folded by router_finalize_kernel (B200VQA_ROUTER_FOLD=0)
   __shared__ bool s_last;
   __shared__ float s_tot[2][8];
   __threadfence();
@@ -399,6 +400,16 @@ bool router_mma_enabled() {
   return v == 1;
 }
 
+// the last block of the forward kernel folds the statistics (default) / a separate finalize launch does (A/B testing)
+bool router_fold_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200VQA_ROUTER_FOLD");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool router_mma_covers(int D, int E, int K) { return router_mma_enabled() && D % 128 == 0 && D <= 2048 && E <= 8 && K <= 8; }
 
 // returns the number of blocks launched (> 0), or -1 when the shape is not covered, or -2 on a launch error
@@ -416,8 +427,10 @@ int launch_router_fwd_mma(const bf16* x, const float* w_gate, int N, int D, int 
   const int grid = mma_grid(N, 1);
   static std::atomic<unsigned int> next_ticket{0};
   unsigned int* tk = nullptr;
-  if (cudaGetSymbolAddress((void**)&tk, g_rm_tickets) != cudaSuccess) return -2;
-  tk += next_ticket.fetch_add(1u) % RM_TICKETS;
+  if (router_fold_enabled()) {
+    if (cudaGetSymbolAddress((void**)&tk, g_rm_tickets) != cudaSuccess) return -2;
+    tk += next_ticket.fetch_add(1u) % RM_TICKETS;
+  }
   launch_kernel(router_fwd_mma_kernel, dim3(grid), dim3(RM_WARPS * 32), smem, stream, x, w_gate, N, D, E, K, idx, w,
                 topk_sum, probs, part, lb_weight, counts, psum, loss, tk);
   if (cudaGetLastError() != cudaSuccess) return -2;
